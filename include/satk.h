@@ -1,0 +1,281 @@
+/*
+ * satk.h — C ABI of libsatk.so: the B200 (sm_100a) kernels behind the teacher-forced training
+ * hot path of Self-Attention Tacotron.
+ *
+ * The reference (nii-yamagishilab/self-attention-tacotron) is pure Python/TF1 and has NO native
+ * seam; nothing in it dictates an FFI.  The entry points below are therefore
+ * the operator boundary this implementation defines: one entry point per row group of SURVEY.md
+ * §8(a), each comment naming the reference code it replaces (paths relative to /root/reference).
+ * The host side (Python, `self-attention-tacotron_b200/engine.py`) mirrors the reference's
+ * module interfaces (encoder / decoder / model_fn) and calls these with raw device pointers.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named `h_*`; the caller owns all buffers, the
+ *     library allocates nothing;
+ *   - tensors are row-major contiguous fp32 unless stated; masks are uint8 (1 = keep);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream;
+ *   - return value: 0 on success, negative satk_status otherwise; `satk_last_error()` returns a
+ *     thread-local message.  No exception crosses the ABI.  No global mutable state.
+ */
+#ifndef SATK_H_
+#define SATK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SATK_OK = 0,
+  SATK_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  SATK_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+  SATK_ERR_UNSUPPORTED = -3  /* device is not sm_100 or resources do not fit */
+} satk_status;
+
+const char* satk_last_error(void);
+int satk_version(void);
+/* fills: [0]=SM count, [1]=cc major, [2]=cc minor, [3]=max co-resident 16-CTA clusters of the
+ * attention-RNN kernel, [4]=max co-resident clusters of the LSTM kernel (H=256) */
+int satk_device_info(int* out5);
+/* sizeof() of the descriptor structs, in declaration order (gemm, lstm_fwd, lstm_bwd, attn_fwd, attn_bwd):
+ * lets a foreign-language binding verify its struct layout */
+int satk_struct_sizes(int* out5);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense tile: C = epilogue( alpha * sum_tap op(A_tap) * op(B_tap) ) (+ beta*C)
+ * Replaces every tf.layers.Dense / tf.tensordot / tf.matmul / tf.layers.Conv1D on the path:
+ * PreNet (module.py:394,426,1509), Conv1d banks and projections (module.py:46-68,78-83),
+ * HighwayNet (module.py:72,91), LSTM input projections, attention memory layers
+ * (forward_attention.py:59-64), MultiHeadAttention projections and QK^T / PV
+ * (self_attention.py:45-65,108-128), Projection (module.py:639-643), and all their gradients.
+ * ------------------------------------------------------------------------------------------ */
+typedef enum { SATK_ACT_NONE = 0, SATK_ACT_RELU = 1, SATK_ACT_TANH = 2, SATK_ACT_SIGMOID = 3 } satk_act;
+
+typedef struct {
+  int M, N, K;
+  int transA;              /* 0: A is [M,K] (lda = row stride); 1: A is [K,M] */
+  int transB;              /* 0: B is [K,N]; 1: B is [N,K] */
+  const float* A; long long lda;
+  const float* B; long long ldb;
+  float* C; long long ldc;
+  float alpha, beta;       /* beta applies to the existing C (0: overwrite) */
+  const float* bias;       /* [N] or NULL, added before the activation */
+  int act;                 /* satk_act */
+  const float* residual;   /* [M,N] (ld = ldres) added AFTER the activation, or NULL */
+  long long ldres;
+  const uint8_t* keep_mask;/* [M,N] (ld = N) dropout keep mask applied after activation, or NULL */
+  float keep_scale;        /* 1/keep_prob */
+  /* batching: grid.z = batch1*batch2; pointer offsets z1*s?1 + z2*s?2 (elements) */
+  int batch1, batch2;
+  long long sA1, sA2, sB1, sB2, sC1, sC2;
+  /* 1-D convolution as shifted GEMMs (tf Conv1D SAME, A.3).  taps>1 (or seq_len>0): the row index
+   * of A is shifted by (shift0 + tap*tap_dir) WITHIN sequences of seq_len rows; rows shifted
+   * outside their sequence read as zero.  For transA=0 the shift applies to the M index; for
+   * transA=1 to the K index (weight gradient).  B advances by sBtap per tap (0 = same B). */
+  int taps, shift0, tap_dir, seq_len;
+  long long sBtap;
+  int shift_per_batch1;    /* extra row shift z1*shift_per_batch1 (weight gradient of a conv: one tap per batch entry) */
+  int split_k;             /* >1: partition K over grid.y slices and atomically add into C
+                              (C must hold the value to accumulate onto; beta ignored; no epilogue
+                              other than alpha) */
+  int causal_skip;         /* 1: batched QK^T / PV with causal structure — skip tiles fully above the diagonal */
+} satk_gemm_desc;
+
+/* engine: 0 = auto, 1 = fp32 SIMT tile, 2 = tcgen05 3xTF32 tile (TMA-fed; falls back with an
+ * error if the shape is not supported by the tensor-core path) */
+int satk_gemm(const satk_gemm_desc* d, int engine, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound pieces
+ * ------------------------------------------------------------------------------------------ */
+/* Embedding lookup, models.py:283,351 (A.1): out[r,:] = table[ids[r]-offset,:] */
+int satk_embedding_fwd(const long long* ids, int rows, int offset, const float* table, int dim, float* out, void* stream);
+int satk_embedding_bwd(const long long* ids, int rows, int offset, const float* dout, int dim, float* dtable, void* stream);
+
+/* Batch-norm statistics over rows (tf.layers.batch_normalization, training=True; A.3).
+ * x [rows, C] with row stride ldx -> mean[C], var[C] (biased).  Optionally updates the moving
+ * statistics in place: mov = mom*mov + (1-mom)*stat (variance Bessel-corrected if bessel!=0). */
+int satk_bn_stats(const float* x, long long ldx, int rows, int C, float* mean, float* var,
+                  float* mov_mean, float* mov_var, float momentum, int bessel, void* stream);
+/* y = act(gamma*(x-mean)*rsqrt(var+eps)+beta) (+residual); optional fused MaxPooling1D(2,1,SAME)
+ * along sequences of seq_len positions (module.py:54,80): y[t] = max(z[t], z[t+1]), y[T-1] = z[T-1].
+ * Position of row r is (r / pos_stride) % seq_len; its neighbours are rows r +- pos_stride
+ * (pos_stride = 1 for batch-major [B,T,C], = B for time-major [T,B,C]). */
+int satk_bn_apply(const float* x, long long ldx, int rows, int C, const float* mean, const float* var,
+                  const float* gamma, const float* beta, float eps, int act, const float* residual,
+                  int maxpool_seq_len, int pos_stride, float* y, long long ldy, void* stream);
+/* Backward of satk_bn_apply (+ optional maxpool, relu) for batch statistics (training) or moving
+ * statistics (use_batch_stats=0).  dy [rows,C] -> dx [rows,C]; accumulates dgamma/dbeta (+=).
+ * scratch: 2*C floats, zeroed by the call. */
+int satk_bn_bwd(const float* x, long long ldx, int rows, int C, const float* mean, const float* var,
+                const float* gamma, const float* beta, float eps, int act, int maxpool_seq_len, int pos_stride,
+                int use_batch_stats, const float* dy, long long lddy, float* dx, long long lddx,
+                float* dgamma, float* dbeta, float* scratch, void* stream);
+
+/* HighwayNet combine (A.4; module.py:91): y = H*T + x*(1-T), H=relu(.), T=sigmoid(.) precomputed. */
+int satk_highway_fwd(const float* H, const float* T, const float* x, float* y, long long n, void* stream);
+/* dHpre = dy*T*(H>0); dTpre = dy*(H-x)*T*(1-T); dx = dy*(1-T) */
+int satk_highway_bwd(const float* H, const float* T, const float* x, const float* dy,
+                     float* dHpre, float* dTpre, float* dx, long long n, void* stream);
+
+/* Pointwise backward through y = act(z) * keep * keep_scale (activation followed by dropout):
+ * dz = dy * keep_scale * act'(y / keep_scale), zero where keep_mask == 0.  For relu the mask may be
+ * NULL: a dropped unit has y == 0 and relu'(0) = 0 already zeroes it. */
+int satk_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, const uint8_t* keep_mask,
+                 float keep_scale, void* stream);
+/* column sums: out[c] += sum_r x[r,c]  (bias gradients) */
+int satk_colsum_acc(const float* x, long long ldx, int rows, int C, float* out, void* stream);
+int satk_add(const float* a, const float* b, float* out, long long n, void* stream);          /* out = a + b */
+int satk_axpy(float alpha, const float* x, float* y, long long n, void* stream);              /* y += alpha*x */
+int satk_transpose(const float* x, int rows, int cols, float* y, void* stream);               /* y[c,r] = x[r,c] */
+int satk_mask_rows(const float* x, const long long* lengths, int B, int T, int C, int time_major,
+                   float* y, void* stream);                                                   /* zero rows t>=len[b] */
+/* softsign(x) = x/(1+|x|) forward/backward (MultiSpeakerPreNet, multi_speaker_modules.py:22) */
+int satk_softsign_fwd(const float* x, float* y, long long n, void* stream);
+int satk_softsign_bwd(const float* x, const float* dy, float* dx, long long n, void* stream);
+/* add a per-batch row vector to every time step: y[t,b,:] += v[b,:] (time-major) and its reduction */
+int satk_add_rowvec_tb(float* y, const float* v, int T, int B, int C, void* stream);
+int satk_sum_over_t(const float* dy, int T, int B, int C, float* dv, void* stream);
+/* uint8 keep-mask generator: counter-based hash RNG (not TF's Philox stream; only the Bernoulli law matters) */
+int satk_bernoulli_mask(uint8_t* out, long long n, float keep_prob, unsigned long long seed, void* stream);
+
+/* Row softmax with optional causal mask + dropout, self_attention.py:45-65,80-86.
+ * S [rows_total = nmat*T, T] in place -> probabilities P (kept for backward / alignments);
+ * Pd (may be NULL) = P * keep_mask * keep_scale. */
+int satk_softmax_fwd(float* S, int nmat, int T, int causal, const uint8_t* keep_mask, float keep_scale, float* Pd, void* stream);
+/* dS = P * (dP' - sum(dP' * P)),  dP' = dPd * keep_mask * keep_scale */
+int satk_softmax_bwd(const float* P, const float* dPd, int nmat, int T, int causal, const uint8_t* keep_mask, float keep_scale,
+                     float* dS, void* stream);
+
+/* TransformerTrainingHelper (helpers.py:13-55,224-225): time-major decoder inputs
+ * out[t,b,:] = mel[b, (t-1)*r + (r-n_feed) ... , :] flattened (zeros at t=0). */
+int satk_teacher_inputs(const float* mel, int B, int Tm, int n_mels, int r, int n_feed, float* out, void* stream);
+
+/* Losses (models.py:467-482; A.9) forward + gradient in one pass.
+ * pred_tm: time-major mel prediction [Td,B,r*n_mels]; stop_tm [Td,B]; target batch-major.
+ * out3 = {mel_loss, done_loss, loss}; dpred_tm/dstop_tm receive dLoss/d(pred). */
+int satk_losses(const float* pred_tm, const float* stop_tm, const float* mel, const float* done,
+                const float* spec_mask, const float* bin_mask, int B, int Tm, int n_mels, int r,
+                float* out3, float* dpred_tm, float* dstop_tm, float* scratch4, void* stream);
+
+/* Optimiser step on the flat buffer (models.py:485-498,595-598): global-norm clip (1.0),
+ * Adam (eps outside the sqrt), gradient pre-scale (1/world_size after the all-reduce).
+ * sumsq: 1 float scratch. */
+int satk_grad_sumsq(const float* g, long long n, float* sumsq, void* stream);
+int satk_adam_clip(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float grad_scale,
+                   float clip_norm, float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Recurrent core
+ * ------------------------------------------------------------------------------------------ */
+/* ZoneoutLSTMCell over a sequence (tacotron2 ZoneoutLSTMCell A.6 / TF LSTMCell A.5), used for the
+ * encoder BiLSTM (module.py:93-110) and decoder LSTM-2/LSTM-3 (DecoderRNNV2, module.py:1525-1534).
+ * The input projection (x.Wx+b) is dense over time and precomputed: xg [T,B,4H] (i,j,f,o).
+ * One thread-block cluster of H/16 CTAs owns 4 batch rows; Wh lives in registers; h is exchanged
+ * through distributed shared memory. */
+typedef struct {
+  int T, B, H;                 /* H in {128, 256} */
+  int reverse;                 /* 1: backward direction of bidirectional_dynamic_rnn (length-reversed) */
+  const float* xg;             /* [T,B,4H] */
+  const float* Wh;             /* [H,4H]   rows of the TF kernel belonging to h */
+  const long long* lengths;    /* [B] or NULL (all T) */
+  const uint8_t* mask_c;       /* [T,B,H] indexed by PROCESSING step, or NULL -> eval interpolation */
+  const uint8_t* mask_h;
+  float zc, zh;
+  float forget_bias;
+  float* out;                  /* [T,B,ld_out] cell output (un-zoned h_new) in columns [0,H), zero past length */
+  long long ld_out;            /* row stride of out (>= H): lets both BiLSTM directions write one [T,B,2H] tensor */
+  /* saved for backward (position-indexed, may be NULL for inference): */
+  float* gates;                /* [T,B,4H] post-nonlinearity i,j,f,o */
+  float* c_prev;               /* [T,B,H] cell state BEFORE the step */
+  float* h_prev;               /* [T,B,H] hidden state BEFORE the step */
+} satk_lstm_fwd_desc;
+int satk_lstm_seq_fwd(const satk_lstm_fwd_desc* d, void* stream);
+
+typedef struct {
+  int T, B, H;
+  int reverse;
+  const float* Wh;
+  const long long* lengths;
+  const uint8_t* mask_c;
+  const uint8_t* mask_h;
+  float zc, zh;
+  const float* gates;          /* saved by forward */
+  const float* c_prev;
+  const float* dout;           /* [T,B,ld_dout] gradient wrt cell output */
+  long long ld_dout;
+  float* dgates;               /* [T,B,4H] gradient wrt pre-activation gates (position-indexed, 0 past length) */
+} satk_lstm_bwd_desc;
+int satk_lstm_seq_bwd(const satk_lstm_bwd_desc* d, void* stream);
+
+/* Attention RNN: LSTM-1 + attention mechanism(s) for all Td steps in one launch.
+ * Replaces the body of dynamic_decode's while_loop for layer 0 of DecoderRNNV2 under teacher
+ * forcing: AttentionWrapper(ZoneoutLSTMCell, [ForwardAttention, BahdanauAttention])
+ * (module.py:1011-1042,1514-1524; forward_attention.py:88-136; A.7,A.8).
+ * One cluster of 16 CTAs owns 4 utterances for all Td steps: LSTM-1's recurrent kernel lives in
+ * registers, the cluster's keys/values/query weights in shared memory, and the per-step exchange
+ * (hidden state, partial energies, context) goes through distributed shared memory. */
+typedef struct {
+  int Td, B, Tt;
+  int H;                       /* 256 */
+  int A1, A2;                  /* score units; A2 = 0 for the single-attention model */
+  int M1, M2;                  /* memory depths (256 / 32 or 0) */
+  int att_kernel;              /* taps of the location convolution (<=32) */
+  int mode;                    /* 0 additive, 1 location_sensitive, 2 forward */
+  int cumulative;
+  const float* xg;             /* [Td,B,4H] = prenet_out.W1x + b1 */
+  const float* Wrec;           /* [ctx+H, 4H] rows of dec.lstm1.W after the pre-net rows */
+  const uint8_t* mask_c;       /* [Td,B,H] or NULL */
+  const uint8_t* mask_h;
+  float zc, zh, forget_bias;
+  const long long* lengths;    /* [B] source lengths */
+  const float* keys1;          /* [Tt,B,A1] (time-major) memory_layer(values1) */
+  const float* values1;        /* [Tt,B,M1] */
+  const float* Wq1;            /* [H,A1] query_layer */
+  const float* v1;             /* [A1] attention_variable / attention_v */
+  const float* b1;             /* [A1] attention_bias (forward_attention.py:22) or NULL */
+  const float* loc_conv_w;     /* [att_kernel, att_filters] location_features_convolution kernel (C_in = 1) */
+  const float* loc_conv_b;     /* [att_filters] */
+  const float* loc_layer_w;    /* [att_filters, A1] location_features_layer */
+  int att_filters;             /* <= 8 */
+  const float* keys2;          /* [Tt,B,A2] */
+  const float* values2;        /* [Tt,B,M2] */
+  const float* Wq2;            /* [H,A2] */
+  const float* v2;             /* [A2] */
+  /* outputs */
+  float* x2;                   /* [Td,B,H+M1+M2] = concat(out1, ctx1, ctx2): input rows of LSTM-2 */
+  float* align1;               /* [Td,B,Tt] alignments that build the context (alpha for forward attention) */
+  float* align2;               /* [Td,B,Tt] or NULL */
+  /* saved for backward (may be NULL): */
+  float* gates;                /* [Td,B,4H] */
+  float* c_prev;               /* [Td,B,H] */
+  float* h_prev;               /* [Td,B,H] */
+  float* soft1;                /* [Td,B,Tt] softmax alignments a_t (forward attention: state field 0) */
+  float* q_save;               /* [Td,B,A1+A2] processed queries (query_layer outputs) */
+} satk_attn_rnn_fwd_desc;
+int satk_attn_rnn_fwd(const satk_attn_rnn_fwd_desc* d, void* stream);
+
+typedef struct {
+  satk_attn_rnn_fwd_desc f;    /* same tensors as forward (its outputs are inputs here) */
+  float* dx2;                  /* IN/OUT [Td,B,H+M1+M2].  in: gradient wrt x2 (from LSTM-2's input projection).
+                                  out: columns [H:] hold the TOTAL gradient wrt (ctx1, ctx2) of each step
+                                  (external + recurrent); the caller turns it into dvalues with one batched
+                                  GEMM  dvalues[b] = align[:,b,:]^T . dctx[:,b,:] */
+  float* dgates;               /* [Td,B,4H] gradient wrt LSTM-1 pre-activation gates */
+  float* dq;                   /* [Td,B,A1+A2] gradient wrt processed queries (dense dWq afterwards) */
+  float* dkeys1;               /* [Tt,B,A1]  (=) ; column sums give d(attention_bias) */
+  float* dkeys2;               /* [Tt,B,A2]  (=) */
+  float* dv1;                  /* [A1] (+=, atomics) */
+  float* dv2;                  /* [A2] (+=) */
+  float* dloc_conv_w;          /* [att_kernel, att_filters] (+=) */
+  float* dloc_conv_b;          /* [att_filters] (+=) */
+  float* dloc_layer_w;         /* [att_filters, A1] (+=) */
+} satk_attn_rnn_bwd_desc;
+int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SATK_H_ */

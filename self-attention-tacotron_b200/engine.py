@@ -1,0 +1,589 @@
+"""Host-side orchestration of the hot path: encoder, decoder, losses, backward, optimiser.
+
+Mirrors the reference's module seam ("Module protocol"):
+  * ``encoder``  : SelfAttentionCBHGEncoder.call / ZoneoutEncoderV1.call   (/root/reference/modules/module.py:425-438, 333-336)
+  * ``decoder``  : DualSourceTransformerDecoder.call / ExtendedDecoder.call (module.py:1493-1559, 562-623)
+  * ``model_fn`` body up to loss/optimiser (/root/reference/models/models.py:351-408, 467-498)
+Every arithmetic step is a libsatk.so kernel (``ops``); torch only owns device memory and streams.
+
+Layout: activations are TIME-MAJOR, rows ordered (t, b): a conv tap / LSTM step / teacher shift is a
+row offset of B, the recurrent kernels read contiguous [B, .] slabs per step, and batched attention
+uses strides (row stride B*D) instead of transposes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops as O
+from .data import mask_keep_prob, mask_shapes
+from .params import ModelDims, ParamStore, dims_from_hparams
+
+BN_EPS = 1e-3          # tf.layers.batch_normalization default
+BN_MOMENTUM = 0.99
+FORGET_BIAS = 1.0      # TF LSTMCell (A.5)
+_MODE = {"additive": 0, "location_sensitive": 1, "forward": 2}
+
+
+def noam_lr(init_rate: float, global_step: int, step_factor: float) -> float:
+    """learning_rate_decay, /root/reference/models/models.py:595-598."""
+    warm = 4000.0
+    step = float(global_step * step_factor + 1)
+    return init_rate * warm ** 0.5 * min(step * warm ** -1.5, step ** -0.5)
+
+
+class TacotronEngine:
+    def __init__(self, hp, device="cuda", params: Optional[ParamStore] = None, seed: int = 1234):
+        self.hp = hp
+        self.d: ModelDims = dims_from_hparams(hp)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise O.L.SatkError("TacotronEngine needs a CUDA device: the product path has no CPU fallback")
+        O.L.load()
+        if self.d.transition_agent:
+            raise NotImplementedError("use_forward_attention_transition_agent=True is not implemented yet")
+        self.ps = params.to(self.device) if params is not None else ParamStore(self.d, self.device).init(seed)
+        self._bufs: Dict[str, torch.Tensor] = {}
+        self._mask_seed = 0x5A7C + seed
+        self.saved = None
+        self.global_step = 0
+        self._sumsq = torch.zeros(1, device=self.device)
+
+    # ------------------------------------------------------------------ helpers
+    def buf(self, name: str, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
+        shape = tuple(int(s) for s in shape)
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.empty(shape, device=self.device, dtype=dtype)
+            self._bufs[name] = t
+        if zero:
+            t.zero_()
+        return t
+
+    def _span(self, store: Dict[str, torch.Tensor], first: str, n: int) -> torch.Tensor:
+        """View of n floats starting at tensor ``first`` of the flat buffer (adjacent tensors)."""
+        base = self.ps.flat if store is self.ps.p else self.ps.grad
+        off = self.ps.offsets[first][0]
+        return base[off:off + n]
+
+    def device_masks(self, B, Tt, Td) -> Dict[str, torch.Tensor]:
+        """TRAIN-mode Bernoulli keep masks generated on the device (satk_bernoulli_mask)."""
+        out = {}
+        for i, (name, shape) in enumerate(mask_shapes(self.d, B, Tt, Td).items()):
+            m = self.buf("mask." + name, shape, torch.uint8)
+            O.bernoulli_mask(m, mask_keep_prob(self.d, name), self._mask_seed * 1000003 + i)
+            out[name] = m
+        self._mask_seed += 1
+        return out
+
+    # ------------------------------------------------------------------ self-attention block
+    def _sa_forward(self, x, T, B, name, heads, causal, mask, keep, key):
+        """SelfAttentionTransformer.call (module.py:363-371) on time-major x [T*B, D]."""
+        p = self.ps.p
+        D = x.shape[1]
+        dh = D // heads
+        R = T * B
+        Kp = O.linear(x, p[name + ".key.W"], self.buf(key + ".K", (R, D)), bias=p[name + ".key.b"])
+        Vp = O.linear(x, p[name + ".value.W"], self.buf(key + ".V", (R, D)), bias=p[name + ".value.b"])
+        Qp = O.linear(x, p[name + ".query.W"], self.buf(key + ".Q", (R, D)), bias=p[name + ".query.b"])
+        S = self.buf(key + ".P", (B, heads, T, T))
+        O.gemm(Qp, Kp, S, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, alpha=1.0 / math.sqrt(dh),
+               batch1=B, batch2=heads, sA=(D, dh), sB=(D, dh), sC=(heads * T * T, T * T), causal_skip=1 if causal else 0)
+        Pd = self.buf(key + ".Pd", (B, heads, T, T)) if mask is not None else None
+        O.softmax_fwd(S, B * heads, T, causal, mask, 1.0 / keep, Pd)
+        Pu = Pd if Pd is not None else S
+        Oc = self.buf(key + ".O", (R, D))
+        O.gemm(Pu, Vp, Oc, T, dh, T, lda=T, ldb=B * D, ldc=B * D, batch1=B, batch2=heads,
+               sA=(heads * T * T, T * T), sB=(D, dh), sC=(D, dh), causal_skip=2 if causal else 0)
+        ao = O.linear(Oc, p[name + ".output.W"], self.buf(key + ".ao", (R, D)), bias=p[name + ".output.b"])
+        tr = O.linear(ao, p[name + ".transform.W"], self.buf(key + ".tr", (R, D)), bias=p[name + ".transform.b"], act="tanh")
+        y = self.buf(key + ".y", (R, D))
+        O.add(x, tr, y)
+        return y, dict(x=x, K=Kp, V=Vp, Q=Qp, P=S, Pd=Pu, O=Oc, ao=ao, tr=tr, T=T, heads=heads, causal=causal,
+                       mask=mask, keep=keep, name=name, key=key)
+
+    def _sa_backward(self, sv, dy, B):
+        p, g = self.ps.p, self.ps.g
+        name, key, T, heads, causal = sv["name"], sv["key"], sv["T"], sv["heads"], sv["causal"]
+        x = sv["x"]
+        R, D = x.shape
+        dh = D // heads
+        scale = 1.0 / math.sqrt(dh)
+        dz = self.buf(key + ".dz", (R, D))
+        O.act_bwd(sv["tr"], dy, dz, "tanh")
+        O.linear_dw(sv["ao"], dz, g[name + ".transform.W"], R, D, D)
+        O.colsum_acc(dz, R, D, g[name + ".transform.b"])
+        dao = self.buf(key + ".dao", (R, D))
+        O.linear_dx(dz, p[name + ".transform.W"], dao, R)
+        O.linear_dw(sv["O"], dao, g[name + ".output.W"], R, D, D)
+        O.colsum_acc(dao, R, D, g[name + ".output.b"])
+        dO = self.buf(key + ".dO", (R, D))
+        O.linear_dx(dao, p[name + ".output.W"], dO, R)
+        bs = dict(batch1=B, batch2=heads)
+        sP, sX = (heads * T * T, T * T), (D, dh)
+        dPd = self.buf(key + ".dPd", (B, heads, T, T))
+        O.gemm(dO, sv["V"], dPd, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, sA=sX, sB=sX, sC=sP,
+               causal_skip=1 if causal else 0, **bs)
+        dV = self.buf(key + ".dV", (R, D))
+        O.gemm(sv["Pd"], dO, dV, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, sA=sP, sB=sX, sC=sX, **bs)
+        dS = self.buf(key + ".dS", (B, heads, T, T))
+        O.softmax_bwd(sv["P"], dPd, B * heads, T, causal, dS, sv["mask"], 1.0 / sv["keep"])
+        dQ = self.buf(key + ".dQ", (R, D))
+        O.gemm(dS, sv["K"], dQ, T, dh, T, lda=T, ldb=B * D, ldc=B * D, alpha=scale, sA=sP, sB=sX, sC=sX,
+               causal_skip=2 if causal else 0, **bs)
+        dK = self.buf(key + ".dK", (R, D))
+        O.gemm(dS, sv["Q"], dK, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, alpha=scale, sA=sP, sB=sX, sC=sX, **bs)
+        dx = self.buf(key + ".dx", (R, D))
+        first = True
+        for nm, dt in (("query", dQ), ("key", dK), ("value", dV)):
+            O.linear_dw(x, dt, g[f"{name}.{nm}.W"], R, D, D)
+            O.colsum_acc(dt, R, D, g[f"{name}.{nm}.b"])
+            if first:   # dx = dy (residual branch) + dQ.Wq^T
+                O.gemm(dt, p[f"{name}.{nm}.W"], dx, R, D, D, lda=D, ldb=D, ldc=D, transB=True, residual=dy, ldres=D)
+                first = False
+            else:
+                O.linear_dx(dt, p[f"{name}.{nm}.W"], dx, R, beta=1.0)
+        return dx
+
+    # ------------------------------------------------------------------ encoder
+    def encoder(self, source, source_length, training, masks):
+        """-> (lstm_output [Tt,B,2H], self_attention_output [Tt,B,32] | None, [alignments])."""
+        d, p = self.d, self.ps.p
+        B, Tt = source.shape
+        R = Tt * B
+        sv = {}
+        ids_tm = source.t().contiguous()
+        sv["ids_tm"] = ids_tm
+        x = self.buf("enc.emb", (R, d.embed))
+        O.embedding_fwd(ids_tm, p["embedding"], x)
+        sv["prenet_in"] = [x]
+        for i, u in enumerate(d.enc_prenet):
+            y = self.buf(f"enc.p{i}", (R, u))
+            O.linear(x, p[f"enc.prenet{i}.W"], y, bias=p[f"enc.prenet{i}.b"], act="relu",
+                     keep_mask=masks[f"enc.prenet{i}"] if training else None, keep_scale=1.0 / (1.0 - d.enc_prenet_drop))
+            x = y
+            sv["prenet_in"].append(x)
+        inp = x
+        C, K, cin = d.conv_ch, d.bank_k, inp.shape[1]
+        KC = C * K
+        raw = self.buf("enc.bank_raw", (R, KC))
+        for k in range(1, K + 1):
+            pl = (k - 1) // 2
+            O.gemm(inp, p[f"cbhg.bank{k}.W"], raw, R, C, cin, lda=cin, ldb=C, ldc=KC, c_off=(k - 1) * C,
+                   taps=k, shift0=-pl * B, tap_dir=B, sBtap=cin * C)
+
+        def bn(xraw, Cc, first, gname, act, out, residual=None, maxpool=False):
+            gamma = self._span(self.ps.p, gname + ".gamma", Cc)
+            beta = self._span(self.ps.p, gname + ".beta", Cc)
+            o = self.ps.bn_off[first]
+            mm, mv = self.ps.bn_mean_flat[o:o + Cc], self.ps.bn_var_flat[o:o + Cc]
+            if training:
+                mean, var = self.buf(first + ".bmean", (Cc,)), self.buf(first + ".bvar", (Cc,))
+                O.bn_stats(xraw, R, Cc, mean, var, mov_mean=mm, mov_var=mv, momentum=BN_MOMENTUM, bessel=True)
+            else:
+                mean, var = mm, mv
+            O.bn_apply(xraw, R, Cc, mean, var, gamma, beta, out, eps=BN_EPS, act=act, residual=residual,
+                       maxpool_seq_len=Tt if maxpool else 0, pos_stride=B)
+            return dict(x=xraw, C=Cc, mean=mean, var=var, gamma=gamma, beta=beta, act=act, maxpool=maxpool, gname=gname)
+
+        mp = self.buf("enc.mp", (R, KC))
+        sv["bn_bank"] = bn(raw, KC, "cbhg.bank1", "cbhg.bank1", "relu", mp, maxpool=True)
+        raw1 = self.buf("enc.raw1", (R, d.proj1))
+        O.gemm(mp, p["cbhg.proj1.W"], raw1, R, d.proj1, KC, lda=KC, ldb=d.proj1, ldc=d.proj1, taps=3, shift0=-B, tap_dir=B,
+               sBtap=KC * d.proj1)
+        p1o = self.buf("enc.p1o", (R, d.proj1))
+        sv["bn_p1"] = bn(raw1, d.proj1, "cbhg.proj1", "cbhg.proj1", "relu", p1o)
+        raw2 = self.buf("enc.raw2", (R, d.proj2))
+        O.gemm(p1o, p["cbhg.proj2.W"], raw2, R, d.proj2, d.proj1, lda=d.proj1, ldb=d.proj2, ldc=d.proj2, taps=3, shift0=-B,
+               tap_dir=B, sBtap=d.proj1 * d.proj2)
+        hw = self.buf("enc.hw0", (R, d.proj2))
+        sv["bn_p2"] = bn(raw2, d.proj2, "cbhg.proj2", "cbhg.proj2", None, hw, residual=inp)
+        sv.update(inp=inp, mp=mp, p1o=p1o)
+        Hn = d.enc_lstm
+        sv["hwy"] = []
+        for i in range(d.n_highway):
+            Hb = O.linear(hw, p[f"cbhg.highway{i}.WH"], self.buf(f"enc.hwH{i}", (R, Hn)), bias=p[f"cbhg.highway{i}.bH"], act="relu")
+            Tb = O.linear(hw, p[f"cbhg.highway{i}.WT"], self.buf(f"enc.hwT{i}", (R, Hn)), bias=p[f"cbhg.highway{i}.bT"], act="sigmoid")
+            y = self.buf(f"enc.hw{i + 1}", (R, Hn))
+            O.highway_fwd(Hb, Tb, hw, y)
+            sv["hwy"].append((Hb, Tb, hw))
+            hw = y
+        sv["lstm_in"] = hw
+        mem1 = self.buf("enc.mem1", (Tt, B, 2 * Hn))
+        sv["lstm"] = {}
+        for j, dr in enumerate(("fw", "bw")):
+            W = p[f"cbhg.lstm_{dr}.W"]
+            xg = O.linear(hw, W[:Hn], self.buf(f"enc.xg_{dr}", (R, 4 * Hn)), bias=p[f"cbhg.lstm_{dr}.b"])
+            gates = self.buf(f"enc.gates_{dr}", (R, 4 * Hn))
+            cp = self.buf(f"enc.cprev_{dr}", (R, Hn))
+            hp_ = self.buf(f"enc.hprev_{dr}", (R, Hn))
+            mc = masks[f"cbhg.lstm_{dr}.c"] if training else None
+            mh = masks[f"cbhg.lstm_{dr}.h"] if training else None
+            O.lstm_seq_fwd(xg, W[Hn:], mem1, Tt, B, Hn, reverse=(j == 1), lengths=source_length, mask_c=mc, mask_h=mh,
+                           zc=d.zc, zh=d.zh, forget_bias=FORGET_BIAS, gates=gates, c_prev=cp, h_prev=hp_,
+                           ld_out=2 * Hn, out_off=j * Hn)
+            sv["lstm"][dr] = dict(gates=gates, c_prev=cp, h_prev=hp_, mc=mc, mh=mh)
+        mem2, aligns = None, []
+        if d.dual:
+            x2 = O.linear(mem1, p["enc.sa_proj.W"], self.buf("enc.sa_in", (R, d.enc_sa)), bias=p["enc.sa_proj.b"])
+            sv["sa"] = []
+            for h in range(d.enc_sa_hops):
+                mk = masks[f"enc.sa{h}"] if training else None
+                x2, s = self._sa_forward(x2, Tt, B, f"enc.sa{h}", d.enc_sa_heads, False, mk, 1.0 - d.enc_sa_drop, f"enc.sa{h}")
+                sv["sa"].append(s)
+                aligns += [s["P"][:, i] for i in range(d.enc_sa_heads)]
+            mem2 = x2
+        self._enc_saved = sv
+        return mem1, mem2, aligns
+
+    def encoder_backward(self, dmem1, dmem2, B, Tt, source_length):
+        d, p, g, sv = self.d, self.ps.p, self.ps.g, self._enc_saved
+        R = Tt * B
+        Hn = d.enc_lstm
+        if d.dual:
+            dx = dmem2
+            for h in reversed(range(d.enc_sa_hops)):
+                dx = self._sa_backward(sv["sa"][h], dx, B)
+            mem1 = self._bufs["enc.mem1"]
+            O.linear_dw(mem1, dx, g["enc.sa_proj.W"], R, 2 * Hn, d.enc_sa)
+            O.colsum_acc(dx, R, d.enc_sa, g["enc.sa_proj.b"])
+            O.linear_dx(dx, p["enc.sa_proj.W"], dmem1, R, beta=1.0)
+        dhw = self.buf("enc.dhw", (R, Hn))
+        for j, dr in enumerate(("fw", "bw")):
+            s = sv["lstm"][dr]
+            W = p[f"cbhg.lstm_{dr}.W"]
+            dg = self.buf(f"enc.dgates_{dr}", (R, 4 * Hn))
+            O.lstm_seq_bwd(W[Hn:], s["gates"], s["c_prev"], dmem1, dg, Tt, B, Hn, reverse=(j == 1), lengths=source_length,
+                           mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh, ld_dout=2 * Hn, dout_off=j * Hn)
+            gW = g[f"cbhg.lstm_{dr}.W"]
+            O.linear_dw(sv["lstm_in"], dg, gW, R, Hn, 4 * Hn)
+            O.linear_dw(s["h_prev"], dg, gW, R, Hn, 4 * Hn, w_off=Hn * 4 * Hn)
+            O.colsum_acc(dg, R, 4 * Hn, g[f"cbhg.lstm_{dr}.b"])
+            O.linear_dx(dg, W[:Hn], dhw, R, beta=0.0 if j == 0 else 1.0)
+        dH, dT = self.buf("enc.dH", (R, Hn)), self.buf("enc.dT", (R, Hn))
+        for i in reversed(range(d.n_highway)):
+            Hb, Tb, x = sv["hwy"][i]
+            dxd = self.buf(f"enc.dhw_in{i % 2}", (R, Hn))
+            O.highway_bwd(Hb, Tb, x, dhw, dH, dT, dxd)
+            O.linear_dw(x, dH, g[f"cbhg.highway{i}.WH"], R, Hn, Hn)
+            O.colsum_acc(dH, R, Hn, g[f"cbhg.highway{i}.bH"])
+            O.linear_dw(x, dT, g[f"cbhg.highway{i}.WT"], R, Hn, Hn)
+            O.colsum_acc(dT, R, Hn, g[f"cbhg.highway{i}.bT"])
+            O.linear_dx(dH, p[f"cbhg.highway{i}.WH"], dxd, R, beta=1.0)
+            O.linear_dx(dT, p[f"cbhg.highway{i}.WT"], dxd, R, beta=1.0)
+            dhw = dxd
+        # dhw = gradient wrt (proj2_bn + inp)
+        scratch = self.buf("enc.bn_scratch", (2 * d.conv_ch * d.bank_k,))
+        training = self._training
+
+        def bn_back(s, dy, dx):
+            first = s["gname"]
+            dgamma = self._span(self.ps.g, first + ".gamma", s["C"])
+            dbeta = self._span(self.ps.g, first + ".beta", s["C"])
+            O.bn_bwd(s["x"], R, s["C"], s["mean"], s["var"], s["gamma"], s["beta"], dy, dx, dgamma, dbeta, scratch, eps=BN_EPS,
+                     act=s["act"], maxpool_seq_len=Tt if s["maxpool"] else 0, pos_stride=B, use_batch_stats=training)
+
+        def conv_back(x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None):
+            """draw: gradient wrt the raw conv output [R, cout] (ld draw_ld); accumulates dW, writes/accumulates dx."""
+            pl = (k - 1) // 2
+            O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True, b_off=draw_off,
+                   batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B, split_k=max(1, min(32, R // 512)), beta=1.0)
+            O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
+                   taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
+
+        draw2 = self.buf("enc.draw2", (R, d.proj2))
+        bn_back(sv["bn_p2"], dhw, draw2)
+        dp1o = self.buf("enc.dp1o", (R, d.proj1))
+        conv_back(sv["p1o"], "cbhg.proj2.W", 3, d.proj1, d.proj2, draw2, dp1o, 0.0)
+        draw1 = self.buf("enc.draw1", (R, d.proj1))
+        bn_back(sv["bn_p1"], dp1o, draw1)
+        KC = d.conv_ch * d.bank_k
+        dmp = self.buf("enc.dmp", (R, KC))
+        conv_back(sv["mp"], "cbhg.proj1.W", 3, KC, d.proj1, draw1, dmp, 0.0)
+        draw = self.buf("enc.dbank_raw", (R, KC))
+        bn_back(sv["bn_bank"], dmp, draw)
+        cin = sv["inp"].shape[1]
+        dinp = self.buf("enc.dinp", (R, cin))
+        for k in range(1, d.bank_k + 1):   # dinp = dhw (residual branch, module.py:86) + sum_k conv_k^T(d bank_k)
+            conv_back(sv["inp"], f"cbhg.bank{k}.W", k, cin, d.conv_ch, draw, dinp, 0.0 if k == 1 else 1.0, draw_ld=KC,
+                      draw_off=(k - 1) * d.conv_ch, residual=dhw if k == 1 else None)
+        # encoder pre-net
+        dy = dinp
+        n = len(d.enc_prenet)
+        for i in reversed(range(n)):
+            y = sv["prenet_in"][i + 1]
+            x = sv["prenet_in"][i]
+            u, cin_i = y.shape[1], x.shape[1]
+            dz = self.buf(f"enc.dz{i}", (R, u))
+            O.act_bwd(y, dy, dz, "relu", None, 1.0 / (1.0 - d.enc_prenet_drop) if training else 1.0)
+            O.linear_dw(x, dz, g[f"enc.prenet{i}.W"], R, cin_i, u)
+            O.colsum_acc(dz, R, u, g[f"enc.prenet{i}.b"])
+            dxp = self.buf(f"enc.dpx{i}", (R, cin_i))
+            O.linear_dx(dz, p[f"enc.prenet{i}.W"], dxp, R)
+            dy = dxp
+        O.embedding_bwd(sv["ids_tm"], dy, g["embedding"])
+
+    # ------------------------------------------------------------------ decoder
+    def decoder(self, mem1, mem2, source_length, target, speaker_embed, training, masks):
+        """Teacher-forced decoder.  -> (mel_tm [Td,B,r*n_mels], stop_tm [Td,B], align1, align2, dec self-attn P)."""
+        d, p = self.d, self.ps.p
+        Tt, B, _ = mem1.shape
+        Tm = target.shape[1]
+        Td = Tm // d.r
+        R, Rd = Tt * B, Td * B
+        sv = {}
+        dec_in = self.buf("dec.in", (Rd, d.dec_in))
+        O.teacher_inputs(target, B, Tm, d.n_mels, d.r, d.n_feed, dec_in)
+        keep = 1.0 - d.dec_prenet_drop
+        m0 = masks["dec.prenet0"] if training else None
+        m1 = masks["dec.prenet1"] if training else None
+        if d.use_speaker:
+            h0 = O.linear(dec_in, p["dec.prenet0.W0"], self.buf("dec.ph0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b0"], act="relu")
+            sp_pre = O.linear(speaker_embed, p["dec.prenet0.Ws"], self.buf("dec.sp_pre", (B, d.dec_prenet[0])), bias=p["dec.prenet0.bs"])
+            sp = self.buf("dec.sp", (B, d.dec_prenet[0]))
+            O.softsign_fwd(sp_pre, sp)
+            O.add_rowvec_tb(h0, sp, Td, B, d.dec_prenet[0])
+            dp0 = O.linear(h0, p["dec.prenet0.W"], self.buf("dec.p0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b"], act="relu",
+                           keep_mask=m0, keep_scale=1.0 / keep)
+            sv.update(h0=h0, sp_pre=sp_pre)
+        else:
+            dp0 = O.linear(dec_in, p["dec.prenet0.W"], self.buf("dec.p0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b"], act="relu",
+                           keep_mask=m0, keep_scale=1.0 / keep)
+        dp1 = O.linear(dp0, p["dec.prenet1.W"], self.buf("dec.p1", (Rd, d.dec_prenet[1])), bias=p["dec.prenet1.b"], act="relu",
+                       keep_mask=m1, keep_scale=1.0 / keep)
+        H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
+        W1 = p["dec.lstm1.W"]
+        xg1 = O.linear(dp1, W1[:P1], self.buf("dec.xg1", (Rd, 4 * H1)), bias=p["dec.lstm1.b"])
+        # attention memories (BahdanauAttention.__init__, A.8): values masked past length, keys = values.W_mem
+        values1 = self.buf("dec.values1", (R, d.mem1))
+        O.mask_rows(mem1, source_length, B, Tt, d.mem1, True, values1)
+        keys1 = O.linear(values1, p["att1.memory.W"], self.buf("dec.keys1", (R, d.att1)))
+        values2 = keys2 = None
+        if d.dual:
+            values2 = self.buf("dec.values2", (R, d.mem2))
+            O.mask_rows(mem2, source_length, B, Tt, d.mem2, True, values2)
+            keys2 = O.linear(values2, p["att2.memory.W"], self.buf("dec.keys2", (R, d.att2)))
+        X2W = H1 + d.ctx
+        x2 = self.buf("dec.x2", (Rd, X2W))
+        al1 = self.buf("dec.align1", (Td, B, Tt))
+        al2 = self.buf("dec.align2", (Td, B, Tt)) if d.dual else None
+        loc = d.attention in ("forward", "location_sensitive")
+        fd = O.attn_rnn_desc(
+            Td=Td, B=B, Tt=Tt, H=H1, A1=d.att1, A2=d.att2, M1=d.mem1, M2=d.mem2,
+            att_kernel=d.att_kernel if loc else 0, mode=_MODE[d.attention], cumulative=int(d.cumulative),
+            xg=xg1, Wrec=W1[P1:], mask_c=masks["dec.lstm1.c"] if training else None,
+            mask_h=masks["dec.lstm1.h"] if training else None, zc=d.zc, zh=d.zh, forget_bias=FORGET_BIAS,
+            lengths=source_length, keys1=keys1, values1=values1, Wq1=p["att1.query.W"], v1=p["att1.v"],
+            b1=p["att1.b"] if loc else None,
+            loc_conv_w=p["att1.loc_conv.W"] if loc else None, loc_conv_b=p["att1.loc_conv.b"] if loc else None,
+            loc_layer_w=p["att1.loc_layer.W"] if loc else None, att_filters=d.att_filters if loc else 0,
+            keys2=keys2, values2=values2, Wq2=p["att2.query.W"] if d.dual else None, v2=p["att2.v"] if d.dual else None,
+            x2=x2, align1=al1, align2=al2,
+            gates=self.buf("dec.gates1", (Rd, 4 * H1)), c_prev=self.buf("dec.cprev1", (Rd, H1)),
+            h_prev=self.buf("dec.hprev1", (Rd, H1)), soft1=self.buf("dec.soft1", (Td, B, Tt)),
+            q_save=self.buf("dec.qsave", (Rd, d.att1 + d.att2)))
+        O.attn_rnn_fwd(fd)
+        sv.update(fd=fd, dec_in=dec_in, dp0=dp0, dp1=dp1, x2=x2, values1=values1, values2=values2, keys1=keys1, keys2=keys2)
+        # LSTM-2, LSTM-3 (DecoderRNNV2)
+        x = x2
+        sv["lstm"] = []
+        for li, kin in ((2, X2W), (3, HD)):
+            W = p[f"dec.lstm{li}.W"]
+            xg = O.linear(x, W[:kin], self.buf(f"dec.xg{li}", (Rd, 4 * HD)), bias=p[f"dec.lstm{li}.b"])
+            out = self.buf(f"dec.out{li}", (Rd, HD))
+            gates = self.buf(f"dec.gates{li}", (Rd, 4 * HD))
+            cp, hp_ = self.buf(f"dec.cprev{li}", (Rd, HD)), self.buf(f"dec.hprev{li}", (Rd, HD))
+            mc = masks[f"dec.lstm{li}.c"] if training else None
+            mh = masks[f"dec.lstm{li}.h"] if training else None
+            O.lstm_seq_fwd(xg, W[kin:], out, Td, B, HD, mask_c=mc, mask_h=mh, zc=d.zc, zh=d.zh, forget_bias=FORGET_BIAS,
+                           gates=gates, c_prev=cp, h_prev=hp_)
+            sv["lstm"].append(dict(x=x, kin=kin, gates=gates, c_prev=cp, h_prev=hp_, mc=mc, mh=mh, li=li))
+            x = out
+        sa_P = []
+        sv["sa"] = []
+        if d.dual:
+            for h in range(d.dec_sa_hops):
+                mk = masks[f"dec.sa{h}"] if training else None
+                x, s = self._sa_forward(x, Td, B, f"dec.sa{h}", d.dec_sa_heads, True, mk, 1.0 - d.dec_sa_drop, f"dec.sa{h}")
+                sv["sa"].append(s)
+                sa_P += [s["P"][:, i] for i in range(d.dec_sa_heads)]
+        sv["proj_in"] = x
+        mel_tm = O.linear(x, p["dec.out_proj.W"], self.buf("dec.mel_tm", (Rd, d.out_units)), bias=p["dec.out_proj.b"])
+        stop_tm = O.linear(x, p["dec.stop_proj.W"], self.buf("dec.stop_tm", (Rd, 1)), bias=p["dec.stop_proj.b"])
+        self._dec_saved = sv
+        return mel_tm, stop_tm, al1, al2, sa_P
+
+    def decoder_backward(self, dmel_tm, dstop_tm, B, Tt, Td, source_length):
+        """-> (dmem1 [Tt,B,mem1], dmem2 | None)"""
+        d, p, g, sv = self.d, self.ps.p, self.ps.g, self._dec_saved
+        training = self._training
+        R, Rd = Tt * B, Td * B
+        H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
+        x = sv["proj_in"]
+        Dp = x.shape[1]
+        O.linear_dw(x, dmel_tm, g["dec.out_proj.W"], Rd, Dp, d.out_units)
+        O.colsum_acc(dmel_tm, Rd, d.out_units, g["dec.out_proj.b"])
+        O.linear_dw(x, dstop_tm, g["dec.stop_proj.W"], Rd, Dp, 1)
+        O.colsum_acc(dstop_tm, Rd, 1, g["dec.stop_proj.b"])
+        dx = self.buf("dec.dproj_in", (Rd, Dp))
+        O.linear_dx(dmel_tm, p["dec.out_proj.W"], dx, Rd)
+        O.linear_dx(dstop_tm, p["dec.stop_proj.W"], dx, Rd, beta=1.0)
+        for h in reversed(range(len(sv["sa"]))):
+            dx = self._sa_backward(sv["sa"][h], dx, B)
+        dout = dx
+        for s in reversed(sv["lstm"]):
+            li, kin = s["li"], s["kin"]
+            W = p[f"dec.lstm{li}.W"]
+            dg = self.buf(f"dec.dgates{li}", (Rd, 4 * HD))
+            O.lstm_seq_bwd(W[kin:], s["gates"], s["c_prev"], dout, dg, Td, B, HD, mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh)
+            gW = g[f"dec.lstm{li}.W"]
+            O.linear_dw(s["x"], dg, gW, Rd, kin, 4 * HD)
+            O.linear_dw(s["h_prev"], dg, gW, Rd, HD, 4 * HD, w_off=kin * 4 * HD)
+            O.colsum_acc(dg, Rd, 4 * HD, g[f"dec.lstm{li}.b"])
+            dxl = self.buf(f"dec.dx_lstm{li}", (Rd, kin))
+            O.linear_dx(dg, W[:kin], dxl, Rd)
+            dout = dxl
+        dx2 = dout                                     # [Rd, H1 + ctx]
+        X2W = H1 + d.ctx
+        fd = sv["fd"]
+        loc = d.attention in ("forward", "location_sensitive")
+        QT = d.att1 + d.att2
+        dg1 = self.buf("dec.dgates1", (Rd, 4 * H1))
+        dq = self.buf("dec.dq", (Rd, QT))
+        dkeys1 = self.buf("dec.dkeys1", (R, d.att1))
+        dkeys2 = self.buf("dec.dkeys2", (R, d.att2)) if d.dual else None
+        O.attn_rnn_bwd(fd, dx2=dx2, dgates=dg1, dq=dq, dkeys1=dkeys1, dkeys2=dkeys2,
+                       dv1=g["att1.v"], dv2=g["att2.v"] if d.dual else None,
+                       dloc_conv_w=g["att1.loc_conv.W"] if loc else None, dloc_conv_b=g["att1.loc_conv.b"] if loc else None,
+                       dloc_layer_w=g["att1.loc_layer.W"] if loc else None)
+        # LSTM-1 weight gradients (dense over time)
+        gW1 = g["dec.lstm1.W"]
+        N4 = 4 * H1
+        O.linear_dw(sv["dp1"], dg1, gW1, Rd, P1, N4)
+        # context rows: input of step t is the context of step t-1 (zero at t=0) -> shift by one time step (B rows)
+        O.linear_dw(sv["x2"], dg1, gW1, Rd, d.ctx, N4, ldx=X2W, x_off=H1, w_off=P1 * N4, shift0=-B)
+        O.linear_dw(self._bufs["dec.hprev1"], dg1, gW1, Rd, H1, N4, w_off=(P1 + d.ctx) * N4)
+        O.colsum_acc(dg1, Rd, N4, g["dec.lstm1.b"])
+        ddp1 = self.buf("dec.ddp1", (Rd, P1))
+        O.linear_dx(dg1, p["dec.lstm1.W"][:P1], ddp1, Rd)
+        # query layers: q = out1 . Wq  (out1 = x2[:, :H1])
+        O.linear_dw(sv["x2"], dq, g["att1.query.W"], Rd, H1, d.att1, ldx=X2W, ldy=QT)
+        if d.dual:
+            O.linear_dw(sv["x2"], dq, g["att2.query.W"], Rd, H1, d.att2, ldx=X2W, ldy=QT, y_off=d.att1)
+        # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]   (dx2[:, H1:] now holds dctx_total)
+        dval1 = self.buf("dec.dvalues1", (R, d.mem1))
+        O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
+               b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
+        # keys = values . W_mem ; attention bias folded into the keys
+        if loc:
+            O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
+        O.linear_dw(sv["values1"], dkeys1, g["att1.memory.W"], R, d.mem1, d.att1)
+        O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
+        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
+        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
+        dmem2 = None
+        if d.dual:
+            dval2 = self.buf("dec.dvalues2", (R, d.mem2))
+            O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
+                   b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
+            O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
+            O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
+            dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
+            O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
+        # decoder pre-net
+        keep_scale = 1.0 / (1.0 - d.dec_prenet_drop) if training else 1.0
+        dz1 = self.buf("dec.dz1", (Rd, P1))
+        O.act_bwd(sv["dp1"], ddp1, dz1, "relu", None, keep_scale)
+        P0 = d.dec_prenet[0]
+        O.linear_dw(sv["dp0"], dz1, g["dec.prenet1.W"], Rd, P0, P1)
+        O.colsum_acc(dz1, Rd, P1, g["dec.prenet1.b"])
+        ddp0 = self.buf("dec.ddp0", (Rd, P0))
+        O.linear_dx(dz1, p["dec.prenet1.W"], ddp0, Rd)
+        dz0 = self.buf("dec.dz0", (Rd, P0))
+        O.act_bwd(sv["dp0"], ddp0, dz0, "relu", None, keep_scale)
+        if d.use_speaker:
+            h0 = sv["h0"]
+            O.linear_dw(h0, dz0, g["dec.prenet0.W"], Rd, P0, P0)
+            O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
+            dh0 = self.buf("dec.dh0", (Rd, P0))
+            O.linear_dx(dz0, p["dec.prenet0.W"], dh0, Rd)
+            # h0 = relu(in.W0+b0) + softsign(spk.Ws+bs): the relu output is h0 - sp, recomputed on the fly
+            dsp = self.buf("dec.dsp", (B, P0))
+            O.sum_over_t(dh0, Td, B, P0, dsp)
+            dsp_pre = self.buf("dec.dsp_pre", (B, P0))
+            O.softsign_bwd(sv["sp_pre"], dsp, dsp_pre)
+            self._dspk_pre = dsp_pre
+            relu0 = self.buf("dec.relu0", (Rd, P0))
+            O.linear(sv["dec_in"], p["dec.prenet0.W0"], relu0, bias=p["dec.prenet0.b0"], act="relu")
+            dz00 = self.buf("dec.dz00", (Rd, P0))
+            O.act_bwd(relu0, dh0, dz00, "relu")
+            O.linear_dw(sv["dec_in"], dz00, g["dec.prenet0.W0"], Rd, d.dec_in, P0)
+            O.colsum_acc(dz00, Rd, P0, g["dec.prenet0.b0"])
+        else:
+            O.linear_dw(sv["dec_in"], dz0, g["dec.prenet0.W"], Rd, d.dec_in, P0)
+            O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
+        return dmem1, dmem2
+
+    # ------------------------------------------------------------------ model_fn body
+    def forward(self, features, labels, training: bool, masks: Optional[Dict[str, torch.Tensor]] = None):
+        """Forward pass + losses (+ loss gradients wrt the predictions).  Inputs must be CUDA tensors."""
+        d = self.d
+        source, source_length = features.source, features.source_length
+        B, Tt = source.shape
+        Tm = labels.mel.shape[1]
+        Td = Tm // d.r
+        if training and masks is None:
+            masks = self.device_masks(B, Tt, Td)
+        self._training = training
+        spk = None
+        if d.use_speaker:
+            spk = self.buf("spk_embed", (B, d.speaker_dim))
+            O.embedding_fwd(features.speaker_id, self.ps.p["speaker_embedding"], spk, offset=d.speaker_offset)
+        mem1, mem2, enc_al = self.encoder(source, source_length, training, masks)
+        mel_tm, stop_tm, al1, al2, dec_sa = self.decoder(mem1, mem2, source_length, labels.mel, spk, training, masks)
+        out3 = self.buf("loss3", (3,))
+        dmel = self.buf("dec.dmel_tm", mel_tm.shape)
+        dstop = self.buf("dec.dstop_tm", stop_tm.shape)
+        O.losses(mel_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
+                 out3, dmel, dstop, self.buf("loss_scratch", (4,)))
+        self.saved = dict(B=B, Tt=Tt, Td=Td, Tm=Tm, source_length=source_length, dmel=dmel, dstop=dstop, features=features)
+        return dict(mel_tm=mel_tm, stop_tm=stop_tm, align1_tm=al1, align2_tm=al2, enc_self_P=enc_al, dec_self_P=dec_sa,
+                    memory1_tm=mem1, memory2_tm=mem2, losses=out3)
+
+    def backward(self):
+        """BPTT through decoder and encoder; gradients land in ``self.ps.grad`` (zeroed first)."""
+        s = self.saved
+        self.ps.grad.zero_()
+        dmem1, dmem2 = self.decoder_backward(s["dmel"], s["dstop"], s["B"], s["Tt"], s["Td"], s["source_length"])
+        if self.d.use_speaker:
+            g, p = self.ps.g, self.ps.p
+            dsp_pre = self._dspk_pre
+            spk = self._bufs["spk_embed"]
+            O.linear_dw(spk, dsp_pre, g["dec.prenet0.Ws"], s["B"], self.d.speaker_dim, self.d.dec_prenet[0], split_k=1)
+            O.colsum_acc(dsp_pre, s["B"], self.d.dec_prenet[0], g["dec.prenet0.bs"])
+            dspk = self.buf("dspk_embed", (s["B"], self.d.speaker_dim))
+            O.linear_dx(dsp_pre, p["dec.prenet0.Ws"], dspk, s["B"])
+            O.embedding_bwd(s["features"].speaker_id, dspk, g["speaker_embedding"], offset=self.d.speaker_offset)
+        self.encoder_backward(dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
+
+    def optimizer_step(self, world_size: int = 1):
+        """clip_by_global_norm(1.0) + Adam + noam LR (models.py:485-498).  With world_size > 1 the caller has
+        all-reduced (summed) ``ps.grad``; the 1/world_size average is folded into the kernel."""
+        hp = self.hp
+        lr = noam_lr(hp.initial_learning_rate, self.global_step, hp.learning_rate_step_factor) if hp.decay_learning_rate \
+            else hp.initial_learning_rate
+        O.grad_sumsq(self.ps.grad, self._sumsq)
+        O.adam_clip(self.ps.flat, self.ps.grad, self.ps.adam_m, self.ps.adam_v, self._sumsq, 1.0 / world_size, 1.0, lr,
+                    hp.adam_beta1, hp.adam_beta2, hp.adam_eps, self.global_step + 1)
+        self.global_step += 1
+        return lr
+
+    def train_step(self, features, labels, masks=None, allreduce=None, world_size: int = 1):
+        out = self.forward(features, labels, True, masks)
+        self.backward()
+        if allreduce is not None:
+            allreduce(self.ps.grad)
+        out["lr"] = self.optimizer_step(world_size)
+        return out

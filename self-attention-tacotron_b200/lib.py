@@ -1,0 +1,130 @@
+"""ctypes binding of libsatk.so (the C ABI declared in include/satk.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``make -C csrc``) and must be present:
+every op below raises ``SatkError`` if the shared object is missing or a call fails — there is no
+CPU / PyTorch fallback on the product path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsatk.so")
+
+
+class SatkError(RuntimeError):
+    pass
+
+
+fp = C.c_void_p
+i32 = C.c_int
+i64 = C.c_longlong
+f32 = C.c_float
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("M", i32), ("N", i32), ("K", i32), ("transA", i32), ("transB", i32),
+        ("A", fp), ("lda", i64), ("B", fp), ("ldb", i64), ("C", fp), ("ldc", i64),
+        ("alpha", f32), ("beta", f32), ("bias", fp), ("act", i32), ("residual", fp), ("ldres", i64),
+        ("keep_mask", fp), ("keep_scale", f32),
+        ("batch1", i32), ("batch2", i32),
+        ("sA1", i64), ("sA2", i64), ("sB1", i64), ("sB2", i64), ("sC1", i64), ("sC2", i64),
+        ("taps", i32), ("shift0", i32), ("tap_dir", i32), ("seq_len", i32), ("sBtap", i64),
+        ("shift_per_batch1", i32), ("split_k", i32), ("causal_skip", i32),
+    ]
+
+
+class LstmFwdDesc(C.Structure):
+    _fields_ = [
+        ("T", i32), ("B", i32), ("H", i32), ("reverse", i32),
+        ("xg", fp), ("Wh", fp), ("lengths", fp), ("mask_c", fp), ("mask_h", fp),
+        ("zc", f32), ("zh", f32), ("forget_bias", f32),
+        ("out", fp), ("ld_out", i64), ("gates", fp), ("c_prev", fp), ("h_prev", fp),
+    ]
+
+
+class LstmBwdDesc(C.Structure):
+    _fields_ = [
+        ("T", i32), ("B", i32), ("H", i32), ("reverse", i32),
+        ("Wh", fp), ("lengths", fp), ("mask_c", fp), ("mask_h", fp),
+        ("zc", f32), ("zh", f32),
+        ("gates", fp), ("c_prev", fp), ("dout", fp), ("ld_dout", i64), ("dgates", fp),
+    ]
+
+
+class AttnRnnFwdDesc(C.Structure):
+    _fields_ = [
+        ("Td", i32), ("B", i32), ("Tt", i32), ("H", i32), ("A1", i32), ("A2", i32), ("M1", i32), ("M2", i32),
+        ("att_kernel", i32), ("mode", i32), ("cumulative", i32),
+        ("xg", fp), ("Wrec", fp), ("mask_c", fp), ("mask_h", fp),
+        ("zc", f32), ("zh", f32), ("forget_bias", f32),
+        ("lengths", fp), ("keys1", fp), ("values1", fp), ("Wq1", fp), ("v1", fp), ("b1", fp),
+        ("loc_conv_w", fp), ("loc_conv_b", fp), ("loc_layer_w", fp), ("att_filters", i32),
+        ("keys2", fp), ("values2", fp), ("Wq2", fp), ("v2", fp),
+        ("x2", fp), ("align1", fp), ("align2", fp),
+        ("gates", fp), ("c_prev", fp), ("h_prev", fp), ("soft1", fp), ("q_save", fp),
+    ]
+
+
+class AttnRnnBwdDesc(C.Structure):
+    _fields_ = [
+        ("f", AttnRnnFwdDesc),
+        ("dx2", fp), ("dgates", fp), ("dq", fp), ("dkeys1", fp), ("dkeys2", fp),
+        ("dv1", fp), ("dv2", fp), ("dloc_conv_w", fp), ("dloc_conv_b", fp), ("dloc_layer_w", fp),
+    ]
+
+
+ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
+
+_lib: Optional[C.CDLL] = None
+
+# every symbol include/satk.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "satk_last_error", "satk_version", "satk_device_info", "satk_struct_sizes", "satk_gemm",
+    "satk_embedding_fwd", "satk_embedding_bwd", "satk_bn_stats", "satk_bn_apply", "satk_bn_bwd",
+    "satk_highway_fwd", "satk_highway_bwd", "satk_act_bwd", "satk_colsum_acc", "satk_add", "satk_axpy",
+    "satk_transpose", "satk_mask_rows", "satk_softsign_fwd", "satk_softsign_bwd", "satk_add_rowvec_tb",
+    "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
+    "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
+    "satk_attn_rnn_fwd", "satk_attn_rnn_bwd",
+]
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SatkError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.satk_last_error.restype = C.c_char_p
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().satk_last_error().decode(errors="replace")
+        raise SatkError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous from that pointer on."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def device_info():
+    out = (C.c_int * 5)()
+    check(load().satk_device_info(out), "satk_device_info")
+    return dict(sms=out[0], cc=(out[1], out[2]), attn_rnn_clusters=out[3], lstm_clusters=out[4])

@@ -1,0 +1,308 @@
+"""Tensor-level wrappers over the C ABI (one per entry point of include/satk.h).
+
+Tensors are CUDA fp32 (masks uint8, ids/lengths int64).  These wrappers only translate tensors to
+raw device pointers + the current CUDA stream; all arithmetic happens in libsatk.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, check, load, ptr, stream_ptr
+
+# GEMM engine: 0 auto (tcgen05 tile when the shape allows, else SIMT), 1 SIMT fp32, 2 tcgen05 only
+GEMM_ENGINE = 0
+_launches = 0
+
+
+def launches() -> int:
+    """Number of libsatk kernel-launching calls issued so far (bench.py reports the per-step delta)."""
+    return _launches
+
+
+def _count(n: int = 1) -> None:
+    global _launches
+    _launches += n
+
+
+def _req(t: torch.Tensor, dtype=torch.float32) -> None:
+    if not t.is_cuda:
+        raise L.SatkError("satk ops need CUDA tensors (no CPU fallback)")
+    if t.dtype != dtype:
+        raise L.SatkError(f"expected dtype {dtype}, got {t.dtype}")
+
+
+def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: int, *, lda: int, ldb: int, ldc: int,
+         transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=None, residual=None, ldres=0,
+         keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0),
+         taps=1, shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0,
+         a_off=0, b_off=0, c_off=0, engine=None) -> None:
+    """C = epi(alpha * sum_taps op(A) op(B)) (+beta*C).  ``*_off`` are element offsets into the tensors."""
+    _req(A); _req(B); _req(C_)
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.transA, d.transB = int(transA), int(transB)
+    d.A, d.lda = A.data_ptr() + 4 * a_off, lda
+    d.B, d.ldb = B.data_ptr() + 4 * b_off, ldb
+    d.C, d.ldc = C_.data_ptr() + 4 * c_off, ldc
+    d.alpha, d.beta = alpha, beta
+    d.bias = ptr(bias)
+    d.act = ACT[act]
+    d.residual, d.ldres = ptr(residual), ldres
+    d.keep_mask, d.keep_scale = ptr(keep_mask), keep_scale
+    d.batch1, d.batch2 = batch1, batch2
+    d.sA1, d.sA2 = sA
+    d.sB1, d.sB2 = sB
+    d.sC1, d.sC2 = sC
+    d.taps, d.shift0, d.tap_dir, d.seq_len, d.sBtap = taps, shift0, tap_dir, seq_len, sBtap
+    d.shift_per_batch1, d.split_k, d.causal_skip = shift_per_batch1, split_k, causal_skip
+    check(load().satk_gemm(C.byref(d), GEMM_ENGINE if engine is None else engine, C.c_void_p(stream_ptr())), "satk_gemm")
+    _count()
+
+
+def linear(x: torch.Tensor, W: torch.Tensor, out: torch.Tensor, bias=None, act=None, residual=None, keep_mask=None,
+           keep_scale=1.0, ldc=None, c_off=0, lda=None, a_off=0) -> torch.Tensor:
+    """out[rows, N] = epi(x[rows, K] @ W[K, N] + bias); rows = x.numel() // K unless lda is given."""
+    K, N = W.shape
+    lda = lda or K
+    rows = (x.numel() - a_off) // lda if lda != K else x.numel() // K
+    gemm(x, W, out, rows, N, K, lda=lda, ldb=N, ldc=ldc or N, bias=bias, act=act, residual=residual,
+         ldres=(residual.shape[-1] if residual is not None else 0), keep_mask=keep_mask, keep_scale=keep_scale,
+         c_off=c_off, a_off=a_off)
+    return out
+
+
+def linear_dx(dy: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, rows: int, beta=0.0, ldy=None, y_off=0, ldx=None,
+              x_off=0, w_off=0, K=None, N=None, ldw=None) -> None:
+    """dx[rows, K] (+)= dy[rows, N] @ W[K, N]^T"""
+    Kw, Nw = W.shape[-2], W.shape[-1]
+    K = K or Kw
+    N = N or Nw
+    gemm(dy, W, dx, rows, K, N, lda=ldy or N, ldb=ldw or Nw, ldc=ldx or K, transB=True, beta=beta, a_off=y_off, c_off=x_off,
+         b_off=w_off)
+
+
+def linear_dw(x: torch.Tensor, dy: torch.Tensor, dW: torch.Tensor, rows: int, K: int, N: int, ldx=None, x_off=0, ldy=None,
+              y_off=0, ldw=None, w_off=0, shift0=0, split_k=None) -> None:
+    """dW[K, N] += x[rows, K]^T @ dy[rows, N]  (split-K over rows, atomically accumulated)."""
+    if split_k is None:
+        split_k = max(1, min(64, rows // 256))
+    gemm(x, dy, dW, K, N, rows, lda=ldx or K, ldb=ldy or N, ldc=ldw or N, transA=True, a_off=x_off, b_off=y_off,
+         c_off=w_off, shift0=shift0, split_k=split_k, beta=1.0)
+    # split_k == 1 goes through the plain epilogue with beta = 1 (accumulate), >1 through atomics: same result
+
+
+def colsum_acc(x: torch.Tensor, rows: int, Ccols: int, out: torch.Tensor, ldx=None, x_off=0) -> None:
+    check(load().satk_colsum_acc(C.c_void_p(x.data_ptr() + 4 * x_off), C.c_longlong(ldx or Ccols), rows, Ccols,
+                                 C.c_void_p(out.data_ptr()), C.c_void_p(stream_ptr())), "satk_colsum_acc")
+    _count()
+
+
+def embedding_fwd(ids, table, out, offset=0):
+    check(load().satk_embedding_fwd(C.c_void_p(ids.data_ptr()), ids.numel(), offset, C.c_void_p(table.data_ptr()),
+                                    table.shape[1], C.c_void_p(out.data_ptr()), C.c_void_p(stream_ptr())), "satk_embedding_fwd")
+    _count()
+
+
+def embedding_bwd(ids, dout, dtable, offset=0):
+    check(load().satk_embedding_bwd(C.c_void_p(ids.data_ptr()), ids.numel(), offset, C.c_void_p(dout.data_ptr()),
+                                    dtable.shape[1], C.c_void_p(dtable.data_ptr()), C.c_void_p(stream_ptr())), "satk_embedding_bwd")
+    _count()
+
+
+def bn_stats(x, rows, Cc, mean, var, ldx=None, x_off=0, mov_mean=None, mov_var=None, momentum=0.99, bessel=True):
+    check(load().satk_bn_stats(C.c_void_p(x.data_ptr() + 4 * x_off), C.c_longlong(ldx or Cc), rows, Cc,
+                               C.c_void_p(mean.data_ptr()), C.c_void_p(var.data_ptr()), C.c_void_p(ptr(mov_mean)),
+                               C.c_void_p(ptr(mov_var)), C.c_float(momentum), int(bessel), C.c_void_p(stream_ptr())), "satk_bn_stats")
+    _count(4)
+
+
+def bn_apply(x, rows, Cc, mean, var, gamma, beta, y, eps=1e-3, act=None, residual=None, maxpool_seq_len=0, pos_stride=1, ldx=None,
+             x_off=0, ldy=None, y_off=0):
+    check(load().satk_bn_apply(C.c_void_p(x.data_ptr() + 4 * x_off), C.c_longlong(ldx or Cc), rows, Cc,
+                               C.c_void_p(mean.data_ptr()), C.c_void_p(var.data_ptr()), C.c_void_p(gamma.data_ptr()),
+                               C.c_void_p(beta.data_ptr()), C.c_float(eps), ACT[act], C.c_void_p(ptr(residual)),
+                               maxpool_seq_len, pos_stride, C.c_void_p(y.data_ptr() + 4 * y_off), C.c_longlong(ldy or Cc),
+                               C.c_void_p(stream_ptr())), "satk_bn_apply")
+    _count()
+
+
+def bn_bwd(x, rows, Cc, mean, var, gamma, beta, dy, dx, dgamma, dbeta, scratch, eps=1e-3, act=None, maxpool_seq_len=0,
+           pos_stride=1, use_batch_stats=True, ldx=None, x_off=0, lddy=None, dy_off=0, lddx=None, dx_off=0):
+    check(load().satk_bn_bwd(C.c_void_p(x.data_ptr() + 4 * x_off), C.c_longlong(ldx or Cc), rows, Cc,
+                             C.c_void_p(mean.data_ptr()), C.c_void_p(var.data_ptr()), C.c_void_p(gamma.data_ptr()),
+                             C.c_void_p(beta.data_ptr()), C.c_float(eps), ACT[act], maxpool_seq_len, pos_stride, int(use_batch_stats),
+                             C.c_void_p(dy.data_ptr() + 4 * dy_off), C.c_longlong(lddy or Cc),
+                             C.c_void_p(dx.data_ptr() + 4 * dx_off), C.c_longlong(lddx or Cc),
+                             C.c_void_p(dgamma.data_ptr()), C.c_void_p(dbeta.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                             C.c_void_p(stream_ptr())), "satk_bn_bwd")
+    _count(3)
+
+
+def highway_fwd(Hh, T, x, y):
+    check(load().satk_highway_fwd(C.c_void_p(Hh.data_ptr()), C.c_void_p(T.data_ptr()), C.c_void_p(x.data_ptr()),
+                                  C.c_void_p(y.data_ptr()), C.c_longlong(x.numel()), C.c_void_p(stream_ptr())), "satk_highway_fwd")
+    _count()
+
+
+def highway_bwd(Hh, T, x, dy, dH, dT, dx):
+    check(load().satk_highway_bwd(C.c_void_p(Hh.data_ptr()), C.c_void_p(T.data_ptr()), C.c_void_p(x.data_ptr()),
+                                  C.c_void_p(dy.data_ptr()), C.c_void_p(dH.data_ptr()), C.c_void_p(dT.data_ptr()),
+                                  C.c_void_p(dx.data_ptr()), C.c_longlong(x.numel()), C.c_void_p(stream_ptr())), "satk_highway_bwd")
+    _count()
+
+
+def act_bwd(y, dy, dz, act, keep_mask=None, keep_scale=1.0):
+    check(load().satk_act_bwd(C.c_void_p(y.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dz.data_ptr()),
+                              C.c_longlong(y.numel()), ACT[act], C.c_void_p(ptr(keep_mask)), C.c_float(keep_scale),
+                              C.c_void_p(stream_ptr())), "satk_act_bwd")
+    _count()
+
+
+def add(a, b, out):
+    check(load().satk_add(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
+                          C.c_longlong(out.numel()), C.c_void_p(stream_ptr())), "satk_add")
+    _count()
+
+
+def axpy(alpha, x, y):
+    check(load().satk_axpy(C.c_float(alpha), C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_longlong(y.numel()),
+                           C.c_void_p(stream_ptr())), "satk_axpy")
+    _count()
+
+
+def transpose(x, rows, cols, y):
+    check(load().satk_transpose(C.c_void_p(x.data_ptr()), rows, cols, C.c_void_p(y.data_ptr()), C.c_void_p(stream_ptr())),
+          "satk_transpose")
+    _count()
+
+
+def mask_rows(x, lengths, B, T, Cc, time_major, y):
+    check(load().satk_mask_rows(C.c_void_p(x.data_ptr()), C.c_void_p(lengths.data_ptr()), B, T, Cc, int(time_major),
+                                C.c_void_p(y.data_ptr()), C.c_void_p(stream_ptr())), "satk_mask_rows")
+    _count()
+
+
+def softsign_fwd(x, y):
+    check(load().satk_softsign_fwd(C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()), C.c_longlong(x.numel()),
+                                   C.c_void_p(stream_ptr())), "satk_softsign_fwd")
+    _count()
+
+
+def softsign_bwd(x, dy, dx):
+    check(load().satk_softsign_bwd(C.c_void_p(x.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()),
+                                   C.c_longlong(x.numel()), C.c_void_p(stream_ptr())), "satk_softsign_bwd")
+    _count()
+
+
+def add_rowvec_tb(y, v, T, B, Cc):
+    check(load().satk_add_rowvec_tb(C.c_void_p(y.data_ptr()), C.c_void_p(v.data_ptr()), T, B, Cc, C.c_void_p(stream_ptr())),
+          "satk_add_rowvec_tb")
+    _count()
+
+
+def sum_over_t(dy, T, B, Cc, dv):
+    check(load().satk_sum_over_t(C.c_void_p(dy.data_ptr()), T, B, Cc, C.c_void_p(dv.data_ptr()), C.c_void_p(stream_ptr())),
+          "satk_sum_over_t")
+    _count()
+
+
+def bernoulli_mask(out, keep_prob, seed):
+    check(load().satk_bernoulli_mask(C.c_void_p(out.data_ptr()), C.c_longlong(out.numel()), C.c_float(keep_prob),
+                                     C.c_ulonglong(seed), C.c_void_p(stream_ptr())), "satk_bernoulli_mask")
+    _count()
+
+
+def softmax_fwd(S, nmat, T, causal, keep_mask=None, keep_scale=1.0, Pd=None):
+    check(load().satk_softmax_fwd(C.c_void_p(S.data_ptr()), nmat, T, int(causal), C.c_void_p(ptr(keep_mask)),
+                                  C.c_float(keep_scale), C.c_void_p(ptr(Pd)), C.c_void_p(stream_ptr())), "satk_softmax_fwd")
+    _count()
+
+
+def softmax_bwd(P, dPd, nmat, T, causal, dS, keep_mask=None, keep_scale=1.0):
+    check(load().satk_softmax_bwd(C.c_void_p(P.data_ptr()), C.c_void_p(dPd.data_ptr()), nmat, T, int(causal),
+                                  C.c_void_p(ptr(keep_mask)), C.c_float(keep_scale), C.c_void_p(dS.data_ptr()),
+                                  C.c_void_p(stream_ptr())), "satk_softmax_bwd")
+    _count()
+
+
+def teacher_inputs(mel, B, Tm, n_mels, r, n_feed, out):
+    check(load().satk_teacher_inputs(C.c_void_p(mel.data_ptr()), B, Tm, n_mels, r, n_feed, C.c_void_p(out.data_ptr()),
+                                     C.c_void_p(stream_ptr())), "satk_teacher_inputs")
+    _count()
+
+
+def losses(pred_tm, stop_tm, mel, done, spec_mask, bin_mask, B, Tm, n_mels, r, out3, dpred, dstop, scratch4):
+    check(load().satk_losses(C.c_void_p(pred_tm.data_ptr()), C.c_void_p(stop_tm.data_ptr()), C.c_void_p(mel.data_ptr()),
+                             C.c_void_p(done.data_ptr()), C.c_void_p(spec_mask.data_ptr()), C.c_void_p(bin_mask.data_ptr()),
+                             B, Tm, n_mels, r, C.c_void_p(out3.data_ptr()), C.c_void_p(dpred.data_ptr()),
+                             C.c_void_p(dstop.data_ptr()), C.c_void_p(scratch4.data_ptr()), C.c_void_p(stream_ptr())), "satk_losses")
+    _count(2)
+
+
+def grad_sumsq(g, sumsq):
+    check(load().satk_grad_sumsq(C.c_void_p(g.data_ptr()), C.c_longlong(g.numel()), C.c_void_p(sumsq.data_ptr()),
+                                 C.c_void_p(stream_ptr())), "satk_grad_sumsq")
+    _count()
+
+
+def adam_clip(p, g, m, v, sumsq, grad_scale, clip_norm, lr, b1, b2, eps, step):
+    check(load().satk_adam_clip(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(m.data_ptr()),
+                                C.c_void_p(v.data_ptr()), C.c_longlong(p.numel()), C.c_void_p(sumsq.data_ptr()),
+                                C.c_float(grad_scale), C.c_float(clip_norm), C.c_float(lr), C.c_float(b1), C.c_float(b2),
+                                C.c_float(eps), int(step), C.c_void_p(stream_ptr())), "satk_adam_clip")
+    _count()
+
+
+def lstm_seq_fwd(xg, Wh, out, T, B, H, *, reverse=False, lengths=None, mask_c=None, mask_h=None, zc=0.0, zh=0.0,
+                 forget_bias=1.0, gates=None, c_prev=None, h_prev=None, wh_off=0, ld_out=None, out_off=0):
+    d = LstmFwdDesc()
+    d.T, d.B, d.H, d.reverse = T, B, H, int(reverse)
+    d.xg, d.Wh = xg.data_ptr(), Wh.data_ptr() + 4 * wh_off
+    d.lengths, d.mask_c, d.mask_h = ptr(lengths), ptr(mask_c), ptr(mask_h)
+    d.zc, d.zh, d.forget_bias = zc, zh, forget_bias
+    d.out, d.gates, d.c_prev, d.h_prev = out.data_ptr() + 4 * out_off, ptr(gates), ptr(c_prev), ptr(h_prev)
+    d.ld_out = ld_out or H
+    check(load().satk_lstm_seq_fwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_lstm_seq_fwd")
+    _count()
+
+
+def lstm_seq_bwd(Wh, gates, c_prev, dout, dgates, T, B, H, *, reverse=False, lengths=None, mask_c=None, mask_h=None,
+                 zc=0.0, zh=0.0, wh_off=0, ld_dout=None, dout_off=0):
+    d = LstmBwdDesc()
+    d.T, d.B, d.H, d.reverse = T, B, H, int(reverse)
+    d.Wh = Wh.data_ptr() + 4 * wh_off
+    d.lengths, d.mask_c, d.mask_h = ptr(lengths), ptr(mask_c), ptr(mask_h)
+    d.zc, d.zh = zc, zh
+    d.gates, d.c_prev, d.dout, d.dgates = gates.data_ptr(), c_prev.data_ptr(), dout.data_ptr() + 4 * dout_off, dgates.data_ptr()
+    d.ld_dout = ld_dout or H
+    check(load().satk_lstm_seq_bwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_lstm_seq_bwd")
+    _count()
+
+
+def attn_rnn_desc(**kw) -> AttnRnnFwdDesc:
+    d = AttnRnnFwdDesc()
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(d, k, v)
+    return d
+
+
+def attn_rnn_fwd(d: AttnRnnFwdDesc):
+    check(load().satk_attn_rnn_fwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_rnn_fwd")
+    _count()
+
+
+def attn_rnn_bwd(f: AttnRnnFwdDesc, **kw):
+    d = AttnRnnBwdDesc()
+    d.f = f
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = v.data_ptr()
+        setattr(d, k, v)
+    check(load().satk_attn_rnn_bwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_rnn_bwd")
+    _count()
