@@ -222,9 +222,9 @@ def model_case(cfg, B, Tt, Tm, training, tag, check_grads=True, overrides=None):
     out = eng.forward(fd, ld, training, md)
     torch.cuda.synchronize()
     Td = Tm // d.r
-    report(tag + ".memory1", out["memory1_tm"].transpose(0, 1), ref["memory1"])
+    report(tag + ".memory1", out["memory1_tm"].view(Tt, B, -1).transpose(0, 1), ref["memory1"])
     if d.dual:
-        report(tag + ".memory2", out["memory2_tm"].transpose(0, 1), ref["memory2"])
+        report(tag + ".memory2", out["memory2_tm"].view(Tt, B, -1).transpose(0, 1), ref["memory2"])
         report(tag + ".enc_self_align0", out["enc_self_P"][0].transpose(1, 2), ref["enc_self_alignments"][0])
     report(tag + ".alignment", out["align1_tm"].permute(1, 2, 0), ref["alignment"])
     if d.dual:
