@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""Benchmark of the teacher-forced training hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle restatement of the
+                                                           # reference's TF1 graph on the host cores
+
+A "step" is one full train step (forward, backward, gradient all-reduce when N>1, clip + Adam) on a
+synthetic LJSpeech-shaped batch: configs[1] of BASELINE.json = examples/ljspeech self-attention
+Tacotron, B=32 per GPU, T_text=148, T_mel=800, 80 mel channels (weak scaling: MirroredStrategy
+semantics, per-replica batch = batch_size).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = "ljspeech_self-attention-tacotron.json"
+B, TT, TM = 32, 148, 800
+METRIC = "teacher_forced_mel_frames_per_sec"
+UNIT = "mel-frames/s"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_sample(hp, satk, steps, warmup, sample_b):
+    """CPU arm: full train step (fwd, autograd bwd, clip, Adam) of the oracle on a bounded sample."""
+    import torch
+    from oracle import model as OR
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(1234, "glorot")
+    tr = OR.OracleTrainer(d, hp, ps.as_dict())
+    f, l = satk.synthetic_batch(hp, sample_b, TT, TM, seed=1234)
+    masks = satk.make_masks(d, sample_b, TT, TM // d.r, seed=99)
+    for _ in range(warmup):
+        tr.train_step(f, l, masks)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.train_step(f, l, masks)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return sample_b * TM / dt, dt, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import satk_path
+    satk = satk_path.load()
+    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG))
+    sample_b = 8
+    value, dt, cores = oracle_sample(hp, satk, args.steps, min(args.warmup, 1), sample_b)
+    sample = (f"{sample_b} of the {B} utterances of the batch (same T_text={TT}, T_mel={TM}), full train step per step; "
+              "torch-CPU fp32 restatement of the TF1 graph (TF1 itself cannot run here)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{CFG} B={B}/GPU T_text={TT} T_mel={TM} n_mels=80 teacher-forced train step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_satk(args, rank, world, local_rank):
+    import torch
+    import satk_path
+    satk = satk_path.load()
+    from importlib import import_module
+    M = import_module("self-attention-tacotron_b200.models")
+    O = import_module("self-attention-tacotron_b200.ops")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG))
+
+    def allreduce(flat):
+        dist.all_reduce(flat)      # ONE ncclAllReduce(sum) over the flat fp32 gradient buffer
+
+    model = M.tacotron_model_factory(hp, None, None, device=str(dev), allreduce=allreduce if world > 1 else None, world_size=world)
+    eng = model.engine
+    nb = 4   # distinct batches rotated through the timed region
+    host, devb = [], []
+    for i in range(nb):
+        f, l = satk.synthetic_batch(hp, B, TT, TM, seed=1234 + 100 * rank + i)
+        fp = satk.SourceData(*[x.pin_memory() if torch.is_tensor(x) else x for x in f])
+        lp = satk.MelData(*[x.pin_memory() if torch.is_tensor(x) else x for x in l])
+        host.append((fp, lp))
+        devb.append((satk.SourceData(*[x.to(dev) if torch.is_tensor(x) else x for x in f]),
+                     satk.MelData(*[x.to(dev) if torch.is_tensor(x) else x for x in l])))
+    h2d = sum(x.numel() * x.element_size() for nt in host[0] for x in nt if torch.is_tensor(x))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        f, l = devb[i % nb]
+        eng.train_step(f, l, None, allreduce=allreduce if world > 1 else None, world_size=world)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    eng.timers = {}
+    l0 = O.launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        f, l = devb[i % nb]
+        eng.train_step(f, l, None, allreduce=allreduce if world > 1 else None, world_size=world)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = O.launches() - l0
+    timers = eng.timers
+    eng.timers = None
+    # ---- timed region 2: end to end through the Estimator surface, host (pinned) buffers in, loss out
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    loss = 0.0
+    for i in range(args.steps):
+        f, l = host[i % nb]
+        spec = model.model_fn(f, l, M.ModeKeys.TRAIN, hp)
+        loss = float(spec.loss)       # device -> host read of the step's loss (4 bytes)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = world * B * TM * args.steps
+    value = frames / (ms * 1e-3)
+    e2e = frames / (ms_e2e * 1e-3)
+    # ---- roofline of the dominant kernel (attention-RNN forward / backward), CUDA-event timed in region 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    d = eng.d
+    td = TM // d.r
+    w_seq = (d.ctx + d.att_rnn) * 4 * d.att_rnn + d.att_rnn * d.att1 + d.att_filters * d.att1 + d.att_kernel * d.att_filters \
+        + d.att_rnn * d.att2
+    bytes_step = 2 * (w_seq + B * TT * (d.att1 + d.mem1 + d.att2 + d.mem2))      # SURVEY §8(d), LSTM-2/3 rows excluded
+    kt = {}
+    for name, evs in (timers or {}).items():
+        torch.cuda.synchronize()
+        kt[name] = statistics.mean(a.elapsed_time(b) for a, b in evs)
+    roof = None
+    if kt:
+        dom = max(kt, key=kt.get)
+        alg = bytes_step * td * (2 if dom.endswith("bwd") else 1)
+        ach = alg / (kt[dom] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kt[dom], "us_per_decoder_step": kt[dom] * 1e3 / td,
+                "kernel_ms": kt}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{CFG} B={B}/GPU T_text={TT} T_mel={TM} n_mels=80 teacher-forced train step "
+                               "(fwd+bwd+allreduce+clip+Adam)", "parallelism": f"dp{world}",
+                   "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; 4 distinct batches rotated"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                "last_loss": loss},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, cores = oracle_sample(hp, satk, 1, 1, 8)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"1 timed train step (after 1 warm-up) on 8 of the {B} utterances, T_text={TT}, T_mel={TM}; "
+                                         "oracle = torch-CPU fp32 restatement of the TF1 graph"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="satk", choices=["satk", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_satk(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

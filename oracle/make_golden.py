@@ -1,0 +1,31 @@
+"""Writes tests/golden/oracle_small.npz from the oracle itself (run: python -m oracle.make_golden).
+Self-generated fixture: the reference has no golden vectors and cannot run here."""
+import os
+import sys
+
+import numpy as np
+
+
+def golden_case(satk, root):
+    from oracle import model as OR
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(2024, "random")
+    f, l = satk.synthetic_batch(hp, 2, 12, 16, seed=2024)
+    masks = satk.make_masks(d, 2, 12, 8, seed=2024)
+    tr = OR.OracleTrainer(d, hp, ps.as_dict())
+    out, grads, _ = tr.loss_and_grads(f, l, masks, True)
+    return out, grads
+
+
+if __name__ == "__main__":
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import satk_path
+    satk = satk_path.load()
+    out, grads = golden_case(satk, root)
+    np.savez_compressed(os.path.join(root, "tests", "golden", "oracle_small.npz"), mel=out["mel"].detach().numpy(),
+                        stop=out["stop"].detach().numpy(), alignment=out["alignment"].detach().numpy(),
+                        alignment2=out["alignment2"].detach().numpy(), loss=float(out["loss"].detach()),
+                        grad_dec_lstm1_W_slice=grads["dec.lstm1.W"].numpy()[100:164, :64], grad_att1_v=grads["att1.v"].numpy())
+    print("written")

@@ -50,6 +50,17 @@ class TacotronEngine:
         self.saved = None
         self.global_step = 0
         self._sumsq = torch.zeros(1, device=self.device)
+        self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
+
+    def _timed(self, name, fn, *a, **k):
+        if self.timers is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        self.timers.setdefault(name, []).append((e0, e1))
+        return r
 
     # ------------------------------------------------------------------ helpers
     def buf(self, name: str, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
@@ -384,7 +395,7 @@ class TacotronEngine:
             gates=self.buf("dec.gates1", (Rd, 4 * H1)), c_prev=self.buf("dec.cprev1", (Rd, H1)),
             h_prev=self.buf("dec.hprev1", (Rd, H1)), soft1=self.buf("dec.soft1", (Td, B, Tt)),
             q_save=self.buf("dec.qsave", (Rd, d.att1 + d.att2)))
-        O.attn_rnn_fwd(fd)
+        self._timed("attn_rnn_fwd", O.attn_rnn_fwd, fd)
         sv.update(fd=fd, dec_in=dec_in, dp0=dp0, dp1=dp1, x2=x2, values1=values1, values2=values2, keys1=keys1, keys2=keys2)
         # LSTM-2, LSTM-3 (DecoderRNNV2)
         x = x2
@@ -454,7 +465,7 @@ class TacotronEngine:
         dq = self.buf("dec.dq", (Rd, QT))
         dkeys1 = self.buf("dec.dkeys1", (R, d.att1))
         dkeys2 = self.buf("dec.dkeys2", (R, d.att2)) if d.dual else None
-        O.attn_rnn_bwd(fd, dx2=dx2, dgates=dg1, dq=dq, dkeys1=dkeys1, dkeys2=dkeys2,
+        self._timed("attn_rnn_bwd", O.attn_rnn_bwd, fd, dx2=dx2, dgates=dg1, dq=dq, dkeys1=dkeys1, dkeys2=dkeys2,
                        dv1=g["att1.v"], dv2=g["att2.v"] if d.dual else None,
                        dloc_conv_w=g["att1.loc_conv.W"] if loc else None, dloc_conv_b=g["att1.loc_conv.b"] if loc else None,
                        dloc_layer_w=g["att1.loc_layer.W"] if loc else None)

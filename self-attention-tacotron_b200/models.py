@@ -1,0 +1,177 @@
+"""Estimator surface of the hot path ("Estimator surface").
+
+Mirrors what ``train.py`` / ``predict_mel.py`` touch in the reference:
+  * ``tacotron_model_factory(hparams, model_dir, run_config, warm_start_from=None)``
+    (/root/reference/models/models.py:1363-1381) selecting by ``hparams.tacotron_model``;
+  * objects with ``model_fn(features, labels, mode, params)`` returning a spec that carries
+    ``loss`` / ``train_op`` / ``predictions`` (models.py:278,514,562,588), and ``train`` /
+    ``evaluate`` / ``predict`` drivers (tf.estimator.Estimator's public methods used at
+    train.py:88 and predict_mel.py:54).
+TensorFlow's session/graph machinery is replaced by eager calls into the CUDA engine; the tensors
+flowing through ``features`` / ``labels`` keep the reference's field names (data.py).
+"""
+from __future__ import annotations
+
+import os
+from collections import namedtuple
+from typing import Callable, Dict, Iterable, Optional
+
+import torch
+
+from .data import MelData, SourceData
+from .engine import TacotronEngine
+
+
+class ModeKeys:
+    TRAIN = "train"
+    EVAL = "eval"
+    PREDICT = "infer"
+
+
+EstimatorSpec = namedtuple("EstimatorSpec", ["mode", "loss", "train_op", "predictions", "eval_metric_ops", "scalars"])
+EstimatorSpec.__new__.__defaults__ = (None, None, None, None, None)
+
+
+def _to_device(nt, device):
+    """Host -> device copy of every tensor field (non-blocking: pinned host buffers overlap with compute)."""
+    return type(nt)(*[x.to(device, non_blocking=True) if torch.is_tensor(x) else x for x in nt])
+
+
+class _TacotronEstimator:
+    """Common driver: owns the engine (weights, optimiser state) and the checkpoint directory."""
+
+    _model_name = ""
+
+    def __init__(self, params, model_dir: Optional[str] = None, config=None, warm_start_from: Optional[str] = None,
+                 device: Optional[str] = None, allreduce: Optional[Callable[[torch.Tensor], None]] = None, world_size: int = 1):
+        if params.tacotron_model != self._model_name:
+            raise ValueError(f"{type(self).__name__} built with tacotron_model={params.tacotron_model}")
+        self.params = params
+        self.model_dir = model_dir
+        self.config = config
+        self.device = torch.device(device or "cuda")
+        self.engine = TacotronEngine(params, self.device)
+        self._allreduce = allreduce
+        self._world_size = world_size
+        if warm_start_from:
+            self.restore(warm_start_from)
+        elif model_dir and os.path.exists(self._ckpt_path()):
+            self.restore(self._ckpt_path())          # resume = re-run with the same --checkpoint-dir (train.py:70-80)
+
+    # ---- checkpointing (flat buffers; a TF-variable name map is a later row of SURVEY §8f)
+    def _ckpt_path(self) -> str:
+        return os.path.join(self.model_dir, "model.satk.pt")
+
+    def save(self, path: Optional[str] = None) -> str:
+        path = path or self._ckpt_path()
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        ps = self.engine.ps
+        torch.save(dict(flat=ps.flat.cpu(), adam_m=ps.adam_m.cpu(), adam_v=ps.adam_v.cpu(), bn_mean=ps.bn_mean_flat.cpu(),
+                        bn_var=ps.bn_var_flat.cpu(), global_step=self.engine.global_step,
+                        names=list(ps.offsets.keys())), path)
+        return path
+
+    def restore(self, path: str) -> None:
+        st = torch.load(path, map_location="cpu")
+        ps = self.engine.ps
+        if st["names"] != list(ps.offsets.keys()) or st["flat"].numel() != ps.flat.numel():
+            raise ValueError(f"checkpoint {path} does not match this model's parameter set")
+        ps.flat.copy_(st["flat"]); ps.adam_m.copy_(st["adam_m"]); ps.adam_v.copy_(st["adam_v"])
+        ps.bn_mean_flat.copy_(st["bn_mean"]); ps.bn_var_flat.copy_(st["bn_var"])
+        self.engine.global_step = int(st["global_step"])
+
+    # ---- model_fn (models.py:278 / :23)
+    def model_fn(self, features, labels, mode, params=None, masks=None) -> EstimatorSpec:
+        eng, d = self.engine, self.engine.d
+        if mode == ModeKeys.PREDICT:
+            raise NotImplementedError("free-running PREDICT (predict_mel.py path) is SURVEY §8(f1): not built yet; "
+                                      "use mode=EVAL for the teacher-forced decode")
+        features = _to_device(features, self.device)
+        labels = _to_device(labels, self.device)
+        training = mode == ModeKeys.TRAIN
+        if training:
+            out = eng.train_step(features, labels, masks, allreduce=self._allreduce, world_size=self._world_size)
+        else:
+            out = eng.forward(features, labels, False)
+        B, Tm = labels.mel.shape[0], labels.mel.shape[1]
+        Td = Tm // d.r
+        losses = out["losses"]
+        preds = None
+        if not training:
+            mel = out["mel_tm"].view(Td, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, Tm, d.n_mels)
+            preds = {"id": features.id, "key": features.key, "mel": mel, "ground_truth_mel": labels.mel,
+                     "stop_token": out["stop_tm"].view(Td, B).t(),
+                     "alignment": out["align1_tm"].permute(1, 2, 0),             # (B, Tt, Td), models.py:406
+                     "source": features.source, "text": features.text}
+            if d.dual:
+                preds["alignment2"] = out["align2_tm"].permute(1, 2, 0)          # models.py:407
+                for i, a in enumerate(out["dec_self_P"]):                        # alignment3/4, models.py:403-404
+                    preds[f"alignment{3 + i}"] = a.transpose(1, 2)
+                for i, a in enumerate(out["enc_self_P"]):                        # alignment5.., models.py:398
+                    preds[f"alignment{5 + i}"] = a.transpose(1, 2)
+        scalars = {"loss_with_teacher": losses[2], "mel_loss_with_teacher": losses[0], "done_loss_with_teacher": losses[1],
+                   "mel_loss": losses[0], "done_loss": losses[1]}
+        if training:
+            scalars["learning_rate"] = out["lr"]
+        return EstimatorSpec(mode=mode, loss=losses[2], train_op=eng.global_step if training else None, predictions=preds,
+                             eval_metric_ops=None if training else dict(scalars), scalars=scalars)
+
+    # ---- drivers (tf.estimator.Estimator.train / evaluate / predict)
+    def train(self, input_fn: Callable[[], Iterable], steps: Optional[int] = None, max_steps: Optional[int] = None, hooks=None):
+        n = 0
+        last = None
+        for features, labels in input_fn():
+            if steps is not None and n >= steps:
+                break
+            if max_steps is not None and self.engine.global_step >= max_steps:
+                break
+            last = self.model_fn(features, labels, ModeKeys.TRAIN, self.params)
+            n += 1
+            every = getattr(self.params, "save_checkpoints_steps", 0)
+            if self.model_dir and every and self.engine.global_step % every == 0:
+                self.save()
+        if self.model_dir and n:
+            self.save()
+        return last
+
+    def evaluate(self, input_fn: Callable[[], Iterable], steps: Optional[int] = None) -> Dict[str, float]:
+        sums: Dict[str, float] = {}
+        n = 0
+        for features, labels in input_fn():
+            if steps is not None and n >= steps:
+                break
+            spec = self.model_fn(features, labels, ModeKeys.EVAL, self.params)
+            for k, v in spec.eval_metric_ops.items():
+                sums[k] = sums.get(k, 0.0) + float(v)
+            n += 1
+        return {k: v / max(n, 1) for k, v in sums.items()} | {"global_step": self.engine.global_step}
+
+    def predict(self, input_fn: Callable[[], Iterable], checkpoint_path: Optional[str] = None):
+        if checkpoint_path:
+            self.restore(checkpoint_path)
+        for item in input_fn():
+            features, labels = item if isinstance(item, tuple) and len(item) == 2 else (item, None)
+            if labels is None:
+                raise NotImplementedError("free-running PREDICT is SURVEY §8(f1): not built yet")
+            yield self.model_fn(features, labels, ModeKeys.EVAL, self.params).predictions
+
+
+class DualSourceSelfAttentionTacotronModel(_TacotronEstimator):
+    """models/models.py:275"""
+    _model_name = "DualSourceSelfAttentionTacotronModel"
+
+
+class ExtendedTacotronV1Model(_TacotronEstimator):
+    """models/models.py:20"""
+    _model_name = "ExtendedTacotronV1Model"
+
+
+def tacotron_model_factory(hparams, model_dir, run_config, warm_start_from=None, **kw):
+    """models/models.py:1363-1381 (the MGC/LF0 vocoder-parameter models are out of scope)."""
+    if hparams.tacotron_model == "DualSourceSelfAttentionTacotronModel":
+        return DualSourceSelfAttentionTacotronModel(hparams, model_dir, config=run_config, warm_start_from=warm_start_from, **kw)
+    if hparams.tacotron_model == "ExtendedTacotronV1Model":
+        return ExtendedTacotronV1Model(hparams, model_dir, config=run_config, warm_start_from=warm_start_from, **kw)
+    if hparams.tacotron_model in ("MgcLf0TacotronModel", "DualSourceSelfAttentionMgcLf0TacotronModel"):
+        raise NotImplementedError(f"{hparams.tacotron_model}: MGC/LF0 models are outside the hot-path scope")
+    raise ValueError(f"Unknown Tacotron model: {hparams.tacotron_model}")

@@ -1,0 +1,198 @@
+"""GPU unit tests of individual C-ABI entry points against plain torch / oracle primitives."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import model as OR  # noqa: E402
+
+
+def _O():
+    from importlib import import_module
+    return import_module("self-attention-tacotron_b200.ops")
+
+
+def _close(a, b, tol, what):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    d, s = (a - b).abs().max().item(), b.abs().max().item()
+    assert d <= tol * max(s, 1e-6), f"{what}: {d:.3e} vs {s:.3e}"
+
+
+@pytest.mark.parametrize("engine", [1, 0])
+def test_gemm_variants(engine):
+    O = _O()
+    g = torch.Generator().manual_seed(0)
+    for (M, N, K) in ((150, 70, 45), (256, 256, 128), (1, 1, 7), (65, 129, 257)):
+        A, B = torch.randn(M, K, generator=g).cuda(), torch.randn(K, N, generator=g).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        C = torch.empty(M, N, device="cuda")
+        O.gemm(A, B, C, M, N, K, lda=K, ldb=N, ldc=N, bias=bias, act="tanh", engine=engine)
+        _close(C, torch.tanh(A @ B + bias), 2e-5, f"gemm {M}x{N}x{K}")
+        O.gemm(A.t().contiguous(), B.t().contiguous(), C, M, N, K, lda=M, ldb=K, ldc=N, transA=True, transB=True, alpha=0.25, engine=engine)
+        _close(C, 0.25 * (A @ B), 2e-5, "gemm transA transB")
+        C2 = torch.randn(M, N, generator=g).cuda()
+        ref = C2 + A @ B
+        O.gemm(A, B, C2, M, N, K, lda=K, ldb=N, ldc=N, split_k=3, engine=engine)
+        _close(C2, ref, 2e-5, "gemm split-k accumulate")
+
+
+def test_gemm_time_major_conv_and_grads():
+    O = _O()
+    g = torch.Generator().manual_seed(1)
+    for k in (1, 2, 3, 10, 16):
+        T, Bb, Cin, Cout = 19, 3, 20, 24
+        x = torch.randn(T, Bb, Cin, generator=g)
+        W = torch.randn(k, Cin, Cout, generator=g)
+        xr, Wr = x.transpose(0, 1).clone().requires_grad_(True), W.clone().requires_grad_(True)
+        yr = OR.conv1d_same(xr, Wr).transpose(0, 1).reshape(T * Bb, Cout)
+        dy = torch.randn(T * Bb, Cout, generator=g)
+        (yr * dy).sum().backward()
+        pl = (k - 1) // 2
+        xd, Wd, dyd = x.cuda(), W.cuda(), dy.cuda()
+        y = torch.empty(T * Bb, Cout, device="cuda")
+        O.gemm(xd, Wd, y, T * Bb, Cout, Cin, lda=Cin, ldb=Cout, ldc=Cout, taps=k, shift0=-pl * Bb, tap_dir=Bb, sBtap=Cin * Cout)
+        _close(y, yr, 1e-5, f"conv k={k}")
+        dW = torch.zeros_like(Wd)
+        O.gemm(xd, dyd, dW, Cin, Cout, T * Bb, lda=Cin, ldb=Cout, ldc=Cout, transA=True, batch1=k, sC=(Cin * Cout, 0),
+               shift0=-pl * Bb, shift_per_batch1=Bb, split_k=2, beta=1.0)
+        _close(dW, Wr.grad, 1e-5, f"conv dW k={k}")
+        dx = torch.empty(T * Bb, Cin, device="cuda")
+        O.gemm(dyd, Wd, dx, T * Bb, Cin, Cout, lda=Cout, ldb=Cout, ldc=Cin, transB=True, taps=k, shift0=pl * Bb, tap_dir=-Bb,
+               sBtap=Cin * Cout)
+        _close(dx, xr.grad.transpose(0, 1).reshape(T * Bb, Cin), 1e-5, f"conv dx k={k}")
+
+
+def test_batch_norm_relu_maxpool_fwd_bwd():
+    O = _O()
+    g = torch.Generator().manual_seed(2)
+    T, Bb, Cc = 11, 3, 40
+    R = T * Bb
+    x = (torch.randn(R, Cc, generator=g) * 2 + 1)
+    gamma, beta = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g)
+    xd = x.cuda()
+    mean, var = torch.empty(Cc, device="cuda"), torch.empty(Cc, device="cuda")
+    mm, mv = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    O.bn_stats(xd, R, Cc, mean, var, mov_mean=mm, mov_var=mv)
+    _close(mean, x.mean(0), 1e-5, "mean")
+    _close(var, x.var(0, unbiased=False), 1e-5, "var")
+    _close(mv, 0.99 + 0.01 * x.var(0, unbiased=True), 1e-5, "moving var (Bessel)")
+    y = torch.empty(R, Cc, device="cuda")
+    O.bn_apply(xd, R, Cc, mean, var, gamma.cuda(), beta.cuda(), y, act="relu", maxpool_seq_len=T, pos_stride=Bb)
+    xr, gr, br = x.clone().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = OR.batch_norm(xr.view(T, Bb, Cc).transpose(0, 1), gr, br, None, None, True)
+    yr = OR.maxpool2_same(torch.relu(z)).transpose(0, 1).reshape(R, Cc)
+    _close(y, yr, 1e-5, "bn+relu+maxpool")
+    dy = torch.randn(R, Cc, generator=g)
+    (yr * dy).sum().backward()
+    dx, dg, db = torch.empty(R, Cc, device="cuda"), torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    O.bn_bwd(xd, R, Cc, mean, var, gamma.cuda(), beta.cuda(), dy.cuda(), dx, dg, db, torch.empty(2 * Cc, device="cuda"), act="relu",
+             maxpool_seq_len=T, pos_stride=Bb)
+    _close(dx, xr.grad, 1e-4, "bn dx")
+    _close(dg, gr.grad, 1e-4, "bn dgamma")
+    _close(db, br.grad, 1e-4, "bn dbeta")
+
+
+def test_softmax_causal_dropout_fwd_bwd():
+    O = _O()
+    g = torch.Generator().manual_seed(3)
+    nm, T = 6, 37
+    S = torch.randn(nm, T, T, generator=g)
+    mask = (torch.rand(nm, T, T, generator=g) < 0.9).to(torch.uint8)
+    Sd, Pd = S.clone().cuda(), torch.empty(nm, T, T, device="cuda")
+    O.softmax_fwd(Sd, nm, T, True, mask.cuda(), 1 / 0.9, Pd)
+    Sr = S.clone().requires_grad_(True)
+    tri = torch.ones(T, T, dtype=torch.bool).tril()
+    Pr = torch.softmax(torch.where(tri, Sr, torch.full_like(Sr, -float("inf"))), -1)
+    Pdr = Pr * mask / 0.9
+    _close(Sd, Pr, 1e-5, "P")
+    _close(Pd, Pdr, 1e-5, "Pd")
+    dP = torch.randn(nm, T, T, generator=g)
+    (Pdr * dP).sum().backward()
+    dS = torch.empty(nm, T, T, device="cuda")
+    O.softmax_bwd(Sd, dP.cuda(), nm, T, True, dS, mask.cuda(), 1 / 0.9)
+    _close(dS, Sr.grad, 1e-5, "dS")
+
+
+@pytest.mark.parametrize("H,Bb,T,rev", [(128, 5, 9, False), (128, 5, 9, True), (256, 3, 7, False), (256, 9, 12, True)])
+def test_zoneout_lstm_sequence(H, Bb, T, rev):
+    O = _O()
+    g = torch.Generator().manual_seed(4)
+    W, b = torch.randn(2 * H, 4 * H, generator=g) * 0.08, torch.randn(4 * H, generator=g) * 0.1
+    x = torch.randn(Bb, T, H, generator=g)
+    lens = torch.randint(1, T + 1, (Bb,), generator=g)
+    lens[0] = T
+    mc = (torch.rand(T, Bb, H, generator=g) < 0.9).to(torch.uint8)
+    mh = (torch.rand(T, Bb, H, generator=g) < 0.9).to(torch.uint8)
+    Wr, br, xr = W.clone().requires_grad_(True), b.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    yr = OR.zoneout_lstm_sequence(xr, lens, Wr, br, mc, mh, 0.1, 0.1, True, reverse=rev)
+    dy = torch.randn(Bb, T, H, generator=g)
+    (yr * dy).sum().backward()
+    Wd = W.cuda()
+    x_tm = x.transpose(0, 1).contiguous().cuda()
+    xg = torch.empty(T * Bb, 4 * H, device="cuda")
+    O.linear(x_tm, Wd[:H], xg, bias=b.cuda())
+    out = torch.full((T, Bb, H), 7.0, device="cuda")
+    gates, cp, hp = (torch.empty(T * Bb, 4 * H, device="cuda"), torch.empty(T * Bb, H, device="cuda"), torch.empty(T * Bb, H, device="cuda"))
+    O.lstm_seq_fwd(xg, Wd[H:], out, T, Bb, H, reverse=rev, lengths=lens.cuda(), mask_c=mc.cuda(), mask_h=mh.cuda(), gates=gates,
+                   c_prev=cp, h_prev=hp)
+    _close(out.transpose(0, 1), yr, 1e-4, "lstm out")
+    dg = torch.empty(T * Bb, 4 * H, device="cuda")
+    O.lstm_seq_bwd(Wd[H:], gates, cp, dy.transpose(0, 1).contiguous().cuda(), dg, T, Bb, H, reverse=rev, lengths=lens.cuda(),
+                   mask_c=mc.cuda(), mask_h=mh.cuda())
+    dW = torch.zeros(2 * H, 4 * H, device="cuda")
+    O.linear_dw(x_tm, dg, dW, T * Bb, H, 4 * H)
+    O.linear_dw(hp, dg, dW, T * Bb, H, 4 * H, w_off=H * 4 * H)
+    _close(dW, Wr.grad, 1e-3, "lstm dW")
+    _close(dg.sum(0), br.grad, 1e-3, "lstm db")
+    dx = torch.empty(T * Bb, H, device="cuda")
+    O.linear_dx(dg, Wd[:H], dx, T * Bb)
+    _close(dx.view(T, Bb, H).transpose(0, 1), xr.grad, 1e-3, "lstm dx")
+    # eval-mode interpolation (no masks)
+    yr2 = OR.zoneout_lstm_sequence(x, lens, W, b, None, None, 0.1, 0.1, False, reverse=rev)
+    O.lstm_seq_fwd(xg, Wd[H:], out, T, Bb, H, reverse=rev, lengths=lens.cuda(), zc=0.1, zh=0.1)
+    _close(out.transpose(0, 1), yr2, 1e-4, "lstm eval out")
+
+
+def test_adam_clip_and_losses():
+    O = _O()
+    g = torch.Generator().manual_seed(5)
+    n = 1003
+    p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 3
+    m, v = torch.zeros(n), torch.zeros(n)
+    pd, gd, md, vd, ss = p.cuda(), gr.cuda(), m.cuda(), v.cuda(), torch.zeros(1, device="cuda")
+    O.grad_sumsq(gd, ss)
+    O.adam_clip(pd, gd, md, vd, ss, 0.5, 1.0, 1e-3, 0.9, 0.999, 1e-8, 3)
+    cl, _ = OR.clip_by_global_norm([gr * 0.5], 1.0)
+    OR.adam_update(p, cl[0], m, v, 1e-3, 3, 0.9, 0.999, 1e-8)
+    _close(pd, p, 1e-6, "adam p")
+    _close(md, m, 1e-5, "adam m")
+    # losses: time-major predictions vs batch-major targets
+    B, Tm, nm, r = 3, 12, 8, 2
+    Td = Tm // r
+    pred = torch.randn(Td, B, r * nm, generator=g)
+    stop = torch.randn(Td, B, generator=g)
+    mel = torch.randn(B, Tm, nm, generator=g)
+    lens = torch.tensor([12, 8, 6])
+    sm = (torch.arange(Tm)[None] < lens[:, None]).float()
+    bm = (torch.arange(Td)[None] < (lens // r)[:, None]).float()
+    done = (torch.arange(Td)[None] >= (lens // r)[:, None] - 1).float()
+    pr, sr = pred.clone().requires_grad_(True), stop.clone().requires_grad_(True)
+    melp = pr.view(Td, B, r, nm).permute(1, 0, 2, 3).reshape(B, Tm, nm)
+    l1 = OR.spec_loss_l1(melp, mel, sm)
+    l2 = OR.binary_loss(sr.t().unsqueeze(-1), done, bm)
+    (l1 + l2).backward()
+    out3, dp, ds = torch.empty(3, device="cuda"), torch.empty(Td, B, r * nm, device="cuda"), torch.empty(Td, B, device="cuda")
+    O.losses(pred.cuda(), stop.cuda(), mel.cuda(), done.cuda(), sm.cuda(), bm.cuda(), B, Tm, nm, r, out3, dp, ds, torch.empty(4, device="cuda"))
+    _close(out3, torch.stack([l1, l2, l1 + l2]), 1e-5, "losses")
+    _close(dp, pr.grad, 1e-5, "dpred")
+    _close(ds, sr.grad, 1e-5, "dstop")
+
+
+def test_bernoulli_mask_rate():
+    O = _O()
+    m = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    O.bernoulli_mask(m, 0.9, 12345)
+    assert abs(m.float().mean().item() - 0.9) < 2e-3
+    m2 = torch.empty_like(m)
+    O.bernoulli_mask(m2, 0.9, 12346)
+    assert (m != m2).float().mean().item() > 0.1

@@ -1,0 +1,147 @@
+"""CPU tests of the oracle restatement: invariants, the reference's one property test
+(modules/transformer_test.py:40-82) re-expressed, numpy-vs-torch twins, and the golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import model as OR
+from oracle import np_primitives as NP
+
+
+def _small(satk, cfg="ljspeech_self-attention-tacotron.json", B=3, Tt=14, Tm=16, seed=3, overrides=None, root=None):
+    hp = satk.load_hparams(os.path.join(root, "examples", cfg), overrides)
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(seed, "random")
+    f, l = satk.synthetic_batch(hp, B, Tt, Tm, seed=seed)
+    masks = satk.make_masks(d, B, Tt, Tm // d.r, seed=seed)
+    return hp, d, ps, f, l, masks
+
+
+def test_param_count_matches_survey(satk, root):
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    assert satk.num_trainable(satk.dims_from_hparams(hp)) == 6246104       # SURVEY §8(a) total / BASELINE.md §4
+
+
+def test_invariants(satk, root):
+    hp, d, ps, f, l, masks = _small(satk, root=root)
+    out = OR.model_forward(ps.as_dict(), d, f, l, True, masks)
+    al = out["alignment"]                                   # (B, Tt, Td)
+    assert torch.allclose(al.sum(1), torch.ones_like(al.sum(1)), atol=1e-5)
+    for b in range(al.shape[0]):
+        n = int(f.source_length[b])
+        if n < al.shape[1]:
+            assert al[b, n:].abs().max() == 0                            # zero past source_length
+            assert out["memory1"][b, n:].abs().max() == 0                # BiLSTM output zero past length
+    assert (f.source_length < al.shape[1]).any()
+    assert torch.allclose(out["alignment2"].sum(1), torch.ones_like(al.sum(1)), atol=1e-5)
+    P = out["dec_self_alignments"][0].transpose(1, 2)       # back to (B, Tq, Tk)
+    assert P.triu(1).abs().max() == 0                       # causal
+    assert torch.isfinite(out["loss"])
+
+
+def test_first_step_alpha_is_one_hot(satk, root):
+    """alpha_0 = one-hot(0) (forward_attention.py:131-133): after one step alpha concentrates on j in {0,1}... the
+    recursion can only move one position per step."""
+    hp, d, ps, f, l, masks = _small(satk, root=root)
+    out = OR.model_forward(ps.as_dict(), d, f, l, False, None)
+    al = out["alignment"]
+    for t in range(min(4, al.shape[2])):
+        assert al[:, t + 2:, t].max() < 1e-4                # mass cannot be further than t+1 after t+1 steps
+
+
+@settings(max_examples=12, deadline=None)
+@given(bs=st.integers(1, 3), r=st.integers(1, 2), tf=st.integers(2, 8), dim=st.integers(1, 10).map(lambda x: 2 * x),
+       seed=st.integers(0, 1000))
+def test_training_branch_equals_inference_branch(bs, r, tf, dim, seed):
+    """modules/transformer_test.py:40-82: RNNTransformer training branch (batched causal self-attention after the
+    loop) == inference branch (step-wise re-attention over the growing history); drop_rate 0, 2 heads, 1 hop."""
+    g = torch.Generator().manual_seed(seed)
+    D = dim * r
+    T = tf
+    x = torch.randint(-1, 2, (bs, T, D), generator=g).float()
+    P = {}
+    for nm in ("key", "value", "query", "output", "transform"):
+        P[f"sa.{nm}.W"] = torch.randn(D, D, generator=g) * 0.3
+        P[f"sa.{nm}.b"] = torch.randn(D, generator=g) * 0.1
+    full, _ = OR.self_attention_transformer(x, P, "sa", 2, True, None, 1.0)
+    rows = []
+    for t in range(T):
+        h, _ = OR.self_attention_transformer(x[:, :t + 1], P, "sa", 2, True, None, 1.0)
+        rows.append(h[:, -1])
+    step = torch.stack(rows, 1)
+    assert torch.allclose(full, step, rtol=1e-5, atol=1e-5)
+
+
+def test_decoder_inference_branch_matches(satk, root):
+    hp, d, ps, f, l, masks = _small(satk, B=2, Tt=10, Tm=12, root=root)
+    P = ps.as_dict()
+    m1, m2, _ = OR.encoder_forward(P, d, f.source, f.source_length, False)
+    a = OR.decoder_forward(P, d, m1, m2, f.source_length, l.mel, None, False)
+    b = OR.decoder_forward(P, d, m1, m2, f.source_length, l.mel, None, False, inference_branch=True)
+    assert torch.allclose(a[0], b[0], atol=2e-5) and torch.allclose(a[1], b[1], atol=2e-5)
+
+
+def test_numpy_twins():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 9, 5))
+    for k in (1, 2, 3, 4, 10):
+        W = rng.standard_normal((k, 5, 4))
+        ref = NP.conv1d_same(x, W)
+        got = OR.conv1d_same(torch.tensor(x), torch.tensor(W)).numpy()
+        assert np.allclose(ref, got, atol=1e-10), k
+    assert np.allclose(NP.maxpool2_same(x), OR.maxpool2_same(torch.tensor(x)).numpy())
+    H = 6
+    W = rng.standard_normal((5 + H, 4 * H)); b = rng.standard_normal(4 * H)
+    c = rng.standard_normal((2, H)); h = rng.standard_normal((2, H)); xi = rng.standard_normal((2, 5))
+    cn, hn = NP.lstm_cell(xi, c, h, W, b)
+    cn2, hn2 = OR.lstm_cell(torch.tensor(xi), torch.tensor(c), torch.tensor(h), torch.tensor(W), torch.tensor(b))
+    assert np.allclose(cn, cn2.numpy()) and np.allclose(hn, hn2.numpy())
+
+
+def test_forward_attention_twin(satk, root):
+    hp, d, ps, f, l, masks = _small(satk, root=root)
+    P = {k: v.double() for k, v in ps.as_dict().items()}
+    rng = np.random.default_rng(1)
+    T, B = 14, 2
+    keys = torch.tensor(rng.standard_normal((B, T, d.att1)))
+    values = torch.tensor(rng.standard_normal((B, T, d.mem1)))
+    q = torch.tensor(rng.standard_normal((B, d.att_rnn)))
+    lens = torch.tensor([T, 9])
+    pa = torch.tensor(rng.random((B, T))); pa[1, 9:] = 0; pa = pa / pa.sum(1, keepdim=True)
+    pal = torch.tensor(rng.random((B, T))); pal[1, 9:] = 0; pal = pal / pal.sum(1, keepdim=True)
+    alpha, st_ = OR.attention1_step(P, d, q, (pa, pal, torch.full((B, 1), 0.5, dtype=torch.float64)), keys, values, lens)
+    for b in range(B):
+        a_np, al_np = NP.forward_attention_step(q[b].numpy(), pa[b].numpy(), pal[b].numpy(), keys[b].numpy(), int(lens[b]),
+                                                P["att1.query.W"].numpy(), P["att1.loc_conv.W"].numpy(), P["att1.loc_conv.b"].numpy(),
+                                                P["att1.loc_layer.W"].numpy(), P["att1.v"].numpy(), P["att1.b"].numpy())
+        assert np.allclose(st_[0][b].numpy(), a_np, atol=1e-10)
+        assert np.allclose(alpha[b].numpy(), al_np, atol=1e-10)
+
+
+def test_fp32_vs_fp64_gradients(satk, root):
+    """The fp32 oracle's autograd gradients agree with the fp64 run (the gradient oracle of SURVEY §7 step 1)."""
+    hp, d, ps, f, l, masks = _small(satk, B=2, Tt=10, Tm=12, root=root)
+    t32 = OR.OracleTrainer(d, hp, ps.as_dict())
+    t64 = OR.OracleTrainer(d, hp, ps.as_dict(), dtype=torch.float64)
+    _, g32, _ = t32.loss_and_grads(f, l, masks)
+    _, g64, _ = t64.loss_and_grads(f, l, masks)
+    for n in t32.names:
+        s = g64[n].abs().max().item()
+        assert (g32[n].double() - g64[n]).abs().max().item() <= 2e-4 * max(s, 1e-6) + 1e-9, n
+
+
+def test_golden_fixture(satk, root):
+    """tests/golden/oracle_small.npz was produced by oracle/make_golden.py (self-generated: the reference ships no
+    vectors, SURVEY F6 — parity is UNPINNED; the fixture only freezes the oracle against accidental drift)."""
+    z = np.load(os.path.join(root, "tests", "golden", "oracle_small.npz"))
+    from oracle.make_golden import golden_case
+    out, grads = golden_case(satk, root)
+    assert np.allclose(out["mel"].detach().numpy(), z["mel"], atol=2e-5)
+    assert np.allclose(out["alignment"].detach().numpy(), z["alignment"], atol=2e-6)
+    assert abs(float(out["loss"]) - float(z["loss"])) < 1e-5
+    assert np.allclose(grads["dec.lstm1.W"].numpy()[100:164, :64], z["grad_dec_lstm1_W_slice"], atol=1e-6)
+    assert np.allclose(grads["att1.v"].numpy(), z["grad_att1_v"], atol=1e-6)

@@ -1,0 +1,187 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star: "within 1e-3 rel fp32"): for every compared tensor
+max|cuda - oracle| <= 1e-3 * max|oracle| (outputs) and <= 2e-3 * max|oracle| (gradients; parameters whose
+true gradient is exactly zero, e.g. the key bias under softmax shift invariance, are compared absolutely).
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import model as OR  # noqa: E402
+
+RTOL_OUT, RTOL_GRAD = 1e-3, 2e-3
+
+
+def _mods():
+    from importlib import import_module
+    return (import_module("self-attention-tacotron_b200.engine"), import_module("self-attention-tacotron_b200.ops"),
+            import_module("self-attention-tacotron_b200.lib"), import_module("self-attention-tacotron_b200.models"))
+
+
+def _close(a, b, rtol, what, atol=0.0):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    d = (a - b).abs().max().item()
+    s = b.abs().max().item()
+    assert d <= rtol * s + atol, f"{what}: max abs err {d:.3e} vs scale {s:.3e}"
+
+
+def _case(satk, root, cfg, B, Tt, Tm, training, overrides=None, grads=True, seed=7):
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", cfg), overrides)
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(seed, "random")
+    f, l = satk.synthetic_batch(hp, B, Tt, Tm, seed=seed + 4)
+    masks = satk.make_masks(d, B, Tt, Tm // d.r, seed=seed + 1) if training else None
+    tr = OR.OracleTrainer(d, hp, ps.as_dict())
+    ref, rg, stats = tr.loss_and_grads(f, l, masks, training)
+    eng = E.TacotronEngine(hp, "cuda", params=ps)
+    fd = satk.SourceData(*[x.cuda() if torch.is_tensor(x) else x for x in f])
+    ld = satk.MelData(*[x.cuda() if torch.is_tensor(x) else x for x in l])
+    md = {k: v.cuda() for k, v in masks.items()} if masks else None
+    out = eng.forward(fd, ld, training, md)
+    Td = Tm // d.r
+    _close(out["memory1_tm"].view(Tt, B, -1).transpose(0, 1), ref["memory1"], RTOL_OUT, "encoder lstm_output")
+    _close(out["align1_tm"].permute(1, 2, 0), ref["alignment"], RTOL_OUT, "alignment", 1e-6)
+    if d.dual:
+        _close(out["memory2_tm"].view(Tt, B, -1).transpose(0, 1), ref["memory2"], RTOL_OUT, "encoder self-attention output")
+        _close(out["align2_tm"].permute(1, 2, 0), ref["alignment2"], RTOL_OUT, "alignment2", 1e-6)
+        for i, a in enumerate(out["enc_self_P"]):
+            _close(a.transpose(1, 2), ref["enc_self_alignments"][i], RTOL_OUT, f"encoder self-attention head {i}", 1e-6)
+        for i, a in enumerate(out["dec_self_P"]):
+            _close(a.transpose(1, 2), ref["dec_self_alignments"][i], RTOL_OUT, f"decoder self-attention head {i}", 1e-6)
+    _close(out["mel_tm"].view(Td, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, Tm, d.n_mels), ref["mel"], RTOL_OUT, "mel")
+    _close(out["stop_tm"].view(Td, B).t(), ref["stop"].squeeze(-1), RTOL_OUT, "stop logits")
+    _close(out["losses"], torch.stack([ref["mel_loss"], ref["done_loss"], ref["loss"]]), RTOL_OUT, "losses")
+    if grads:
+        eng.backward()
+        gmax = max(rg[n].abs().max().item() for n in tr.names)
+        for n in tr.names:
+            _close(eng.ps.g[n], rg[n], RTOL_GRAD, f"grad {n}", atol=1e-6 * gmax)
+    if training:   # batch-norm moving statistics (UPDATE_OPS, models.py:497)
+        for key, (mean, var) in stats.items():
+            _close(eng.ps.bn[key + ".mean"], 0.99 * ps.bn[key + ".mean"] + 0.01 * mean, 1e-4, f"moving mean {key}")
+            _close(eng.ps.bn[key + ".var"], 0.99 * ps.bn[key + ".var"] + 0.01 * var, 1e-4, f"moving var {key}")
+    return eng, tr, (fd, ld, md), (f, l, masks)
+
+
+def test_dual_eval_ragged_batch(satk, root):
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 3, 20, 24, False)            # B not a multiple of 4
+
+
+def test_dual_train_masks(satk, root):
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 5, 23, 28, True)
+
+
+def test_single_attention_model_config1(satk, root):
+    """BASELINE.json configs[0]: examples/ljspeech/tacotron.json, batch 2 (ExtendedTacotronV1Model)."""
+    _case(satk, root, "ljspeech_tacotron.json", 2, 21, 20, True)
+
+
+def test_vctk_multispeaker(satk, root):
+    _case(satk, root, "vctk_self-attention-tacotron.json", 4, 18, 16, True)
+
+
+def test_variant_location_sensitive(satk, root):
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 3, 20, 24, True, overrides="attention=location_sensitive")
+
+
+def test_variant_additive(satk, root):
+    _case(satk, root, "ljspeech_tacotron.json", 3, 20, 24, True, overrides="attention=additive")
+
+
+def test_dual_medium_long_sequences(satk, root):
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 8, 70, 120, True)
+
+
+def test_single_utterance_and_minimum_lengths(satk, root):
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 1, 5, 6, True)
+
+
+def test_train_step_matches_oracle_optimizer(satk, root):
+    """Two full train steps (clip-by-global-norm + Adam + noam LR): parameters track the oracle's."""
+    eng, tr, (fd, ld, md), (f, l, masks) = _case(satk, root, "ljspeech_self-attention-tacotron.json", 4, 16, 20, True, grads=False)
+    E, O, L, M = _mods()
+    # _case already ran one forward (which updated BN moving stats once) -> rebuild both sides for a clean comparison
+    hp = eng.hp
+    ps = satk.ParamStore(eng.d).init(7, "random")
+    eng = E.TacotronEngine(hp, "cuda", params=ps)
+    tr = OR.OracleTrainer(eng.d, hp, ps.as_dict())
+    for _ in range(2):
+        eng.train_step(fd, ld, md)
+        tr.train_step(f, l, masks)
+    for n in tr.names:
+        # Adam's first steps move every weight by ~lr regardless of gradient scale: compare the UPDATE, absolutely
+        _close(eng.ps.p[n], tr.P[n], 0.0, f"param {n}", atol=2e-7 + 2e-3 * 2 * OR.noam_lr(hp.initial_learning_rate, 1, 1))
+
+
+def test_full_size_batch_properties(satk, root):
+    """BASELINE.json configs[1] at full size (B=32, T_text=148, T_mel=800): size-independent properties, and
+    eval-mode rows checked against the oracle on a 3-utterance sub-batch (utterances are independent in eval mode)."""
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(3, "random")
+    B, Tt, Tm = 32, 148, 800
+    f, l = satk.synthetic_batch(hp, B, Tt, Tm, seed=21)
+    eng = E.TacotronEngine(hp, "cuda", params=ps)
+    fd = satk.SourceData(*[x.cuda() if torch.is_tensor(x) else x for x in f])
+    ld = satk.MelData(*[x.cuda() if torch.is_tensor(x) else x for x in l])
+    out = eng.forward(fd, ld, False)
+    al = out["align1_tm"]                                       # [Td,B,Tt]
+    assert torch.allclose(al.sum(-1), torch.ones_like(al.sum(-1)), atol=1e-4)
+    assert torch.allclose(out["align2_tm"].sum(-1), torch.ones_like(al.sum(-1)), atol=1e-4)
+    pos = torch.arange(Tt, device="cuda")[None, None, :]
+    assert (al * (pos >= fd.source_length[None, :, None])).abs().max() == 0
+    mem1 = out["memory1_tm"].view(Tt, B, -1)
+    assert (mem1 * (torch.arange(Tt, device="cuda")[:, None, None] >= fd.source_length[None, :, None])).abs().max() == 0
+    assert out["dec_self_P"][0].triu(1).abs().max() == 0
+    assert torch.isfinite(out["losses"]).all()
+    idx = [0, 13, 31]
+    fs = satk.SourceData(f.id[idx], [f.key[i] for i in idx], f.source[idx], f.source_length[idx], [f.text[i] for i in idx], None)
+    ls = satk.MelData(l.id[idx], [l.key[i] for i in idx], l.mel[idx], l.mel_width[idx], l.target_length[idx], l.done[idx],
+                      l.spec_loss_mask[idx], l.binary_loss_mask[idx])
+    ref = OR.model_forward(ps.as_dict(), d, fs, ls, False)
+    Td = Tm // d.r
+    mel = out["mel_tm"].view(Td, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, Tm, d.n_mels)
+    _close(mel[idx], ref["mel"], RTOL_OUT, "mel rows at full size")
+    _close(al.permute(1, 2, 0)[idx], ref["alignment"], RTOL_OUT, "alignment rows at full size", 1e-6)
+    # a train step at full size stays finite and lowers the loss on the same batch
+    l0 = eng.train_step(fd, ld)["losses"][2].item()
+    for _ in range(3):
+        l1 = eng.train_step(fd, ld)["losses"][2].item()
+    assert l1 == l1 and l1 < l0 + 0.05
+
+
+def test_estimator_surface(satk, root, tmp_path):
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    model = M.tacotron_model_factory(hp, str(tmp_path), None)
+    assert isinstance(model, M.DualSourceSelfAttentionTacotronModel)
+    f, l = satk.synthetic_batch(hp, 4, 20, 24, seed=2)
+
+    def input_fn():
+        for _ in range(3):
+            yield f, l
+    spec = model.train(input_fn, steps=2)
+    assert spec.train_op == 2 and torch.isfinite(spec.loss)
+    ev = model.evaluate(input_fn, steps=1)
+    assert {"loss_with_teacher", "mel_loss_with_teacher", "done_loss_with_teacher", "global_step"} <= set(ev)
+    pred = next(model.predict(input_fn))
+    assert pred["mel"].shape == (4, 24, 80) and pred["alignment"].shape == (4, 20, 12) and "alignment2" in pred
+    model2 = M.tacotron_model_factory(hp, str(tmp_path), None)           # resume from model_dir
+    assert model2.engine.global_step == 2
+    assert torch.equal(model2.engine.ps.flat, model.engine.ps.flat)
+    with pytest.raises(ValueError, match="Unknown Tacotron model"):
+        M.tacotron_model_factory(satk.load_hparams(None, "tacotron_model=Foo"), None, None)
+
+
+def test_ops_fail_loudly_on_cpu_tensors(satk):
+    E, O, L, M = _mods()
+    a = torch.zeros(4, 4)
+    with pytest.raises(L.SatkError):
+        O.gemm(a, a, a, 4, 4, 4, lda=4, ldb=4, ldc=4)

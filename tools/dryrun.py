@@ -78,6 +78,7 @@ def run(cfg, B, Tt, Tm, overrides=None):
     eng.saved = None
     eng.global_step = 0
     eng._sumsq = torch.zeros(1)
+    eng.timers = None
     f, l = satk.synthetic_batch(hp, B, Tt, Tm)
     for training in (False, True):
         eng.forward(f, l, training)
