@@ -8,11 +8,23 @@
 // Math: TF LSTMCell (i,j,f,o; forget_bias) + tacotron2 ZoneoutLSTMCell, SURVEY.md A.5/A.6;
 // sequence-length semantics of tf.nn.bidirectional_dynamic_rnn (module.py:93-108).
 #include <cooperative_groups.h>
+#include "cluster_sync.cuh"
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace satk {
+
+#ifdef SATK_PHASE_TIMING
+__device__ long long g_phase[16];
+#define PT_DECL long long pt_t = clock64(), pt_acc[6] = {0, 0, 0, 0, 0, 0};
+#define PT(i) { long long pt_n = clock64(); pt_acc[i] += pt_n - pt_t; pt_t = pt_n; }
+#define PT_FLUSH(n) if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < 6; ++i_) g_phase[i_] = pt_acc[i_] / (n); }
+#else
+#define PT_DECL
+#define PT(i)
+#define PT_FLUSH(n)
+#endif
 
 constexpr int LBG = 4;    // batch rows per cluster
 constexpr int LUH = 16;   // hidden units per CTA
@@ -24,10 +36,23 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
 
+// cp.async helpers (LDGSTS): asynchronous global -> shared prefetch rings, several steps ahead
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cl::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int RING = 8;   // prefetch ring slots
+constexpr int PFD = 6;    // prefetch distance in steps (>> HBM latency / step time)
+
 template <int H>
-__global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const satk_lstm_fwd_desc d) {
+__global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_desc d) {
   constexpr int CS = H / LUH;
-  constexpr int KPT = H / 4;  // k's per thread
+  constexpr int KPT = H / 4;  // weights per thread
+  constexpr uint32_t SLICE_BYTES = LUH * LBG * 4;          // one CTA's slice of the hidden state
+  constexpr uint32_t RX_BYTES = (CS - 1) * SLICE_BYTES;    // received from the peers every step
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int bg = blockIdx.x / CS;
@@ -36,20 +61,33 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const satk_lstm_fwd_de
 
   __shared__ __align__(16) float hbuf[2][H][LBG];
   __shared__ float gsm[LBG][64];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ float xg_ring[RING][256];                      // this thread's x-projection element, PFD steps ahead
+  __shared__ __align__(4) uint8_t mk_ring[RING][2][LBG][LUH];  // zoneout keep masks (c, h) of this CTA's units
+  __shared__ float save_st[7][64];                          // activations saved for backward, staged for the saver warps
 
-  // --- gate-GEMM role: thread = (col 0..63, kq 0..3)
-  const int col = tid >> 2, kq = tid & 3;
-  const int gate = col >> 4, unit = col & 15;
-  const int gcol = gate * H + rank * LUH + unit;  // column in the [.,4H] kernel
-  float w[KPT];
+  // --- gate-GEMM role: thread = (kq = lane & 15, column group cgp = tid >> 4): 4 gate columns x the k's
+  // congruent to kq mod 16.  One LDS.128 of h[k][0..3] feeds 16 FMAs (4 columns x 4 rows); the 16 partial
+  // sums are reduce-scattered over the 16 kq lanes, so lane L ends with (column cgp*4 + (L>>2)&3, row L&3).
+  const int lane = tid & 31;
+  const int kq = tid & 15, cgp = tid >> 4;
+  float w[KPT / 4][4];
 #pragma unroll
-  for (int i = 0; i < KPT; ++i) w[i] = __ldg(d.Wh + (long long)(kq + 4 * i) * (4 * H) + gcol);
-
-  const int myb = b0 + kq;  // batch row whose xg this thread adds
+  for (int i = 0; i < KPT / 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int colc = cgp * 4 + c;                                  // CTA-local gate column = gate*16 + unit
+      const int gc = (colc >> 4) * H + rank * LUH + (colc & 15);     // column in the [.,4H] kernel
+      w[i][c] = __ldg(d.Wh + (long long)(kq + 16 * i) * (4 * H) + gc);
+    }
+  const int col = cgp * 4 + ((kq >> 2) & 3);                         // the column / row this lane finalises
+  const int gcol = (col >> 4) * H + rank * LUH + (col & 15);
+  const int myb = b0 + (kq & 3);
   const bool myb_ok = myb < d.B;
   const int mylen = myb_ok ? (d.lengths ? (int)d.lengths[myb] : d.T) : 0;
 
-  // --- pointwise role: tid < 64 -> (pb, pu)
+  // --- pointwise role: tid < 64 -> (pb, pu).  These two warps touch NO global memory: stores issued by the warp
+  // that also issues the st.async exchange would sit in front of it in the LSU and delay every peer.
   const int pb = tid >> 4, pu = tid & 15;
   const int prow = b0 + pb;
   const bool prow_ok = (tid < 64) && prow < d.B;
@@ -57,137 +95,234 @@ __global__ void __launch_bounds__(256, 1) lstm_fwd_kernel(const satk_lstm_fwd_de
   const int pidx = rank * LUH + pu;
   float c_st = 0.f, h_st = 0.f;
 
+  // --- saver / mask-prefetch role: tid in [64,128) -> (sb, su)
+  const int sb = (tid - 64) >> 4, su = tid & 15;
+  const int srow = b0 + sb;
+  const bool srow_ok = (tid >= 64 && tid < 128) && srow < d.B;
+  const int slen = srow_ok ? (d.lengths ? (int)d.lengths[srow] : d.T) : 0;
+
+  if (tid == 0) {
+    cl::mbar_init(&bars[0], 1);
+    cl::mbar_init(&bars[1], 1);
+    cl::fence_mbar_init();
+  }
   for (int i = tid; i < 2 * H * LBG; i += 256) (&hbuf[0][0][0])[i] = 0.f;
+  for (int i = tid; i < RING * 2 * LBG * LUH; i += 256) (&mk_ring[0][0][0][0])[i] = 0;
   cluster.sync();
 
-  auto xg_at = [&](int s) -> float {
-    if (!(s < mylen)) return 0.f;
-    int p = d.reverse ? (mylen - 1 - s) : s;
-    return __ldg(d.xg + ((long long)p * d.B + myb) * (4 * H) + gcol);
+  // issue the prefetch of processing step s into ring slot s % RING (always commits one group)
+  auto prefetch = [&](int s) {
+    if (s < d.T) {
+      if (s < mylen) {
+        const int p = d.reverse ? (mylen - 1 - s) : s;
+        cp_async4(&xg_ring[s % RING][tid], d.xg + ((long long)p * d.B + myb) * (4 * H) + gcol);
+      }
+      // masks are indexed by processing step; 4 units (4 bytes) per copy: saver threads with su % 4 == 0
+      if (srow_ok && (su & 3) == 0 && s < slen) {
+        const long long om = ((long long)s * d.B + srow) * H + rank * LUH + su;
+        if (d.mask_c) cp_async4(&mk_ring[s % RING][0][sb][su], d.mask_c + om);
+        if (d.mask_h) cp_async4(&mk_ring[s % RING][1][sb][su], d.mask_h + om);
+      }
+    }
+    cp_async_commit();
   };
-  float xg_next = xg_at(0);
+#pragma unroll 1
+  for (int s = 0; s < PFD; ++s) prefetch(s);
 
+  PT_DECL
+#pragma unroll 1
   for (int s = 0; s < d.T; ++s) {
     const int cur = s & 1, nxt = cur ^ 1;
-    const float xg_cur = xg_next;
-    if (s + 1 < d.T) xg_next = xg_at(s + 1);
-
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    PT(5)
+    prefetch(s + PFD);
+    cp_async_wait<PFD>();                                              // step s's ring slot has landed
+    if (s > 0) cl::mbar_wait(&bars[cur], ((s - 1) >> 1) & 1);         // peers' h(s) has landed
+    if (tid == 0 && s + 1 < d.T) cl::mbar_arrive_expect_tx(&bars[nxt], RX_BYTES);  // arm the barrier of step s+1
+    PT(0)
+    float acc[16];
 #pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-      const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][kq + 4 * i][0]);
-      acc0 = fmaf(w[i], hv.x, acc0);
-      acc1 = fmaf(w[i], hv.y, acc1);
-      acc2 = fmaf(w[i], hv.z, acc2);
-      acc3 = fmaf(w[i], hv.w, acc3);
-    }
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-      acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
+    for (int i = 0; i < KPT / 4; ++i) {
+      const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][kq + 16 * i][0]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[c * 4 + 0] = fmaf(w[i][c], hv.x, acc[c * 4 + 0]);
+        acc[c * 4 + 1] = fmaf(w[i][c], hv.y, acc[c * 4 + 1]);
+        acc[c * 4 + 2] = fmaf(w[i][c], hv.z, acc[c * 4 + 2]);
+        acc[c * 4 + 3] = fmaf(w[i][c], hv.w, acc[c * 4 + 3]);
+      }
     }
-    float mine = (kq == 0) ? acc0 : (kq == 1) ? acc1 : (kq == 2) ? acc2 : acc3;
-    gsm[kq][col] = mine + xg_cur;
+    const float mine = cl::reduce_scatter16(acc, lane);
+    gsm[kq & 3][col] = mine + ((s < mylen) ? xg_ring[s % RING][tid] : 0.f);
+    PT(1)
     __syncthreads();
-
+    PT(2)
     if (tid < 64) {
       const bool valid = prow_ok && (s < plen);
-      float h_new_state = h_st;
+      float gi = 0.f, gj = 0.f, gf = 0.f, go = 0.f, h_new = 0.f;
+      const float c_old = c_st, h_old = h_st;
       if (valid) {
-        const int p = d.reverse ? (plen - 1 - s) : s;
-        float gi = fast_sigmoid(gsm[pb][0 * 16 + pu]);
-        float gj = fast_tanh(gsm[pb][1 * 16 + pu]);
-        float gf = fast_sigmoid(gsm[pb][2 * 16 + pu] + d.forget_bias);
-        float go = fast_sigmoid(gsm[pb][3 * 16 + pu]);
-        float c_new = gf * c_st + gi * gj;
-        float h_new = go * fast_tanh(c_new);
-        const long long o1 = ((long long)p * d.B + prow) * H + pidx;
-        d.out[((long long)p * d.B + prow) * d.ld_out + pidx] = h_new;
-        if (d.gates) {
-          const long long o4 = ((long long)p * d.B + prow) * (4 * H) + pidx;
-          d.gates[o4] = gi;
-          d.gates[o4 + H] = gj;
-          d.gates[o4 + 2 * H] = gf;
-          d.gates[o4 + 3 * H] = go;
-          d.c_prev[o1] = c_st;
-          d.h_prev[o1] = h_st;
-        }
-        const long long om = ((long long)s * d.B + prow) * H + pidx;  // masks are indexed by processing step
-        float mc = d.mask_c ? (float)d.mask_c[om] : (1.f - d.zc);
-        float mh = d.mask_h ? (float)d.mask_h[om] : (1.f - d.zh);
+        const float mc = d.mask_c ? (float)mk_ring[s % RING][0][pb][pu] : (1.f - d.zc);
+        const float mh = d.mask_h ? (float)mk_ring[s % RING][1][pb][pu] : (1.f - d.zh);
+        gi = fast_sigmoid(gsm[pb][0 * 16 + pu]);
+        gj = fast_tanh(gsm[pb][1 * 16 + pu]);
+        gf = fast_sigmoid(gsm[pb][2 * 16 + pu] + d.forget_bias);
+        go = fast_sigmoid(gsm[pb][3 * 16 + pu]);
+        const float c_new = gf * c_st + gi * gj;
+        h_new = go * fast_tanh(c_new);
         c_st = c_st + mc * (c_new - c_st);
-        h_new_state = h_st + mh * (h_new - h_st);
-        h_st = h_new_state;
-      } else if (prow_ok) {
-        // position s is past this row's length: zero output (dynamic_rnn), state frozen
-        const long long o1 = ((long long)s * d.B + prow) * H + pidx;
-        d.out[((long long)s * d.B + prow) * d.ld_out + pidx] = 0.f;
-        if (d.gates) {
-          const long long o4 = ((long long)s * d.B + prow) * (4 * H) + pidx;
-          d.gates[o4] = 0.f; d.gates[o4 + H] = 0.f; d.gates[o4 + 2 * H] = 0.f; d.gates[o4 + 3 * H] = 0.f;
-          d.c_prev[o1] = 0.f;
-          d.h_prev[o1] = 0.f;
-        }
+        h_st = h_st + mh * (h_new - h_st);
       }
-      // publish the new hidden state to every CTA of the cluster
-#pragma unroll 4
-      for (int r = 0; r < CS; ++r) {
-        float* remote = cluster.map_shared_rank(&hbuf[nxt][pidx][pb], r);
-        *remote = h_new_state;
+      if (s + 1 < d.T) {
+        // publish h(s+1): local store + one 4-byte st.async per peer (completes 4 bytes on the peer's barrier)
+        hbuf[nxt][pidx][pb] = h_st;
+        const uint32_t dsta = cl::smem_u32(&hbuf[nxt][pidx][pb]);
+        const uint32_t bara = cl::smem_u32(&bars[nxt]);
+#pragma unroll
+        for (int r = 0; r < CS; ++r)
+          if (r != rank) cl::st_async_f32(cl::mapa(dsta, r), h_st, cl::mapa(bara, r));
+      }
+      // stage what the backward pass needs; zero past the row's length (dynamic_rnn semantics)
+      save_st[0][tid] = gi; save_st[1][tid] = gj; save_st[2][tid] = gf; save_st[3][tid] = go;
+      save_st[4][tid] = valid ? c_old : 0.f;
+      save_st[5][tid] = valid ? h_old : 0.f;
+      save_st[6][tid] = h_new;
+    }
+    PT(3)
+    __syncthreads();
+    PT(4)
+    if (srow_ok) {
+      // saver warps: staged activations -> global memory (position-indexed), off the exchange's critical path
+      const int e = tid - 64;
+      const bool valid = s < slen;
+      const int p = valid ? (d.reverse ? (slen - 1 - s) : s) : s;
+      const int sidx = rank * LUH + su;
+      const long long o1 = ((long long)p * d.B + srow) * H + sidx;
+      d.out[((long long)p * d.B + srow) * d.ld_out + sidx] = save_st[6][e];
+      if (d.gates) {
+        const long long o4 = ((long long)p * d.B + srow) * (4 * H) + sidx;
+        d.gates[o4] = save_st[0][e];
+        d.gates[o4 + H] = save_st[1][e];
+        d.gates[o4 + 2 * H] = save_st[2][e];
+        d.gates[o4 + 3 * H] = save_st[3][e];
+        d.c_prev[o1] = save_st[4][e];
+        d.h_prev[o1] = save_st[5][e];
       }
     }
-    cluster.sync();
   }
+  PT_FLUSH(d.T)
+  cp_async_wait<0>();
+  cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
+}
+
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, float a, float b, float c, float d, uint32_t mbar_cluster_addr) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster_addr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
+               "r"(mbar_cluster_addr)
+               : "memory");
 }
 
 template <int H>
-__global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const satk_lstm_bwd_desc d) {
+__global__ void __launch_bounds__(256, 2) lstm_bwd_kernel(const satk_lstm_bwd_desc d) {
   constexpr int CS = H / LUH;
   constexpr int K4 = 4 * H;
-  constexpr int KPT = K4 / 16;  // 64 (H=256) or 32 (H=128)
+  constexpr int NI = H / 64;                               // source units per thread in the GEMM
+  constexpr uint32_t SLICE_BYTES = 4 * LUH * LBG * 4;      // one CTA's d(gates): 16 units x 4 rows x 4 gates
+  constexpr uint32_t RX_BYTES = (CS - 1) * SLICE_BYTES;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int bg = blockIdx.x / CS;
   const int b0 = bg * LBG;
   const int tid = threadIdx.x;
 
-  __shared__ __align__(16) float dgbuf[2][K4][LBG];
-  __shared__ float dhsm[LBG][LUH];
+  // d(gates) exchange buffer: [source unit][row][gate] -> one float4 per (unit, row), written with ONE st.async.v4 per peer
+  __shared__ __align__(16) float dgx[2][H][LBG][4];
+  __shared__ float dhpart[4][LBG][LUH];                    // [16-lane group of the k split][row][unit]
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ float in_ring[RING][6][64];                   // gates i,j,f,o, c_prev, dout of this CTA's units, PFD steps ahead
+  __shared__ __align__(4) uint8_t mk_ring[RING][2][LBG][LUH];
+  __shared__ __align__(16) float save_st[64][4];           // d(gates) staged for the saver warps
 
-  // --- GEMM role (dh_prev = dg . Wh^T restricted to my 16 units): thread = (unit 0..15, kq 0..15)
-  const int gu = tid >> 4, kq = tid & 15;
-  float w[KPT];
+  // --- GEMM role (dh_prev = dg . Wh^T restricted to my 16 units): thread = (kq = tid & 63, out-unit group ug = tid >> 6)
+  const int lane = tid & 31;
+  const int kq = tid & 63, ug = tid >> 6;
+  float w[NI][4][4];                                        // [i][out unit c][gate]
 #pragma unroll
-  for (int i = 0; i < KPT; ++i) w[i] = __ldg(d.Wh + (long long)(rank * LUH + gu) * K4 + kq + 16 * i);
+  for (int i = 0; i < NI; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4)
+        w[i][c][g4] = __ldg(d.Wh + (long long)(rank * LUH + ug * 4 + c) * K4 + g4 * H + kq + 64 * i);
 
-  // --- pointwise role
+  // --- pointwise role (no global memory traffic in these two warps besides the async prefetch)
   const int pb = tid >> 4, pu = tid & 15;
   const int prow = b0 + pb;
   const bool prow_ok = (tid < 64) && prow < d.B;
   const int plen = prow_ok ? (d.lengths ? (int)d.lengths[prow] : d.T) : 0;
   const int pidx = rank * LUH + pu;
   float dc = 0.f, dh = 0.f;
+  // --- saver role: tid in [64,128)
+  const int sb = (tid - 64) >> 4, su = tid & 15;
+  const int srow = b0 + sb;
+  const bool srow_ok = (tid >= 64 && tid < 128) && srow < d.B;
+  const int slen = srow_ok ? (d.lengths ? (int)d.lengths[srow] : d.T) : 0;
 
+  if (tid == 0) {
+    cl::mbar_init(&bars[0], 1);
+    cl::mbar_init(&bars[1], 1);
+    cl::fence_mbar_init();
+  }
+  for (int i = tid; i < RING * 2 * LBG * LUH; i += 256) (&mk_ring[0][0][0][0])[i] = 0;
+  cluster.sync();
+
+  // prefetch of everything the pointwise step u (processing step s = T-1-u) reads from global memory
+  auto prefetch = [&](int u) {
+    const int s = d.T - 1 - u;
+    if (s >= 0) {
+      if (prow_ok && s < plen) {
+        const int p = d.reverse ? (plen - 1 - s) : s;
+        const long long o1 = ((long long)p * d.B + prow) * H + pidx;
+        const long long o4 = ((long long)p * d.B + prow) * K4 + pidx;
+        float* slot = &in_ring[u % RING][0][tid];
+        cp_async4(slot + 0 * 64, d.gates + o4);
+        cp_async4(slot + 1 * 64, d.gates + o4 + H);
+        cp_async4(slot + 2 * 64, d.gates + o4 + 2 * H);
+        cp_async4(slot + 3 * 64, d.gates + o4 + 3 * H);
+        cp_async4(slot + 4 * 64, d.c_prev + o1);
+        cp_async4(slot + 5 * 64, d.dout + ((long long)p * d.B + prow) * d.ld_dout + pidx);
+        if ((pu & 3) == 0) {
+          const long long om = ((long long)s * d.B + prow) * H + pidx;
+          if (d.mask_c) cp_async4(&mk_ring[u % RING][0][pb][pu], d.mask_c + om);
+          if (d.mask_h) cp_async4(&mk_ring[u % RING][1][pb][pu], d.mask_h + om);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int u = 0; u < PFD; ++u) prefetch(u);
+
+#pragma unroll 1
   for (int s = d.T - 1; s >= 0; --s) {
-    const int cur = s & 1;
+    const int u = d.T - 1 - s, cur = u & 1;
+    prefetch(u + PFD);
+    cp_async_wait<PFD>();
+    // the 4-byte mask words are fetched by every 4th lane: make them visible to the other pointwise lanes
+    if (tid < 64) cl::named_bar_sync(1, 64);
     float dh_part = dh;
     if (tid < 64) {
       float dgi = 0.f, dgj = 0.f, dgf = 0.f, dgo = 0.f;
       const bool valid = prow_ok && (s < plen);
       if (valid) {
-        const int p = d.reverse ? (plen - 1 - s) : s;
-        const long long o1 = ((long long)p * d.B + prow) * H + pidx;
-        const long long o4 = ((long long)p * d.B + prow) * K4 + pidx;
-        const float gi = d.gates[o4], gj = d.gates[o4 + H], gf = d.gates[o4 + 2 * H], go = d.gates[o4 + 3 * H];
-        const float cp = d.c_prev[o1];
-        const long long om = ((long long)s * d.B + prow) * H + pidx;
-        const float mc = d.mask_c ? (float)d.mask_c[om] : (1.f - d.zc);
-        const float mh = d.mask_h ? (float)d.mask_h[om] : (1.f - d.zh);
+        const float* slot = &in_ring[u % RING][0][tid];
+        const float gi = slot[0], gj = slot[64], gf = slot[128], go = slot[192], cp = slot[256], dout = slot[320];
+        const float mc = d.mask_c ? (float)mk_ring[u % RING][0][pb][pu] : (1.f - d.zc);
+        const float mh = d.mask_h ? (float)mk_ring[u % RING][1][pb][pu] : (1.f - d.zh);
         const float c_new = gf * cp + gi * gj;
         const float tc = fast_tanh(c_new);
-        const float dh_new = d.dout[((long long)p * d.B + prow) * d.ld_dout + pidx] + mh * dh;
+        const float dh_new = dout + mh * dh;
         dh_part = (1.f - mh) * dh;
         const float dcn = mc * dc + dh_new * go * (1.f - tc * tc);
         dgo = dh_new * tc * go * (1.f - go);
@@ -195,43 +330,58 @@ __global__ void __launch_bounds__(256, 1) lstm_bwd_kernel(const satk_lstm_bwd_de
         dgj = dcn * gi * (1.f - gj * gj);
         dgf = dcn * cp * gf * (1.f - gf);
         dc = (1.f - mc) * dc + dcn * gf;
-        d.dgates[o4] = dgi; d.dgates[o4 + H] = dgj; d.dgates[o4 + 2 * H] = dgf; d.dgates[o4 + 3 * H] = dgo;
-      } else if (prow_ok) {
-        const long long o4 = ((long long)s * d.B + prow) * K4 + pidx;
-        d.dgates[o4] = 0.f; d.dgates[o4 + H] = 0.f; d.dgates[o4 + 2 * H] = 0.f; d.dgates[o4 + 3 * H] = 0.f;
       }
-#pragma unroll 4
-      for (int r = 0; r < CS; ++r) {
-        float* base = cluster.map_shared_rank(&dgbuf[cur][0][0], r);
-        base[(0 * H + pidx) * LBG + pb] = dgi;
-        base[(1 * H + pidx) * LBG + pb] = dgj;
-        base[(2 * H + pidx) * LBG + pb] = dgf;
-        base[(3 * H + pidx) * LBG + pb] = dgo;
+      if (s > 0) {
+        // publish d(gates): local float4 + ONE st.async.v4 per peer
+        if (tid == 0) cl::mbar_arrive_expect_tx(&bars[cur], RX_BYTES);
+        float* slot = &dgx[cur][pidx][pb][0];
+        *reinterpret_cast<float4*>(slot) = make_float4(dgi, dgj, dgf, dgo);
+        const uint32_t dsta = cl::smem_u32(slot), bara = cl::smem_u32(&bars[cur]);
+#pragma unroll
+        for (int r = 0; r < CS; ++r)
+          if (r != rank) st_async_v4(cl::mapa(dsta, r), dgi, dgj, dgf, dgo, cl::mapa(bara, r));
       }
+      *reinterpret_cast<float4*>(&save_st[tid][0]) = make_float4(dgi, dgj, dgf, dgo);
     }
-    cluster.sync();
+    __syncthreads();     // own slice + staged d(gates) visible to every thread of this CTA
+    if (srow_ok) {
+      const int e = tid - 64;
+      const bool valid = s < slen;
+      const int p = valid ? (d.reverse ? (slen - 1 - s) : s) : s;
+      const long long o4 = ((long long)p * d.B + srow) * K4 + rank * LUH + su;
+      const float4 v = *reinterpret_cast<const float4*>(&save_st[e][0]);
+      d.dgates[o4] = v.x; d.dgates[o4 + H] = v.y; d.dgates[o4 + 2 * H] = v.z; d.dgates[o4 + 3 * H] = v.w;
+    }
     if (s == 0) break;  // no earlier step consumes dh_prev
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    cl::mbar_wait(&bars[cur], (u >> 1) & 1);
+    float acc[16];
 #pragma unroll
-    for (int i = 0; i < KPT; ++i) {
-      const float4 g4 = *reinterpret_cast<const float4*>(&dgbuf[cur][kq + 16 * i][0]);
-      acc0 = fmaf(w[i], g4.x, acc0);
-      acc1 = fmaf(w[i], g4.y, acc1);
-      acc2 = fmaf(w[i], g4.z, acc2);
-      acc3 = fmaf(w[i], g4.w, acc3);
-    }
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
 #pragma unroll
-    for (int o = 1; o <= 8; o <<= 1) {
-      acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-      acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-      acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
-      acc3 += __shfl_xor_sync(0xffffffffu, acc3, o);
+    for (int i = 0; i < NI; ++i) {
+#pragma unroll
+      for (int b = 0; b < LBG; ++b) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&dgx[cur][kq + 64 * i][b][0]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float a = acc[c * 4 + b];
+          a = fmaf(w[i][c][0], g4.x, a);
+          a = fmaf(w[i][c][1], g4.y, a);
+          a = fmaf(w[i][c][2], g4.z, a);
+          a = fmaf(w[i][c][3], g4.w, a);
+          acc[c * 4 + b] = a;
+        }
+      }
     }
-    if (kq < 4) dhsm[kq][gu] = (kq == 0) ? acc0 : (kq == 1) ? acc1 : (kq == 2) ? acc2 : acc3;
+    {
+      const float v = cl::reduce_scatter16(acc, lane);       // lane L: unit ug*4 + ((L>>2)&3), row L&3
+      dhpart[(kq >> 4) & 3][lane & 3][ug * 4 + ((lane >> 2) & 3)] = v;
+    }
     __syncthreads();
-    if (tid < 64) dh = dh_part + dhsm[pb][pu];
-    __syncthreads();
+    if (tid < 64) dh = dh_part + dhpart[0][pb][pu] + dhpart[1][pb][pu] + dhpart[2][pb][pu] + dhpart[3][pb][pu];
   }
+  cp_async_wait<0>();
+  cluster.sync();
 }
 
 template <typename Kern, typename Desc>
@@ -251,6 +401,8 @@ static int launch_cluster(Kern kern, const Desc& d, int H, int B, cudaStream_t s
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   if (CS > 8) SATK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  // two CTAs per SM (two clusters interleave on the same SMs and hide each other's exchange latency)
+  SATK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SATK_CUDA(cudaLaunchKernelEx(&cfg, kern, d));
   return SATK_OK;
 }
@@ -277,6 +429,17 @@ int lstm_max_clusters_h256() {
 using namespace satk;
 
 extern "C" {
+
+int satk_debug_phase_cycles(long long* out16) {
+#ifdef SATK_PHASE_TIMING
+  SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
+  return 0;
+#else
+  (void)out16;
+  satk::set_error("library built without -DSATK_PHASE_TIMING");
+  return SATK_ERR_UNSUPPORTED;
+#endif
+}
 
 int satk_lstm_seq_fwd(const satk_lstm_fwd_desc* d, void* stream) {
   SATK_CHECK_ARG(d->H == 128 || d->H == 256, "lstm_seq_fwd: H=%d unsupported (128 or 256)", d->H);

@@ -91,7 +91,7 @@ SYMBOLS = [
     "satk_transpose", "satk_mask_rows", "satk_softsign_fwd", "satk_softsign_bwd", "satk_add_rowvec_tb",
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
-    "satk_attn_rnn_fwd", "satk_attn_rnn_bwd",
+    "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_debug_phase_cycles",
 ]
 
 
