@@ -193,8 +193,9 @@ typedef struct {
   float* h_prev;               /* [T,B,H] hidden state BEFORE the step */
 } satk_lstm_fwd_desc;
 int satk_lstm_seq_fwd(const satk_lstm_fwd_desc* d, void* stream);
-/* developer aid: per-phase cycle averages of the last lstm_seq_fwd launch (only with -DSATK_PHASE_TIMING builds) */
-int satk_debug_phase_cycles(long long* out16);
+/* developer aid: per-phase cycle averages of the last launch of kernel family `which` (0 lstm fwd, 1 attention-RNN fwd,
+ * 2 attention-RNN bwd); only meaningful in -DSATK_PHASE_TIMING builds */
+int satk_debug_phase_cycles(int which, long long* out16);
 
 typedef struct {
   int T, B, H;

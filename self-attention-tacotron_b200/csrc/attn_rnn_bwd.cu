@@ -644,6 +644,15 @@ static int launch16b(Kern kern, const satk_attn_rnn_bwd_desc& d, size_t smem, cu
 
 int attn_rnn_check(const satk_attn_rnn_fwd_desc* d, bool& has2);
 
+int attn_bwd_phase_cycles(long long* out16) {
+#ifdef SATK_PHASE_TIMING
+  SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+#endif
+  return 0;
+}
+
 }  // namespace arnn
 }  // namespace satk
 

@@ -2,30 +2,46 @@
 // launch.  A cluster of 16 CTAs owns 4 utterances:
 //   P1  gate GEMM  [4 x (ctx+h)] x [(ctx+h) x 64 cols]  — each CTA owns 16 hidden units, its slice of
 //       the recurrent kernel stays in registers for all steps; LSTM pointwise + zoneout;
-//       h -> every CTA (DSMEM), out1 -> the 4 CTAs of that utterance.
+//       h -> every CTA, out1 -> the 4 CTAs of that utterance.
 //   P2  each utterance is served by 4 CTAs that split the SCORE CHANNELS: query slice, location
 //       features, partial energies sum_c v_c tanh(keys + q + f.Wf) over their 56(+8) channels for all
-//       Tt positions; partial energies -> the 4 CTAs of the utterance (DSMEM).
+//       Tt positions; partial energies -> the 4 CTAs of the utterance.
 //   P3  masked softmax, forward-attention recursion (one warp per mechanism), context slice
-//       (64(+8) value columns) -> every CTA (DSMEM) for the next step's gate GEMM.
-// Three hardware cluster barriers per step, no global synchronisation, keys/values/weights never
-// re-read from HBM.  Reference semantics: forward_attention.py:88-136 (+ :13-26), TF
-// BahdanauAttention / AttentionWrapper, ZoneoutLSTMCell (A.5, A.6).
+//       (64(+8) value columns) -> every CTA for the next step's gate GEMM.
+// Exchange = st.async / cp.async.bulk into the peers' shared memory completing mbarrier transactions
+// (cluster_sync.cuh): no cluster-wide barrier inside the loop, every CTA proceeds as soon as ITS inputs
+// have landed.  The warps that issue the exchange touch no global memory (stores queued in front of a
+// st.async delay every peer); saved activations and alignments are staged in shared memory and written
+// out by other warps; x-projection and zoneout masks arrive through cp.async rings 6 steps ahead.
+// Keys / values / weights are never re-read from HBM.
+// Reference semantics: forward_attention.py:88-136 (+ :13-26), TF BahdanauAttention / AttentionWrapper
+// (SURVEY.md A.7, A.8), ZoneoutLSTMCell (A.5, A.6).
 #include "attn_rnn.cuh"
+#include "cluster_sync.cuh"
 
 namespace satk {
 namespace arnn {
 
+using cl::cp_async4;
+using cl::cp_async_commit;
+using cl::cp_async_wait;
+using cl::st_async_v4;
+using cl::RING;
+using cl::PFD;
+
 template <bool HAS2>
 struct FwdSmem {
   using D = Dims<HAS2>;
-  int TtP;
+  int TtP, Tt4;
   float *xrec, *gsm, *out1buf, *Wqs, *keyS, *valS, *fS, *Wfs, *wconv, *bconv, *vs, *qs, *qpart, *epart, *aprev, *alphaS,
-      *w1S, *w2S, *cpart;
+      *w1S, *w2S, *softS, *cpart, *ctxS, *save1, *xg_ring;
+  uint8_t* mk_ring;
+  uint64_t* bars;   // [0..1] X, [2..3] O, [4..5] E
   __host__ __device__ size_t carve(float* base, int Tt) {
     TtP = tt_pad(Tt);
+    Tt4 = (Tt + 3) & ~3;
     float* p = base;
-    xrec = p; p += 2 * D::KREC * BG;
+    xrec = p; p += 2 * BG * D::KREC;                 // [buf][row][k]
     gsm = p; p += BG * 64;
     out1buf = p; p += H;
     Wqs = p; p += H * QC;
@@ -38,12 +54,18 @@ struct FwdSmem {
     vs = p; p += QC;
     qs = p; p += QC;
     qpart = p; p += 8 * QC;
-    epart = p; p += 2 * 4 * (size_t)TtP;
+    epart = p; p += 2 * 4 * (size_t)TtP;             // [att][source CTA of the row][j]
     aprev = p; p += TtP + 2 * HALO;
     alphaS = p; p += TtP;
     w1S = p; p += TtP;
     w2S = p; p += TtP;
+    softS = p; p += TtP;
     cpart = p; p += 8 * VC;
+    ctxS = p; p += VC + 8;
+    save1 = p; p += 7 * 64;
+    xg_ring = p; p += RING * 256;
+    mk_ring = reinterpret_cast<uint8_t*>(p); p += RING * 2 * BG * UH / 4;
+    bars = reinterpret_cast<uint64_t*>(p); p += 2 * 6;
     return (size_t)(p - base) * sizeof(float);
   }
 };
@@ -51,7 +73,12 @@ struct FwdSmem {
 template <bool HAS2, int AFT, int NP>
 __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn_fwd_desc d) {
   using D = Dims<HAS2>;
-  constexpr int KREC = D::KREC, KPT = D::KPT, A1Q = D::A1Q, NI1 = D::NI1;
+  constexpr int KREC = D::KREC, A1Q = D::A1Q, NI1 = D::NI1, M2 = D::M2, X2W = D::X2W;
+  constexpr int KPT = KREC / 32;                       // k's per lane in the gate GEMM (17 / 16)
+  constexpr int VCW = HAS2 ? VC : 64;                  // context columns produced per CTA
+  constexpr int NATT = HAS2 ? 2 : 1;
+  constexpr uint32_t RX_X = (uint32_t)((CS - 1) * UH * BG + (BG * (M1 + M2) - VCW)) * 4u;
+  constexpr uint32_t RX_O = (uint32_t)(CS - 1) * UH * 4u;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int bg = blockIdx.x / CS;
@@ -62,7 +89,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
   extern __shared__ __align__(16) float smem_raw[];
   FwdSmem<HAS2> S;
   S.carve(smem_raw, Tt);
-  const int TtP = S.TtP;
+  const int TtP = S.TtP, Tt4 = S.Tt4;
+  const uint32_t RX_E = 3u * NATT * (uint32_t)Tt4 * 4u;
+  uint64_t* barX = S.bars;
+  uint64_t* barO = S.bars + 2;
+  uint64_t* barE = S.bars + 4;
 
   // attention role of this CTA
   const int ab = rank >> 2, cq = rank & 3;
@@ -87,7 +118,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
       if (c < A1Q) kv = __ldg(d.keys1 + rowi * d.A1 + cq * A1Q + c) + (d.b1 ? __ldg(d.b1 + cq * A1Q + c) : 0.f);
       else if (HAS2 && c < QC) kv = __ldg(d.keys2 + rowi * d.A2 + cq * 8 + (c - A1Q));
       if (c < 64) vv = __ldg(d.values1 + rowi * M1 + cq * 64 + c);
-      else if (HAS2) vv = __ldg(d.values2 + rowi * D::M2 + cq * 8 + (c - 64));
+      else if (HAS2) vv = __ldg(d.values2 + rowi * M2 + cq * 8 + (c - 64));
     }
     S.keyS[i] = kv;
     S.valS[i] = vv;
@@ -106,99 +137,181 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
     if (tid < A1Q) v = __ldg(d.v1 + cq * A1Q + tid);
     else if (HAS2) v = __ldg(d.v2 + cq * 8 + (tid - A1Q));
     S.vs[tid] = v;
+    S.qs[tid] = 0.f;
   }
-  for (int i = tid; i < 2 * KREC * BG; i += NT) S.xrec[i] = 0.f;
+  for (int i = tid; i < 2 * BG * KREC; i += NT) S.xrec[i] = 0.f;
   for (int i = tid; i < TtP + 2 * HALO; i += NT) S.aprev[i] = 0.f;
   for (int i = tid; i < TtP; i += NT) {
     S.alphaS[i] = (d.mode == 2 && i == 0) ? 1.f : 0.f;  // alpha_0 = one-hot(0), forward_attention.py:131-133
     S.w1S[i] = 0.f;
     S.w2S[i] = 0.f;
+    S.softS[i] = 0.f;
   }
   for (int i = tid; i < TtP * MAXF; i += NT) S.fS[i] = 0.f;
+  for (int i = tid; i < 2 * 4 * TtP; i += NT) S.epart[i] = 0.f;
+  for (int i = tid; i < RING * 2 * BG * UH; i += NT) S.mk_ring[i] = 0;
+  if (tid < H) S.out1buf[tid] = 0.f;
+  if (tid < VC + 8) S.ctxS[tid] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 6; ++i) cl::mbar_init(&S.bars[i], 1);
+    cl::fence_mbar_init();
+  }
 
-  // ---------------- P1 role: thread = (col 0..63, kq 0..7)
-  const int col = tid >> 3, kq = tid & 7;
-  const int gate = col >> 4, unit = col & 15;
-  const int gcol = gate * H + rank * UH + unit;
-  float w[KPT];
+  // ---------------- P1 role: thread = (kq = lane, column group = warp): 4 gate columns x the k's congruent to
+  // lane mod 32; x[row][k] scalars feed 16 FMAs per k; partial sums reduce-scattered over the lanes.
+  float w[KPT][4];
 #pragma unroll
-  for (int i = 0; i < KPT; ++i) w[i] = __ldg(d.Wrec + (long long)(kq + 8 * i) * (4 * H) + gcol);
-  const int xb = b0 + (kq & 3);
-  const bool xb_ok = (kq < 4) && xb < B;
-  // pointwise role: tid < 64 -> (pb, pu)
+  for (int i = 0; i < KPT; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int colc = warp * 4 + c;                                   // CTA-local gate column = gate*16 + unit
+      w[i][c] = __ldg(d.Wrec + (long long)(lane + 32 * i) * (4 * H) + (colc >> 4) * H + rank * UH + (colc & 15));
+    }
+  // lanes < 16 finalise (column warp*4 + (lane>>2), row lane&3)
+  const int fcol = warp * 4 + ((lane >> 2) & 3), frow = lane & 3;
+  const int fgcol = (fcol >> 4) * H + rank * UH + (fcol & 15);
+  const int xb = b0 + frow;
+  const bool xb_ok = (lane < 16) && xb < B;
+  const int xslot = warp * 16 + (lane & 15);
+  // pointwise role: tid < 64 -> (pb, pu); these warps issue the exchange and touch no global memory
   const int pb = tid >> 4, pu = tid & 15;
   const int prow = b0 + pb;
   const bool prow_ok = (tid < 64) && prow < B;
   const int pidx = rank * UH + pu;
   float c_st = 0.f, h_st = 0.f;
-
+  // saver role A (LSTM activations): tid in [128,192) -> (sb, su)
+  const int sb = (tid - 128) >> 4, su = tid & 15;
+  const int srow = b0 + sb;
+  const bool srow_ok = (tid >= 128 && tid < 192) && srow < B;
   // P2 role: position group / channel lane
-  const int pg = warp * 4 + (lane >> 3), cl = lane & 7;
+  const int pg = warp * 4 + (lane >> 3), cl_ = lane & 7;
 
   cluster.sync();
 
-  float xg_next = xb_ok ? __ldg(d.xg + ((long long)0 * B + xb) * (4 * H) + gcol) : 0.f;
+  auto prefetch = [&](int t) {
+    if (t < d.Td) {
+      if (xb_ok) cp_async4(&S.xg_ring[(t % RING) * 256 + xslot], d.xg + ((long long)t * B + xb) * (4 * H) + fgcol);
+      if (srow_ok && (su & 3) == 0) {
+        const long long om = ((long long)t * B + srow) * H + rank * UH + su;
+        uint8_t* mr = S.mk_ring + (t % RING) * 2 * BG * UH;
+        if (d.mask_c) cp_async4(mr + (0 * BG + sb) * UH + su, d.mask_c + om);
+        if (d.mask_h) cp_async4(mr + (1 * BG + sb) * UH + su, d.mask_h + om);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int t = 0; t < PFD; ++t) prefetch(t);
 
+  PT_DECL
+#pragma unroll 1
   for (int t = 0; t < d.Td; ++t) {
     const int cur = t & 1, nxt = cur ^ 1;
+    PT(15)
+    const uint32_t par = (uint32_t)(t >> 1) & 1u;
+    const bool last = (t + 1 == d.Td);
+    prefetch(t + PFD);
+    cp_async_wait<PFD>();
+    if (t > 0) cl::mbar_wait(&barX[cur], (uint32_t)((t - 1) >> 1) & 1u);    // h(t), ctx(t-1) of every peer have landed
+    if (tid == 0) {
+      if (!last) cl::mbar_arrive_expect_tx(&barX[nxt], RX_X);
+      cl::mbar_arrive_expect_tx(&barO[cur], RX_O);
+      cl::mbar_arrive_expect_tx(&barE[cur], RX_E);
+    }
+    PT(0)
     // ======================= P1: gates + LSTM cell
     {
-      const float xg_cur = xg_next;
-      if (t + 1 < d.Td && xb_ok) xg_next = __ldg(d.xg + ((long long)(t + 1) * B + xb) * (4 * H) + gcol);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const float* xr = S.xrec + cur * KREC * BG;
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      const float* xr = S.xrec + cur * BG * KREC;
 #pragma unroll
       for (int i = 0; i < KPT; ++i) {
-        const float4 xv = *reinterpret_cast<const float4*>(xr + (kq + 8 * i) * BG);
-        a0 = fmaf(w[i], xv.x, a0);
-        a1 = fmaf(w[i], xv.y, a1);
-        a2 = fmaf(w[i], xv.z, a2);
-        a3 = fmaf(w[i], xv.w, a3);
-      }
+        const int k = lane + 32 * i;
+        const float x0 = xr[0 * KREC + k], x1 = xr[1 * KREC + k], x2v = xr[2 * KREC + k], x3 = xr[3 * KREC + k];
 #pragma unroll
-      for (int o = 1; o <= 4; o <<= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+        for (int c = 0; c < 4; ++c) {
+          acc[c * 4 + 0] = fmaf(w[i][c], x0, acc[c * 4 + 0]);
+          acc[c * 4 + 1] = fmaf(w[i][c], x1, acc[c * 4 + 1]);
+          acc[c * 4 + 2] = fmaf(w[i][c], x2v, acc[c * 4 + 2]);
+          acc[c * 4 + 3] = fmaf(w[i][c], x3, acc[c * 4 + 3]);
+        }
       }
-      if (kq < 4) S.gsm[kq * 64 + col] = ((kq == 0) ? a0 : (kq == 1) ? a1 : (kq == 2) ? a2 : a3) + xg_cur;
+      float v = cl::reduce_scatter16(acc, lane);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 16) S.gsm[frow * 64 + fcol] = v + (xb_ok ? S.xg_ring[(t % RING) * 256 + xslot] : 0.f);
     }
+    PT(1)
     __syncthreads();
-    if (tid < 64 && prow_ok) {
-      float gi = fsigmoid(S.gsm[pb * 64 + 0 * 16 + pu]);
-      float gj = ftanh(S.gsm[pb * 64 + 1 * 16 + pu]);
-      float gf = fsigmoid(S.gsm[pb * 64 + 2 * 16 + pu] + d.forget_bias);
-      float go = fsigmoid(S.gsm[pb * 64 + 3 * 16 + pu]);
-      float c_new = gf * c_st + gi * gj;
-      float h_new = go * ftanh(c_new);
-      const long long o1 = ((long long)t * B + prow) * H + pidx;
-      if (d.gates) {
-        const long long o4 = ((long long)t * B + prow) * (4 * H) + pidx;
-        d.gates[o4] = gi; d.gates[o4 + H] = gj; d.gates[o4 + 2 * H] = gf; d.gates[o4 + 3 * H] = go;
-        d.c_prev[o1] = c_st;
-        d.h_prev[o1] = h_st;
+    PT(2)
+    if (tid < 64) {
+      float gi = 0.f, gj = 0.f, gf = 0.f, go = 0.f, h_new = 0.f;
+      const float c_old = c_st, h_old = h_st;
+      if (prow_ok) {
+        const uint8_t* mr = S.mk_ring + (t % RING) * 2 * BG * UH;
+        const float mc = d.mask_c ? (float)mr[(0 * BG + pb) * UH + pu] : (1.f - d.zc);
+        const float mh = d.mask_h ? (float)mr[(1 * BG + pb) * UH + pu] : (1.f - d.zh);
+        gi = fsigmoid(S.gsm[pb * 64 + 0 * 16 + pu]);
+        gj = ftanh(S.gsm[pb * 64 + 1 * 16 + pu]);
+        gf = fsigmoid(S.gsm[pb * 64 + 2 * 16 + pu] + d.forget_bias);
+        go = fsigmoid(S.gsm[pb * 64 + 3 * 16 + pu]);
+        const float c_new = gf * c_st + gi * gj;
+        h_new = go * ftanh(c_new);
+        c_st = c_st + mc * (c_new - c_st);
+        h_st = h_st + mh * (h_new - h_st);
       }
-      float mc = d.mask_c ? (float)d.mask_c[o1] : (1.f - d.zc);
-      float mh = d.mask_h ? (float)d.mask_h[o1] : (1.f - d.zh);
-      c_st = c_st + mc * (c_new - c_st);
-      h_st = h_st + mh * (h_new - h_st);
-      d.x2[((long long)t * B + prow) * D::X2W + pidx] = h_new;
-#pragma unroll 4
-      for (int r = 0; r < CS; ++r) {
-        float* rx = cluster.map_shared_rank(S.xrec, r);
-        rx[(nxt * KREC + (M1 + D::M2) + pidx) * BG + pb] = h_st;
-      }
+      // ---- exchange: 4 consecutive units of a row travel as one 16-byte st.async
+      const int l4 = lane & ~3;
+      const float hs0 = __shfl_sync(0xffffffffu, h_st, l4), hs1 = __shfl_sync(0xffffffffu, h_st, l4 + 1);
+      const float hs2 = __shfl_sync(0xffffffffu, h_st, l4 + 2), hs3 = __shfl_sync(0xffffffffu, h_st, l4 + 3);
+      const float hn0 = __shfl_sync(0xffffffffu, h_new, l4), hn1 = __shfl_sync(0xffffffffu, h_new, l4 + 1);
+      const float hn2 = __shfl_sync(0xffffffffu, h_new, l4 + 2), hn3 = __shfl_sync(0xffffffffu, h_new, l4 + 3);
+      if (!last) S.xrec[(nxt * BG + pb) * KREC + (M1 + M2) + pidx] = h_st;
+      S.save1[0 * 64 + tid] = gi; S.save1[1 * 64 + tid] = gj; S.save1[2 * 64 + tid] = gf; S.save1[3 * 64 + tid] = go;
+      S.save1[4 * 64 + tid] = c_old; S.save1[5 * 64 + tid] = h_old; S.save1[6 * 64 + tid] = h_new;
+      if (pb == ab) S.out1buf[pidx] = h_new;   // own utterance: local copy
+      if ((lane & 3) == 0) {
+        const int u0 = rank * UH + (pu & ~3);
+        if (!last) {
+          const uint32_t dsta = cl::smem_u32(&S.xrec[(nxt * BG + pb) * KREC + (M1 + M2) + u0]);
+          const uint32_t bara = cl::smem_u32(&barX[nxt]);
 #pragma unroll
-      for (int r4 = 0; r4 < 4; ++r4) {
-        float* ro = cluster.map_shared_rank(S.out1buf, pb * 4 + r4);
-        ro[pidx] = h_new;
+          for (int r = 0; r < CS; ++r)
+            if (r != rank) st_async_v4(cl::mapa(dsta, r), hs0, hs1, hs2, hs3, cl::mapa(bara, r));
+        }
+        const uint32_t dsto = cl::smem_u32(&S.out1buf[u0]);
+        const uint32_t baro = cl::smem_u32(&barO[cur]);
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int r = pb * 4 + r4;
+          if (r != rank) st_async_v4(cl::mapa(dsto, r), hn0, hn1, hn2, hn3, cl::mapa(baro, r));
+        }
       }
     }
-    cluster.sync();  // ---- barrier A: out1 / h published
+    PT(3)
+    __syncthreads();
+    PT(4)
+    if (srow_ok) {
+      // saver A: LSTM activations of step t -> global (fire and forget, off the exchange warps)
+      const int e = tid - 128;
+      const int sidx = rank * UH + su;
+      const long long o1 = ((long long)t * B + srow) * H + sidx;
+      d.x2[((long long)t * B + srow) * X2W + sidx] = S.save1[6 * 64 + e];
+      if (d.gates) {
+        const long long o4 = ((long long)t * B + srow) * (4 * H) + sidx;
+        d.gates[o4] = S.save1[0 * 64 + e];
+        d.gates[o4 + H] = S.save1[1 * 64 + e];
+        d.gates[o4 + 2 * H] = S.save1[2 * 64 + e];
+        d.gates[o4 + 3 * H] = S.save1[3 * 64 + e];
+        d.c_prev[o1] = S.save1[4 * 64 + e];
+        d.h_prev[o1] = S.save1[5 * 64 + e];
+      }
+    }
+    cl::mbar_wait(&barO[cur], par);   // out1 of my utterance complete
+    PT(5)
 
     // ======================= P2: query slice, location features, partial energies
-    if (arow_ok) {
+    {
       // location features f[j][.] = conv1d(a_prev) (forward_attention.py:98-100)
       if (d.att_kernel > 0) {
         for (int idx = tid; idx < Tt * AFT; idx += NT) {
@@ -210,27 +323,23 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         }
       }
       // query slice partials
-      {
-        const int c = tid & 63, uq = tid >> 6;
-        float acc = 0.f;
+      const int c = tid & 63, uq = tid >> 6;
+      float acc = 0.f;
 #pragma unroll 8
-        for (int u = uq * 32; u < uq * 32 + 32; ++u) acc = fmaf(S.out1buf[u], S.Wqs[u * QC + c], acc);
-        S.qpart[uq * QC + c] = acc;
-      }
+      for (int u = uq * 32; u < uq * 32 + 32; ++u) acc = fmaf(S.out1buf[u], S.Wqs[u * QC + c], acc);
+      S.qpart[uq * QC + c] = acc;
     }
+    PT(6)
     __syncthreads();
-    if (arow_ok && tid < QC) {
+    if (tid < QC) {
       float q = 0.f;
 #pragma unroll
       for (int u = 0; u < 8; ++u) q += S.qpart[u * QC + tid];
       S.qs[tid] = q;
-      if (d.q_save) {
-        const int qcol = (tid < A1Q) ? (cq * A1Q + tid) : (d.A1 + cq * 8 + (tid - A1Q));
-        d.q_save[((long long)t * B + arow) * (d.A1 + d.A2) + qcol] = q;
-      }
     }
     __syncthreads();
-    if (arow_ok) {
+    PT(7)
+    {
       float e1[NP], e2[NP], fv[NP][AFT];
       int jm[NP];
 #pragma unroll
@@ -244,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
       }
 #pragma unroll
       for (int i = 0; i < NI1; ++i) {
-        const int c = cl + 8 * i;
+        const int c = cl_ + 8 * i;
         float wf[AFT];
 #pragma unroll
         for (int f = 0; f < AFT; ++f) wf[f] = S.Wfs[f * QC + c];
@@ -258,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         }
       }
       if (HAS2) {
-        const int c = A1Q + cl;
+        const int c = A1Q + cl_;
         const float qc = S.qs[c], vc = S.vs[c];
 #pragma unroll
         for (int m = 0; m < NP; ++m) e2[m] = vc * ftanh(S.keyS[jm[m] * KS + c] + qc);
@@ -271,20 +380,38 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
           if (HAS2) e2[m] += __shfl_xor_sync(0xffffffffu, e2[m], o);
         }
       }
-      if (cl < 4) {
-        // lane cl sends to CTA (ab, cl) of this utterance
-        float* re = cluster.map_shared_rank(S.epart, ab * 4 + cl);
+      if (cl_ == 0) {
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
           int j = pg + 64 * m;
           if (j < Tt) {
-            re[(0 * 4 + cq) * TtP + j] = e1[m];
-            if (HAS2) re[(1 * 4 + cq) * TtP + j] = e2[m];
+            S.epart[(0 * 4 + cq) * TtP + j] = e1[m];
+            if (HAS2) S.epart[(1 * 4 + cq) * TtP + j] = e2[m];
           }
         }
       }
     }
-    cluster.sync();  // ---- barrier B: partial energies published
+    PT(8)
+    cl::fence_proxy_async();
+    __syncthreads();
+    PT(9)
+    if (tid < 3 * NATT) {
+      // partial energies -> the three other CTAs of this utterance: one bulk DSMEM copy per (mechanism, peer)
+      const int att = tid / 3, q3 = tid % 3;
+      const int r4 = q3 + (q3 >= cq ? 1 : 0);
+      const uint32_t src = cl::smem_u32(&S.epart[(att * 4 + cq) * TtP]);
+      cl::bulk_copy_to_cta(cl::mapa(src, ab * 4 + r4), src, (uint32_t)Tt4 * 4u, cl::mapa(cl::smem_u32(&barE[cur]), ab * 4 + r4));
+    }
+    if (tid >= 192 && tid < 192 + QC && arow_ok && d.q_save) {
+      // saver: processed queries (for the backward pass)
+      const int qi = tid - 192;
+      if (qi < A1Q || HAS2) {
+        const int qcol = (qi < A1Q) ? (cq * A1Q + qi) : (d.A1 + cq * 8 + (qi - A1Q));
+        d.q_save[((long long)t * B + arow) * (d.A1 + d.A2) + qcol] = S.qs[qi];
+      }
+    }
+    cl::mbar_wait(&barE[cur], par);   // partial energies of my utterance complete
+    PT(10)
 
     // ======================= P3: softmax, forward recursion, context
     if (arow_ok && warp == 0) {
@@ -339,12 +466,8 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
           float wgt = (d.mode == 2) ? apm1[m] * ainv : a;
           if (d.mode == 2) S.alphaS[j] = wgt;
           S.w1S[j] = wgt;
+          S.softS[j] = a;
           if (d.att_kernel > 0) S.aprev[HALO + j] = d.cumulative ? (S.aprev[HALO + j] + a) : a;
-          if (cq == 0 && j < Tt) {
-            const long long oa = ((long long)t * B + arow) * Tt + j;
-            d.align1[oa] = wgt;
-            if (d.soft1) d.soft1[oa] = a;
-          }
         }
     }
     if (HAS2 && arow_ok && warp == 1) {
@@ -373,43 +496,70 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
       const float inv = 1.f / sum;
 #pragma unroll
       for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          int j = lane + 32 * m;
-          float a = e[m] * inv;
-          S.w2S[j] = a;
-          if (cq == 0 && j < Tt) d.align2[((long long)t * B + arow) * Tt + j] = a;
-        }
+        if (m < nm) S.w2S[lane + 32 * m] = e[m] * inv;
     }
+    PT(11)
     __syncthreads();
-    if (arow_ok) {
-      {
-        const int c = tid & 63, jg = tid >> 6;
-        float acc = 0.f;
-        for (int j = jg; j < Tt; j += 8) acc = fmaf(S.w1S[j], S.valS[j * KS + c], acc);
-        S.cpart[jg * VC + c] = acc;
-      }
+    PT(12)
+    {
+      const int c = tid & 63, jg = tid >> 6;
+      float acc = 0.f;
+      for (int j = jg; j < Tt; j += 8) acc = fmaf(S.w1S[j], S.valS[j * KS + c], acc);
+      S.cpart[jg * VC + c] = acc;
       if (HAS2 && tid < 64) {
-        const int c2 = tid & 7, jg = tid >> 3;
-        float acc = 0.f;
-        for (int j = jg; j < Tt; j += 8) acc = fmaf(S.w2S[j], S.valS[j * KS + 64 + c2], acc);
-        S.cpart[jg * VC + 64 + c2] = acc;
+        const int c2 = tid & 7, jg2 = tid >> 3;
+        float acc2 = 0.f;
+        for (int j = jg2; j < Tt; j += 8) acc2 = fmaf(S.w2S[j], S.valS[j * KS + 64 + c2], acc2);
+        S.cpart[jg2 * VC + 64 + c2] = acc2;
       }
     }
     __syncthreads();
-    if (arow_ok && tid < (HAS2 ? VC : 64)) {
+    PT(13)
+    if (tid < 96) {
+      // context slice of my utterance -> every CTA's x[row][k] for the next step (16-byte st.async per 4 columns)
       float cx = 0.f;
+      if (tid < VCW) {
 #pragma unroll
-      for (int jg = 0; jg < 8; ++jg) cx += S.cpart[jg * VC + tid];
-      const int k = (tid < 64) ? (cq * 64 + tid) : (M1 + cq * 8 + (tid - 64));
-      d.x2[((long long)t * B + arow) * D::X2W + H + k] = cx;
-#pragma unroll 4
-      for (int r = 0; r < CS; ++r) {
-        float* rx = cluster.map_shared_rank(S.xrec, r);
-        rx[(nxt * KREC + k) * BG + ab] = cx;
+        for (int jg = 0; jg < 8; ++jg) cx += S.cpart[jg * VC + tid];
+        S.ctxS[tid] = cx;
+      }
+      const int l4 = lane & ~3;
+      const float c0 = __shfl_sync(0xffffffffu, cx, l4), c1 = __shfl_sync(0xffffffffu, cx, l4 + 1);
+      const float c2 = __shfl_sync(0xffffffffu, cx, l4 + 2), c3 = __shfl_sync(0xffffffffu, cx, l4 + 3);
+      if (tid < VCW && !last) {
+        const int k = (tid < 64) ? (cq * 64 + tid) : (M1 + cq * 8 + (tid - 64));
+        S.xrec[(nxt * BG + ab) * KREC + k] = cx;
+        if ((lane & 3) == 0) {
+          const uint32_t dsta = cl::smem_u32(&S.xrec[(nxt * BG + ab) * KREC + k]);
+          const uint32_t bara = cl::smem_u32(&barX[nxt]);
+#pragma unroll
+          for (int r = 0; r < CS; ++r)
+            if (r != rank) st_async_v4(cl::mapa(dsta, r), c0, c1, c2, c3, cl::mapa(bara, r));
+        }
       }
     }
-    cluster.sync();  // ---- barrier C: context published
+    PT(14)
+    __syncthreads();
+    if (arow_ok && tid >= 256) {
+      // saver B: context and alignments of step t -> global
+      const int e = tid - 256;
+      if (e < VCW) {
+        const int k = (e < 64) ? (cq * 64 + e) : (M1 + cq * 8 + (e - 64));
+        d.x2[((long long)t * B + arow) * X2W + H + k] = S.ctxS[e];
+      }
+      if (cq == 0) {
+        const long long oa = ((long long)t * B + arow) * Tt;
+        for (int j = e; j < Tt; j += 256) {
+          d.align1[oa + j] = S.w1S[j];
+          if (d.soft1) d.soft1[oa + j] = S.softS[j];
+          if (HAS2) d.align2[oa + j] = S.w2S[j];
+        }
+      }
+    }
   }
+  PT_FLUSH(d.Td)
+  cp_async_wait<0>();
+  cluster.sync();
 }
 
 template <bool HAS2>
@@ -471,6 +621,15 @@ int attn_rnn_max_clusters() {
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
   return n;
+}
+
+int attn_fwd_phase_cycles(long long* out16) {
+#ifdef SATK_PHASE_TIMING
+  SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+#endif
+  return 0;
 }
 
 }  // namespace arnn

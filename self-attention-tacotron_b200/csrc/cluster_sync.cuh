@@ -66,6 +66,25 @@ __device__ __forceinline__ void st_async_f32(uint32_t dst_cluster_addr, float v,
                : "memory");
 }
 
+// 16-byte remote store (4 floats) completing 16 bytes on the remote mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, float a, float b, float c, float d, uint32_t mbar_cluster_addr) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster_addr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
+               "r"(mbar_cluster_addr)
+               : "memory");
+}
+
+// cp.async (LDGSTS): asynchronous global -> shared prefetch rings, several recurrent steps ahead of their use
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int RING = 8;   // prefetch ring slots
+constexpr int PFD = 6;    // prefetch distance in steps (>> HBM latency / step time)
+
 // named barrier among a subset of warps
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -81,6 +81,18 @@ __device__ __forceinline__ float block_max(float v, float* sh) {
   return r;
 }
 
+// developer aid: per-phase cycle accounting of thread 0 / CTA 0 (build with EXTRA=-DSATK_PHASE_TIMING)
+#ifdef SATK_PHASE_TIMING
+static __device__ long long g_phase[16];   // one copy per translation unit
+#define PT_DECL long long pt_t = clock64(), pt_acc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+#define PT(i) { long long pt_n = clock64(); pt_acc[i] += pt_n - pt_t; pt_t = pt_n; }
+#define PT_FLUSH(n) if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < 16; ++i_) satk::g_phase[i_] = pt_acc[i_] / (n); }
+#else
+#define PT_DECL
+#define PT(i)
+#define PT_FLUSH(n)
+#endif
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 }  // namespace satk

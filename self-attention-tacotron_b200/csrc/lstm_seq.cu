@@ -15,17 +15,6 @@ namespace cg = cooperative_groups;
 
 namespace satk {
 
-#ifdef SATK_PHASE_TIMING
-__device__ long long g_phase[16];
-#define PT_DECL long long pt_t = clock64(), pt_acc[6] = {0, 0, 0, 0, 0, 0};
-#define PT(i) { long long pt_n = clock64(); pt_acc[i] += pt_n - pt_t; pt_t = pt_n; }
-#define PT_FLUSH(n) if (blockIdx.x == 0 && threadIdx.x == 0) { for (int i_ = 0; i_ < 6; ++i_) g_phase[i_] = pt_acc[i_] / (n); }
-#else
-#define PT_DECL
-#define PT(i)
-#define PT_FLUSH(n)
-#endif
-
 constexpr int LBG = 4;    // batch rows per cluster
 constexpr int LUH = 16;   // hidden units per CTA
 
@@ -36,16 +25,12 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return 1.0f - __fdividef(2.0f, 1.0f + e);
 }
 
-// cp.async helpers (LDGSTS): asynchronous global -> shared prefetch rings, several steps ahead
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(cl::smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-constexpr int RING = 8;   // prefetch ring slots
-constexpr int PFD = 6;    // prefetch distance in steps (>> HBM latency / step time)
+using cl::cp_async4;
+using cl::cp_async_commit;
+using cl::cp_async_wait;
+using cl::st_async_v4;
+using cl::RING;
+using cl::PFD;
 
 template <int H>
 __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_desc d) {
@@ -214,13 +199,6 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
   PT_FLUSH(d.T)
   cp_async_wait<0>();
   cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
-}
-
-__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, float a, float b, float c, float d, uint32_t mbar_cluster_addr) {
-  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(dst_cluster_addr),
-               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
-               "r"(mbar_cluster_addr)
-               : "memory");
 }
 
 template <int H>
@@ -426,16 +404,19 @@ int lstm_max_clusters_h256() {
 
 }  // namespace satk
 
+namespace satk { namespace arnn { int attn_fwd_phase_cycles(long long* out16); int attn_bwd_phase_cycles(long long* out16); } }
 using namespace satk;
 
 extern "C" {
 
-int satk_debug_phase_cycles(long long* out16) {
+int satk_debug_phase_cycles(int which, long long* out16) {
 #ifdef SATK_PHASE_TIMING
+  if (which == 1) return satk::arnn::attn_fwd_phase_cycles(out16);
+  if (which == 2) return satk::arnn::attn_bwd_phase_cycles(out16);
   SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
   return 0;
 #else
-  (void)out16;
+  (void)out16; (void)which;
   satk::set_error("library built without -DSATK_PHASE_TIMING");
   return SATK_ERR_UNSUPPORTED;
 #endif

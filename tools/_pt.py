@@ -14,5 +14,5 @@ for H,T,B in ((256,400,28),(128,148,32)):
         if variant=="nosave_nomask": kw.update(mask_c=None,mask_h=None,zc=0.1,zh=0.1)
         for _ in range(3): O.lstm_seq_fwd(xg,Wh,out,T,B,H,**kw)
         torch.cuda.synchronize()
-        o=(ctypes.c_longlong*16)(); L.load().satk_debug_phase_cycles(o)
+        o=(ctypes.c_longlong*16)(); L.load().satk_debug_phase_cycles(0, o)
         print(H, variant, "wait,gemm,sync1,pointwise+send,sync2,looptop:", list(o)[:6], "sum", sum(list(o)[:6]))
