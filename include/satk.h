@@ -130,6 +130,10 @@ int satk_colsum_acc(const float* x, long long ldx, int rows, int C, float* out, 
 int satk_add(const float* a, const float* b, float* out, long long n, void* stream);          /* out = a + b */
 int satk_axpy(float alpha, const float* x, float* y, long long n, void* stream);              /* y += alpha*x */
 int satk_transpose(const float* x, int rows, int cols, float* y, void* stream);               /* y[c,r] = x[r,c] */
+/* n transposes in one launch over two flat buffers with identical offsets: desc[3*i] = {offset, rows, cols} (device,
+ * int32): dst[off + c*rows + r] = src[off + r*cols + c].  Keeps the K-contiguous copy of the weights that the
+ * tcgen05 tile consumes ([in,out] -> [out,in]) in sync after each optimiser step. */
+int satk_transpose_batched(const float* src, float* dst, const int* desc, int n, void* stream);
 int satk_mask_rows(const float* x, const long long* lengths, int B, int T, int C, int time_major,
                    float* y, void* stream);                                                   /* zero rows t>=len[b] */
 /* softsign(x) = x/(1+|x|) forward/backward (MultiSpeakerPreNet, multi_speaker_modules.py:22) */

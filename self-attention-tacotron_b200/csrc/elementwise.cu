@@ -250,6 +250,27 @@ __global__ void transpose_k(const float* __restrict__ x, int rows, int cols, flo
     if (r2 < rows && c2 < cols) y[(long long)c2 * rows + r2] = t[threadIdx.x][j];
   }
 }
+// many small transposes in one launch: desc[3*i] = {offset, rows, cols}; dst[off + c*rows + r] = src[off + r*cols + c]
+__global__ void transpose_batched_k(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ desc) {
+  __shared__ float t[32][33];
+  const int off = desc[3 * blockIdx.y], rows = desc[3 * blockIdx.y + 1], cols = desc[3 * blockIdx.y + 2];
+  const int tx_n = (cols + 31) / 32, ty_n = (rows + 31) / 32;
+  for (int tile = blockIdx.x; tile < tx_n * ty_n; tile += gridDim.x) {
+    const int bx = tile % tx_n, by = tile / tx_n;
+    const int c = bx * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int r = by * 32 + j;
+      if (r < rows && c < cols) t[j][threadIdx.x] = src[off + (long long)r * cols + c];
+    }
+    __syncthreads();
+    const int r2 = by * 32 + threadIdx.x;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const int c2 = bx * 32 + j;
+      if (r2 < rows && c2 < cols) dst[off + (long long)c2 * rows + r2] = t[threadIdx.x][j];
+    }
+    __syncthreads();
+  }
+}
 __global__ void mask_rows_k(const float* __restrict__ x, const long long* __restrict__ len, int B, int T, int C, int tm,
                             float* __restrict__ y) {
   long long n = (long long)B * T * C;
@@ -555,6 +576,13 @@ int satk_axpy(float alpha, const float* x, float* y, long long n, void* stream) 
 int satk_transpose(const float* x, int rows, int cols, float* y, void* stream) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
   transpose_k<<<grid, block, 0, ST>>>(x, rows, cols, y);
+  SATK_LAUNCH_CHECK();
+  return 0;
+}
+int satk_transpose_batched(const float* src, float* dst, const int* desc, int n, void* stream) {
+  if (n <= 0) return 0;
+  dim3 grid(64, n), block(32, 8);
+  transpose_batched_k<<<grid, block, 0, ST>>>(src, dst, desc);
   SATK_LAUNCH_CHECK();
   return 0;
 }

@@ -50,6 +50,7 @@ class TacotronEngine:
         self.saved = None
         self.global_step = 0
         self._sumsq = torch.zeros(1, device=self.device)
+        self.refresh_transposed()
         self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
 
     def _timed(self, name, fn, *a, **k):
@@ -63,6 +64,18 @@ class TacotronEngine:
         return r
 
     # ------------------------------------------------------------------ helpers
+    def refresh_transposed(self):
+        """K-contiguous copies of all matrices (ps.flat -> ps.flat_t), one batched launch."""
+        O.transpose_batched(self.ps.flat, self.ps.flat_t, self.ps.t_desc, self.ps.t_count)
+
+    def lin(self, x, wname, out, *, K=None, k0=0, bias=None, act=None, residual=None, keep_mask=None, keep_scale=1.0):
+        """out = epi(x @ W[k0:k0+K, :] + bias) with the weight read from its K-contiguous copy (tcgen05 operand layout)."""
+        Wt = self.ps.pt[wname]
+        N, Ktot = Wt.shape
+        K = K or Ktot
+        return O.linear_t(x, Wt, out, x.numel() // K, K, N, ldw=Ktot, k_off=k0, bias=bias, act=act, residual=residual,
+                          keep_mask=keep_mask, keep_scale=keep_scale)
+
     def buf(self, name: str, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
         shape = tuple(int(s) for s in shape)
         t = self._bufs.get(name)
@@ -96,9 +109,9 @@ class TacotronEngine:
         D = x.shape[1]
         dh = D // heads
         R = T * B
-        Kp = O.linear(x, p[name + ".key.W"], self.buf(key + ".K", (R, D)), bias=p[name + ".key.b"])
-        Vp = O.linear(x, p[name + ".value.W"], self.buf(key + ".V", (R, D)), bias=p[name + ".value.b"])
-        Qp = O.linear(x, p[name + ".query.W"], self.buf(key + ".Q", (R, D)), bias=p[name + ".query.b"])
+        Kp = self.lin(x, name + ".key.W", self.buf(key + ".K", (R, D)), bias=p[name + ".key.b"])
+        Vp = self.lin(x, name + ".value.W", self.buf(key + ".V", (R, D)), bias=p[name + ".value.b"])
+        Qp = self.lin(x, name + ".query.W", self.buf(key + ".Q", (R, D)), bias=p[name + ".query.b"])
         S = self.buf(key + ".P", (B, heads, T, T))
         O.gemm(Qp, Kp, S, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, alpha=1.0 / math.sqrt(dh),
                batch1=B, batch2=heads, sA=(D, dh), sB=(D, dh), sC=(heads * T * T, T * T), causal_skip=1 if causal else 0)
@@ -108,8 +121,8 @@ class TacotronEngine:
         Oc = self.buf(key + ".O", (R, D))
         O.gemm(Pu, Vp, Oc, T, dh, T, lda=T, ldb=B * D, ldc=B * D, batch1=B, batch2=heads,
                sA=(heads * T * T, T * T), sB=(D, dh), sC=(D, dh), causal_skip=2 if causal else 0)
-        ao = O.linear(Oc, p[name + ".output.W"], self.buf(key + ".ao", (R, D)), bias=p[name + ".output.b"])
-        tr = O.linear(ao, p[name + ".transform.W"], self.buf(key + ".tr", (R, D)), bias=p[name + ".transform.b"], act="tanh")
+        ao = self.lin(Oc, name + ".output.W", self.buf(key + ".ao", (R, D)), bias=p[name + ".output.b"])
+        tr = self.lin(ao, name + ".transform.W", self.buf(key + ".tr", (R, D)), bias=p[name + ".transform.b"], act="tanh")
         y = self.buf(key + ".y", (R, D))
         O.add(x, tr, y)
         return y, dict(x=x, K=Kp, V=Vp, Q=Qp, P=S, Pd=Pu, O=Oc, ao=ao, tr=tr, T=T, heads=heads, causal=causal,
@@ -172,7 +185,7 @@ class TacotronEngine:
         sv["prenet_in"] = [x]
         for i, u in enumerate(d.enc_prenet):
             y = self.buf(f"enc.p{i}", (R, u))
-            O.linear(x, p[f"enc.prenet{i}.W"], y, bias=p[f"enc.prenet{i}.b"], act="relu",
+            self.lin(x, f"enc.prenet{i}.W", y, bias=p[f"enc.prenet{i}.b"], act="relu",
                      keep_mask=masks[f"enc.prenet{i}"] if training else None, keep_scale=1.0 / (1.0 - d.enc_prenet_drop))
             x = y
             sv["prenet_in"].append(x)
@@ -182,7 +195,7 @@ class TacotronEngine:
         raw = self.buf("enc.bank_raw", (R, KC))
         for k in range(1, K + 1):
             pl = (k - 1) // 2
-            O.gemm(inp, p[f"cbhg.bank{k}.W"], raw, R, C, cin, lda=cin, ldb=C, ldc=KC, c_off=(k - 1) * C,
+            O.gemm(inp, self.ps.pt[f"cbhg.bank{k}.W"], raw, R, C, cin, lda=cin, ldb=cin, ldc=KC, c_off=(k - 1) * C, transB=True,
                    taps=k, shift0=-pl * B, tap_dir=B, sBtap=cin * C)
 
         def bn(xraw, Cc, first, gname, act, out, residual=None, maxpool=False):
@@ -202,21 +215,21 @@ class TacotronEngine:
         mp = self.buf("enc.mp", (R, KC))
         sv["bn_bank"] = bn(raw, KC, "cbhg.bank1", "cbhg.bank1", "relu", mp, maxpool=True)
         raw1 = self.buf("enc.raw1", (R, d.proj1))
-        O.gemm(mp, p["cbhg.proj1.W"], raw1, R, d.proj1, KC, lda=KC, ldb=d.proj1, ldc=d.proj1, taps=3, shift0=-B, tap_dir=B,
-               sBtap=KC * d.proj1)
+        O.gemm(mp, self.ps.pt["cbhg.proj1.W"], raw1, R, d.proj1, KC, lda=KC, ldb=KC, ldc=d.proj1, transB=True, taps=3, shift0=-B,
+               tap_dir=B, sBtap=KC * d.proj1)
         p1o = self.buf("enc.p1o", (R, d.proj1))
         sv["bn_p1"] = bn(raw1, d.proj1, "cbhg.proj1", "cbhg.proj1", "relu", p1o)
         raw2 = self.buf("enc.raw2", (R, d.proj2))
-        O.gemm(p1o, p["cbhg.proj2.W"], raw2, R, d.proj2, d.proj1, lda=d.proj1, ldb=d.proj2, ldc=d.proj2, taps=3, shift0=-B,
-               tap_dir=B, sBtap=d.proj1 * d.proj2)
+        O.gemm(p1o, self.ps.pt["cbhg.proj2.W"], raw2, R, d.proj2, d.proj1, lda=d.proj1, ldb=d.proj1, ldc=d.proj2, transB=True, taps=3,
+               shift0=-B, tap_dir=B, sBtap=d.proj1 * d.proj2)
         hw = self.buf("enc.hw0", (R, d.proj2))
         sv["bn_p2"] = bn(raw2, d.proj2, "cbhg.proj2", "cbhg.proj2", None, hw, residual=inp)
         sv.update(inp=inp, mp=mp, p1o=p1o)
         Hn = d.enc_lstm
         sv["hwy"] = []
         for i in range(d.n_highway):
-            Hb = O.linear(hw, p[f"cbhg.highway{i}.WH"], self.buf(f"enc.hwH{i}", (R, Hn)), bias=p[f"cbhg.highway{i}.bH"], act="relu")
-            Tb = O.linear(hw, p[f"cbhg.highway{i}.WT"], self.buf(f"enc.hwT{i}", (R, Hn)), bias=p[f"cbhg.highway{i}.bT"], act="sigmoid")
+            Hb = self.lin(hw, f"cbhg.highway{i}.WH", self.buf(f"enc.hwH{i}", (R, Hn)), bias=p[f"cbhg.highway{i}.bH"], act="relu")
+            Tb = self.lin(hw, f"cbhg.highway{i}.WT", self.buf(f"enc.hwT{i}", (R, Hn)), bias=p[f"cbhg.highway{i}.bT"], act="sigmoid")
             y = self.buf(f"enc.hw{i + 1}", (R, Hn))
             O.highway_fwd(Hb, Tb, hw, y)
             sv["hwy"].append((Hb, Tb, hw))
@@ -226,7 +239,7 @@ class TacotronEngine:
         sv["lstm"] = {}
         for j, dr in enumerate(("fw", "bw")):
             W = p[f"cbhg.lstm_{dr}.W"]
-            xg = O.linear(hw, W[:Hn], self.buf(f"enc.xg_{dr}", (R, 4 * Hn)), bias=p[f"cbhg.lstm_{dr}.b"])
+            xg = self.lin(hw, f"cbhg.lstm_{dr}.W", self.buf(f"enc.xg_{dr}", (R, 4 * Hn)), K=Hn, bias=p[f"cbhg.lstm_{dr}.b"])
             gates = self.buf(f"enc.gates_{dr}", (R, 4 * Hn))
             cp = self.buf(f"enc.cprev_{dr}", (R, Hn))
             hp_ = self.buf(f"enc.hprev_{dr}", (R, Hn))
@@ -238,7 +251,7 @@ class TacotronEngine:
             sv["lstm"][dr] = dict(gates=gates, c_prev=cp, h_prev=hp_, mc=mc, mh=mh)
         mem2, aligns = None, []
         if d.dual:
-            x2 = O.linear(mem1, p["enc.sa_proj.W"], self.buf("enc.sa_in", (R, d.enc_sa)), bias=p["enc.sa_proj.b"])
+            x2 = self.lin(mem1, "enc.sa_proj.W", self.buf("enc.sa_in", (R, d.enc_sa)), bias=p["enc.sa_proj.b"])
             sv["sa"] = []
             for h in range(d.enc_sa_hops):
                 mk = masks[f"enc.sa{h}"] if training else None
@@ -351,31 +364,31 @@ class TacotronEngine:
         m0 = masks["dec.prenet0"] if training else None
         m1 = masks["dec.prenet1"] if training else None
         if d.use_speaker:
-            h0 = O.linear(dec_in, p["dec.prenet0.W0"], self.buf("dec.ph0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b0"], act="relu")
-            sp_pre = O.linear(speaker_embed, p["dec.prenet0.Ws"], self.buf("dec.sp_pre", (B, d.dec_prenet[0])), bias=p["dec.prenet0.bs"])
+            h0 = self.lin(dec_in, "dec.prenet0.W0", self.buf("dec.ph0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b0"], act="relu")
+            sp_pre = self.lin(speaker_embed, "dec.prenet0.Ws", self.buf("dec.sp_pre", (B, d.dec_prenet[0])), bias=p["dec.prenet0.bs"])
             sp = self.buf("dec.sp", (B, d.dec_prenet[0]))
             O.softsign_fwd(sp_pre, sp)
             O.add_rowvec_tb(h0, sp, Td, B, d.dec_prenet[0])
-            dp0 = O.linear(h0, p["dec.prenet0.W"], self.buf("dec.p0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b"], act="relu",
+            dp0 = self.lin(h0, "dec.prenet0.W", self.buf("dec.p0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b"], act="relu",
                            keep_mask=m0, keep_scale=1.0 / keep)
             sv.update(h0=h0, sp_pre=sp_pre)
         else:
-            dp0 = O.linear(dec_in, p["dec.prenet0.W"], self.buf("dec.p0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b"], act="relu",
+            dp0 = self.lin(dec_in, "dec.prenet0.W", self.buf("dec.p0", (Rd, d.dec_prenet[0])), bias=p["dec.prenet0.b"], act="relu",
                            keep_mask=m0, keep_scale=1.0 / keep)
-        dp1 = O.linear(dp0, p["dec.prenet1.W"], self.buf("dec.p1", (Rd, d.dec_prenet[1])), bias=p["dec.prenet1.b"], act="relu",
+        dp1 = self.lin(dp0, "dec.prenet1.W", self.buf("dec.p1", (Rd, d.dec_prenet[1])), bias=p["dec.prenet1.b"], act="relu",
                        keep_mask=m1, keep_scale=1.0 / keep)
         H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
         W1 = p["dec.lstm1.W"]
-        xg1 = O.linear(dp1, W1[:P1], self.buf("dec.xg1", (Rd, 4 * H1)), bias=p["dec.lstm1.b"])
+        xg1 = self.lin(dp1, "dec.lstm1.W", self.buf("dec.xg1", (Rd, 4 * H1)), K=P1, bias=p["dec.lstm1.b"])
         # attention memories (BahdanauAttention.__init__, A.8): values masked past length, keys = values.W_mem
         values1 = self.buf("dec.values1", (R, d.mem1))
         O.mask_rows(mem1, source_length, B, Tt, d.mem1, True, values1)
-        keys1 = O.linear(values1, p["att1.memory.W"], self.buf("dec.keys1", (R, d.att1)))
+        keys1 = self.lin(values1, "att1.memory.W", self.buf("dec.keys1", (R, d.att1)))
         values2 = keys2 = None
         if d.dual:
             values2 = self.buf("dec.values2", (R, d.mem2))
             O.mask_rows(mem2, source_length, B, Tt, d.mem2, True, values2)
-            keys2 = O.linear(values2, p["att2.memory.W"], self.buf("dec.keys2", (R, d.att2)))
+            keys2 = self.lin(values2, "att2.memory.W", self.buf("dec.keys2", (R, d.att2)))
         X2W = H1 + d.ctx
         x2 = self.buf("dec.x2", (Rd, X2W))
         al1 = self.buf("dec.align1", (Td, B, Tt))
@@ -402,7 +415,7 @@ class TacotronEngine:
         sv["lstm"] = []
         for li, kin in ((2, X2W), (3, HD)):
             W = p[f"dec.lstm{li}.W"]
-            xg = O.linear(x, W[:kin], self.buf(f"dec.xg{li}", (Rd, 4 * HD)), bias=p[f"dec.lstm{li}.b"])
+            xg = self.lin(x, f"dec.lstm{li}.W", self.buf(f"dec.xg{li}", (Rd, 4 * HD)), K=kin, bias=p[f"dec.lstm{li}.b"])
             out = self.buf(f"dec.out{li}", (Rd, HD))
             gates = self.buf(f"dec.gates{li}", (Rd, 4 * HD))
             cp, hp_ = self.buf(f"dec.cprev{li}", (Rd, HD)), self.buf(f"dec.hprev{li}", (Rd, HD))
@@ -421,8 +434,8 @@ class TacotronEngine:
                 sv["sa"].append(s)
                 sa_P += [s["P"][:, i] for i in range(d.dec_sa_heads)]
         sv["proj_in"] = x
-        mel_tm = O.linear(x, p["dec.out_proj.W"], self.buf("dec.mel_tm", (Rd, d.out_units)), bias=p["dec.out_proj.b"])
-        stop_tm = O.linear(x, p["dec.stop_proj.W"], self.buf("dec.stop_tm", (Rd, 1)), bias=p["dec.stop_proj.b"])
+        mel_tm = self.lin(x, "dec.out_proj.W", self.buf("dec.mel_tm", (Rd, d.out_units)), bias=p["dec.out_proj.b"])
+        stop_tm = self.lin(x, "dec.stop_proj.W", self.buf("dec.stop_tm", (Rd, 1)), bias=p["dec.stop_proj.b"])
         self._dec_saved = sv
         return mel_tm, stop_tm, al1, al2, sa_P
 
@@ -527,7 +540,7 @@ class TacotronEngine:
             O.softsign_bwd(sv["sp_pre"], dsp, dsp_pre)
             self._dspk_pre = dsp_pre
             relu0 = self.buf("dec.relu0", (Rd, P0))
-            O.linear(sv["dec_in"], p["dec.prenet0.W0"], relu0, bias=p["dec.prenet0.b0"], act="relu")
+            self.lin(sv["dec_in"], "dec.prenet0.W0", relu0, bias=p["dec.prenet0.b0"], act="relu")
             dz00 = self.buf("dec.dz00", (Rd, P0))
             O.act_bwd(relu0, dh0, dz00, "relu")
             O.linear_dw(sv["dec_in"], dz00, g["dec.prenet0.W0"], Rd, d.dec_in, P0)
@@ -588,6 +601,7 @@ class TacotronEngine:
         O.grad_sumsq(self.ps.grad, self._sumsq)
         O.adam_clip(self.ps.flat, self.ps.grad, self.ps.adam_m, self.ps.adam_v, self._sumsq, 1.0 / world_size, 1.0, lr,
                     hp.adam_beta1, hp.adam_beta2, hp.adam_eps, self.global_step + 1)
+        self.refresh_transposed()
         self.global_step += 1
         return lr
 

@@ -79,6 +79,7 @@ class _TacotronEstimator:
         ps.flat.copy_(st["flat"]); ps.adam_m.copy_(st["adam_m"]); ps.adam_v.copy_(st["adam_v"])
         ps.bn_mean_flat.copy_(st["bn_mean"]); ps.bn_var_flat.copy_(st["bn_var"])
         self.engine.global_step = int(st["global_step"])
+        self.engine.refresh_transposed()
 
     # ---- model_fn (models.py:278 / :23)
     def model_fn(self, features, labels, mode, params=None, masks=None) -> EstimatorSpec:

@@ -180,6 +180,22 @@ def transpose(x, rows, cols, y):
     _count()
 
 
+def transpose_batched(src, dst, desc, n):
+    check(load().satk_transpose_batched(C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), C.c_void_p(desc.data_ptr()), n,
+                                        C.c_void_p(stream_ptr())), "satk_transpose_batched")
+    _count()
+
+
+def linear_t(x: torch.Tensor, Wt: torch.Tensor, out: torch.Tensor, rows: int, K: int, N: int, *, ldw: int, k_off=0, lda=None,
+             a_off=0, bias=None, act=None, residual=None, keep_mask=None, keep_scale=1.0, ldc=None, c_off=0) -> torch.Tensor:
+    """out[rows, N] = epi(x[rows, K] @ W[k_off:k_off+K, :N] + bias) with the weight given TRANSPOSED: Wt is [N, ldw]
+    (K-contiguous) — the operand layout of the tcgen05 tile."""
+    gemm(x, Wt, out, rows, N, K, lda=lda or K, ldb=ldw, ldc=ldc or N, transB=True, b_off=k_off, a_off=a_off, c_off=c_off,
+         bias=bias, act=act, residual=residual, ldres=(residual.shape[-1] if residual is not None else 0),
+         keep_mask=keep_mask, keep_scale=keep_scale)
+    return out
+
+
 def mask_rows(x, lengths, B, T, Cc, time_major, y):
     check(load().satk_mask_rows(C.c_void_p(x.data_ptr()), C.c_void_p(lengths.data_ptr()), B, T, Cc, int(time_major),
                                 C.c_void_p(y.data_ptr()), C.c_void_p(stream_ptr())), "satk_mask_rows")

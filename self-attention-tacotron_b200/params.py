@@ -249,6 +249,18 @@ class ParamStore:
         self.adam_v = torch.zeros(off, device=device, dtype=dtype)
         self.p = self._views(self.flat)
         self.g = self._views(self.grad)
+        # K-contiguous ("transposed") copy of every matrix: [..., in, out] -> [..., out, in]; the layout the tcgen05
+        # GEMM tile wants for x.W products.  Refreshed by the engine after each optimiser step (one batched launch).
+        self.flat_t = torch.zeros(off, device=device, dtype=dtype)
+        self.pt = {n: self.flat_t[o:o + _numel(s)].view(s[:-2] + (s[-1], s[-2])) for n, (o, s) in self.offsets.items() if len(s) >= 2}
+        desc = []
+        for n, (o, s) in self.offsets.items():
+            if len(s) >= 2:
+                per = s[-2] * s[-1]
+                for i in range(_numel(s[:-2])):
+                    desc += [o + i * per, s[-2], s[-1]]
+        self.t_desc = torch.tensor(desc, dtype=torch.int32, device=device)
+        self.t_count = len(desc) // 3
         # BN moving statistics: one flat buffer per kind, same ordering as bn_names() (bank layers adjacent)
         self.bn: Dict[str, torch.Tensor] = {}
         tot = sum(c for _, c in bn_names(d))

@@ -36,6 +36,35 @@ def test_gemm_variants(engine):
         _close(C2, ref, 2e-5, "gemm split-k accumulate")
 
 
+def test_gemm_tensor_core_tile():
+    """tcgen05 3xTF32 tile (engine 2) against fp64: plain, epilogue, split-K and tapped (conv) products.
+    Tolerance 1e-7 * K relative: the tensor core accumulates with truncation (measured ~6e-8 * K), not IEEE fp32."""
+    O = _O()
+    g = torch.Generator().manual_seed(7)
+    for (M, N, K) in ((128, 128, 32), (300, 200, 160), (4736, 224, 256), (1000, 1024, 544), (130, 48, 36)):
+        A, Bt = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+        bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+        ref = (torch.tanh(A.double() @ Bt.double().t() + bias.double()) + res.double()).float()
+        C = torch.empty(M, N, device="cuda")
+        O.gemm(A.cuda(), Bt.cuda(), C, M, N, K, lda=K, ldb=K, ldc=N, transB=True, bias=bias.cuda(), act="tanh", residual=res.cuda(),
+               ldres=N, engine=2)
+        _close(C, ref, max(1e-5, 1e-7 * K), f"tc gemm {M}x{N}x{K}")
+        C2 = torch.randn(M, N, generator=g).cuda()
+        ref2 = (C2.cpu().double() + 0.5 * (A.double() @ Bt.double().t())).float()
+        O.gemm(A.cuda(), Bt.cuda(), C2, M, N, K, lda=K, ldb=K, ldc=N, transB=True, alpha=0.5, split_k=2, engine=2)
+        _close(C2, ref2, max(1e-5, 1e-7 * K), f"tc gemm split-k {M}x{N}x{K}")
+    # time-major conv: x [T,B,Cin], transposed taps Wt [k,Cout,Cin]
+    T, Bb, Cin, Cout, k = 40, 4, 128, 128, 5
+    x, W = torch.randn(T, Bb, Cin, generator=g), torch.randn(k, Cin, Cout, generator=g) * 0.1
+    ref = OR.conv1d_same(x.transpose(0, 1).double(), W.double()).transpose(0, 1).reshape(T * Bb, Cout).float()
+    Wt = W.transpose(1, 2).contiguous().cuda()
+    y = torch.empty(T * Bb, Cout, device="cuda")
+    pl = (k - 1) // 2
+    O.gemm(x.cuda(), Wt, y, T * Bb, Cout, Cin, lda=Cin, ldb=Cin, ldc=Cout, transB=True, taps=k, shift0=-pl * Bb, tap_dir=Bb,
+           sBtap=Cin * Cout, engine=2)
+    _close(y, ref, 1e-7 * Cin * k, "tc conv")
+
+
 def test_gemm_time_major_conv_and_grads():
     O = _O()
     g = torch.Generator().manual_seed(1)

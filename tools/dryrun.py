@@ -57,7 +57,7 @@ def install():
     for name in ["colsum_acc", "embedding_fwd", "embedding_bwd", "bn_stats", "bn_apply", "bn_bwd", "highway_fwd", "highway_bwd",
                  "act_bwd", "add", "axpy", "transpose", "mask_rows", "softsign_fwd", "softsign_bwd", "add_rowvec_tb",
                  "sum_over_t", "bernoulli_mask", "softmax_fwd", "softmax_bwd", "teacher_inputs", "losses", "grad_sumsq",
-                 "adam_clip", "lstm_seq_fwd", "lstm_seq_bwd", "attn_rnn_fwd", "attn_rnn_bwd"]:
+                 "adam_clip", "transpose_batched", "lstm_seq_fwd", "lstm_seq_bwd", "attn_rnn_fwd", "attn_rnn_bwd"]:
         setattr(O, name, any_ok)
     real_desc = O.attn_rnn_desc
 
@@ -79,6 +79,7 @@ def run(cfg, B, Tt, Tm, overrides=None):
     eng.global_step = 0
     eng._sumsq = torch.zeros(1)
     eng.timers = None
+    eng.refresh_transposed()
     f, l = satk.synthetic_batch(hp, B, Tt, Tm)
     for training in (False, True):
         eng.forward(f, l, training)
