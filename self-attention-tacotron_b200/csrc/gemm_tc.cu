@@ -24,6 +24,7 @@ constexpr int TILE_BYTES = BM * BK * 4;         // 16 KB (A and B tiles have the
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;     // A_hi(raw) | A_lo | B_hi(raw) | B_lo
 constexpr int NTHREADS = 256;
 constexpr int XFORM_THREADS = 192;              // warps 2..7
+constexpr int XFORM_WARPS = 6;
 constexpr int TMEM_COLS = 128;
 
 struct Params {
@@ -96,7 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       cl::mbar_init(&full_bar[s], 1);
-      cl::mbar_init(&xform_bar[s], XFORM_THREADS);
+      cl::mbar_init(&xform_bar[s], XFORM_WARPS);
       cl::mbar_init(&empty_bar[s], 1);
     }
     cl::mbar_init(&accum_bar, 1);
@@ -167,7 +168,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         *lo = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
       }
       cl::fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&xform_bar[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xform_bar[s]);
     }
   }
 
@@ -176,7 +178,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     cl::mbar_wait(&accum_bar, 0);
     tc_fence_after();
     const int q = warp - 4;
-    const int m = m0 + q * 32 + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -190,23 +191,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < p.M && iters > 0) {
+      // stage the 32x32 block of this warp in shared memory (the operand ring is idle now), then write rows coalesced
+      float* stg = reinterpret_cast<float*>(smem + (smem_base - cl::smem_u32(smem))) + q * (32 * 33);
+      __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + c0 + j;
-          if (n < p.N) {
-            float v = p.alpha * __uint_as_float(r[j]);
-            float* cp = p.C + (long long)m * p.ldc + n;
-            if (p.split_k > 1) {
-              atomicAdd(cp, v);
-            } else {
-              if (p.bias) v += __ldg(p.bias + n);
-              v = apply_act(v, p.act);
-              if (p.keep_mask) v = p.keep_mask[(long long)m * p.N + n] ? v * p.keep_scale : 0.0f;
-              if (p.residual) v += __ldg(p.residual + (long long)m * p.ldres + n);
-              if (p.beta != 0.0f) v += p.beta * (*cp);
-              *cp = v;
-            }
+      for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;
+      if (iters > 0 && n < p.N) {
+        const float bias = (p.bias && p.split_k == 1) ? __ldg(p.bias + n) : 0.f;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int mm = m0 + q * 32 + rr;
+          if (mm >= p.M) break;
+          float v = p.alpha * stg[rr * 33 + lane];
+          float* cp = p.C + (long long)mm * p.ldc + n;
+          if (p.split_k > 1) {
+            atomicAdd(cp, v);
+          } else {
+            v = apply_act(v + bias, p.act);
+            if (p.keep_mask) v = p.keep_mask[(long long)mm * p.N + n] ? v * p.keep_scale : 0.0f;
+            if (p.residual) v += __ldg(p.residual + (long long)mm * p.ldres + n);
+            if (p.beta != 0.0f) v += p.beta * (*cp);
+            *cp = v;
           }
         }
       }
@@ -277,6 +284,17 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   p.keep_mask = d->keep_mask; p.keep_scale = d->keep_scale;
   p.split_k = d->split_k < 1 ? 1 : d->split_k;
   const int kblocks = (d->K + BK - 1) / BK;
+  const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);
+  const bool linear_epi = !d->bias && d->act == 0 && !d->residual && !d->keep_mask && d->beta == 0.0f;
+  if (p.split_k == 1 && linear_epi && tiles < 74 && kblocks * taps >= 16) {
+    // too few tiles for 148 SMs: split K, accumulate with atomics into a zeroed C
+    int sk = (148 + tiles - 1) / tiles;
+    if (sk > kblocks / 4) sk = kblocks / 4;
+    if (sk > 1) {
+      SATK_CUDA(cudaMemset2DAsync(d->C, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, st));
+      p.split_k = sk;
+    }
+  }
   if (p.split_k > kblocks) p.split_k = kblocks;
   if (d->split_k > 1 && p.split_k == 1) p.beta = 1.0f;   // split-K semantics = accumulate onto C
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
