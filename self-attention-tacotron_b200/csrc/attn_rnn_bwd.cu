@@ -1,37 +1,51 @@
 // Attention-RNN backward (BPTT through LSTM-1 + attention mechanisms), one launch for all Td steps.
 // Same cluster geometry as the forward kernel (16 CTAs own 4 utterances).  Per step, descending t:
 //   BA1  total d(ctx) = external + recurrent carry; partial d(weights) = dctx . values^T over this
-//        CTA's value columns                                  -> 4 CTAs of the utterance   [barrier 1]
-//   BA2  forward-attention recursion + softmax backward (one warp per mechanism); energy backward
-//        over this CTA's score channels (recomputes tanh): dkeys (smem accumulators), dq slice,
-//        d(location layer/conv), partial d(state a_{t-1})     -> dq to all CTAs, dstate to 4 [barrier 2]
-//   BB   d(out1) = external + dq . Wq^T (unit owners); LSTM cell backward; d(gates)
-//                                                              -> all CTAs                 [barrier 3]
+//        CTA's value columns                                  -> 3 sibling CTAs of the utterance  [W]
+//   BA2  forward-attention recursion + softmax backward (block-parallel); energy backward over this
+//        CTA's score channels (recomputes tanh): dkeys (smem accumulators), dq slice,
+//        d(location layer/conv), partial d(state a_{t-1})     -> dq to all CTAs [Q], dstate to siblings [W]
+//   BB   d(out1) = external + dq . Wq^T (unit owners); LSTM cell backward; d(gates) -> all CTAs      [G]
 //   BC   d(ctx, h)(t-1) = d(gates) . Wrec^T — each CTA owns 34 rows of Wrec (32 in registers, 2 in
-//        shared memory)                                        -> owners of ctx columns / units [barrier 4]
+//        shared memory)                                        -> owners of ctx columns / units    [C]
+// [X] = mbarrier transaction barrier completed by st.async / bulk DSMEM copies (cluster_sync.cuh); there is no
+// cluster-wide barrier inside the loop.  Global inputs arrive through cp.async rings two steps ahead; global
+// outputs are staged in shared memory and written by warps that issue no exchange traffic.
 // Weight gradients that are dense over time (dWrec, dWq, dW_memory, dvalues) are NOT computed here:
 // the kernel saves d(gates), dq and the total d(ctx) and the caller runs plain GEMMs over all steps.
 #include "attn_rnn.cuh"
+#include "cluster_sync.cuh"
 
 namespace satk {
 namespace arnn {
 
+using cl::cp_async4;
+using cl::cp_async_commit;
+using cl::cp_async_wait;
+using cl::st_async_v4;
+
+constexpr int RINGB = 4;   // ring slots (time-indexed)
+constexpr int PFDB = 2;    // prefetch distance (steps)
+
 template <bool HAS2>
 struct BwdSmem {
   using D = Dims<HAS2>;
-  int TtP, Tt8;
-  float *keyS, *valS, *dkeyS, *WqU, *dgbuf /* aliases stageW */, *WragS, *fS, *dfS, *Wfs, *wconv, *bconv, *vs, *qs, *aprev,
-      *aS, *alphaPrevS, *alphaS, *a2S, *dwpart, *deS, *dstate_part, *dalpha_carry, *dmixS, *dctx_in, *dctxS, *dqB, *dh_in,
-      *dout1S, *stageQ;
+  int TtP, Tt8, Tt4;
+  float *keyS, *valS, *dkeyS, *WqU, *dgx /* aliases stageW */, *WragS, *fS, *dfS, *Wfs, *wconv, *bconv, *vs, *aprev, *alphaPrevS,
+      *dwpart, *deS, *dstate_part, *dstate_own, *dalpha_carry, *dmixS, *dctx_in, *dctxS, *dqB, *dqS, *dh_in, *dout1S, *stageQ,
+      *bcpart, *red, *ringA, *ringB, *save_dg;
+  uint8_t* mk_ring;
+  uint64_t* bars;  // [0..1] W, [2..3] Q, [4..5] G, [6..7] C
   __host__ __device__ size_t carve(float* base, int Tt, int stage_floats) {
     TtP = tt_pad(Tt);
     Tt8 = (Tt + 7) / 8 * 8;
+    Tt4 = (Tt + 3) & ~3;
     float* p = base;
     keyS = p; p += (size_t)Tt8 * KS;
     valS = p; p += (size_t)Tt8 * KS;
     dkeyS = p; p += (size_t)Tt8 * KS;
     WqU = p; p += UH * 256;
-    dgbuf = p; p += (stage_floats > 4 * H * BG) ? stage_floats : 4 * H * BG;  // d(gates) buffer, aliased by the dWf staging area
+    dgx = p; p += (stage_floats > 4 * H * BG) ? stage_floats : 4 * H * BG;  // d(gates) [row][unit][gate]; aliased by the dWf staging
     WragS = p; p += HAS2 ? 2 * 4 * H : 0;
     fS = p; p += (size_t)TtP * MAXF;
     dfS = p; p += (size_t)(TtP + 2 * HALO) * MAXF;
@@ -39,32 +53,56 @@ struct BwdSmem {
     wconv = p; p += MAXK * MAXF;
     bconv = p; p += MAXF;
     vs = p; p += QC;
-    qs = p; p += QC;
     aprev = p; p += TtP + 2 * HALO;
-    aS = p; p += TtP;
     alphaPrevS = p; p += TtP + 8;
-    alphaS = p; p += TtP;
-    a2S = p; p += TtP;
     dwpart = p; p += 2 * 4 * (size_t)TtP;
     deS = p; p += 2 * (size_t)TtP;
     dstate_part = p; p += 2 * 4 * (size_t)TtP;
+    dstate_own = p; p += TtP;
     dalpha_carry = p; p += TtP;
     dmixS = p; p += TtP + 8;
     dctx_in = p; p += VC + 8;
     dctxS = p; p += VC + 8;
     dqB = p; p += BG * 256;
+    dqS = p; p += QC;
     dh_in = p; p += BG * UH;
     dout1S = p; p += BG * UH;
-    stageQ = p; p += 16 * QC;
+    stageQ = p; p += 16 * QC;              // also the BC partial-sum area (phase-disjoint)
+    bcpart = stageQ;
+    red = p; p += 2 * 2 * 8 + 16;          // block-group reduction scratch
+    ringA = p; p += RINGB * 3 * (size_t)TtP;               // soft1 / align1 / align2 of time tau
+    ringB = p; p += RINGB * (QC + VC + 8 + 6 * 64);        // q_save slice, external d(ctx) slice, pointwise inputs
+    save_dg = p; p += 64 * 4;
+    mk_ring = reinterpret_cast<uint8_t*>(p); p += RINGB * 2 * BG * UH / 4;
+    bars = reinterpret_cast<uint64_t*>(p); p += 2 * 8;
     return (size_t)(p - base) * sizeof(float);
   }
 };
+
+// sum of (x, y) over a 256-thread group (8 warps) through shared memory; all 256 threads must call it
+__device__ __forceinline__ void group_sum2(float& x, float& y, float* red, int wig, int lane, int barid) {
+  x = warp_sum(x);
+  y = warp_sum(y);
+  if (lane == 0) { red[wig] = x; red[8 + wig] = y; }
+  cl::named_bar_sync(barid, 256);
+  float sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sx += red[i]; sy += red[8 + i]; }
+  cl::named_bar_sync(barid, 256);
+  x = sx; y = sy;
+}
 
 template <bool HAS2, int AFT, int NP>
 __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn_bwd_desc dd) {
   using D = Dims<HAS2>;
   constexpr int A1Q = D::A1Q, NI1 = D::NI1, X2W = D::X2W, M2 = D::M2;
   constexpr int NCH = NI1 + (HAS2 ? 1 : 0);  // channels per lane (att1 + att2)
+  constexpr int VCW = HAS2 ? VC : 64;
+  constexpr int NATT = HAS2 ? 2 : 1;
+  constexpr int RB = QC + VC + 8 + 6 * 64;   // floats per ringB slot
+  constexpr uint32_t RX_Q = (uint32_t)(CS - 1) * (A1Q + (HAS2 ? 8 : 0)) * 4u;
+  constexpr uint32_t RX_G = (uint32_t)(CS - 1) * UH * BG * 4 * 4u;
+  constexpr uint32_t RX_C = (uint32_t)(VCW + UH * BG) * 4u;
   const satk_attn_rnn_fwd_desc& d = dd.f;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -78,14 +116,19 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
   BwdSmem<HAS2> S;
   constexpr int SW = NI1 * AFT;  // staging stride per (warp, channel lane)
   S.carve(smem_raw, Tt, 16 * 8 * SW);
-  const int TtP = S.TtP;
+  const int TtP = S.TtP, Tt4 = S.Tt4;
+  uint64_t* barW = S.bars;
+  uint64_t* barQ = S.bars + 2;
+  uint64_t* barG = S.bars + 4;
+  uint64_t* barC = S.bars + 6;
 
   const int ab = rank >> 2, cq = rank & 3;
   const int arow = b0 + ab;
   const bool arow_ok = arow < B;
   const int alen = arow_ok ? (int)d.lengths[arow] : 0;
   const int pl = d.att_kernel > 0 ? (d.att_kernel - 1) / 2 : 0;
-  const float u = 0.5f;
+  const float u_tr = 0.5f;
+  const bool loc = d.att_kernel > 0;
 
   // ---------------- one-time loads
   for (int i = tid; i < S.Tt8 * KS; i += NT) {
@@ -116,37 +159,51 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     }
   for (int i = tid; i < MAXF * QC; i += NT) {
     int f = i / QC, c = i % QC;
-    S.Wfs[i] = (f < d.att_filters && c < A1Q && d.att_kernel > 0) ? __ldg(d.loc_layer_w + (long long)f * d.A1 + cq * A1Q + c) : 0.f;
+    S.Wfs[i] = (f < d.att_filters && c < A1Q && loc) ? __ldg(d.loc_layer_w + (long long)f * d.A1 + cq * A1Q + c) : 0.f;
   }
   for (int i = tid; i < MAXK * MAXF; i += NT) {
     int k = i / MAXF, f = i % MAXF;
     S.wconv[i] = (k < d.att_kernel && f < d.att_filters) ? __ldg(d.loc_conv_w + k * d.att_filters + f) : 0.f;
   }
-  if (tid < MAXF) S.bconv[tid] = (tid < d.att_filters && d.att_kernel > 0) ? __ldg(d.loc_conv_b + tid) : 0.f;
+  if (tid < MAXF) S.bconv[tid] = (tid < d.att_filters && loc) ? __ldg(d.loc_conv_b + tid) : 0.f;
   if (tid < QC) {
     float v = 0.f;
     if (tid < A1Q) v = __ldg(d.v1 + cq * A1Q + tid);
     else if (HAS2) v = __ldg(d.v2 + cq * 8 + (tid - A1Q));
     S.vs[tid] = v;
+    S.dqS[tid] = 0.f;
   }
   for (int i = tid; i < TtP + 2 * HALO; i += NT) S.aprev[i] = 0.f;
   for (int i = tid; i < (TtP + 2 * HALO) * MAXF; i += NT) S.dfS[i] = 0.f;
   for (int i = tid; i < TtP * MAXF; i += NT) S.fS[i] = 0.f;
   for (int i = tid; i < 2 * 4 * TtP; i += NT) { S.dstate_part[i] = 0.f; S.dwpart[i] = 0.f; }
-  for (int i = tid; i < TtP; i += NT) { S.dalpha_carry[i] = 0.f; S.aS[i] = 0.f; S.alphaS[i] = 0.f; S.a2S[i] = 0.f; }
+  for (int i = tid; i < TtP; i += NT) { S.dalpha_carry[i] = 0.f; S.dstate_own[i] = 0.f; }
   for (int i = tid; i < TtP + 8; i += NT) { S.alphaPrevS[i] = 0.f; S.dmixS[i] = 0.f; }
   for (int i = tid; i < 2 * TtP; i += NT) S.deS[i] = 0.f;
+  for (int i = tid; i < RINGB * 3 * TtP; i += NT) S.ringA[i] = 0.f;
+  for (int i = tid; i < RINGB * RB; i += NT) S.ringB[i] = 0.f;
+  for (int i = tid; i < RINGB * 2 * BG * UH; i += NT) S.mk_ring[i] = 0;
   if (tid < VC + 8) { S.dctx_in[tid] = 0.f; S.dctxS[tid] = 0.f; }
   if (tid < BG * UH) { S.dh_in[tid] = 0.f; S.dout1S[tid] = 0.f; }
   for (int i = tid; i < BG * 256; i += NT) S.dqB[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 8; ++i) cl::mbar_init(&S.bars[i], 1);
+    cl::fence_mbar_init();
+  }
 
-  // ---------------- BC role: rows [32*rank, 32*rank+32) of Wrec in registers; thread = (kr, cs)
-  const int kr = tid >> 4, cs = tid & 15;
-  float wr[64];
+  // ---------------- BC role: rows [32*rank, 32*rank+32) of Wrec in registers.
+  // thread = (kq = tid & 63, output group og = tid >> 6): 4 rows x the source units congruent to kq mod 64 x 4 gates
+  const int kq = tid & 63, og = tid >> 6;
+  float wr[4][4][4];  // [i][row c][gate]
 #pragma unroll
-  for (int i = 0; i < 64; ++i) wr[i] = __ldg(d.Wrec + (long long)(32 * rank + kr) * (4 * H) + cs + 16 * i);
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4)
+        wr[i][c][g4] = __ldg(d.Wrec + (long long)(32 * rank + og * 4 + c) * (4 * H) + g4 * H + kq + 64 * i);
 
-  // ---------------- pointwise role
+  // ---------------- pointwise role (exchange-issuing warps: no global stores)
   const int pb = tid >> 4, pu = tid & 15;
   const int prow = b0 + pb;
   const bool prow_ok = (tid < 64) && prow < B;
@@ -154,53 +211,102 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
   float dc = 0.f, dh = 0.f;
 
   // ---------------- energy role
-  const int pg = warp * 4 + (lane >> 3), cl = lane & 7;
+  const int pg = warp * 4 + (lane >> 3), cl_ = lane & 7;
   float dv_acc[NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) dv_acc[i] = 0.f;
-  float dWf_acc = 0.f;     // thread (c = tid % 64 .. ) see below: tid < NI1*8*AFT owns (cl_, i_, f_)
-  float dwconv_acc = 0.f;  // thread 320 + (k*AFT + f)
-  float dbconv_acc = 0.f;  // thread 480 + f
+  float dWf_acc = 0.f;     // tid < NI1*8*AFT owns one (channel, filter) entry of d(location_features_layer)
+  float dwconv_acc = 0.f;  // tid in [256, 256 + att_kernel*AFT) owns one (k, f) entry of d(location conv kernel)
+  float dbconv_acc = 0.f;  // tid in [480, 480 + AFT)
 
   cluster.sync();
 
-  for (int t = Td - 1; t >= 0; --t) {
-    const int par = t & 1;
-    // ======================= BA1
-    if (arow_ok) {
-      if (tid < (HAS2 ? VC : 64)) {
-        const int k = (tid < 64) ? (cq * 64 + tid) : (M1 + cq * 8 + (tid - 64));
-        float* gp = dd.dx2 + ((long long)t * B + arow) * X2W + H + k;
-        float v = S.dctx_in[tid] + *gp;
-        *gp = v;  // total d(ctx) for the dense dvalues GEMM
-        S.dctxS[tid] = v;
+  // prefetch of the global inputs of time tau into ring slot tau % RINGB (always commits a group)
+  auto prefetch = [&](int tau) {
+    if (tau >= 0) {
+      const int slot = tau % RINGB;
+      if (arow_ok && tid < Tt) {
+        const long long oa = ((long long)tau * B + arow) * Tt + tid;
+        float* ra = S.ringA + (size_t)slot * 3 * TtP;
+        cp_async4(ra + tid, d.soft1 + oa);
+        cp_async4(ra + TtP + tid, d.align1 + oa);
+        if (HAS2) cp_async4(ra + 2 * TtP + tid, d.align2 + oa);
       }
-      const long long oa = ((long long)t * B + arow) * Tt;
-      for (int j = tid; j < TtP; j += NT) {
-        const bool in = j < Tt;
-        S.aS[j] = (in && d.soft1) ? __ldg(d.soft1 + oa + j) : 0.f;
-        S.alphaS[j] = in ? __ldg(d.align1 + oa + j) : 0.f;
-        if (HAS2) S.a2S[j] = in ? __ldg(d.align2 + oa + j) : 0.f;
-        float ap = 0.f, alp = (j == 0 && d.mode == 2) ? 1.f : 0.f;
-        if (t > 0 && in) {
-          if (d.soft1) ap = __ldg(d.soft1 + oa - (long long)B * Tt + j);
-          alp = __ldg(d.align1 + oa - (long long)B * Tt + j);
+      float* rb = S.ringB + (size_t)slot * RB;
+      if (arow_ok && tid >= 64 && tid < 64 + QC) {
+        const int qi = tid - 64;
+        if (qi < A1Q || HAS2) {
+          const int qcol = (qi < A1Q) ? (cq * A1Q + qi) : (d.A1 + cq * 8 + (qi - A1Q));
+          cp_async4(rb + qi, d.q_save + ((long long)tau * B + arow) * QT + qcol);
         }
-        S.aprev[HALO + j] = ap;
-        S.alphaPrevS[j] = alp;
       }
-      if (tid < QC) {
-        const int qcol = (tid < A1Q) ? (cq * A1Q + tid) : (d.A1 + cq * 8 + (tid - A1Q));
-        S.qs[tid] = (tid < A1Q || HAS2) ? __ldg(d.q_save + ((long long)t * B + arow) * QT + qcol) : 0.f;
+      if (arow_ok && tid >= 128 && tid < 128 + VCW) {
+        const int e = tid - 128;
+        const int k = (e < 64) ? (cq * 64 + e) : (M1 + cq * 8 + (e - 64));
+        cp_async4(rb + QC + e, dd.dx2 + ((long long)tau * B + arow) * X2W + H + k);
+      }
+      if (prow_ok) {
+        const long long o1 = ((long long)tau * B + prow) * H + pidx;
+        const long long o4 = ((long long)tau * B + prow) * (4 * H) + pidx;
+        float* rp = rb + QC + VC + 8 + tid;
+        cp_async4(rp + 0 * 64, d.gates + o4);
+        cp_async4(rp + 1 * 64, d.gates + o4 + H);
+        cp_async4(rp + 2 * 64, d.gates + o4 + 2 * H);
+        cp_async4(rp + 3 * 64, d.gates + o4 + 3 * H);
+        cp_async4(rp + 4 * 64, d.c_prev + o1);
+        cp_async4(rp + 5 * 64, dd.dx2 + ((long long)tau * B + prow) * X2W + pidx);
+        if ((pu & 3) == 0) {
+          uint8_t* mr = S.mk_ring + slot * 2 * BG * UH;
+          if (d.mask_c) cp_async4(mr + (0 * BG + pb) * UH + pu, d.mask_c + o1);
+          if (d.mask_h) cp_async4(mr + (1 * BG + pb) * UH + pu, d.mask_h + o1);
+        }
       }
     }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int i = 0; i <= PFDB; ++i) prefetch(Td - 1 - i);
+
+  PT_DECL
+#pragma unroll 1
+  for (int t = Td - 1; t >= 0; --t) {
+    const int u = Td - 1 - t, cur = u & 1, nxt = cur ^ 1;
+    const uint32_t par = (uint32_t)(u >> 1) & 1u;
+    PT(15)
+    prefetch(t - 1 - PFDB);
+    cp_async_wait<PFDB>();                       // time t and t-1 are resident
+    if (u > 0) cl::mbar_wait(&barC[cur], (uint32_t)((u - 1) >> 1) & 1u);   // recurrent carries of step t+1
+    if (tid == 0) {
+      const uint32_t rxw = 3u * NATT * (uint32_t)Tt4 * 4u + ((u > 0 && loc) ? 3u * (uint32_t)Tt4 * 4u : 0u);
+      cl::mbar_arrive_expect_tx(&barW[cur], rxw);
+      cl::mbar_arrive_expect_tx(&barQ[cur], RX_Q);
+      if (t > 0) cl::mbar_arrive_expect_tx(&barG[cur], RX_G);
+      if (t > 0) cl::mbar_arrive_expect_tx(&barC[nxt], RX_C);
+    }
+    __syncthreads();                             // ring contents (written by other threads' cp.async) visible
+    PT(0)
+    const float* rA = S.ringA + (size_t)(t % RINGB) * 3 * TtP;           // soft1[t], align1[t], align2[t]
+    const float* rAp = S.ringA + (size_t)((t + RINGB - 1) % RINGB) * 3 * TtP;   // time t-1
+    const float* rB = S.ringB + (size_t)(t % RINGB) * RB;
+    const float* aS = rA;
+    const float* alphaS = rA + TtP;
+    const float* a2S = rA + 2 * TtP;
+    const float* qs = rB;
+
+    // ======================= BA1
+    if (tid < VCW) {
+      const float v = S.dctx_in[tid] + rB[QC + tid];
+      S.dctxS[tid] = v;                          // total d(ctx); saved for the dense dvalues GEMM by the saver warps
+    }
+    for (int j = tid; j < TtP; j += NT) {
+      const bool in = j < Tt && t > 0;
+      S.aprev[HALO + j] = in ? rAp[j] : 0.f;
+      S.alphaPrevS[j] = in ? rAp[TtP + j] : ((j == 0 && d.mode == 2) ? 1.f : 0.f);
+    }
     __syncthreads();
-    if (arow_ok) {
+    {
       // partial d(weights): thread = (j = tid>>2 (+128 per pass), part = tid&3)
       const int part = tid & 3;
-      float* rw[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) rw[q] = cluster.map_shared_rank(S.dwpart, ab * 4 + q);
       for (int j0 = 0; j0 < Tt; j0 += 128) {
         const int j = j0 + (tid >> 2);
         float a1 = 0.f, a2 = 0.f;
@@ -208,9 +314,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           const float* vr = S.valS + j * KS;
 #pragma unroll
           for (int i = 0; i < 16; ++i) a1 = fmaf(S.dctxS[part * 16 + i], vr[part * 16 + i], a1);
-          if (HAS2) {
-            a2 = S.dctxS[64 + part * 2] * vr[64 + part * 2] + S.dctxS[64 + part * 2 + 1] * vr[64 + part * 2 + 1];
-          }
+          if (HAS2) a2 = S.dctxS[64 + part * 2] * vr[64 + part * 2] + S.dctxS[64 + part * 2 + 1] * vr[64 + part * 2 + 1];
         }
         a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
         a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
@@ -218,14 +322,13 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
           a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
         }
-        if (j < Tt) {
-          // lane `part` sends to CTA (ab, part)
-          rw[part][(0 * 4 + cq) * TtP + j] = a1;
-          if (HAS2) rw[part][(1 * 4 + cq) * TtP + j] = a2;
+        if (j < Tt && part == 0) {
+          S.dwpart[(0 * 4 + cq) * TtP + j] = a1;
+          if (HAS2) S.dwpart[(1 * 4 + cq) * TtP + j] = a2;
         }
       }
       // location features of this step (input: a_{t-1})
-      if (d.att_kernel > 0) {
+      if (loc) {
         for (int idx = tid; idx < Tt * AFT; idx += NT) {
           int j = idx / AFT, f = idx % AFT;
           float acc = S.bconv[f];
@@ -235,93 +338,70 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         }
       }
     }
-    cluster.sync();  // ---- barrier 1
-
-    // ======================= BA2: recursion / softmax backward
-    if (arow_ok && warp == 0) {
-      constexpr int MAXM = 8;
-      const int nm = TtP / 32;
-      float a[MAXM], dal[MAXM], mix[MAXM], dst[MAXM];
-      float S_ = 0.f, dot = 0.f;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          const int j = lane + 32 * m;
-          a[m] = S.aS[j];
-          float dw = S.dwpart[(0 * 4 + 0) * TtP + j] + S.dwpart[(0 * 4 + 1) * TtP + j] + S.dwpart[(0 * 4 + 2) * TtP + j] +
-                     S.dwpart[(0 * 4 + 3) * TtP + j];
-          dst[m] = S.dstate_part[(par * 4 + 0) * TtP + j] + S.dstate_part[(par * 4 + 1) * TtP + j] +
-                   S.dstate_part[(par * 4 + 2) * TtP + j] + S.dstate_part[(par * 4 + 3) * TtP + j];
-          if (t == Td - 1) dst[m] = 0.f;
-          if (d.mode == 2) {
-            dal[m] = dw + S.dalpha_carry[j];
-            const float apm1 = (j > 0) ? S.alphaPrevS[j - 1] : 0.f;
-            mix[m] = (1.f - u) * S.alphaPrevS[j] + u * apm1 + 1e-7f;
-            S_ += mix[m] * a[m];
-            dot += dal[m] * S.alphaS[j];
-          } else {
-            dal[m] = dw;
-          }
-        }
-      float da[MAXM];
-      if (d.mode == 2) {
-        S_ = warp_sum(S_);
-        dot = warp_sum(dot);
-        const float invS = 1.f / S_;
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m)
-          if (m < nm) {
-            const int j = lane + 32 * m;
-            const float dau = (j < alen) ? (dal[m] - dot) * invS : 0.f;
-            da[m] = dau * mix[m] + dst[m];
-            S.dmixS[j] = dau * a[m];
-          }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m)
-          if (m < nm) {
-            const int j = lane + 32 * m;
-            const float nx = (j + 1 < TtP) ? S.dmixS[j + 1] : 0.f;
-            S.dalpha_carry[j] = (1.f - u) * S.dmixS[j] + u * nx;  // adjoint of the shift (forward_attention.py:108-109)
-          }
-      } else {
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m)
-          if (m < nm) da[m] = dal[m] + dst[m];
-      }
-      float dot2 = 0.f;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) dot2 += da[m] * a[m];
-      dot2 = warp_sum(dot2);
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) S.deS[0 * TtP + lane + 32 * m] = a[m] * (da[m] - dot2);
+    cl::fence_proxy_async();
+    __syncthreads();
+    if (tid < 3 * NATT) {
+      const int att = tid / 3, q3 = tid % 3;
+      const int r4 = q3 + (q3 >= cq ? 1 : 0);
+      const uint32_t src = cl::smem_u32(&S.dwpart[(att * 4 + cq) * TtP]);
+      cl::bulk_copy_to_cta(cl::mapa(src, ab * 4 + r4), src, (uint32_t)Tt4 * 4u, cl::mapa(cl::smem_u32(&barW[cur]), ab * 4 + r4));
     }
-    if (HAS2 && arow_ok && warp == 1) {
-      constexpr int MAXM = 8;
-      const int nm = TtP / 32;
-      float a[MAXM], dw[MAXM];
-      float dot = 0.f;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          const int j = lane + 32 * m;
-          a[m] = S.a2S[j];
-          dw[m] = S.dwpart[(1 * 4 + 0) * TtP + j] + S.dwpart[(1 * 4 + 1) * TtP + j] + S.dwpart[(1 * 4 + 2) * TtP + j] +
-                  S.dwpart[(1 * 4 + 3) * TtP + j];
-          dot += dw[m] * a[m];
+    PT(1)
+    cl::mbar_wait(&barW[cur], par);
+    PT(2)
+
+    // ======================= BA2a: recursion / softmax backward, block-parallel (one position per thread)
+    if (tid >= 256) {
+      // attention 1: threads 256..511
+      const int j = tid - 256;
+      const bool in = j < TtP;
+      const float a = in ? aS[j] : 0.f;
+      float dw = 0.f, dst = 0.f;
+      if (in) {
+        dw = S.dwpart[(0 * 4 + 0) * TtP + j] + S.dwpart[(0 * 4 + 1) * TtP + j] + S.dwpart[(0 * 4 + 2) * TtP + j] + S.dwpart[(0 * 4 + 3) * TtP + j];
+        if (u > 0 && loc)
+          dst = S.dstate_part[(cur * 4 + 0) * TtP + j] + S.dstate_part[(cur * 4 + 1) * TtP + j] + S.dstate_part[(cur * 4 + 2) * TtP + j] +
+                S.dstate_part[(cur * 4 + 3) * TtP + j];
+      }
+      float da;
+      if (d.mode == 2) {
+        const float dal = in ? dw + S.dalpha_carry[j] : 0.f;
+        const float apm1 = (in && j > 0) ? S.alphaPrevS[j - 1] : 0.f;
+        const float mix = in ? ((1.f - u_tr) * S.alphaPrevS[j] + u_tr * apm1 + 1e-7f) : 0.f;
+        float s1 = mix * a, s2 = in ? dal * alphaS[j] : 0.f;
+        group_sum2(s1, s2, S.red, warp & 7, lane, 2);
+        const float dau = (in && j < alen) ? (dal - s2) / s1 : 0.f;
+        da = dau * mix + dst;
+        if (in) S.dmixS[j] = dau * a;
+      } else {
+        da = dw + dst;
+      }
+      float dot2 = da * a, dummy = 0.f;
+      group_sum2(dot2, dummy, S.red, warp & 7, lane, 2);
+      if (in) {
+        S.deS[0 * TtP + j] = a * (da - dot2);
+        if (d.mode == 2) {
+          const float nx = (j + 1 < TtP) ? S.dmixS[j + 1] : 0.f;
+          S.dalpha_carry[j] = (1.f - u_tr) * S.dmixS[j] + u_tr * nx;  // adjoint of the shift (forward_attention.py:108-109)
         }
-      dot = warp_sum(dot);
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) S.deS[1 * TtP + lane + 32 * m] = a[m] * (dw[m] - dot);
+      }
+    } else if (HAS2) {
+      // attention 2: threads 0..255
+      const int j = tid;
+      const bool in = j < TtP;
+      const float a = in ? a2S[j] : 0.f;
+      float dw = 0.f;
+      if (in) dw = S.dwpart[(1 * 4 + 0) * TtP + j] + S.dwpart[(1 * 4 + 1) * TtP + j] + S.dwpart[(1 * 4 + 2) * TtP + j] + S.dwpart[(1 * 4 + 3) * TtP + j];
+      float dot = dw * a, dummy = 0.f;
+      group_sum2(dot, dummy, S.red + 16, warp & 7, lane, 3);
+      if (in) S.deS[1 * TtP + j] = a * (dw - dot);
     }
     __syncthreads();
+    PT(3)
 
-    // ---- energy backward over this CTA's channels
-    float* stageW = S.dgbuf;  // aliased: d(gates) buffer is idle during BA2
-    if (arow_ok) {
+    // ======================= BA2b: energy backward over this CTA's channels
+    float* stageW = S.dgx;  // aliased: the d(gates) buffer is idle during BA2
+    {
       float fv[NP][AFT], dfp[NP][AFT], de1[NP], de2[NP];
       int jm[NP];
       bool jok[NP];
@@ -341,11 +421,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       float dq_acc[NCH];
 #pragma unroll
       for (int i = 0; i < NI1; ++i) {
-        const int c = cl + 8 * i;
+        const int c = cl_ + 8 * i;
         float wf[AFT], P[AFT];
 #pragma unroll
         for (int f = 0; f < AFT; ++f) { wf[f] = S.Wfs[f * QC + c]; P[f] = 0.f; }
-        const float qc = S.qs[c], vc = S.vs[c];
+        const float qc = qs[c], vc = S.vs[c];
         float dq = 0.f;
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
@@ -372,12 +452,12 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         }
         if (lane < 8) {
 #pragma unroll
-          for (int f = 0; f < AFT; ++f) stageW[(warp * 8 + cl) * SW + i * AFT + f] = P[f];
+          for (int f = 0; f < AFT; ++f) stageW[(warp * 8 + cl_) * SW + i * AFT + f] = P[f];
         }
       }
       if (HAS2) {
-        const int c = A1Q + cl;
-        const float qc = S.qs[c], vc = S.vs[c];
+        const int c = A1Q + cl_;
+        const float qc = qs[c], vc = S.vs[c];
         float dq = 0.f;
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
@@ -394,7 +474,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       for (int i = 0; i < NCH; ++i) {
         dq_acc[i] += __shfl_xor_sync(0xffffffffu, dq_acc[i], 8);
         dq_acc[i] += __shfl_xor_sync(0xffffffffu, dq_acc[i], 16);
-        if (lane < 8) S.stageQ[warp * QC + cl + 8 * i] = dq_acc[i];
+        if (lane < 8) S.stageQ[warp * QC + cl_ + 8 * i] = dq_acc[i];
       }
       // d(location features): reduce over the 8 channel lanes
 #pragma unroll
@@ -405,53 +485,47 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (cl == 0 && jok[m]) S.dfS[(HALO + jm[m]) * MAXF + f] = v;
+          if (cl_ == 0 && jok[m]) S.dfS[(HALO + jm[m]) * MAXF + f] = v;
         }
       }
     }
     __syncthreads();
-    if (arow_ok) {
+    PT(4)
+    {
       if (tid < QC) {
         float q = 0.f;
         if (tid < A1Q || HAS2) {
 #pragma unroll
           for (int w_ = 0; w_ < 16; ++w_) q += S.stageQ[w_ * QC + tid];
-          const int qcol = (tid < A1Q) ? (cq * A1Q + tid) : (d.A1 + cq * 8 + (tid - A1Q));
-          dd.dq[((long long)t * B + arow) * QT + qcol] = q;
-#pragma unroll 4
-          for (int r = 0; r < CS; ++r) {
-            float* rq = cluster.map_shared_rank(S.dqB, r);
-            rq[ab * 256 + qcol] = q;
-          }
         }
+        S.dqS[tid] = q;
+        const int qcol = (tid < A1Q) ? (cq * A1Q + tid) : (d.A1 + cq * 8 + (tid - A1Q));
+        if (tid < A1Q || HAS2) S.dqB[ab * 256 + qcol] = q;    // own copy
       }
-      if (d.att_kernel > 0) {
+      if (loc) {
         if (tid < NI1 * 8 * AFT) {
-          // thread owns (cl_, i_, f_) of d(location_features_layer)
-          const int cl_ = tid / SW, rem = tid % SW;
+          // thread owns (channel lane, i, f) of d(location_features_layer)
+          const int c8 = tid / SW, rem = tid % SW;
           float acc = 0.f;
 #pragma unroll
-          for (int w_ = 0; w_ < 16; ++w_) acc += stageW[(w_ * 8 + cl_) * SW + rem];
+          for (int w_ = 0; w_ < 16; ++w_) acc += stageW[(w_ * 8 + c8) * SW + rem];
           dWf_acc += acc;
         }
         // partial d(state a_{t-1}) = conv-transpose of d(location features)
         if (t > 0) {
-          float* rs[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rs[q] = cluster.map_shared_rank(S.dstate_part, ab * 4 + q);
-          for (int j = tid; j < Tt; j += NT) {
+          for (int j = tid; j < Tt4; j += NT) {
             float acc = 0.f;
-            for (int k = 0; k < d.att_kernel; ++k) {
-              const float* dfr = S.dfS + (HALO + j - k + pl) * MAXF;  // rows outside [0,Tt) are zero
+            if (j < Tt)
+              for (int k = 0; k < d.att_kernel; ++k) {
+                const float* dfr = S.dfS + (HALO + j - k + pl) * MAXF;  // rows outside [0,Tt) are zero
 #pragma unroll
-              for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f], S.wconv[k * MAXF + f], acc);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rs[q][((par ^ 1) * 4 + cq) * TtP + j] = acc;
+                for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f], S.wconv[k * MAXF + f], acc);
+              }
+            S.dstate_own[j] = acc;
+            S.dstate_part[(nxt * 4 + cq) * TtP + j] = acc;   // own contribution for step t-1
           }
         }
         if (tid >= 256 && tid - 256 < d.att_kernel * AFT) {
-          // thread owns (k, f) of d(location conv kernel)
           const int e = tid - 256, k = e / AFT, f = e % AFT;
           float acc = 0.f;
           for (int j = 0; j < Tt; ++j) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[(HALO + j) * MAXF + f], acc);
@@ -465,7 +539,30 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         }
       }
     }
-    cluster.sync();  // ---- barrier 2: dq, dstate parts published
+    cl::fence_proxy_async();
+    __syncthreads();
+    if (tid < 16) {
+      // dq slice -> every CTA (16-byte st.async per 4 columns)
+      const int nq4 = (A1Q + (HAS2 ? 8 : 0)) / 4;
+      if (tid < nq4) {
+        const int c4 = tid * 4;
+        const int qcol = (c4 < A1Q) ? (cq * A1Q + c4) : (d.A1 + cq * 8 + (c4 - A1Q));
+        const uint32_t dsta = cl::smem_u32(&S.dqB[ab * 256 + qcol]), bara = cl::smem_u32(&barQ[cur]);
+        const float q0 = S.dqS[c4], q1 = S.dqS[c4 + 1], q2 = S.dqS[c4 + 2], q3 = S.dqS[c4 + 3];
+#pragma unroll
+        for (int r = 0; r < CS; ++r)
+          if (r != rank) st_async_v4(cl::mapa(dsta, r), q0, q1, q2, q3, cl::mapa(bara, r));
+      }
+    } else if (tid >= 32 && tid < 35 && t > 0 && loc) {
+      const int q3 = tid - 32;
+      const int r4 = q3 + (q3 >= cq ? 1 : 0);
+      const uint32_t src = cl::smem_u32(S.dstate_own);
+      cl::bulk_copy_to_cta(cl::mapa(cl::smem_u32(&S.dstate_part[(nxt * 4 + cq) * TtP]), ab * 4 + r4), src, (uint32_t)Tt4 * 4u,
+                           cl::mapa(cl::smem_u32(&barW[nxt]), ab * 4 + r4));
+    }
+    PT(5)
+    cl::mbar_wait(&barQ[cur], par);
+    PT(6)
 
     // ======================= BB: d(out1), LSTM cell backward
     {
@@ -486,15 +583,14 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       float dgi = 0.f, dgj = 0.f, dgf = 0.f, dgo = 0.f;
       if (prow_ok) {
         dh += S.dh_in[pb * UH + pu];  // recurrent carry delivered by BC of step t+1
-        const long long o1 = ((long long)t * B + prow) * H + pidx;
-        const long long o4 = ((long long)t * B + prow) * (4 * H) + pidx;
-        const float gi = d.gates[o4], gj = d.gates[o4 + H], gf = d.gates[o4 + 2 * H], go = d.gates[o4 + 3 * H];
-        const float cp = d.c_prev[o1];
-        const float mc = d.mask_c ? (float)d.mask_c[o1] : (1.f - d.zc);
-        const float mh = d.mask_h ? (float)d.mask_h[o1] : (1.f - d.zh);
+        const float* rp = rB + QC + VC + 8 + tid;
+        const float gi = rp[0], gj = rp[64], gf = rp[128], go = rp[192], cp = rp[256], dx2o = rp[320];
+        const uint8_t* mr = S.mk_ring + (t % RINGB) * 2 * BG * UH;
+        const float mc = d.mask_c ? (float)mr[(0 * BG + pb) * UH + pu] : (1.f - d.zc);
+        const float mh = d.mask_h ? (float)mr[(1 * BG + pb) * UH + pu] : (1.f - d.zh);
         const float c_new = gf * cp + gi * gj;
         const float tc = ftanh(c_new);
-        const float dout1 = dd.dx2[((long long)t * B + prow) * X2W + pidx] + S.dout1S[pb * UH + pu];
+        const float dout1 = dx2o + S.dout1S[pb * UH + pu];
         const float dh_new = dout1 + mh * dh;
         dh = (1.f - mh) * dh;
         const float dcn = mc * dc + dh_new * go * (1.f - tc * tc);
@@ -503,86 +599,134 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         dgj = dcn * gi * (1.f - gj * gj);
         dgf = dcn * cp * gf * (1.f - gf);
         dc = (1.f - mc) * dc + dcn * gf;
-        dd.dgates[o4] = dgi; dd.dgates[o4 + H] = dgj; dd.dgates[o4 + 2 * H] = dgf; dd.dgates[o4 + 3 * H] = dgo;
       }
-#pragma unroll 4
-      for (int r = 0; r < CS; ++r) {
-        float* base = cluster.map_shared_rank(S.dgbuf, r);
-        base[(0 * H + pidx) * BG + pb] = dgi;
-        base[(1 * H + pidx) * BG + pb] = dgj;
-        base[(2 * H + pidx) * BG + pb] = dgf;
-        base[(3 * H + pidx) * BG + pb] = dgo;
+      float* slot = &S.dgx[((size_t)pb * H + pidx) * 4];
+      *reinterpret_cast<float4*>(slot) = make_float4(dgi, dgj, dgf, dgo);
+      *reinterpret_cast<float4*>(&S.save_dg[tid * 4]) = make_float4(dgi, dgj, dgf, dgo);
+      if (t > 0) {
+        const uint32_t dsta = cl::smem_u32(slot), bara = cl::smem_u32(&barG[cur]);
+#pragma unroll
+        for (int r = 0; r < CS; ++r)
+          if (r != rank) st_async_v4(cl::mapa(dsta, r), dgi, dgj, dgf, dgo, cl::mapa(bara, r));
       }
     }
-    cluster.sync();  // ---- barrier 3: d(gates) published
+    __syncthreads();
+    PT(7)
+    if (tid >= 256) {
+      // saver warps: d(gates), dq slice and total d(ctx) of step t -> global memory
+      const int e = tid - 256;
+      if (e < 64) {
+        const int sb = e >> 4, su = e & 15;
+        if (b0 + sb < B) {
+          const long long o4 = ((long long)t * B + b0 + sb) * (4 * H) + rank * UH + su;
+          const float4 v = *reinterpret_cast<const float4*>(&S.save_dg[e * 4]);
+          dd.dgates[o4] = v.x; dd.dgates[o4 + H] = v.y; dd.dgates[o4 + 2 * H] = v.z; dd.dgates[o4 + 3 * H] = v.w;
+        }
+      } else if (e < 64 + QC) {
+        const int qi = e - 64;
+        if (arow_ok && (qi < A1Q || HAS2)) {
+          const int qcol = (qi < A1Q) ? (cq * A1Q + qi) : (d.A1 + cq * 8 + (qi - A1Q));
+          dd.dq[((long long)t * B + arow) * QT + qcol] = S.dqS[qi];
+        }
+      } else if (e < 64 + QC + VCW) {
+        const int ci = e - 64 - QC;
+        if (arow_ok) {
+          const int k = (ci < 64) ? (cq * 64 + ci) : (M1 + cq * 8 + (ci - 64));
+          dd.dx2[((long long)t * B + arow) * X2W + H + k] = S.dctxS[ci];
+        }
+      }
+    }
+    if (t == 0) break;
+    cl::mbar_wait(&barG[cur], par);
+    PT(8)
 
     // ======================= BC: d(ctx, h)(t-1) = d(gates) . Wrec^T
-    if (t > 0) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    {
+      float acc[16];
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const float4 g4 = *reinterpret_cast<const float4*>(S.dgbuf + (cs + 16 * i) * BG);
-        a0 = fmaf(wr[i], g4.x, a0);
-        a1 = fmaf(wr[i], g4.y, a1);
-        a2 = fmaf(wr[i], g4.z, a2);
-        a3 = fmaf(wr[i], g4.w, a3);
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int b = 0; b < BG; ++b) {
+          const float4 g4 = *reinterpret_cast<const float4*>(&S.dgx[((size_t)b * H + kq + 64 * i) * 4]);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float a = acc[c * 4 + b];
+            a = fmaf(wr[i][c][0], g4.x, a);
+            a = fmaf(wr[i][c][1], g4.y, a);
+            a = fmaf(wr[i][c][2], g4.z, a);
+            a = fmaf(wr[i][c][3], g4.w, a);
+            acc[c * 4 + b] = a;
+          }
+        }
+      }
+      const float v = cl::reduce_scatter16(acc, lane);   // lane L: row og*4 + ((L>>2)&3), batch row L&3
+      S.bcpart[(((kq >> 4) & 3) * 32 + og * 4 + ((lane >> 2) & 3)) * 4 + (lane & 3)] = v;
+    }
+    if (HAS2 && warp == 15) {
+      // ragged rows 512 + 2*rank + {0,1} (hidden units 224..255), weights in shared memory
+      float ragged[4] = {0.f, 0.f, 0.f, 0.f};
+      const int rr = lane >> 4, c16 = lane & 15;
+      const float* wrow = S.WragS + rr * 4 * H;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int un = c16 + 16 * i;
+#pragma unroll
+        for (int b = 0; b < BG; ++b) {
+          const float4 g4 = *reinterpret_cast<const float4*>(&S.dgx[((size_t)b * H + un) * 4]);
+          ragged[b] = fmaf(wrow[0 * H + un], g4.x, ragged[b]);
+          ragged[b] = fmaf(wrow[1 * H + un], g4.y, ragged[b]);
+          ragged[b] = fmaf(wrow[2 * H + un], g4.z, ragged[b]);
+          ragged[b] = fmaf(wrow[3 * H + un], g4.w, ragged[b]);
+        }
       }
 #pragma unroll
       for (int o = 1; o <= 8; o <<= 1) {
-        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        a3 += __shfl_xor_sync(0xffffffffu, a3, o);
-      }
-      if (cs < 4) {
-        const float v = (cs == 0) ? a0 : (cs == 1) ? a1 : (cs == 2) ? a2 : a3;
-        const int k = 32 * rank + kr;  // row of Wrec, < 512
-        const int bb = cs;
-        if (k < M1) {
-          float* dst = cluster.map_shared_rank(S.dctx_in, bb * 4 + (k >> 6));
-          dst[k & 63] = v;
-        } else if (k < M1 + M2) {
-          float* dst = cluster.map_shared_rank(S.dctx_in, bb * 4 + ((k - M1) >> 3));
-          dst[64 + ((k - M1) & 7)] = v;
-        } else {
-          const int un = k - (M1 + M2);
-          float* dst = cluster.map_shared_rank(S.dh_in, un >> 4);
-          dst[bb * UH + (un & 15)] = v;
-        }
-      }
-      if (HAS2 && warp == 15) {
-        // ragged rows 512 + 2*rank + {0,1} (hidden units 224..255), weights in shared memory
-        const int rr = lane >> 4, c16 = lane & 15;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-        const float* wrow = S.WragS + rr * 4 * H;
-#pragma unroll 8
-        for (int i = 0; i < 64; ++i) {
-          const float wv = wrow[c16 + 16 * i];
-          const float4 g4 = *reinterpret_cast<const float4*>(S.dgbuf + (c16 + 16 * i) * BG);
-          r0 = fmaf(wv, g4.x, r0);
-          r1 = fmaf(wv, g4.y, r1);
-          r2 = fmaf(wv, g4.z, r2);
-          r3 = fmaf(wv, g4.w, r3);
-        }
 #pragma unroll
-        for (int o = 1; o <= 8; o <<= 1) {
-          r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-          r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-          r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-          r3 += __shfl_xor_sync(0xffffffffu, r3, o);
-        }
-        if (c16 < 4) {
-          const float v = (c16 == 0) ? r0 : (c16 == 1) ? r1 : (c16 == 2) ? r2 : r3;
-          const int un = (512 + 2 * rank + rr) - (M1 + M2);
-          float* dst = cluster.map_shared_rank(S.dh_in, un >> 4);
-          dst[c16 * UH + (un & 15)] = v;
-        }
+        for (int b = 0; b < BG; ++b) ragged[b] += __shfl_xor_sync(0xffffffffu, ragged[b], o);
+      }
+      if (c16 < 4) {
+        const float v = (c16 == 0) ? ragged[0] : (c16 == 1) ? ragged[1] : (c16 == 2) ? ragged[2] : ragged[3];
+        const int un = (512 + 2 * rank + rr) - (M1 + M2);
+        const int dst = un >> 4;
+        cl::st_async_f32(cl::mapa(cl::smem_u32(&S.dh_in[c16 * UH + (un & 15)]), dst), v, cl::mapa(cl::smem_u32(&barC[nxt]), dst));
       }
     }
-    cluster.sync();  // ---- barrier 4: recurrent carries delivered
+    __syncthreads();
+    if (tid < 128) {
+      // finalise: thread = (batch row b = tid >> 5, row k = tid & 31) -> 4 consecutive rows travel as one st.async.v4
+      const int b = tid >> 5, k = tid & 31;
+      const float v = S.bcpart[(0 * 32 + k) * 4 + b] + S.bcpart[(1 * 32 + k) * 4 + b] + S.bcpart[(2 * 32 + k) * 4 + b] +
+                      S.bcpart[(3 * 32 + k) * 4 + b];
+      const int l4 = lane & ~3;
+      const float v0 = __shfl_sync(0xffffffffu, v, l4), v1 = __shfl_sync(0xffffffffu, v, l4 + 1);
+      const float v2 = __shfl_sync(0xffffffffu, v, l4 + 2), v3 = __shfl_sync(0xffffffffu, v, l4 + 3);
+      if ((lane & 3) == 0) {
+        const int kg = 32 * rank + k;   // row of Wrec (< 512)
+        int dst;
+        uint32_t addr;
+        if (kg < M1) {
+          dst = b * 4 + (kg >> 6);
+          addr = cl::smem_u32(&S.dctx_in[kg & 63]);
+        } else if (kg < M1 + M2) {
+          dst = b * 4 + ((kg - M1) >> 3);
+          addr = cl::smem_u32(&S.dctx_in[64 + ((kg - M1) & 7)]);
+        } else {
+          const int un = kg - (M1 + M2);
+          dst = un >> 4;
+          addr = cl::smem_u32(&S.dh_in[b * UH + (un & 15)]);
+        }
+        st_async_v4(cl::mapa(addr, dst), v0, v1, v2, v3, cl::mapa(cl::smem_u32(&barC[nxt]), dst));
+      }
+    }
+    PT(9)
   }
+  PT_FLUSH(Td)
+  cp_async_wait<0>();
 
   // ---------------- epilogue: flush accumulators
+  __syncthreads();
   if (arow_ok) {
     for (int i = tid; i < Tt * QC; i += NT) {
       const int j = i / QC, c = i % QC;
@@ -596,16 +740,16 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       v += __shfl_xor_sync(0xffffffffu, v, 8);
       v += __shfl_xor_sync(0xffffffffu, v, 16);
       if (lane < 8) {
-        const int c = cl + 8 * i;
+        const int c = cl_ + 8 * i;
         if (i < NI1) atomicAdd(dd.dv1 + cq * A1Q + c, v);
-        else atomicAdd(dd.dv2 + cq * 8 + cl, v);
+        else atomicAdd(dd.dv2 + cq * 8 + cl_, v);
       }
     }
-    if (d.att_kernel > 0) {
+    if (loc) {
       if (tid < NI1 * 8 * AFT) {
-        const int cl_ = tid / SW, rem = tid % SW;
+        const int c8 = tid / SW, rem = tid % SW;
         const int i_ = rem / AFT, f_ = rem % AFT;
-        if (f_ < d.att_filters) atomicAdd(dd.dloc_layer_w + (long long)f_ * d.A1 + cq * A1Q + cl_ + 8 * i_, dWf_acc);
+        if (f_ < d.att_filters) atomicAdd(dd.dloc_layer_w + (long long)f_ * d.A1 + cq * A1Q + c8 + 8 * i_, dWf_acc);
       }
       if (tid >= 256 && tid - 256 < d.att_kernel * AFT) {
         const int e = tid - 256, k = e / AFT, f = e % AFT;
@@ -614,6 +758,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       if (tid >= 480 && tid < 480 + AFT && (tid - 480) < d.att_filters) atomicAdd(dd.dloc_conv_b + (tid - 480), dbconv_acc);
     }
   }
+  cluster.sync();
 }
 
 template <bool HAS2>
