@@ -79,18 +79,7 @@ struct BwdSmem {
   }
 };
 
-// sum of (x, y) over a 256-thread group (8 warps) through shared memory; all 256 threads must call it
-__device__ __forceinline__ void group_sum2(float& x, float& y, float* red, int wig, int lane, int barid) {
-  x = warp_sum(x);
-  y = warp_sum(y);
-  if (lane == 0) { red[wig] = x; red[8 + wig] = y; }
-  cl::named_bar_sync(barid, 256);
-  float sx = 0.f, sy = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { sx += red[i]; sy += red[8 + i]; }
-  cl::named_bar_sync(barid, 256);
-  x = sx; y = sy;
-}
+using cl::group_sum2;
 
 template <bool HAS2, int AFT, int NP>
 __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn_bwd_desc dd) {

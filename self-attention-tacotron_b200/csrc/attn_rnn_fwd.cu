@@ -34,7 +34,7 @@ struct FwdSmem {
   using D = Dims<HAS2>;
   int TtP, Tt4;
   float *xrec, *gsm, *out1buf, *Wqs, *keyS, *valS, *fS, *Wfs, *wconv, *bconv, *vs, *qs, *qpart, *epart, *aprev, *alphaS,
-      *w1S, *w2S, *softS, *cpart, *ctxS, *save1, *xg_ring;
+      *w1S, *w2S, *softS, *cpart, *ctxS, *save1, *xg_ring, *red;
   uint8_t* mk_ring;
   uint64_t* bars;   // [0..1] X, [2..3] O, [4..5] E
   __host__ __device__ size_t carve(float* base, int Tt) {
@@ -63,6 +63,7 @@ struct FwdSmem {
     cpart = p; p += 8 * VC;
     ctxS = p; p += VC + 8;
     save1 = p; p += 7 * 64;
+    red = p; p += 32;
     xg_ring = p; p += RING * 256;
     mk_ring = reinterpret_cast<uint8_t*>(p); p += RING * 2 * BG * UH / 4;
     bars = reinterpret_cast<uint64_t*>(p); p += 2 * 6;
@@ -414,98 +415,59 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
     PT(10)
 
     // ======================= P3: softmax, forward recursion, context
-    if (arow_ok && warp == 0) {
-      constexpr int MAXM = 8;
-      const int nm = TtP / 32;
-      float e[MAXM], ap_[MAXM], apm1[MAXM];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m) {
-        if (m < nm) {
-          int j = lane + 32 * m;
-          float v = S.epart[(0 * 4 + 0) * TtP + j] + S.epart[(0 * 4 + 1) * TtP + j] + S.epart[(0 * 4 + 2) * TtP + j] +
-                    S.epart[(0 * 4 + 3) * TtP + j];
-          e[m] = (j < alen) ? v : -INFINITY;
-          mx = fmaxf(mx, e[m]);
-          ap_[m] = S.alphaS[j];
-          apm1[m] = (j > 0) ? S.alphaS[j - 1] : 0.f;
-        }
-      }
-      mx = warp_max(mx);
-      float sum = 0.f;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          e[m] = (lane + 32 * m < alen) ? __expf(e[m] - mx) : 0.f;
-          sum += e[m];
-        }
-      sum = warp_sum(sum);
-      const float inv = 1.f / sum;
-      float asum = 0.f;
+    if (tid >= 256) {
+      // attention 1: one position per thread (threads 256..511), reductions over the 8-warp group
+      const int j = tid - 256;
+      const bool in = j < TtP && arow_ok;
+      float e = -INFINITY;
+      if (in && j < alen)
+        e = S.epart[(0 * 4 + 0) * TtP + j] + S.epart[(0 * 4 + 1) * TtP + j] + S.epart[(0 * 4 + 2) * TtP + j] + S.epart[(0 * 4 + 3) * TtP + j];
+      const float mx = cl::group_max(e, S.red, warp & 7, lane, 2);
+      const float pexp = (in && j < alen) ? __expf(e - mx) : 0.f;
       const float u = 0.5f;  // transition factor stays at its initial value without the agent (forward_attention.py:116,135)
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          e[m] *= inv;  // a_t
-          if (d.mode == 2) {
-            apm1[m] = ((1.f - u) * ap_[m] + u * apm1[m] + 1e-7f) * e[m];  // forward_attention.py:109
-            asum += apm1[m];
-          }
-        }
-      __syncwarp();
-      float ainv = 1.f;
-      if (d.mode == 2) {
-        asum = warp_sum(asum);
-        ainv = 1.f / asum;
+      float mixp = 0.f;
+      if (d.mode == 2 && in) {
+        const float apm1 = (j > 0) ? S.alphaS[j - 1] : 0.f;
+        mixp = ((1.f - u) * S.alphaS[j] + u * apm1 + 1e-7f) * pexp;     // forward_attention.py:109 (up to the softmax normaliser)
       }
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          int j = lane + 32 * m;
-          float a = e[m];
-          float wgt = (d.mode == 2) ? apm1[m] * ainv : a;
-          if (d.mode == 2) S.alphaS[j] = wgt;
-          S.w1S[j] = wgt;
-          S.softS[j] = a;
-          if (d.att_kernel > 0) S.aprev[HALO + j] = d.cumulative ? (S.aprev[HALO + j] + a) : a;
-        }
-    }
-    if (HAS2 && arow_ok && warp == 1) {
-      constexpr int MAXM = 8;
-      const int nm = TtP / 32;
-      float e[MAXM];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          int j = lane + 32 * m;
-          float v = S.epart[(1 * 4 + 0) * TtP + j] + S.epart[(1 * 4 + 1) * TtP + j] + S.epart[(1 * 4 + 2) * TtP + j] +
-                    S.epart[(1 * 4 + 3) * TtP + j];
-          e[m] = (j < alen) ? v : -INFINITY;
-          mx = fmaxf(mx, e[m]);
-        }
-      mx = warp_max(mx);
-      float sum = 0.f;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) {
-          e[m] = (lane + 32 * m < alen) ? __expf(e[m] - mx) : 0.f;
-          sum += e[m];
-        }
-      sum = warp_sum(sum);
-      const float inv = 1.f / sum;
-#pragma unroll
-      for (int m = 0; m < MAXM; ++m)
-        if (m < nm) S.w2S[lane + 32 * m] = e[m] * inv;
+      float s1 = pexp, s2 = mixp;
+      cl::group_sum2(s1, s2, S.red, warp & 7, lane, 2);                  // the barrier inside also orders the alphaS reads above
+      if (in) {
+        const float a = pexp / s1;                                      // softmax alignment a_t
+        const float wgt = (d.mode == 2) ? mixp / s2 : a;                // alpha_t = mix*a / sum(mix*a): the 1/sum(p) cancels
+        if (d.mode == 2) S.alphaS[j] = wgt;
+        S.w1S[j] = wgt;
+        S.softS[j] = a;
+        if (d.att_kernel > 0) S.aprev[HALO + j] = d.cumulative ? (S.aprev[HALO + j] + a) : a;
+      }
+    } else if (HAS2) {
+      // attention 2: threads 0..255
+      const int j = tid;
+      const bool in = j < TtP && arow_ok;
+      float e = -INFINITY;
+      if (in && j < alen)
+        e = S.epart[(1 * 4 + 0) * TtP + j] + S.epart[(1 * 4 + 1) * TtP + j] + S.epart[(1 * 4 + 2) * TtP + j] + S.epart[(1 * 4 + 3) * TtP + j];
+      const float mx = cl::group_max(e, S.red + 16, warp & 7, lane, 3);
+      float pexp = (in && j < alen) ? __expf(e - mx) : 0.f, dummy = 0.f;
+      float s1 = pexp;
+      cl::group_sum2(s1, dummy, S.red + 16, warp & 7, lane, 3);
+      if (in) S.w2S[j] = pexp / s1;
     }
     PT(11)
     __syncthreads();
     PT(12)
     {
       const int c = tid & 63, jg = tid >> 6;
-      float acc = 0.f;
-      for (int j = jg; j < Tt; j += 8) acc = fmaf(S.w1S[j], S.valS[j * KS + c], acc);
-      S.cpart[jg * VC + c] = acc;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      int j = jg;
+      for (; j + 24 < Tt; j += 32) {
+        acc0 = fmaf(S.w1S[j], S.valS[j * KS + c], acc0);
+        acc1 = fmaf(S.w1S[j + 8], S.valS[(j + 8) * KS + c], acc1);
+        acc2 = fmaf(S.w1S[j + 16], S.valS[(j + 16) * KS + c], acc2);
+        acc3 = fmaf(S.w1S[j + 24], S.valS[(j + 24) * KS + c], acc3);
+      }
+      for (; j < Tt; j += 8) acc0 = fmaf(S.w1S[j], S.valS[j * KS + c], acc0);
+      S.cpart[jg * VC + c] = (acc0 + acc1) + (acc2 + acc3);
       if (HAS2 && tid < 64) {
         const int c2 = tid & 7, jg2 = tid >> 3;
         float acc2 = 0.f;

@@ -107,5 +107,34 @@ __device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
   return v[0];
 }
 
+
+// Reductions over a 256-thread group (8 warps) through shared memory + a named barrier; all 256 threads call them.
+// `red` needs 16 floats; `wig` = warp index inside the group (0..7).
+__device__ __forceinline__ void group_sum2(float& x, float& y, float* red, int wig, int lane, int barid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
+  }
+  if (lane == 0) { red[wig] = x; red[8 + wig] = y; }
+  named_bar_sync(barid, 256);
+  float sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sx += red[i]; sy += red[8 + i]; }
+  named_bar_sync(barid, 256);
+  x = sx; y = sy;
+}
+__device__ __forceinline__ float group_max(float x, float* red, int wig, int lane, int barid) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  if (lane == 0) red[wig] = x;
+  named_bar_sync(barid, 256);
+  float m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  named_bar_sync(barid, 256);
+  return m;
+}
+
 }  // namespace cl
 }  // namespace satk
