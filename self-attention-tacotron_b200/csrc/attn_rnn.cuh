@@ -19,7 +19,7 @@ constexpr int KS = 72;      // padded row stride of keyS/valS (bank-conflict-fre
 constexpr int VC = 72;      // value columns per CTA: 64 of memory-1 + 8 of memory-2
 constexpr int MAXF = 8;     // max location filters
 constexpr int MAXK = 32;    // max location kernel taps
-constexpr int HALO = 32;
+constexpr int HALO = 16;     // zero halo around per-position arrays (>= half the widest location kernel)
 
 __device__ __forceinline__ float fsigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float ftanh(float x) {
@@ -41,6 +41,25 @@ struct Dims {
 
 // round Tt up to a multiple of 32 for per-lane loops
 __host__ __device__ inline int tt_pad(int Tt) { return (Tt + 31) / 32 * 32; }
+
+// location features f[j][.] = conv1d(a_prev) + bias for all positions (forward_attention.py:98-100); fully unrolled for the
+// shipped configuration (10 taps), generic otherwise
+template <int AFT>
+__device__ __forceinline__ void location_features(float* fS, const float* aprev, const float* wconv, const float* bconv, int Tt,
+                                                  int att_kernel, int pl, int tid, int nthreads) {
+  for (int idx = tid; idx < Tt * AFT; idx += nthreads) {
+    const int j = idx / AFT, f = idx % AFT;
+    float acc = bconv[f];
+    const float* ap = aprev + HALO + j - pl;
+    if (att_kernel == 10) {
+#pragma unroll
+      for (int k = 0; k < 10; ++k) acc = fmaf(ap[k], wconv[k * MAXF + f], acc);
+    } else {
+      for (int k = 0; k < att_kernel; ++k) acc = fmaf(ap[k], wconv[k * MAXF + f], acc);
+    }
+    fS[j * MAXF + f] = acc;
+  }
+}
 
 }  // namespace arnn
 }  // namespace satk

@@ -26,6 +26,7 @@ using cl::st_async_v4;
 
 constexpr int RINGB = 4;   // ring slots (time-indexed)
 constexpr int PFDB = 2;    // prefetch distance (steps)
+constexpr int WQS = 264;   // padded row stride of the per-unit query weights
 
 template <bool HAS2>
 struct BwdSmem {
@@ -33,7 +34,7 @@ struct BwdSmem {
   int TtP, Tt8, Tt4;
   float *keyS, *valS, *dkeyS, *WqU, *dgx /* aliases stageW */, *WragS, *fS, *dfS, *Wfs, *wconv, *bconv, *vs, *aprev, *alphaPrevS,
       *dwpart, *deS, *dstate_part, *dstate_own, *dalpha_carry, *dmixS, *dctx_in, *dctxS, *dqB, *dqS, *dh_in, *dout1S, *stageQ,
-      *bcpart, *red, *ringA, *ringB, *save_dg;
+      *bcpart, *red, *ringA, *ringB, *save_dg, *dwconvS;
   uint8_t* mk_ring;
   uint64_t* bars;  // [0..1] W, [2..3] Q, [4..5] G, [6..7] C
   __host__ __device__ size_t carve(float* base, int Tt, int stage_floats) {
@@ -44,7 +45,7 @@ struct BwdSmem {
     keyS = p; p += (size_t)Tt8 * KS;
     valS = p; p += (size_t)Tt8 * KS;
     dkeyS = p; p += (size_t)Tt8 * KS;
-    WqU = p; p += UH * 256;
+    WqU = p; p += UH * WQS;                 // [unit][264]: row stride padded so 4 units x 8 lanes hit 32 distinct banks
     dgx = p; p += (stage_floats > 4 * H * BG) ? stage_floats : 4 * H * BG;  // d(gates) [row][unit][gate]; aliased by the dWf staging
     WragS = p; p += HAS2 ? 2 * 4 * H : 0;
     fS = p; p += (size_t)TtP * MAXF;
@@ -73,6 +74,7 @@ struct BwdSmem {
     ringA = p; p += RINGB * 3 * (size_t)TtP;               // soft1 / align1 / align2 of time tau
     ringB = p; p += RINGB * (QC + VC + 8 + 6 * 64);        // q_save slice, external d(ctx) slice, pointwise inputs
     save_dg = p; p += 64 * 4;
+    dwconvS = p; p += MAXK * MAXF + MAXF;   // d(location conv kernel) [k][f] + d(bias) accumulators
     mk_ring = reinterpret_cast<uint8_t*>(p); p += RINGB * 2 * BG * UH / 4;
     bars = reinterpret_cast<uint64_t*>(p); p += 2 * 8;
     return (size_t)(p - base) * sizeof(float);
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     float v = 0.f;
     if (c < d.A1) v = __ldg(d.Wq1 + (long long)(rank * UH + uu) * d.A1 + c);
     else if (HAS2 && c < QT) v = __ldg(d.Wq2 + (long long)(rank * UH + uu) * d.A2 + (c - d.A1));
-    S.WqU[i] = v;
+    S.WqU[uu * WQS + c] = v;
   }
   if (HAS2)
     for (int i = tid; i < 2 * 4 * H; i += NT) {
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
   if (tid < VC + 8) { S.dctx_in[tid] = 0.f; S.dctxS[tid] = 0.f; }
   if (tid < BG * UH) { S.dh_in[tid] = 0.f; S.dout1S[tid] = 0.f; }
   for (int i = tid; i < BG * 256; i += NT) S.dqB[i] = 0.f;
+  for (int i = tid; i < MAXK * MAXF + MAXF; i += NT) S.dwconvS[i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) cl::mbar_init(&S.bars[i], 1);
     cl::fence_mbar_init();
@@ -205,8 +208,6 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
 #pragma unroll
   for (int i = 0; i < NCH; ++i) dv_acc[i] = 0.f;
   float dWf_acc = 0.f;     // tid < NI1*8*AFT owns one (channel, filter) entry of d(location_features_layer)
-  float dwconv_acc = 0.f;  // tid in [256, 256 + att_kernel*AFT) owns one (k, f) entry of d(location conv kernel)
-  float dbconv_acc = 0.f;  // tid in [480, 480 + AFT)
 
   cluster.sync();
 
@@ -294,37 +295,26 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     }
     __syncthreads();
     {
-      // partial d(weights): thread = (j = tid>>2 (+128 per pass), part = tid&3)
-      const int part = tid & 3;
-      for (int j0 = 0; j0 < Tt; j0 += 128) {
-        const int j = j0 + (tid >> 2);
-        float a1 = 0.f, a2 = 0.f;
-        if (j < Tt) {
-          const float* vr = S.valS + j * KS;
+      // partial d(weights): one warp per position, lanes over this CTA's value columns (conflict-free rows)
+      const float dc0 = S.dctxS[lane], dc1 = S.dctxS[32 + lane];
+      const float dc2 = (HAS2 && lane < 8) ? S.dctxS[64 + lane] : 0.f;
+      for (int j = warp; j < Tt; j += NT / 32) {
+        const float* vr = S.valS + j * KS;
+        float a1 = fmaf(dc0, vr[lane], dc1 * vr[32 + lane]);
+        float a2 = (HAS2 && lane < 8) ? dc2 * vr[64 + lane] : 0.f;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) a1 = fmaf(S.dctxS[part * 16 + i], vr[part * 16 + i], a1);
-          if (HAS2) a2 = S.dctxS[64 + part * 2] * vr[64 + part * 2] + S.dctxS[64 + part * 2 + 1] * vr[64 + part * 2 + 1];
+        for (int o = 16; o > 0; o >>= 1) {
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+          if (HAS2 && o < 8) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
         }
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-        if (HAS2) {
-          a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
-          a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
-        }
-        if (j < Tt && part == 0) {
+        if (lane == 0) {
           S.dwpart[(0 * 4 + cq) * TtP + j] = a1;
           if (HAS2) S.dwpart[(1 * 4 + cq) * TtP + j] = a2;
         }
       }
       // location features of this step (input: a_{t-1})
       if (loc) {
-        for (int idx = tid; idx < Tt * AFT; idx += NT) {
-          int j = idx / AFT, f = idx % AFT;
-          float acc = S.bconv[f];
-          const float* ap = S.aprev + HALO + j - pl;
-          for (int k = 0; k < d.att_kernel; ++k) acc = fmaf(ap[k], S.wconv[k * MAXF + f], acc);
-          S.fS[j * MAXF + f] = acc;
-        }
+        location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, Tt, d.att_kernel, pl, tid, NT);
       }
     }
     cl::fence_proxy_async();
@@ -514,17 +504,23 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
             S.dstate_part[(nxt * 4 + cq) * TtP + j] = acc;   // own contribution for step t-1
           }
         }
-        if (tid >= 256 && tid - 256 < d.att_kernel * AFT) {
-          const int e = tid - 256, k = e / AFT, f = e % AFT;
+        // d(location conv kernel)[k][f] += sum_j a_prev[j+k-pl] * df[j][f]: 8 lanes per (k,f), accumulators in shared memory
+        for (int e0 = 0; e0 < d.att_kernel * AFT; e0 += NT / 8) {   // warp-uniform trip count: the shuffles need all lanes
+          const int e = e0 + (tid >> 3);
+          const bool ok = e < d.att_kernel * AFT;
+          const int k = ok ? e / AFT : 0, f = ok ? e % AFT : 0;
           float acc = 0.f;
-          for (int j = 0; j < Tt; ++j) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[(HALO + j) * MAXF + f], acc);
-          dwconv_acc += acc;
+          for (int j = lane & 7; j < Tt; j += 8) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[(HALO + j) * MAXF + f], acc);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+          if (ok && (lane & 7) == 0) S.dwconvS[k * MAXF + f] += acc;
         }
-        if (tid >= 480 && tid < 480 + AFT) {
-          const int f = tid - 480;
+        if (warp < AFT) {
           float acc = 0.f;
-          for (int j = 0; j < Tt; ++j) acc += S.dfS[(HALO + j) * MAXF + f];
-          dbconv_acc += acc;
+          for (int j = lane; j < Tt; j += 32) acc += S.dfS[(HALO + j) * MAXF + warp];
+          acc = warp_sum(acc);
+          if (lane == 0) S.dwconvS[MAXK * MAXF + warp] += acc;
         }
       }
     }
@@ -558,10 +554,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       // thread = (b = tid>>7, u = (tid>>3)&15, part = tid&7): 32 columns of dq each
       const int bb = tid >> 7, uu = (tid >> 3) & 15, part = tid & 7;
       float acc = 0.f;
-      const float* qrow = S.dqB + bb * 256 + part * 32;
-      const float* wrow = S.WqU + uu * 256 + part * 32;
+      // lane `part` takes the columns congruent to part mod 8: consecutive lanes read consecutive banks
+      const float* qrow = S.dqB + bb * 256 + part;
+      const float* wrow = S.WqU + uu * WQS + part;
 #pragma unroll 8
-      for (int c = 0; c < 32; ++c) acc = fmaf(qrow[c], wrow[c], acc);
+      for (int c = 0; c < 32; ++c) acc = fmaf(qrow[8 * c], wrow[8 * c], acc);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -740,11 +737,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         const int i_ = rem / AFT, f_ = rem % AFT;
         if (f_ < d.att_filters) atomicAdd(dd.dloc_layer_w + (long long)f_ * d.A1 + cq * A1Q + c8 + 8 * i_, dWf_acc);
       }
-      if (tid >= 256 && tid - 256 < d.att_kernel * AFT) {
-        const int e = tid - 256, k = e / AFT, f = e % AFT;
-        if (f < d.att_filters) atomicAdd(dd.dloc_conv_w + k * d.att_filters + f, dwconv_acc);
+      for (int e = tid; e < d.att_kernel * AFT; e += NT) {
+        const int k = e / AFT, f = e % AFT;
+        if (f < d.att_filters) atomicAdd(dd.dloc_conv_w + k * d.att_filters + f, S.dwconvS[k * MAXF + f]);
       }
-      if (tid >= 480 && tid < 480 + AFT && (tid - 480) < d.att_filters) atomicAdd(dd.dloc_conv_b + (tid - 480), dbconv_acc);
+      if (tid < d.att_filters) atomicAdd(dd.dloc_conv_b + tid, S.dwconvS[MAXK * MAXF + tid]);
     }
   }
   cluster.sync();

@@ -315,13 +315,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
     {
       // location features f[j][.] = conv1d(a_prev) (forward_attention.py:98-100)
       if (d.att_kernel > 0) {
-        for (int idx = tid; idx < Tt * AFT; idx += NT) {
-          int j = idx / AFT, f = idx % AFT;
-          float acc = S.bconv[f];
-          const float* ap = S.aprev + HALO + j - pl;
-          for (int k = 0; k < d.att_kernel; ++k) acc = fmaf(ap[k], S.wconv[k * MAXF + f], acc);
-          S.fS[j * MAXF + f] = acc;
-        }
+        location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, Tt, d.att_kernel, pl, tid, NT);
       }
       // query slice partials
       const int c = tid & 63, uq = tid >> 6;
@@ -457,32 +451,30 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
     __syncthreads();
     PT(12)
     {
-      const int c = tid & 63, jg = tid >> 6;
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-      int j = jg;
-      for (; j + 24 < Tt; j += 32) {
-        acc0 = fmaf(S.w1S[j], S.valS[j * KS + c], acc0);
-        acc1 = fmaf(S.w1S[j + 8], S.valS[(j + 8) * KS + c], acc1);
-        acc2 = fmaf(S.w1S[j + 16], S.valS[(j + 16) * KS + c], acc2);
-        acc3 = fmaf(S.w1S[j + 24], S.valS[(j + 24) * KS + c], acc3);
-      }
-      for (; j < Tt; j += 8) acc0 = fmaf(S.w1S[j], S.valS[j * KS + c], acc0);
-      S.cpart[jg * VC + c] = (acc0 + acc1) + (acc2 + acc3);
-      if (HAS2 && tid < 64) {
-        const int c2 = tid & 7, jg2 = tid >> 3;
-        float acc2 = 0.f;
-        for (int j = jg2; j < Tt; j += 8) acc2 = fmaf(S.w2S[j], S.valS[j * KS + 64 + c2], acc2);
-        S.cpart[jg2 * VC + 64 + c2] = acc2;
+      // context partial sums: thread = (column c of the 64(+8) value columns, position group jg of 7)
+      if (tid < VCW * 7) {
+        const int c = tid % VCW, jg = tid / VCW;
+        const float* wS = (c < 64) ? S.w1S : S.w2S;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        int j = jg;
+        for (; j + 21 < Tt; j += 28) {
+          acc0 = fmaf(wS[j], S.valS[j * KS + c], acc0);
+          acc1 = fmaf(wS[j + 7], S.valS[(j + 7) * KS + c], acc1);
+          acc2 = fmaf(wS[j + 14], S.valS[(j + 14) * KS + c], acc2);
+          acc3 = fmaf(wS[j + 21], S.valS[(j + 21) * KS + c], acc3);
+        }
+        for (; j < Tt; j += 7) acc0 = fmaf(wS[j], S.valS[j * KS + c], acc0);
+        S.cpart[jg * VC + c] = (acc0 + acc1) + (acc2 + acc3);
       }
     }
-    __syncthreads();
     PT(13)
+    __syncthreads();
     if (tid < 96) {
       // context slice of my utterance -> every CTA's x[row][k] for the next step (16-byte st.async per 4 columns)
       float cx = 0.f;
       if (tid < VCW) {
 #pragma unroll
-        for (int jg = 0; jg < 8; ++jg) cx += S.cpart[jg * VC + tid];
+        for (int jg = 0; jg < 7; ++jg) cx += S.cpart[jg * VC + tid];
         S.ctxS[tid] = cx;
       }
       const int l4 = lane & ~3;
