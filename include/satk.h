@@ -130,6 +130,9 @@ int satk_colsum_acc(const float* x, long long ldx, int rows, int C, float* out, 
 int satk_add(const float* a, const float* b, float* out, long long n, void* stream);          /* out = a + b */
 int satk_axpy(float alpha, const float* x, float* y, long long n, void* stream);              /* y += alpha*x */
 int satk_transpose(const float* x, int rows, int cols, float* y, void* stream);               /* y[c,r] = x[r,c] */
+/* strided transpose: y[c*ldy + r] = x[r*ldx + c]; feeds the weight-gradient products (X^T dY) to the tcgen05 tile, which
+ * wants both operands contiguous along the reduction (row) dimension */
+int satk_transpose_strided(const float* x, long long ldx, int rows, int cols, float* y, long long ldy, void* stream);
 /* n transposes in one launch over two flat buffers with identical offsets: desc[3*i] = {offset, rows, cols} (device,
  * int32): dst[off + c*rows + r] = src[off + r*cols + c].  Keeps the K-contiguous copy of the weights that the
  * tcgen05 tile consumes ([in,out] -> [out,in]) in sync after each optimiser step. */

@@ -250,6 +250,22 @@ __global__ void transpose_k(const float* __restrict__ x, int rows, int cols, flo
     if (r2 < rows && c2 < cols) y[(long long)c2 * rows + r2] = t[threadIdx.x][j];
   }
 }
+// strided variant: y[c * ldy + r] = x[r * ldx + c]
+__global__ void transpose_strided_k(const float* __restrict__ x, long long ldx, int rows, int cols, float* __restrict__ y,
+                                    long long ldy) {
+  __shared__ float t[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int r = blockIdx.y * 32 + j;
+    if (r < rows && c < cols) t[j][threadIdx.x] = x[(long long)r * ldx + c];
+  }
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const int c2 = blockIdx.x * 32 + j;
+    if (r2 < rows && c2 < cols) y[(long long)c2 * ldy + r2] = t[threadIdx.x][j];
+  }
+}
 // many small transposes in one launch: desc[3*i] = {offset, rows, cols}; dst[off + c*rows + r] = src[off + r*cols + c]
 __global__ void transpose_batched_k(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ desc) {
   __shared__ float t[32][33];
@@ -576,6 +592,14 @@ int satk_axpy(float alpha, const float* x, float* y, long long n, void* stream) 
 int satk_transpose(const float* x, int rows, int cols, float* y, void* stream) {
   dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
   transpose_k<<<grid, block, 0, ST>>>(x, rows, cols, y);
+  SATK_LAUNCH_CHECK();
+  return 0;
+}
+int satk_transpose_strided(const float* x, long long ldx, int rows, int cols, float* y, long long ldy, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  SATK_CHECK_ARG(ldx >= cols && ldy >= rows, "transpose_strided: ldx=%lld < cols=%d or ldy=%lld < rows=%d", ldx, cols, ldy, rows);
+  dim3 grid(ceil_div(cols, 32), ceil_div(rows, 32)), block(32, 8);
+  transpose_strided_k<<<grid, block, 0, ST>>>(x, ldx, rows, cols, y, ldy);
   SATK_LAUNCH_CHECK();
   return 0;
 }

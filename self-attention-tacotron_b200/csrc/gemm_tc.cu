@@ -27,6 +27,12 @@ constexpr int XFORM_THREADS = 192;              // warps 2..7
 constexpr int XFORM_WARPS = 6;
 constexpr int TMEM_COLS = 128;
 
+#ifdef SATK_PHASE_TIMING
+#define TC_TRACE(ev) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it >= 6 && it < 10) satk::g_phase[(it - 6) * 4 + (ev)] = clock64() - t_start;
+#else
+#define TC_TRACE(ev)
+#endif
+
 struct Params {
   int M, N, K;
   int taps, shift0, tap_dir;
@@ -93,6 +99,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int kb_beg = ks * kb_per, kb_end = min(kblocks_total, kb_beg + kb_per);
   const int nkb = max(0, kb_end - kb_beg);
   const int iters = nkb * p.taps;
+#ifdef SATK_PHASE_TIMING
+  const long long t_start = clock64();
+#endif
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -121,6 +130,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (use > 0) cl::mbar_wait(&empty_bar[s], (use - 1) & 1);
       const int tap = it / nkb, kb = kb_beg + it % nkb;
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
+      TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
       tma_load_2d(sa, &mapA, kb * BK, m0 + p.shift0 + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
       if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap, cl::smem_u32(&full_bar[s]));
@@ -132,6 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       cl::mbar_wait(&xform_bar[s], use & 1);
+      TC_TRACE(2)
       tc_fence_after();
       const uint32_t sa = smem_base + s * STAGE_BYTES;
       const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_BYTES);
@@ -144,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
       }
       tc_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
+      TC_TRACE(3)
     }
     tc_commit(&accum_bar);               // accumulator complete
   } else if (warp >= 2) {
@@ -152,6 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       cl::mbar_wait(&full_bar[s], use & 1);
+      if (tid == 64) { TC_TRACE(1) }
       uint8_t* base = smem + (smem_base - cl::smem_u32(smem)) + s * STAGE_BYTES;
 #pragma unroll 2
       for (int i = xt; i < 2 * (TILE_BYTES / 16); i += XFORM_THREADS) {
@@ -255,6 +268,13 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+int tc_trace(long long* out16) {
+#ifdef SATK_PHASE_TIMING
+  SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
+#endif
+  return 0;
 }
 
 }  // namespace tc

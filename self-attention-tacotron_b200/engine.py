@@ -463,8 +463,10 @@ class TacotronEngine:
             dg = self.buf(f"dec.dgates{li}", (Rd, 4 * HD))
             O.lstm_seq_bwd(W[kin:], s["gates"], s["c_prev"], dout, dg, Td, B, HD, mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh)
             gW = g[f"dec.lstm{li}.W"]
-            O.linear_dw(s["x"], dg, gW, Rd, kin, 4 * HD)
-            O.linear_dw(s["h_prev"], dg, gW, Rd, HD, 4 * HD, w_off=kin * 4 * HD)
+            dgT = O.transposed_rows(dg, Rd, 4 * HD) if Rd >= O.DW_TC_MIN_ROWS else None
+            O.linear_dw(s["x"], dg, gW, Rd, kin, 4 * HD, yT=dgT)
+            O.linear_dw(s["h_prev"], dg, gW, Rd, HD, 4 * HD, w_off=kin * 4 * HD, yT=dgT)
+            del dgT
             O.colsum_acc(dg, Rd, 4 * HD, g[f"dec.lstm{li}.b"])
             dxl = self.buf(f"dec.dx_lstm{li}", (Rd, kin))
             O.linear_dx(dg, W[:kin], dxl, Rd)
@@ -485,10 +487,13 @@ class TacotronEngine:
         # LSTM-1 weight gradients (dense over time)
         gW1 = g["dec.lstm1.W"]
         N4 = 4 * H1
-        O.linear_dw(sv["dp1"], dg1, gW1, Rd, P1, N4)
+        tc_dw = Rd >= O.DW_TC_MIN_ROWS
+        dg1T = O.transposed_rows(dg1, Rd, N4) if tc_dw else None     # shared by the three row blocks of dec.lstm1.W
+        O.linear_dw(sv["dp1"], dg1, gW1, Rd, P1, N4, yT=dg1T)
         # context rows: input of step t is the context of step t-1 (zero at t=0) -> shift by one time step (B rows)
-        O.linear_dw(sv["x2"], dg1, gW1, Rd, d.ctx, N4, ldx=X2W, x_off=H1, w_off=P1 * N4, shift0=-B)
-        O.linear_dw(self._bufs["dec.hprev1"], dg1, gW1, Rd, H1, N4, w_off=(P1 + d.ctx) * N4)
+        O.linear_dw(sv["x2"], dg1, gW1, Rd, d.ctx, N4, ldx=X2W, x_off=H1, w_off=P1 * N4, shift0=-B, yT=dg1T)
+        O.linear_dw(self._bufs["dec.hprev1"], dg1, gW1, Rd, H1, N4, w_off=(P1 + d.ctx) * N4, yT=dg1T)
+        del dg1T
         O.colsum_acc(dg1, Rd, N4, g["dec.lstm1.b"])
         ddp1 = self.buf("dec.ddp1", (Rd, P1))
         O.linear_dx(dg1, p["dec.lstm1.W"][:P1], ddp1, Rd)

@@ -85,9 +85,40 @@ def linear_dx(dy: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, rows: int, be
          b_off=w_off)
 
 
+def transposed_rows(x: torch.Tensor, rows: int, cols: int, ldx=None, x_off=0, front=0) -> torch.Tensor:
+    """[cols, ld] copy of x[rows, cols] with the ROW index contiguous (ld = front + rows rounded up to 4); `front` leading and the
+    trailing pad columns are zero.  Operand layout of the tcgen05 tile for products that reduce over rows (weight gradients)."""
+    ld = (front + rows + 3) // 4 * 4
+    pad = ld != rows
+    y = (torch.zeros if pad else torch.empty)((cols, ld), device=x.device, dtype=torch.float32)
+    check(load().satk_transpose_strided(C.c_void_p(x.data_ptr() + 4 * x_off), C.c_longlong(ldx or cols), rows, cols,
+                                        C.c_void_p(y.data_ptr() + 4 * front), C.c_longlong(ld), C.c_void_p(stream_ptr())),
+          "satk_transpose_strided")
+    _count()
+    return y
+
+
+DW_TC_MIN_ROWS = 2048      # below this the two transposes cost more than the SIMT split-K product saves
+
+
 def linear_dw(x: torch.Tensor, dy: torch.Tensor, dW: torch.Tensor, rows: int, K: int, N: int, ldx=None, x_off=0, ldy=None,
-              y_off=0, ldw=None, w_off=0, shift0=0, split_k=None) -> None:
-    """dW[K, N] += x[rows, K]^T @ dy[rows, N]  (split-K over rows, atomically accumulated)."""
+              y_off=0, ldw=None, w_off=0, shift0=0, split_k=None, xT=None, yT=None) -> None:
+    """dW[K, N] += x[rows, K]^T @ dy[rows, N]  (split-K over rows, atomically accumulated).
+
+    Large products run on the tcgen05 tile: both operands are first transposed so that the reduction (row) index is contiguous
+    (``xT`` / ``yT`` may be passed in when the caller already holds a transposed copy, see ``transposed_rows``); a negative
+    ``shift0`` (x delayed by -shift0 rows, zeros before the start) becomes leading zero columns of xT."""
+    if rows >= DW_TC_MIN_ROWS and K >= 64 and N >= 48 and shift0 <= 0 and split_k is None:
+        front = -shift0
+        if xT is None:
+            xT = transposed_rows(x, rows, K, ldx, x_off, front)
+        if yT is None:
+            yT = transposed_rows(dy, rows, N, ldy, y_off, 0)
+        kk = (rows + 3) // 4 * 4
+        tiles = ((K + 127) // 128) * ((N + 127) // 128)
+        sk = max(1, min(kk // 128, (148 + tiles // 2) // tiles))
+        gemm(xT, yT, dW, K, N, kk, lda=xT.shape[1], ldb=yT.shape[1], ldc=ldw or N, transB=True, c_off=w_off, split_k=sk, beta=1.0)
+        return
     if split_k is None:
         split_k = max(1, min(64, rows // 256))
     gemm(x, dy, dW, K, N, rows, lda=ldx or K, ldb=ldy or N, ldc=ldw or N, transA=True, a_off=x_off, b_off=y_off,

@@ -65,6 +65,28 @@ def test_gemm_tensor_core_tile():
     _close(y, ref, 1e-7 * Cin * k, "tc conv")
 
 
+def test_weight_gradient_products_tensor_core_path():
+    """dW += X^T dY through the transposed-operand tcgen05 path (rows >= DW_TC_MIN_ROWS): plain, strided with a delayed X
+    (shift0 < 0, the LSTM-1 context rows), shared transposed dY, ragged row count; against fp64."""
+    O = _O()
+    g = torch.Generator().manual_seed(11)
+    for (rows, K, N, ldx, x_off, shift0) in ((2304, 96, 80, None, 0, 0), (4096, 288, 1024, 544, 256, -32), (2051, 64, 48, None, 0, -3)):
+        x = torch.randn(rows, ldx or K, generator=g)
+        dy = torch.randn(rows, N, generator=g)
+        dW0 = torch.randn(K, N, generator=g)
+        xs = x[:, x_off:x_off + K].double()
+        if shift0 < 0:
+            xs = torch.cat([torch.zeros(-shift0, K, dtype=torch.float64), xs[:shift0]], 0)
+        ref = (dW0.double() + xs.t() @ dy.double()).float()
+        dW = dW0.clone().cuda()
+        O.linear_dw(x.cuda(), dy.cuda(), dW, rows, K, N, ldx=ldx, x_off=x_off, shift0=shift0)
+        _close(dW, ref, 1e-7 * rows, f"dW tc {rows}x{K}x{N}")
+        dW = dW0.clone().cuda()
+        yT = O.transposed_rows(dy.cuda(), rows, N)
+        O.linear_dw(x.cuda(), dy.cuda(), dW, rows, K, N, ldx=ldx, x_off=x_off, shift0=shift0, yT=yT)
+        _close(dW, ref, 1e-7 * rows, f"dW tc shared yT {rows}x{K}x{N}")
+
+
 def test_gemm_time_major_conv_and_grads():
     O = _O()
     g = torch.Generator().manual_seed(1)

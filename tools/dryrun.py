@@ -59,6 +59,11 @@ def install():
                  "sum_over_t", "bernoulli_mask", "softmax_fwd", "softmax_bwd", "teacher_inputs", "losses", "grad_sumsq",
                  "adam_clip", "transpose_batched", "lstm_seq_fwd", "lstm_seq_bwd", "attn_rnn_fwd", "attn_rnn_bwd"]:
         setattr(O, name, any_ok)
+
+    def transposed_rows(x, rows, cols, ldx=None, x_off=0, front=0):
+        _extent(x, x_off, (rows - 1) * (ldx or cols) + cols, "transposed_rows x")
+        return torch.empty((cols, (front + rows + 3) // 4 * 4))
+    O.transposed_rows = transposed_rows
     real_desc = O.attn_rnn_desc
 
     def desc(**kw):
