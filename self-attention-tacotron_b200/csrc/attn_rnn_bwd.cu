@@ -49,7 +49,7 @@ struct BwdSmem {
     dgx = p; p += (stage_floats > 4 * H * BG) ? stage_floats : 4 * H * BG;  // d(gates) [row][unit][gate]; aliased by the dWf staging
     WragS = p; p += HAS2 ? 2 * 4 * H : 0;
     fS = p; p += (size_t)TtP * MAXF;
-    dfS = p; p += (size_t)(TtP + 2 * HALO) * MAXF;
+    dfS = p; p += (size_t)(TtP + 2 * HALO) * MAXF;   // d(location features), filter-major [f][HALO + j] (conflict-free over j)
     Wfs = p; p += MAXF * QC;
     wconv = p; p += MAXK * MAXF;
     bconv = p; p += MAXF;
@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
   constexpr int SW = NI1 * AFT;  // staging stride per (warp, channel lane)
   S.carve(smem_raw, Tt, 16 * 8 * SW);
   const int TtP = S.TtP, Tt4 = S.Tt4;
+  const int DFW = TtP + 2 * HALO;   // row pitch of dfS
   uint64_t* barW = S.bars;
   uint64_t* barQ = S.bars + 2;
   uint64_t* barG = S.bars + 4;
@@ -295,19 +296,32 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     }
     __syncthreads();
     {
-      // partial d(weights): one warp per position, lanes over this CTA's value columns (conflict-free rows)
-      const float dc0 = S.dctxS[lane], dc1 = S.dctxS[32 + lane];
-      const float dc2 = (HAS2 && lane < 8) ? S.dctxS[64 + lane] : 0.f;
-      for (int j = warp; j < Tt; j += NT / 32) {
-        const float* vr = S.valS + j * KS;
-        float a1 = fmaf(dc0, vr[lane], dc1 * vr[32 + lane]);
-        float a2 = (HAS2 && lane < 8) ? dc2 * vr[64 + lane] : 0.f;
+      // partial d(weights)[j] = d(ctx) . values[j, this CTA's columns]: thread = (position pg + 64m, lane cl_ of 8); lane cl_ takes the
+      // columns congruent to cl_ mod 8, so the 4 positions x 8 lanes of a warp hit 32 distinct banks (row stride 72)
+      float dcx[8], dcx2 = HAS2 ? S.dctxS[64 + cl_] : 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-          if (HAS2 && o < 8) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      for (int i = 0; i < 8; ++i) dcx[i] = S.dctxS[cl_ + 8 * i];
+#pragma unroll
+      for (int m = 0; m < NP; ++m) {
+        const int j = pg + 64 * m;
+        const float* vr = S.valS + (j < Tt ? j : 0) * KS + cl_;
+        float a1 = 0.f, a1b = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          a1 = fmaf(dcx[i], vr[8 * i], a1);
+          a1b = fmaf(dcx[i + 1], vr[8 * i + 8], a1b);
         }
-        if (lane == 0) {
+        a1 += a1b;
+        float a2 = HAS2 ? dcx2 * vr[64] : 0.f;
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 4);
+        if (HAS2) {
+          a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+          a2 += __shfl_xor_sync(0xffffffffu, a2, 4);
+        }
+        if (cl_ == 0 && j < Tt) {
           S.dwpart[(0 * 4 + cq) * TtP + j] = a1;
           if (HAS2) S.dwpart[(1 * 4 + cq) * TtP + j] = a2;
         }
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (cl_ == 0 && jok[m]) S.dfS[(HALO + jm[m]) * MAXF + f] = v;
+          if (cl_ == 0 && jok[m]) S.dfS[f * DFW + HALO + jm[m]] = v;
         }
       }
     }
@@ -492,14 +506,21 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         }
         // partial d(state a_{t-1}) = conv-transpose of d(location features)
         if (t > 0) {
-          for (int j = tid; j < Tt4; j += NT) {
+          for (int j = NT - 1 - tid; j < Tt4; j += NT) {   // last warps: the first ones carry the dq / dWf reductions
             float acc = 0.f;
-            if (j < Tt)
-              for (int k = 0; k < d.att_kernel; ++k) {
-                const float* dfr = S.dfS + (HALO + j - k + pl) * MAXF;  // rows outside [0,Tt) are zero
+            if (j < Tt) {
+              const float* dfr = S.dfS + HALO + j + pl;   // columns outside [0,Tt) are zero
+              if (d.att_kernel == 10) {
 #pragma unroll
-                for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f], S.wconv[k * MAXF + f], acc);
+                for (int k = 0; k < 10; ++k)
+#pragma unroll
+                  for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f * DFW - k], S.wconv[k * MAXF + f], acc);
+              } else {
+                for (int k = 0; k < d.att_kernel; ++k)
+#pragma unroll
+                  for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f * DFW - k], S.wconv[k * MAXF + f], acc);
               }
+            }
             S.dstate_own[j] = acc;
             S.dstate_part[(nxt * 4 + cq) * TtP + j] = acc;   // own contribution for step t-1
           }
@@ -510,17 +531,18 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           const bool ok = e < d.att_kernel * AFT;
           const int k = ok ? e / AFT : 0, f = ok ? e % AFT : 0;
           float acc = 0.f;
-          for (int j = lane & 7; j < Tt; j += 8) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[(HALO + j) * MAXF + f], acc);
+          for (int j = lane & 7; j < Tt; j += 8) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[f * DFW + HALO + j], acc);
           acc += __shfl_xor_sync(0xffffffffu, acc, 1);
           acc += __shfl_xor_sync(0xffffffffu, acc, 2);
           acc += __shfl_xor_sync(0xffffffffu, acc, 4);
           if (ok && (lane & 7) == 0) S.dwconvS[k * MAXF + f] += acc;
         }
-        if (warp < AFT) {
+        if (warp >= 6 && warp < 6 + AFT) {
+          const int f = warp - 6;
           float acc = 0.f;
-          for (int j = lane; j < Tt; j += 32) acc += S.dfS[(HALO + j) * MAXF + warp];
+          for (int j = lane; j < Tt; j += 32) acc += S.dfS[f * DFW + HALO + j];
           acc = warp_sum(acc);
-          if (lane == 0) S.dwconvS[MAXK * MAXF + warp] += acc;
+          if (lane == 0) S.dwconvS[MAXK * MAXF + f] += acc;
         }
       }
     }
@@ -650,33 +672,29 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       const float v = cl::reduce_scatter16(acc, lane);   // lane L: row og*4 + ((L>>2)&3), batch row L&3
       S.bcpart[(((kq >> 4) & 3) * 32 + og * 4 + ((lane >> 2) & 3)) * 4 + (lane & 3)] = v;
     }
-    if (HAS2 && warp == 15) {
-      // ragged rows 512 + 2*rank + {0,1} (hidden units 224..255), weights in shared memory
-      float ragged[4] = {0.f, 0.f, 0.f, 0.f};
-      const int rr = lane >> 4, c16 = lane & 15;
-      const float* wrow = S.WragS + rr * 4 * H;
-#pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int un = c16 + 16 * i;
+    if (HAS2) {
+      // ragged rows 512 + 2*rank + {0,1} of Wrec (hidden units 224..255; weights in shared memory), spread over all warps:
+      // thread (kq, og) takes row og&1 and source unit kq + 64*(og>>1); per-warp totals land in bcpart[512 + warp*4 + b]
+      const int un = kq + 64 * (og >> 1);
+      const float* wrow = S.WragS + (og & 1) * 4 * H + un;
+      const float w0 = wrow[0], w1 = wrow[H], w2 = wrow[2 * H], w3 = wrow[3 * H];
+      float rg[4];
 #pragma unroll
-        for (int b = 0; b < BG; ++b) {
-          const float4 g4 = *reinterpret_cast<const float4*>(&S.dgx[((size_t)b * H + un) * 4]);
-          ragged[b] = fmaf(wrow[0 * H + un], g4.x, ragged[b]);
-          ragged[b] = fmaf(wrow[1 * H + un], g4.y, ragged[b]);
-          ragged[b] = fmaf(wrow[2 * H + un], g4.z, ragged[b]);
-          ragged[b] = fmaf(wrow[3 * H + un], g4.w, ragged[b]);
-        }
+      for (int b = 0; b < BG; ++b) {
+        const float4 g4 = *reinterpret_cast<const float4*>(&S.dgx[((size_t)b * H + un) * 4]);
+        rg[b] = fmaf(w0, g4.x, fmaf(w1, g4.y, fmaf(w2, g4.z, w3 * g4.w)));
       }
-#pragma unroll
-      for (int o = 1; o <= 8; o <<= 1) {
-#pragma unroll
-        for (int b = 0; b < BG; ++b) ragged[b] += __shfl_xor_sync(0xffffffffu, ragged[b], o);
-      }
-      if (c16 < 4) {
-        const float v = (c16 == 0) ? ragged[0] : (c16 == 1) ? ragged[1] : (c16 == 2) ? ragged[2] : ragged[3];
-        const int un = (512 + 2 * rank + rr) - (M1 + M2);
-        const int dst = un >> 4;
-        cl::st_async_f32(cl::mapa(cl::smem_u32(&S.dh_in[c16 * UH + (un & 15)]), dst), v, cl::mapa(cl::smem_u32(&barC[nxt]), dst));
+      {
+        const bool up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
+        const float s0 = up2 ? rg[0] : rg[2], s1 = up2 ? rg[1] : rg[3];
+        float k0 = up2 ? rg[2] : rg[0], k1 = up2 ? rg[3] : rg[1];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        float v = (up1 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up1 ? k0 : k1, 1);   // lane L: batch row L&3
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 4) S.bcpart[512 + warp * 4 + lane] = v;
       }
     }
     __syncthreads();
@@ -705,6 +723,15 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         }
         st_async_v4(cl::mapa(addr, dst), v0, v1, v2, v3, cl::mapa(cl::smem_u32(&barC[nxt]), dst));
       }
+    } else if (HAS2 && tid < 136) {
+      // ragged rows: (row rr, batch row b) = sum over the 8 warps with ((warp >> 1) & 1) == rr
+      const int rr = (tid - 128) >> 2, b = tid & 3;
+      float v = 0.f;
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) v += S.bcpart[512 + (w4 * 4 + rr * 2) * 4 + b] + S.bcpart[512 + (w4 * 4 + rr * 2 + 1) * 4 + b];
+      const int un = (512 + 2 * rank + rr) - (M1 + M2);
+      const int dst = un >> 4;
+      cl::st_async_f32(cl::mapa(cl::smem_u32(&S.dh_in[b * UH + (un & 15)]), dst), v, cl::mapa(cl::smem_u32(&barC[nxt]), dst));
     }
     PT(9)
   }
