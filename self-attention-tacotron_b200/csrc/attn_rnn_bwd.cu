@@ -266,6 +266,22 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     PT(15)
     prefetch(t - 1 - PFDB);
     cp_async_wait<PFDB>();                       // time t and t-1 are resident
+    __syncthreads();                             // ring contents (written by other threads' cp.async) visible
+    const float* rA = S.ringA + (size_t)(t % RINGB) * 3 * TtP;           // soft1[t], align1[t], align2[t]
+    const float* rAp = S.ringA + (size_t)((t + RINGB - 1) % RINGB) * 3 * TtP;   // time t-1
+    const float* rB = S.ringB + (size_t)(t % RINGB) * RB;
+    const float* aS = rA;
+    const float* alphaS = rA + TtP;
+    const float* a2S = rA + 2 * TtP;
+    const float* qs = rB;
+    for (int j = tid; j < TtP; j += NT) {
+      const bool in = j < Tt && t > 0;
+      S.aprev[HALO + j] = in ? rAp[j] : 0.f;
+      S.alphaPrevS[j] = in ? rAp[TtP + j] : ((j == 0 && d.mode == 2) ? 1.f : 0.f);
+    }
+    __syncthreads();
+    // location features of this step (input: a_{t-1}); independent of the recurrent carries, so computed before waiting for them
+    if (loc) location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, Tt, d.att_kernel, pl, tid, NT);
     if (u > 0) cl::mbar_wait(&barC[cur], (uint32_t)((u - 1) >> 1) & 1u);   // recurrent carries of step t+1
     if (tid == 0) {
       const uint32_t rxw = 3u * NATT * (uint32_t)Tt4 * 4u + ((u > 0 && loc) ? 3u * (uint32_t)Tt4 * 4u : 0u);
@@ -274,25 +290,12 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       if (t > 0) cl::mbar_arrive_expect_tx(&barG[cur], RX_G);
       if (t > 0) cl::mbar_arrive_expect_tx(&barC[nxt], RX_C);
     }
-    __syncthreads();                             // ring contents (written by other threads' cp.async) visible
     PT(0)
-    const float* rA = S.ringA + (size_t)(t % RINGB) * 3 * TtP;           // soft1[t], align1[t], align2[t]
-    const float* rAp = S.ringA + (size_t)((t + RINGB - 1) % RINGB) * 3 * TtP;   // time t-1
-    const float* rB = S.ringB + (size_t)(t % RINGB) * RB;
-    const float* aS = rA;
-    const float* alphaS = rA + TtP;
-    const float* a2S = rA + 2 * TtP;
-    const float* qs = rB;
 
     // ======================= BA1
     if (tid < VCW) {
       const float v = S.dctx_in[tid] + rB[QC + tid];
       S.dctxS[tid] = v;                          // total d(ctx); saved for the dense dvalues GEMM by the saver warps
-    }
-    for (int j = tid; j < TtP; j += NT) {
-      const bool in = j < Tt && t > 0;
-      S.aprev[HALO + j] = in ? rAp[j] : 0.f;
-      S.alphaPrevS[j] = in ? rAp[TtP + j] : ((j == 0 && d.mode == 2) ? 1.f : 0.f);
     }
     __syncthreads();
     {
@@ -325,10 +328,6 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           S.dwpart[(0 * 4 + cq) * TtP + j] = a1;
           if (HAS2) S.dwpart[(1 * 4 + cq) * TtP + j] = a2;
         }
-      }
-      // location features of this step (input: a_{t-1})
-      if (loc) {
-        location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, Tt, d.att_kernel, pl, tid, NT);
       }
     }
     cl::fence_proxy_async();
@@ -428,7 +427,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           const float th = ftanh(s);
           const float dsv = de1[m] * vc * (1.f - th * th);
           dv_acc[i] = fmaf(de1[m], th, dv_acc[i]);
-          if (jok[m]) S.dkeyS[jm[m] * KS + c] += dsv;
+          if (jok[m]) cl::sts_noalias(&S.dkeyS[jm[m] * KS + c], S.dkeyS[jm[m] * KS + c] + dsv);
           dq += dsv;
 #pragma unroll
           for (int f = 0; f < AFT; ++f) {
@@ -445,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         }
         if (lane < 8) {
 #pragma unroll
-          for (int f = 0; f < AFT; ++f) stageW[(warp * 8 + cl_) * SW + i * AFT + f] = P[f];
+          for (int f = 0; f < AFT; ++f) cl::sts_noalias(&stageW[(warp * 8 + cl_) * SW + i * AFT + f], P[f]);
         }
       }
       if (HAS2) {
@@ -457,7 +456,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           const float th = ftanh(S.keyS[jm[m] * KS + c] + qc);
           const float dsv = de2[m] * vc * (1.f - th * th);
           dv_acc[NI1] = fmaf(de2[m], th, dv_acc[NI1]);
-          if (jok[m]) S.dkeyS[jm[m] * KS + c] += dsv;
+          if (jok[m]) cl::sts_noalias(&S.dkeyS[jm[m] * KS + c], S.dkeyS[jm[m] * KS + c] + dsv);
           dq += dsv;
         }
         dq_acc[NI1] = dq;
@@ -467,7 +466,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       for (int i = 0; i < NCH; ++i) {
         dq_acc[i] += __shfl_xor_sync(0xffffffffu, dq_acc[i], 8);
         dq_acc[i] += __shfl_xor_sync(0xffffffffu, dq_acc[i], 16);
-        if (lane < 8) S.stageQ[warp * QC + cl_ + 8 * i] = dq_acc[i];
+        if (lane < 8) cl::sts_noalias(&S.stageQ[warp * QC + cl_ + 8 * i], dq_acc[i]);
       }
       // d(location features): reduce over the 8 channel lanes
 #pragma unroll
@@ -478,7 +477,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 4);
-          if (cl_ == 0 && jok[m]) S.dfS[f * DFW + HALO + jm[m]] = v;
+          if (cl_ == 0 && jok[m]) cl::sts_noalias(&S.dfS[f * DFW + HALO + jm[m]], v);
         }
       }
     }

@@ -93,6 +93,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Reduce-scatter of 16 per-lane partial sums over a 16-lane group (xor 8,4,2,1): 15 shuffles instead of the 64
 // of a plain butterfly.  On return v[0] of lane L holds the group sum of element (L & 15).
+// Shared-memory store the compiler does not treat as a memory operation: ordinary loads may be scheduled across it. Only for
+// addresses that no ordinary load/store of the same thread touches before the next barrier (keeps long unrolled
+// load -> math -> store chains from being serialised by may-alias analysis).
+__device__ __forceinline__ void sts_noalias(float* p, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v));
+}
+
 __device__ __forceinline__ float reduce_scatter16(float (&v)[16], int lane) {
 #pragma unroll
   for (int hs = 8; hs >= 1; hs >>= 1) {
