@@ -204,7 +204,12 @@ def run_satk(args, rank, world, local_rank):
         dom = max(kt, key=kt.get)
         alg = bytes_step * td * (2 if dom.endswith("bwd") else 1)
         ach = alg / (kt[dom] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same shapes only)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                 "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kt[dom], "us_per_decoder_step": kt[dom] * 1e3 / td,
                 "kernel_ms": kt}
