@@ -42,6 +42,8 @@ int satk_device_info(int* out5);
 /* sizeof() of the descriptor structs, in declaration order (gemm, lstm_fwd, lstm_bwd, attn_fwd, attn_bwd):
  * lets a foreign-language binding verify its struct layout */
 int satk_struct_sizes(int* out5);
+/* same for the decode-step descriptors (rowgemm, attn_step, sa_step) */
+int satk_struct_sizes_decode(int* out3);
 
 /* ------------------------------------------------------------------------------------------
  * Dense tile: C = epilogue( alpha * sum_tap op(A_tap) * op(B_tap) ) (+ beta*C)
@@ -284,6 +286,75 @@ typedef struct {
   float* dloc_layer_w;         /* [att_filters, A1] (+=) */
 } satk_attn_rnn_bwd_desc;
 int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Free-running decoder step (PREDICT mode, predict_mel.py:36-74): the inference-branch cells of
+ * rnn_wrappers.py:47-124,188-214 and module.py:762-778 with the decoder self-attention served from a
+ * key/value cache instead of re-attending over the whole history every step.  Every kernel reads the
+ * step index t from device memory (`t_ptr`), so one step can be captured in a CUDA graph and replayed.
+ * ------------------------------------------------------------------------------------------ */
+/* Skinny dense layer(s): C_i[M,N_i] = act_i(A[M,K] . W_i[K,N_i] + bias_i) (+ residual_i), up to 3 matrices sharing A.
+ * W_i is the TF kernel layout [in,out].  `*_tstride` (elements) are multiplied by t = *t_ptr and added to the base
+ * pointer, so histories / caches [Tmax, B, .] are addressed without host involvement. */
+typedef struct {
+  int M, K;
+  const float* A; long long lda; long long a_tstride;
+  const int* t_ptr;            /* device int (NULL: t = 0) */
+  int nmat;                    /* 1..3 */
+  const float* W[3];
+  const float* bias[3];        /* or NULL */
+  float* C[3]; long long ldc[3]; long long c_tstride[3];
+  int N[3]; int act[3];
+  const float* residual[3]; long long ldres[3]; long long res_tstride[3];   /* added after the activation, or NULL */
+} satk_rowgemm_desc;
+int satk_rowgemm(const satk_rowgemm_desc* d, void* stream);
+
+/* ZoneoutLSTMCell pointwise part in inference mode (A.5, A.6): gates [B,4H] pre-activation (i,j,f,o; bias included),
+ * c/h [B,H] state updated in place with the zoneout expectation (1-z)*new + z*old; the cell output (un-zoned h) goes to
+ * out[b*ld_out + u], the new h state additionally to hdst[b*ld_h + u] (either may be NULL). */
+int satk_lstm_point(const float* gates, float* c, float* h, int B, int H, float zc, float zh, float forget_bias,
+                    float* out, long long ld_out, float* hdst, long long ld_h, void* stream);
+
+/* One step of the attention mechanism(s) for every utterance (forward_attention.py:88-122,:13-26; TF BahdanauAttention
+ * A.8; transition agent :111-114).  State (aprev, alpha, u) is updated in place; contexts [ctx1|ctx2] are written to up to
+ * two destinations (the next LSTM-1 input row and the LSTM-2 input row). */
+typedef struct {
+  int B, Tt, A1, A2, M1, M2;
+  int att_kernel, att_filters; /* 0 for additive attention */
+  int mode;                    /* 0 additive, 1 location_sensitive, 2 forward */
+  int cumulative, use_agent;
+  const int* t_ptr;            /* device step index (row of align1/align2), NULL: 0 */
+  const long long* lengths;    /* [B] */
+  const float* q; long long ldq;               /* [B, A1+A2] processed queries (query_layer outputs) */
+  const float* keys1; const float* values1;    /* [Tt,B,A1], [Tt,B,M1] time-major */
+  const float* v1; const float* b1;            /* [A1]; b1 may be NULL */
+  const float* loc_conv_w; const float* loc_conv_b; const float* loc_layer_w;
+  const float* keys2; const float* values2; const float* v2;
+  const float* agent_w; const float* agent_b;  /* [M1+A1], [1] transition_factor_projection */
+  float* aprev;                /* [B,Tt] previous (or cumulative) alignments */
+  float* alpha;                /* [B,Tt] forward variable */
+  float* u;                    /* [B] transition factor */
+  float* ctx_dst0; long long ld0;
+  float* ctx_dst1; long long ld1;
+  float* align1;               /* [Tmax,B,Tt] or NULL */
+  float* align2;
+} satk_attn_step_desc;
+int satk_attn_step(const satk_attn_step_desc* d, void* stream);
+
+/* Newest query against the cached keys / values of decoder steps 0..t (causal row t of self_attention.py:45-65). */
+typedef struct {
+  int B, D, heads, Tmax;
+  const int* t_ptr;
+  const float* q; long long ldq;   /* [B,D] */
+  const float* Kc; const float* Vc;/* [Tmax,B,D]; rows 0..t valid */
+  float* out; long long ldo;       /* [B,D] heads concatenated */
+  float* probs;                    /* [B,heads,Tmax,Tmax] row t receives the alignment, or NULL */
+} satk_sa_step_desc;
+int satk_sa_step(const satk_sa_step_desc* d, void* stream);
+
+/* End of a step: records the first step at which sigmoid(stop[t,b]) > 0.5 for all b and t > min_iters into *done_step
+ * (initialised to -1 by the caller; stop may be NULL), then *t_ptr += 1. */
+int satk_decode_tick(int* t_ptr, const float* stop, int B, int min_iters, int* done_step, void* stream);
 
 #ifdef __cplusplus
 }

@@ -411,6 +411,75 @@ def decoder_forward(P, d, memory1, memory2, source_length, target, spk_embed, tr
     return mel.reshape(B, -1, d.n_mels), stop, al1, al2, sa_aligns            # module.py:1558
 
 
+def decoder_free_running(P, d, memory1, memory2, source_length, spk_embed, max_iters, min_iters=10, use_stop_token=True):
+    """PREDICT-mode decoder (module.py:762-778): dynamic_decode of
+    OutputAndStopTokenTransparentWrapper(TransformerWrapper(RNNStateHistoryWrapper(decoder_cell))) driven by
+    StopTokenBasedInferenceHelper.  Each step: the decoder cell (pre-net, LSTM-1 + attention(s), LSTM-2/3) on the
+    previous step's last n_feed_frame predicted frames (zeros at t=0, helpers.py:224-225); its output is appended to the
+    history (rnn_wrappers.py:69-75); the self-attention stack is re-run over the WHOLE history with the causal mask and the
+    last row is kept (rnn_wrappers.py:111-124); mel and stop projections (rnn_wrappers.py:188-214).  The loop ends after the
+    first step t with sigmoid(stop) > 0.5 for every utterance and t > min_iters (helpers.py:103-107 semantics), or after
+    max_iters steps.  Returns mel [B, T*r, n_mels], stop [B, T], alignments (B, Tt, T)."""
+    B = memory1.shape[0]
+    Tt = memory1.shape[1]
+    dt, dev = memory1.dtype, memory1.device
+    keys1, values1 = attention_memory(memory1, source_length, P["att1.memory.W"])
+    if d.dual:
+        keys2, values2 = attention_memory(memory2, source_length, P["att2.memory.W"])
+    H1, HD = d.att_rnn, d.dec_out
+    c1 = h1 = memory1.new_zeros(B, H1)
+    c2 = h2 = memory1.new_zeros(B, HD)
+    c3 = h3 = memory1.new_zeros(B, HD)
+    attn = memory1.new_zeros(B, d.ctx)
+    st1 = attention1_initial_state(d, B, Tt, dt, dev)
+    inp = memory1.new_zeros(B, d.n_mels * d.n_feed)
+    hist, mels, stops, al1, al2 = [], [], [], [], []
+    for t in range(max_iters):
+        pre = decoder_prenet(P, d, inp, spk_embed, None, False, step=t)
+        cell_in = torch.cat([pre, attn], dim=-1)
+        out1, c1, h1 = zoneout_lstm_step(cell_in, c1, h1, P["dec.lstm1.W"], P["dec.lstm1.b"], None, None, d.zc, d.zh, False)
+        a1, st1 = attention1_step(P, d, out1, st1, keys1, values1, source_length)
+        ctx1 = (a1[:, None, :] @ values1).squeeze(1)
+        al1.append(a1)
+        if d.dual:
+            a2 = attention2_step(P, out1, keys2, source_length)
+            ctx2 = (a2[:, None, :] @ values2).squeeze(1)
+            al2.append(a2)
+            attn = torch.cat([ctx1, ctx2], dim=-1)
+        else:
+            attn = ctx1
+        x2 = torch.cat([out1, attn], dim=-1)
+        out2, c2, h2 = zoneout_lstm_step(x2, c2, h2, P["dec.lstm2.W"], P["dec.lstm2.b"], None, None, d.zc, d.zh, False)
+        out3, c3, h3 = zoneout_lstm_step(out2, c3, h3, P["dec.lstm3.W"], P["dec.lstm3.b"], None, None, d.zc, d.zh, False)
+        hist.append(out3)
+        x = out3
+        if d.dual:
+            full = torch.stack(hist, dim=1)
+            for h in range(d.dec_sa_hops):
+                full, _ = self_attention_transformer(full, P, f"dec.sa{h}", d.dec_sa_heads, True, None, 1.0)
+            x = full[:, -1]
+        mel_t = dense(x, P["dec.out_proj.W"], P["dec.out_proj.b"])
+        stop_t = dense(x, P["dec.stop_proj.W"], P["dec.stop_proj.b"]).squeeze(-1)
+        mels.append(mel_t)
+        stops.append(stop_t)
+        inp = mel_t[:, -d.n_mels * d.n_feed:]
+        if use_stop_token and t > min_iters and bool((torch.sigmoid(stop_t) > 0.5).all()):
+            break
+    mel = torch.stack(mels, dim=1).reshape(B, -1, d.n_mels)
+    return (mel, torch.stack(stops, dim=1), torch.stack(al1, dim=2), torch.stack(al2, dim=2) if d.dual else None)
+
+
+def model_predict(P, d, features, max_iters=None, min_iters=10, use_stop_token=True):
+    """model_fn in PREDICT mode (models/models.py:351-408 with is_training=False, no labels)."""
+    spk = None
+    if d.use_speaker:
+        spk = P["speaker_embedding"][features.speaker_id - d.speaker_offset]
+    mem1, mem2, enc_aligns = encoder_forward(P, d, features.source, features.source_length, False, None, None)
+    mel, stop, al1, al2 = decoder_free_running(P, d, mem1, mem2, features.source_length, spk, max_iters or d.max_iters,
+                                               min_iters, use_stop_token)
+    return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2)
+
+
 # ----------------------------------------------------------------------------------------------
 # model_fn body: losses and optimiser (models/models.py:351-408, 467-498, 595-598)
 # ----------------------------------------------------------------------------------------------

@@ -48,6 +48,13 @@ int satk_struct_sizes(int* out5) {
   return 0;
 }
 
+int satk_struct_sizes_decode(int* out3) {
+  out3[0] = (int)sizeof(satk_rowgemm_desc);
+  out3[1] = (int)sizeof(satk_attn_step_desc);
+  out3[2] = (int)sizeof(satk_sa_step_desc);
+  return 0;
+}
+
 int satk_gemm(const satk_gemm_desc* d, int engine, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (engine == 1) return satk::gemm_simt_launch(d, st);

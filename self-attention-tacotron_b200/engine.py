@@ -42,8 +42,6 @@ class TacotronEngine:
         if self.device.type != "cuda":
             raise O.L.SatkError("TacotronEngine needs a CUDA device: the product path has no CPU fallback")
         O.L.load()
-        if self.d.transition_agent:
-            raise NotImplementedError("use_forward_attention_transition_agent=True is not implemented yet")
         self.ps = params.to(self.device) if params is not None else ParamStore(self.d, self.device).init(seed)
         self._bufs: Dict[str, torch.Tensor] = {}
         self._mask_seed = 0x5A7C + seed
@@ -563,6 +561,9 @@ class TacotronEngine:
         B, Tt = source.shape
         Tm = labels.mel.shape[1]
         Td = Tm // d.r
+        if d.transition_agent:
+            raise NotImplementedError("use_forward_attention_transition_agent=True: only the free-running decode (predict) "
+                                      "implements the transition agent; the teacher-forced attention-RNN kernels do not yet")
         if training and masks is None:
             masks = self.device_masks(B, Tt, Td)
         self._training = training
@@ -580,6 +581,200 @@ class TacotronEngine:
         self.saved = dict(B=B, Tt=Tt, Td=Td, Tm=Tm, source_length=source_length, dmel=dmel, dstop=dstop, features=features)
         return dict(mel_tm=mel_tm, stop_tm=stop_tm, align1_tm=al1, align2_tm=al2, enc_self_P=enc_al, dec_self_P=dec_sa,
                     memory1_tm=mem1, memory2_tm=mem2, losses=out3)
+
+    # ------------------------------------------------------------------ free-running decode (PREDICT)
+    def _build_decode_step(self, B, Tt, Tmax, use_stop_token, min_iters):
+        """Descriptors + launch sequence of ONE free-running decoder step (module.py:762-778, rnn_wrappers.py:47-124,188-214).
+        All tensors are persistent buffers and every kernel reads the step index from ``t_dev``, so the returned closure can
+        be captured once in a CUDA graph and replayed."""
+        d, p = self.d, self.ps.p
+        H1, HD, P1, P0 = d.att_rnn, d.dec_out, d.dec_prenet[1], d.dec_prenet[0]
+        CTX, OU = d.ctx, d.out_units
+        X2W = H1 + CTX
+        W1C, W2C, W3C = P1 + CTX + H1, X2W + HD, 2 * HD
+        b_ = self.buf
+        t_dev = b_("pred.t", (1,), torch.int32)
+        done = b_("pred.done", (1,), torch.int32)
+        mel_hist = b_("pred.mel_hist", (Tmax + 1, B, OU))
+        stop_hist = b_("pred.stop_hist", (Tmax, B))
+        cell_in, x2c, x3c = b_("pred.cell_in", (B, W1C)), b_("pred.x2cat", (B, W2C)), b_("pred.x3cat", (B, W3C))
+        g1, g2, g3 = b_("pred.g1", (B, 4 * H1)), b_("pred.g2", (B, 4 * HD)), b_("pred.g3", (B, 4 * HD))
+        st = {n: b_("pred." + n, (B, H1 if n.endswith("1") else HD)) for n in ("c1", "h1", "c2", "h2", "c3", "h3")}
+        q = b_("pred.q", (B, d.att1 + d.att2))
+        o3 = b_("pred.o3", (B, HD))
+        pp0, pp1 = b_("pred.pp0", (B, P0)), None
+        aprev, alpha, u = b_("pred.aprev", (B, Tt)), b_("pred.alpha", (B, Tt)), b_("pred.u", (B,))
+        al1 = b_("pred.align1", (Tmax, B, Tt))
+        al2 = b_("pred.align2", (Tmax, B, Tt)) if d.dual else None
+        lengths = b_("pred.lengths", (B,), torch.int64)
+        loc = d.attention in ("forward", "location_sensitive")
+        steps = []
+        # pre-net (module.py:1509-1511; speaker variant multi_speaker_modules.py:27-32); no dropout outside training
+        a_in = dict(lda=OU, a_off=OU - d.dec_in, a_tstride=B * OU, t_ptr=t_dev)
+        if d.use_speaker:
+            h0 = b_("pred.h0", (B, P0))
+            sp = b_("dec.sp", (B, P0))
+            steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W0"], bias=p["dec.prenet0.b0"], act="relu", C=h0,
+                                                                      residual=sp)], **a_in))
+            steps.append(O.rowgemm_desc(h0, B, P0, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)]))
+        else:
+            steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)],
+                                        **a_in))
+        steps.append(O.rowgemm_desc(pp0, B, P0, [dict(W=p["dec.prenet1.W"], bias=p["dec.prenet1.b"], act="relu", C=cell_in, ldc=W1C)]))
+        # LSTM-1 on [prenet | attention | h] (AttentionWrapper concat, A.7)
+        steps.append(O.rowgemm_desc(cell_in, B, W1C, [dict(W=p["dec.lstm1.W"], bias=p["dec.lstm1.b"], C=g1)]))
+        steps.append(("lstm", g1, st["c1"], st["h1"], H1, dict(out=x2c, ld_out=W2C, hdst=cell_in, ld_h=W1C, h_off=P1 + CTX)))
+        qm = [dict(W=p["att1.query.W"], C=q, ldc=d.att1 + d.att2)]
+        if d.dual:
+            qm.append(dict(W=p["att2.query.W"], C=q, ldc=d.att1 + d.att2, c_off=d.att1))
+        steps.append(O.rowgemm_desc(x2c, B, H1, qm, lda=W2C))
+        bufs = self._bufs
+        agent = d.attention == "forward" and d.transition_agent
+        steps.append(O.attn_step_desc(
+            B=B, Tt=Tt, A1=d.att1, A2=d.att2, M1=d.mem1, M2=d.mem2, att_kernel=d.att_kernel if loc else 0,
+            att_filters=d.att_filters if loc else 0, mode=_MODE[d.attention], cumulative=int(d.cumulative), use_agent=int(agent),
+            t_ptr=t_dev, lengths=lengths, q=q, ldq=d.att1 + d.att2, keys1=bufs["dec.keys1"], values1=bufs["dec.values1"],
+            v1=p["att1.v"], b1=p["att1.b"] if loc else None, loc_conv_w=p["att1.loc_conv.W"] if loc else None,
+            loc_conv_b=p["att1.loc_conv.b"] if loc else None, loc_layer_w=p["att1.loc_layer.W"] if loc else None,
+            keys2=bufs["dec.keys2"] if d.dual else None, values2=bufs["dec.values2"] if d.dual else None,
+            v2=p["att2.v"] if d.dual else None, agent_w=p["att1.agent.W"] if agent else None,
+            agent_b=p["att1.agent.b"] if agent else None, aprev=aprev, alpha=alpha, u=u,
+            ctx_dst0=cell_in.data_ptr() + 4 * P1, ld0=W1C, ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, align1=al1, align2=al2))
+        # LSTM-2 / LSTM-3 (DecoderRNNV2 on ConcatOutputAndAttentionWrapper, module.py:1024,1525-1534)
+        steps.append(O.rowgemm_desc(x2c, B, W2C, [dict(W=p["dec.lstm2.W"], bias=p["dec.lstm2.b"], C=g2)]))
+        steps.append(("lstm", g2, st["c2"], st["h2"], HD, dict(out=x3c, ld_out=W3C, hdst=x2c, ld_h=W2C, h_off=X2W)))
+        steps.append(O.rowgemm_desc(x3c, B, W3C, [dict(W=p["dec.lstm3.W"], bias=p["dec.lstm3.b"], C=g3)]))
+        steps.append(("lstm", g3, st["c3"], st["h3"], HD, dict(out=o3, ld_out=HD, hdst=x3c, ld_h=W3C, h_off=HD)))
+        x = o3
+        probs = []
+        if d.dual:
+            # TransformerWrapper (rnn_wrappers.py:111-124) with cached keys / values: row t of the causal attention
+            for h in range(d.dec_sa_hops):
+                n = f"dec.sa{h}"
+                D = HD
+                Kc, Vc = b_(f"pred.K{h}", (Tmax, B, D)), b_(f"pred.V{h}", (Tmax, B, D))
+                Qb, Ob, ao, y = b_(f"pred.Q{h}", (B, D)), b_(f"pred.O{h}", (B, D)), b_(f"pred.ao{h}", (B, D)), b_(f"pred.y{h}", (B, D))
+                pr = b_(f"pred.P{h}", (B, d.dec_sa_heads, Tmax, Tmax), zero=True)
+                probs.append(pr)
+                steps.append(O.rowgemm_desc(x, B, D, [
+                    dict(W=p[n + ".key.W"], bias=p[n + ".key.b"], C=Kc, c_tstride=B * D),
+                    dict(W=p[n + ".value.W"], bias=p[n + ".value.b"], C=Vc, c_tstride=B * D),
+                    dict(W=p[n + ".query.W"], bias=p[n + ".query.b"], C=Qb)], t_ptr=t_dev))
+                steps.append(O.sa_step_desc(B=B, D=D, heads=d.dec_sa_heads, Tmax=Tmax, t_ptr=t_dev, q=Qb, ldq=D, Kc=Kc, Vc=Vc, out=Ob,
+                                            ldo=D, probs=pr))
+                steps.append(O.rowgemm_desc(Ob, B, D, [dict(W=p[n + ".output.W"], bias=p[n + ".output.b"], C=ao)]))
+                steps.append(O.rowgemm_desc(ao, B, D, [dict(W=p[n + ".transform.W"], bias=p[n + ".transform.b"], act="tanh", C=y,
+                                                            residual=x)]))
+                x = y
+        # OutputAndStopTokenTransparentWrapper (rnn_wrappers.py:188-214): mel frames of step t -> row t+1 (row 0 = go frame)
+        steps.append(O.rowgemm_desc(x, B, HD, [
+            dict(W=p["dec.out_proj.W"], bias=p["dec.out_proj.b"], C=mel_hist, c_off=B * OU, c_tstride=B * OU),
+            dict(W=p["dec.stop_proj.W"], bias=p["dec.stop_proj.b"], C=stop_hist, ldc=1, c_tstride=B)], t_ptr=t_dev))
+        zc, zh = d.zc, d.zh
+
+        def run_step():
+            for s_ in steps:
+                if isinstance(s_, tuple):
+                    _, g, c, h, H, kw = s_
+                    O.lstm_point(g, c, h, B, H, zc, zh, FORGET_BIAS, **kw)
+                elif isinstance(s_, O.RowGemmDesc):
+                    O.rowgemm(s_)
+                elif isinstance(s_, O.AttnStepDesc):
+                    O.attn_step(s_)
+                else:
+                    O.sa_step(s_)
+            O.decode_tick(t_dev, stop_hist if use_stop_token else None, B, min_iters, done)
+
+        state = dict(t_dev=t_dev, done=done, mel_hist=mel_hist, stop_hist=stop_hist, cell_in=cell_in, x2c=x2c, x3c=x3c, st=st,
+                     aprev=aprev, alpha=alpha, u=u, al1=al1, al2=al2, lengths=lengths, probs=probs, steps=steps)
+        return run_step, state
+
+    def predict(self, features, max_iters: Optional[int] = None, use_stop_token: bool = True, min_iters: int = 10,
+                use_graph: bool = True, check_every: int = 64):
+        """Free-running inference (model_fn in PREDICT mode, models/models.py:351-408 with is_training=False; decoder
+        branch module.py:762-778).  Returns mel [B, T*r, n_mels], stop logits [B, T], alignments (B, Tt, T) and the decoder
+        self-attention alignments; T = number of executed steps (stop token or max_iters)."""
+        d = self.d
+        source, source_length = features.source, features.source_length
+        B, Tt = source.shape
+        Tmax = int(max_iters or d.max_iters)
+        self._training = False
+        spk = None
+        if d.use_speaker:
+            spk = self.buf("spk_embed", (B, d.speaker_dim))
+            O.embedding_fwd(features.speaker_id, self.ps.p["speaker_embedding"], spk, offset=d.speaker_offset)
+        mem1, mem2, enc_al = self.encoder(source, source_length, False, None)
+        p = self.ps.p
+        R = Tt * B
+        # attention memories (BahdanauAttention.__init__, A.8) — same buffers as the teacher-forced decoder
+        values1 = self.buf("dec.values1", (R, d.mem1))
+        O.mask_rows(mem1, source_length, B, Tt, d.mem1, True, values1)
+        self.lin(values1, "att1.memory.W", self.buf("dec.keys1", (R, d.att1)))
+        if d.dual:
+            values2 = self.buf("dec.values2", (R, d.mem2))
+            O.mask_rows(mem2, source_length, B, Tt, d.mem2, True, values2)
+            self.lin(values2, "att2.memory.W", self.buf("dec.keys2", (R, d.att2)))
+        if d.use_speaker:
+            sp_pre = self.lin(spk, "dec.prenet0.Ws", self.buf("dec.sp_pre", (B, d.dec_prenet[0])), bias=p["dec.prenet0.bs"])
+            O.softsign_fwd(sp_pre, self.buf("dec.sp", (B, d.dec_prenet[0])))
+        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters))
+        cache = getattr(self, "_decode_cache", None)
+        if cache is None or cache["key"] != key:
+            run_step, stt = self._build_decode_step(B, Tt, Tmax, use_stop_token, min_iters)
+            cache = self._decode_cache = dict(key=key, run_step=run_step, state=stt, graph=None)
+        run_step, stt = cache["run_step"], cache["state"]
+        # initial state: zero LSTM states / attention, alpha_0 = one-hot(0), u_0 = 0.5 (forward_attention.py:128-136)
+        for k in ("cell_in", "x2c", "x3c", "aprev", "alpha"):
+            stt[k].zero_()
+        for v in stt["st"].values():
+            v.zero_()
+        stt["mel_hist"][0].zero_()
+        stt["alpha"][:, 0] = 1.0
+        stt["u"].fill_(0.5)
+        stt["t_dev"].zero_()
+        stt["done"].fill_(-1)
+        stt["lengths"].copy_(source_length)
+        for pr in stt["probs"]:
+            pr.zero_()
+        n_run = 0
+        if use_graph and Tmax > 1:
+            run_step()                                   # step 0 eagerly (also sets kernel attributes before the capture)
+            n_run = 1
+            if cache["graph"] is None:
+                torch.cuda.synchronize()
+                saved_state = {k: v.clone() for k, v in self._bufs.items() if k.startswith("pred.")}
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run_step()
+                cache["graph"] = g
+                for k, v in saved_state.items():         # the capture does not execute, but keep the state provably intact
+                    self._bufs[k].copy_(v)
+            g = cache["graph"]
+        T_done = None
+        while n_run < Tmax:
+            chunk = min(check_every, Tmax - n_run)
+            for _ in range(chunk):
+                if use_graph and Tmax > 1:
+                    g.replay()
+                else:
+                    run_step()
+            n_run += chunk
+            if use_stop_token:
+                ds = int(stt["done"].item())
+                if ds >= 0:
+                    T_done = ds + 1
+                    break
+        T = T_done if T_done is not None else Tmax
+        if use_stop_token and T_done is None:
+            ds = int(stt["done"].item())
+            if ds >= 0:
+                T = ds + 1
+        mel = stt["mel_hist"][1:T + 1].view(T, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, T * d.r, d.n_mels)
+        out = dict(mel=mel, stop=stt["stop_hist"][:T].t(), alignment=stt["al1"][:T].permute(1, 2, 0),
+                   alignment2=stt["al2"][:T].permute(1, 2, 0) if d.dual else None,
+                   dec_self_P=[pr[:, i, :T, :T] for pr in stt["probs"] for i in range(d.dec_sa_heads)],
+                   enc_self_P=enc_al, steps=T, steps_executed=n_run)
+        return out
 
     def backward(self):
         """BPTT through decoder and encoder; gradients land in ``self.ps.grad`` (zeroed first)."""

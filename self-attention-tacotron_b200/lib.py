@@ -79,6 +79,34 @@ class AttnRnnBwdDesc(C.Structure):
     ]
 
 
+class RowGemmDesc(C.Structure):
+    _fields_ = [
+        ("M", i32), ("K", i32), ("A", fp), ("lda", i64), ("a_tstride", i64), ("t_ptr", fp), ("nmat", i32),
+        ("W", fp * 3), ("bias", fp * 3), ("C", fp * 3), ("ldc", i64 * 3), ("c_tstride", i64 * 3),
+        ("N", i32 * 3), ("act", i32 * 3), ("residual", fp * 3), ("ldres", i64 * 3), ("res_tstride", i64 * 3),
+    ]
+
+
+class AttnStepDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("Tt", i32), ("A1", i32), ("A2", i32), ("M1", i32), ("M2", i32),
+        ("att_kernel", i32), ("att_filters", i32), ("mode", i32), ("cumulative", i32), ("use_agent", i32),
+        ("t_ptr", fp), ("lengths", fp), ("q", fp), ("ldq", i64),
+        ("keys1", fp), ("values1", fp), ("v1", fp), ("b1", fp),
+        ("loc_conv_w", fp), ("loc_conv_b", fp), ("loc_layer_w", fp),
+        ("keys2", fp), ("values2", fp), ("v2", fp), ("agent_w", fp), ("agent_b", fp),
+        ("aprev", fp), ("alpha", fp), ("u", fp),
+        ("ctx_dst0", fp), ("ld0", i64), ("ctx_dst1", fp), ("ld1", i64), ("align1", fp), ("align2", fp),
+    ]
+
+
+class SaStepDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("D", i32), ("heads", i32), ("Tmax", i32), ("t_ptr", fp), ("q", fp), ("ldq", i64),
+        ("Kc", fp), ("Vc", fp), ("out", fp), ("ldo", i64), ("probs", fp),
+    ]
+
+
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
 
 _lib: Optional[C.CDLL] = None
@@ -92,6 +120,7 @@ SYMBOLS = [
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
     "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_debug_phase_cycles",
+    "satk_struct_sizes_decode", "satk_rowgemm", "satk_lstm_point", "satk_attn_step", "satk_sa_step", "satk_decode_tick",
 ]
 
 

@@ -84,10 +84,24 @@ class _TacotronEstimator:
     # ---- model_fn (models.py:278 / :23)
     def model_fn(self, features, labels, mode, params=None, masks=None) -> EstimatorSpec:
         eng, d = self.engine, self.engine.d
-        if mode == ModeKeys.PREDICT:
-            raise NotImplementedError("free-running PREDICT (predict_mel.py path) is SURVEY §8(f1): not built yet; "
-                                      "use mode=EVAL for the teacher-forced decode")
         features = _to_device(features, self.device)
+        if mode == ModeKeys.PREDICT:
+            # free-running decode (predict_mel.py:36-74; decoder branch module.py:762-778), stop-token terminated
+            out = eng.predict(features, max_iters=getattr(params or self.params, "max_iters", None))
+            preds = {"id": features.id, "key": features.key, "mel": out["mel"], "stop_token": out["stop"],
+                     "alignment": out["alignment"], "source": features.source, "text": features.text}
+            gt = getattr(features, "mel", None)
+            if gt is None and labels is not None:
+                gt = labels.mel
+            if gt is not None:
+                preds["ground_truth_mel"] = gt
+            if d.dual:
+                preds["alignment2"] = out["alignment2"]
+                for i, a in enumerate(out["dec_self_P"]):
+                    preds[f"alignment{3 + i}"] = a.transpose(1, 2)
+                for i, a in enumerate(out["enc_self_P"]):
+                    preds[f"alignment{5 + i}"] = a.transpose(1, 2)
+            return EstimatorSpec(mode=mode, predictions=preds)
         labels = _to_device(labels, self.device)
         training = mode == ModeKeys.TRAIN
         if training:
@@ -151,10 +165,10 @@ class _TacotronEstimator:
         if checkpoint_path:
             self.restore(checkpoint_path)
         for item in input_fn():
-            features, labels = item if isinstance(item, tuple) and len(item) == 2 else (item, None)
-            if labels is None:
-                raise NotImplementedError("free-running PREDICT is SURVEY §8(f1): not built yet")
-            yield self.model_fn(features, labels, ModeKeys.EVAL, self.params).predictions
+            # tf.estimator.Estimator.predict runs model_fn in PREDICT mode on the features alone (predict_mel.py:54); a
+            # (features, labels) pair is accepted so the training input_fn can be reused — labels only add ground_truth_mel
+            features, labels = item if (isinstance(item, tuple) and len(item) == 2 and not hasattr(item, "_fields")) else (item, None)
+            yield self.model_fn(features, labels, ModeKeys.PREDICT, self.params).predictions
 
 
 class DualSourceSelfAttentionTacotronModel(_TacotronEstimator):

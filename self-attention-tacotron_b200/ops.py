@@ -11,7 +11,8 @@ from typing import Optional
 import torch
 
 from . import lib as L
-from .lib import ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, check, load, ptr, stream_ptr
+from .lib import (ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, AttnStepDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, RowGemmDesc, SaStepDesc,
+                  check, load, ptr, stream_ptr)
 
 # GEMM engine: 0 auto (tcgen05 tile when the shape allows, else SIMT), 1 SIMT fp32, 2 tcgen05 only
 GEMM_ENGINE = 0
@@ -352,4 +353,89 @@ def attn_rnn_bwd(f: AttnRnnFwdDesc, **kw):
             v = v.data_ptr()
         setattr(d, k, v)
     check(load().satk_attn_rnn_bwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_rnn_bwd")
+    _count()
+
+
+# ---------------------------------------------------------------------------------------------- free-running decode step
+def rowgemm_desc(A, M, K, mats, *, lda=None, a_off=0, a_tstride=0, t_ptr=None) -> RowGemmDesc:
+    """Descriptor of up to three skinny dense layers sharing the input rows ``A`` [M,K].
+
+    ``mats``: list of dicts with W [K,N] (TF layout), optional bias / act / residual (+ ldres, res_off, res_tstride),
+    C (+ ldc, c_off, c_tstride).  Offsets are in elements.  The tensors must stay alive while the descriptor is used."""
+    _req(A)
+    d = RowGemmDesc()
+    d.M, d.K = M, K
+    d.A, d.lda, d.a_tstride = A.data_ptr() + 4 * a_off, lda or K, a_tstride
+    d.t_ptr = ptr(t_ptr)
+    d.nmat = len(mats)
+    for i, m in enumerate(mats):
+        W = m["W"]
+        _req(W); _req(m["C"])
+        if W.shape[0] != K:
+            raise L.SatkError(f"rowgemm: weight {tuple(W.shape)} does not match K={K}")
+        N = W.shape[1]
+        d.W[i] = W.data_ptr()
+        d.bias[i] = ptr(m.get("bias"))
+        d.C[i] = m["C"].data_ptr() + 4 * m.get("c_off", 0)
+        d.ldc[i] = m.get("ldc", N)
+        d.c_tstride[i] = m.get("c_tstride", 0)
+        d.N[i] = N
+        d.act[i] = ACT[m.get("act")]
+        res = m.get("residual")
+        d.residual[i] = (res.data_ptr() + 4 * m.get("res_off", 0)) if res is not None else None
+        d.ldres[i] = m.get("ldres", N)
+        d.res_tstride[i] = m.get("res_tstride", 0)
+    return d
+
+
+def rowgemm(d: RowGemmDesc) -> None:
+    check(load().satk_rowgemm(C.byref(d), C.c_void_p(stream_ptr())), "satk_rowgemm")
+    _count()
+
+
+def lstm_point(gates, c, h, B, H, zc, zh, forget_bias, out=None, ld_out=0, out_off=0, hdst=None, ld_h=0, h_off=0) -> None:
+    _req(gates); _req(c); _req(h)
+    o = (out.data_ptr() + 4 * out_off) if out is not None else None
+    hd = (hdst.data_ptr() + 4 * h_off) if hdst is not None else None
+    check(load().satk_lstm_point(C.c_void_p(ptr(gates)), C.c_void_p(ptr(c)), C.c_void_p(ptr(h)), B, H, C.c_float(zc), C.c_float(zh),
+                                 C.c_float(forget_bias), C.c_void_p(o), C.c_longlong(ld_out), C.c_void_p(hd), C.c_longlong(ld_h),
+                                 C.c_void_p(stream_ptr())), "satk_lstm_point")
+    _count()
+
+
+def attn_step_desc(**kw) -> AttnStepDesc:
+    d = AttnStepDesc()
+    for k, v in kw.items():
+        if torch.is_tensor(v):
+            if not v.is_cuda:
+                raise L.SatkError("satk ops need CUDA tensors (no CPU fallback)")
+            v = v.data_ptr()
+        setattr(d, k, v)
+    return d
+
+
+def attn_step(d: AttnStepDesc) -> None:
+    check(load().satk_attn_step(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_step")
+    _count()
+
+
+def sa_step_desc(**kw) -> SaStepDesc:
+    d = SaStepDesc()
+    for k, v in kw.items():
+        if torch.is_tensor(v):
+            if not v.is_cuda:
+                raise L.SatkError("satk ops need CUDA tensors (no CPU fallback)")
+            v = v.data_ptr()
+        setattr(d, k, v)
+    return d
+
+
+def sa_step(d: SaStepDesc) -> None:
+    check(load().satk_sa_step(C.byref(d), C.c_void_p(stream_ptr())), "satk_sa_step")
+    _count()
+
+
+def decode_tick(t_dev, stop, B, min_iters, done_step) -> None:
+    check(load().satk_decode_tick(C.c_void_p(ptr(t_dev)), C.c_void_p(ptr(stop)), B, min_iters, C.c_void_p(ptr(done_step)),
+                                  C.c_void_p(stream_ptr())), "satk_decode_tick")
     _count()

@@ -145,3 +145,31 @@ def test_golden_fixture(satk, root):
     assert abs(float(out["loss"]) - float(z["loss"])) < 1e-5
     assert np.allclose(grads["dec.lstm1.W"].numpy()[100:164, :64], z["grad_dec_lstm1_W_slice"], atol=1e-6)
     assert np.allclose(grads["att1.v"].numpy(), z["grad_att1_v"], atol=1e-6)
+
+
+def test_free_running_oracle_is_consistent_with_teacher_forcing(satk, root):
+    """PREDICT-branch restatement (oracle.decoder_free_running, module.py:762-778) vs the teacher-forced restatement: feeding
+    the free-running output back as the target reproduces it (eval mode), for the dual and the single-attention model."""
+    for cfg in ("ljspeech_self-attention-tacotron.json", "ljspeech_tacotron.json"):
+        hp = satk.load_hparams(os.path.join(root, "examples", cfg))
+        d = satk.dims_from_hparams(hp)
+        P = satk.ParamStore(d).init(11, "random").as_dict()
+        f, l = satk.synthetic_batch(hp, 2, 12, 8 * d.r, seed=4)
+        with torch.no_grad():
+            pr = OR.model_predict(P, d, f, max_iters=8, use_stop_token=False)
+            m1, m2, _ = OR.encoder_forward(P, d, f.source, f.source_length, False, None, None)
+            mel, stop, al1, al2, _ = OR.decoder_forward(P, d, m1, m2, f.source_length, pr["mel"], None, False)
+        assert pr["mel"].shape == (2, 8 * d.r, d.n_mels)
+        assert torch.allclose(mel, pr["mel"], atol=2e-5) and torch.allclose(stop.squeeze(-1), pr["stop"], atol=2e-5)
+        assert torch.allclose(al1, pr["alignment"], atol=1e-6)
+
+
+def test_free_running_oracle_stop_token(satk, root):
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    P = satk.ParamStore(d).init(11, "random").as_dict()
+    P["dec.stop_proj.b"] = torch.full_like(P["dec.stop_proj.b"], 50.0)
+    f, _ = satk.synthetic_batch(hp, 2, 10, 8 * d.r, seed=4)
+    with torch.no_grad():
+        pr = OR.model_predict(P, d, f, max_iters=30, min_iters=3, use_stop_token=True)
+    assert pr["stop"].shape == (2, 5)          # first t > min_iters is t = 4 -> 5 executed steps
