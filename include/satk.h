@@ -306,18 +306,25 @@ typedef struct {
   float* C[3]; long long ldc[3]; long long c_tstride[3];
   int N[3]; int act[3];
   const float* residual[3]; long long ldres[3]; long long res_tstride[3];   /* added after the activation, or NULL */
+  /* double-buffered rows: A += (t & 1) * a_pstride, C_i += (t & 1) * c_pstride[i]  (0: single buffer).  The recurrent input
+   * rows [x | h] are read by every CTA of a launch while the LSTM epilogue of the same launch produces the next h, so the
+   * concatenated rows live in two buffers alternating with the parity of t. */
+  long long a_pstride; long long c_pstride[3];
+  /* lstm_H > 0: the single matrix is an LSTM kernel [K, 4H] (gate order i,j,f,o) and the epilogue is the ZoneoutLSTMCell
+   * pointwise update in inference mode (A.5, A.6): c/h [M,H] are updated in place with (1-z)*new + z*old, the cell output
+   * (un-zoned h) goes to lstm_out[(t&1)*out_pstride + row*ld_out + u] and the new h state to
+   * lstm_hdst[((t+1)&1)*hdst_pstride + row*ld_hdst + u] (next step's input row); C / act / residual are unused. */
+  int lstm_H;
+  float* lstm_c; float* lstm_h;
+  float zc, zh, forget_bias;
+  float* lstm_out; long long ld_out; long long out_pstride;
+  float* lstm_hdst; long long ld_hdst; long long hdst_pstride;
 } satk_rowgemm_desc;
 int satk_rowgemm(const satk_rowgemm_desc* d, void* stream);
 
-/* ZoneoutLSTMCell pointwise part in inference mode (A.5, A.6): gates [B,4H] pre-activation (i,j,f,o; bias included),
- * c/h [B,H] state updated in place with the zoneout expectation (1-z)*new + z*old; the cell output (un-zoned h) goes to
- * out[b*ld_out + u], the new h state additionally to hdst[b*ld_h + u] (either may be NULL). */
-int satk_lstm_point(const float* gates, float* c, float* h, int B, int H, float zc, float zh, float forget_bias,
-                    float* out, long long ld_out, float* hdst, long long ld_h, void* stream);
-
 /* One step of the attention mechanism(s) for every utterance (forward_attention.py:88-122,:13-26; TF BahdanauAttention
  * A.8; transition agent :111-114).  State (aprev, alpha, u) is updated in place; contexts [ctx1|ctx2] are written to up to
- * two destinations (the next LSTM-1 input row and the LSTM-2 input row). */
+ * two destinations (the next LSTM-1 input row and the LSTM-2 input row).  A cluster of 8 CTAs serves one utterance. */
 typedef struct {
   int B, Tt, A1, A2, M1, M2;
   int att_kernel, att_filters; /* 0 for additive attention */
@@ -334,8 +341,8 @@ typedef struct {
   float* aprev;                /* [B,Tt] previous (or cumulative) alignments */
   float* alpha;                /* [B,Tt] forward variable */
   float* u;                    /* [B] transition factor */
-  float* ctx_dst0; long long ld0;
-  float* ctx_dst1; long long ld1;
+  float* ctx_dst0; long long ld0; long long pstride0;   /* written at parity (t+1)&1: LSTM-1 input row of the NEXT step */
+  float* ctx_dst1; long long ld1; long long pstride1;   /* written at parity t&1: LSTM-2 input row of THIS step */
   float* align1;               /* [Tmax,B,Tt] or NULL */
   float* align2;
 } satk_attn_step_desc;

@@ -5,60 +5,83 @@
 // rnn_wrappers.py:111-124; here keys/values of past steps are cached and only row t is computed: O(T^2)).
 //   rowgemm      skinny dense layers  C[M<=batch, N] = act(A.W + b) (+res): pre-net, LSTM gate rows, query / K / V / Q / O
 //                projections, transform, mel + stop projections.  Weights stream from L2 once per launch.
-//   lstm_point   ZoneoutLSTMCell pointwise part, inference interpolation (tacotron2 ZoneoutLSTMCell, A.5/A.6)
-//   attn_step    ForwardAttention / LocationSensitive / Bahdanau step for one utterance per CTA
+//                With lstm_H > 0 the epilogue is the ZoneoutLSTMCell pointwise update (inference interpolation, A.5/A.6).
+//   attn_step    ForwardAttention / LocationSensitive / Bahdanau step, one cluster of 8 CTAs per utterance
 //                (forward_attention.py:88-122, :13-26; A.8) incl. the transition agent (:111-114)
 //   sa_step      causal scaled-dot-product attention of the newest query over the cached history (self_attention.py:45-65)
 //   tick         t += 1 and stop-token bookkeeping (StopTokenBasedInferenceHelper: sigmoid(stop) > 0.5 for the whole batch
 //                after min_iters)
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace satk {
 namespace dstep {
 
+namespace cg = cooperative_groups;
+
 constexpr int MR = 16;     // rows per pass
 constexpr int KC = 128;    // reduction chunk staged in shared memory
 constexpr int NC = 32;     // columns per CTA (one per lane)
 
+__device__ __forceinline__ float ftanh_(float x) {
+  x = fminf(fmaxf(x, -15.f), 15.f);
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+
+// Skinny GEMM.  A cluster of KS CTAs shares one block of 32 output columns and splits the reduction; the partial
+// [16 x 32] tiles are summed by rank 0 through distributed shared memory, which then runs the epilogue: bias / activation /
+// residual, or (lstm_H > 0) the whole ZoneoutLSTMCell pointwise update — in that mode the 32 columns are the 4 gates of 8
+// hidden units, so the gate pre-activations never leave the chip.
+template <int KS>
 __global__ void __launch_bounds__(256) rowgemm_k(const satk_rowgemm_desc d) {
   __shared__ __align__(16) float As[KC][MR];
   __shared__ float red[8][MR][NC + 1];
+  __shared__ float part[MR * NC];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = KS > 1 ? (int)cluster.block_rank() : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // which matrix / column block
-  int i = 0, cb = blockIdx.x;
-  while (i < d.nmat - 1 && cb >= (d.N[i] + NC - 1) / NC) { cb -= (d.N[i] + NC - 1) / NC; ++i; }
+  int i = 0, cb = blockIdx.x / KS;
+  const bool lstm = d.lstm_H > 0;
+  if (!lstm)
+    while (i < d.nmat - 1 && cb >= (d.N[i] + NC - 1) / NC) { cb -= (d.N[i] + NC - 1) / NC; ++i; }
   const int N = d.N[i];
-  const long long t = d.t_ptr ? (long long)(*d.t_ptr) : 0;
-  const float* __restrict__ A = d.A + t * d.a_tstride;
+  const int tt = d.t_ptr ? *d.t_ptr : 0;
+  const long long t = tt;
+  const float* __restrict__ A = d.A + t * d.a_tstride + (long long)(tt & 1) * d.a_pstride;
   const float* __restrict__ W = d.W[i];
-  const int col = cb * NC + lane;
+  const int col = lstm ? ((lane >> 3) * d.lstm_H + cb * 8 + (lane & 7)) : (cb * NC + lane);
   const bool cok = col < N;
+  const int kper = (((d.K + KS - 1) / KS) + 15) / 16 * 16;
+  const int kr0 = rank * kper, kr1 = min(d.K, kr0 + kper);
   for (int m0 = 0; m0 < d.M; m0 += MR) {
     float acc[MR];
 #pragma unroll
     for (int m = 0; m < MR; ++m) acc[m] = 0.f;
-    for (int k0 = 0; k0 < d.K; k0 += KC) {
+    for (int k0 = kr0; k0 < kr1; k0 += KC) {
       __syncthreads();
       for (int idx = tid; idx < MR * KC; idx += 256) {
         const int m = idx % MR, k = idx / MR;
-        As[k][m] = (m0 + m < d.M && k0 + k < d.K) ? A[(long long)(m0 + m) * d.lda + k0 + k] : 0.f;
+        As[k][m] = (m0 + m < d.M && k0 + k < kr1) ? A[(long long)(m0 + m) * d.lda + k0 + k] : 0.f;
       }
       __syncthreads();
-      // warp w owns k = k0 + 16w .. +15: all 16 weight loads are issued before the first FMA
-      float wv[16];
       const int kb = k0 + warp * 16;
+      if (kb < kr1) {
+        // all 16 weight loads of this warp are in flight before the first FMA
+        float wv[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) wv[q] = (cok && kb + q < d.K) ? __ldg(W + (long long)(kb + q) * N + col) : 0.f;
+        for (int q = 0; q < 16; ++q) wv[q] = (cok && kb + q < kr1) ? __ldg(W + (long long)(kb + q) * N + col) : 0.f;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float4* a4 = reinterpret_cast<const float4*>(&As[warp * 16 + q][0]);
+        for (int q = 0; q < 16; ++q) {
+          const float4* a4 = reinterpret_cast<const float4*>(&As[warp * 16 + q][0]);
 #pragma unroll
-        for (int r = 0; r < MR / 4; ++r) {
-          const float4 a = a4[r];
-          acc[4 * r + 0] = fmaf(a.x, wv[q], acc[4 * r + 0]);
-          acc[4 * r + 1] = fmaf(a.y, wv[q], acc[4 * r + 1]);
-          acc[4 * r + 2] = fmaf(a.z, wv[q], acc[4 * r + 2]);
-          acc[4 * r + 3] = fmaf(a.w, wv[q], acc[4 * r + 3]);
+          for (int r = 0; r < MR / 4; ++r) {
+            const float4 a = a4[r];
+            acc[4 * r + 0] = fmaf(a.x, wv[q], acc[4 * r + 0]);
+            acc[4 * r + 1] = fmaf(a.y, wv[q], acc[4 * r + 1]);
+            acc[4 * r + 2] = fmaf(a.z, wv[q], acc[4 * r + 2]);
+            acc[4 * r + 3] = fmaf(a.w, wv[q], acc[4 * r + 3]);
+          }
         }
       }
     }
@@ -67,70 +90,111 @@ __global__ void __launch_bounds__(256) rowgemm_k(const satk_rowgemm_desc d) {
     __syncthreads();
     for (int o = tid; o < MR * NC; o += 256) {
       const int m = o / NC, c = o % NC;
-      const int cc = cb * NC + c;
-      if (m0 + m < d.M && cc < N) {
-        float s = 0.f;
+      float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][m][c];
-        if (d.bias[i]) s += __ldg(d.bias[i] + cc);
-        s = apply_act(s, d.act[i]);
-        if (d.residual[i]) s += d.residual[i][t * d.res_tstride[i] + (long long)(m0 + m) * d.ldres[i] + cc];
-        d.C[i][t * d.c_tstride[i] + (long long)(m0 + m) * d.ldc[i] + cc] = s;
+      for (int w = 0; w < 8; ++w) s += red[w][m][c];
+      part[o] = s;
+    }
+    if (KS > 1) cluster.sync(); else __syncthreads();
+    if (rank == 0) {
+      if (KS > 1) {
+        float sv[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int o = tid + 256 * h;
+          float s = part[o];
+#pragma unroll
+          for (int r = 1; r < KS; ++r) s += cluster.map_shared_rank(part, r)[o];
+          sv[h] = s;
+        }
+        __syncthreads();
+        part[tid] = sv[0];
+        part[tid + 256] = sv[1];
+        __syncthreads();
+      }
+      if (!lstm) {
+        for (int o = tid; o < MR * NC; o += 256) {
+          const int m = o / NC, c = o % NC;
+          const int cc = cb * NC + c;
+          if (m0 + m < d.M && cc < N) {
+            float s = part[o];
+            if (d.bias[i]) s += __ldg(d.bias[i] + cc);
+            s = apply_act(s, d.act[i]);
+            if (d.residual[i]) s += d.residual[i][t * d.res_tstride[i] + (long long)(m0 + m) * d.ldres[i] + cc];
+            d.C[i][t * d.c_tstride[i] + (long long)(tt & 1) * d.c_pstride[i] + (long long)(m0 + m) * d.ldc[i] + cc] = s;
+          }
+        }
+      } else if (tid < MR * 8) {
+        // ZoneoutLSTMCell pointwise (TF LSTMCell gate order i,j,f,o, A.5; eval-mode zoneout = expectation of the mask, A.6)
+        const int m = tid >> 3, uu = tid & 7, H = d.lstm_H;
+        const int row = m0 + m, unit = cb * 8 + uu;
+        if (row < d.M && unit < H) {
+          const float* bs = d.bias[0];
+          const float* pr = part + m * NC;
+          const float gi = sigmoidf_(pr[uu] + (bs ? __ldg(bs + unit) : 0.f));
+          const float gj = tanhf_(pr[8 + uu] + (bs ? __ldg(bs + H + unit) : 0.f));
+          const float gf = sigmoidf_(pr[16 + uu] + (bs ? __ldg(bs + 2 * H + unit) : 0.f) + d.forget_bias);
+          const float go = sigmoidf_(pr[24 + uu] + (bs ? __ldg(bs + 3 * H + unit) : 0.f));
+          const long long si = (long long)row * H + unit;
+          const float c_old = d.lstm_c[si], h_old = d.lstm_h[si];
+          const float c_new = gf * c_old + gi * gj;
+          const float h_new = go * tanhf_(c_new);
+          const float h_st = (1.f - d.zh) * h_new + d.zh * h_old;
+          d.lstm_c[si] = (1.f - d.zc) * c_new + d.zc * c_old;
+          d.lstm_h[si] = h_st;
+          // cell output is the un-zoned h (as in the training kernels); the zoned state feeds the next step's input row
+          if (d.lstm_out) d.lstm_out[(long long)(tt & 1) * d.out_pstride + (long long)row * d.ld_out + unit] = h_new;
+          if (d.lstm_hdst) d.lstm_hdst[(long long)((tt + 1) & 1) * d.hdst_pstride + (long long)row * d.ld_hdst + unit] = h_st;
+        }
       }
     }
+    if (KS > 1) cluster.sync();     // peers keep their partial tiles alive until rank 0 has read them
+    else __syncthreads();
   }
 }
 
-// gates [B,4H] pre-activation (bias included), order i,j,f,o (TF LSTMCell, A.5)
-__global__ void lstm_point_k(const float* __restrict__ gates, float* c, float* h, int B, int H, float zc, float zh, float forget_bias,
-                             float* out, long long ld_out, float* hdst, long long ld_h) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * H) return;
-  const int b = idx / H, u = idx % H;
-  const float* g = gates + (long long)b * 4 * H;
-  const float gi = sigmoidf_(g[u]), gj = tanhf_(g[H + u]), gf = sigmoidf_(g[2 * H + u] + forget_bias), go = sigmoidf_(g[3 * H + u]);
-  const float c_old = c[idx], h_old = h[idx];
-  const float c_new = gf * c_old + gi * gj;
-  const float h_new = go * tanhf_(c_new);
-  const float c_st = (1.f - zc) * c_new + zc * c_old;       // eval-mode zoneout: expectation of the keep mask (A.6)
-  const float h_st = (1.f - zh) * h_new + zh * h_old;
-  c[idx] = c_st;
-  h[idx] = h_st;
-  if (out) out[(long long)b * ld_out + u] = h_new;           // cell output is the un-zoned h (matches the training kernels)
-  if (hdst) hdst[(long long)b * ld_h + u] = h_st;
-}
-
-// one CTA (512 threads) per utterance
-__global__ void __launch_bounds__(512) attn_step_k(const satk_attn_step_desc d) {
+// Attention step: a cluster of 8 CTAs per utterance.  Each CTA computes the energies of 1/8 of the source positions and
+// scatters them into every peer's shared memory (DSMEM); after one cluster barrier each CTA holds all energies, repeats the
+// (tiny) softmax / forward recursion locally and produces 1/8 of the context columns.
+constexpr int ACS = 8;
+__global__ void __cluster_dims__(ACS, 1, 1) __launch_bounds__(256) attn_step_k(const satk_attn_step_desc d) {
   extern __shared__ float sm[];
   __shared__ float redbuf[32];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ float upart[ACS];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / ACS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tt = d.Tt, B = d.B, A1 = d.A1, A2 = d.A2, M1 = d.M1, M2 = d.M2, AF = d.att_filters;
-  const int t = d.t_ptr ? *d.t_ptr : 0;
+  const int tt = d.t_ptr ? *d.t_ptr : 0;
   const int len = (int)d.lengths[b];
+  const int AFp = AF > 0 ? AF : 1;
+  const int PP = (Tt + ACS - 1) / ACS;            // positions per CTA
+  const int j0 = min(Tt, rank * PP), j1 = min(Tt, j0 + PP);
   float* qs = sm;                         // [A1+A2]
-  float* fS = qs + A1 + A2;               // [Tt][AF]
-  float* WfS = fS + Tt * (AF > 0 ? AF : 1);   // [AF][A1]
-  float* e1 = WfS + (AF > 0 ? AF : 1) * A1;   // [Tt]
+  float* fS = qs + A1 + A2;               // [PP][AF]
+  float* WfS = fS + PP * AFp;             // [AF][A1]
+  float* e1 = WfS + AFp * A1;             // [Tt]  (filled by all CTAs of the cluster)
   float* e2 = e1 + Tt;                    // [Tt]
   float* w1 = e2 + Tt;                    // [Tt] weights that build context 1
   float* apv = w1 + Tt;                   // [Tt] previous alignments (location input)
   float* alo = apv + Tt;                  // [Tt] previous alpha
-  float* cpart = alo + Tt;                // [2][M1+M2]
+  float* cpart = alo + Tt;                // [groups][cols per CTA]
   const bool loc = d.att_kernel > 0;
-  for (int i = tid; i < A1 + A2; i += 512) qs[i] = d.q[(long long)b * d.ldq + i];
-  for (int i = tid; i < Tt; i += 512) {
+  for (int i = tid; i < A1 + A2; i += 256) qs[i] = d.q[(long long)b * d.ldq + i];
+  for (int i = tid; i < Tt; i += 256) {
     apv[i] = loc ? d.aprev[(long long)b * Tt + i] : 0.f;
     alo[i] = (d.mode == 2) ? d.alpha[(long long)b * Tt + i] : 0.f;
   }
   if (loc)
-    for (int i = tid; i < AF * A1; i += 512) WfS[i] = __ldg(d.loc_layer_w + i);
-  __syncthreads();
+    for (int i = tid; i < AF * A1; i += 256) WfS[i] = __ldg(d.loc_layer_w + i);
+  const float u = (d.mode == 2) ? d.u[b] : 0.f;
+  // every CTA has read the recurrent state (aprev / alpha / u) before rank 0 may overwrite it below
+  cluster.sync();
   if (loc) {
     // location features f = conv1d(prev alignments) + bias, SAME padding: left pad (k-1)/2 (forward_attention.py:98-100)
     const int pl = (d.att_kernel - 1) / 2;
-    for (int i = tid; i < Tt * AF; i += 512) {
-      const int j = i / AF, f = i % AF;
+    for (int i = tid; i < (j1 - j0) * AF; i += 256) {
+      const int j = j0 + i / AF, f = i % AF;
       float acc = __ldg(d.loc_conv_b + f);
       for (int k = 0; k < d.att_kernel; ++k) {
         const int jj = j - pl + k;
@@ -140,45 +204,45 @@ __global__ void __launch_bounds__(512) attn_step_k(const satk_attn_step_desc d) 
     }
   }
   __syncthreads();
-  // energies: warp per position, lanes over score channels
-  for (int j = warp; j < Tt; j += 16) {
+  // energies of my positions: warp per position, lanes over score channels; result -> every CTA of the cluster
+  for (int j = j0 + warp; j < j1; j += 8) {
     const float* kr = d.keys1 + ((long long)j * B + b) * A1;
-    float s1 = 0.f;
+    float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < A1; c += 32) {
       float s = __ldg(kr + c) + qs[c];
       if (d.b1) s += __ldg(d.b1 + c);
       if (loc)
-        for (int f = 0; f < AF; ++f) s = fmaf(fS[j * AF + f], WfS[f * A1 + c], s);
-      s1 = fmaf(__ldg(d.v1 + c), tanhf_(s), s1);
+        for (int f = 0; f < AF; ++f) s = fmaf(fS[(j - j0) * AF + f], WfS[f * A1 + c], s);
+      s1 = fmaf(__ldg(d.v1 + c), ftanh_(s), s1);
     }
     s1 = warp_sum(s1);
-    if (lane == 0) e1[j] = s1;
     if (A2 > 0) {
       const float* k2 = d.keys2 + ((long long)j * B + b) * A2;
-      float s2 = 0.f;
-      for (int c = lane; c < A2; c += 32) s2 = fmaf(__ldg(d.v2 + c), tanhf_(__ldg(k2 + c) + qs[A1 + c]), s2);
+      for (int c = lane; c < A2; c += 32) s2 = fmaf(__ldg(d.v2 + c), ftanh_(__ldg(k2 + c) + qs[A1 + c]), s2);
       s2 = warp_sum(s2);
-      if (lane == 0) e2[j] = s2;
+    }
+    if (lane < ACS) {
+      cluster.map_shared_rank(e1, lane)[j] = s1;
+      if (A2 > 0) cluster.map_shared_rank(e2, lane)[j] = s2;
     }
   }
-  __syncthreads();
-  // masked softmax (scores past the source length are -inf, A.8), positions strided over the block
+  cluster.sync();
+  // masked softmax (scores past the source length are -inf, A.8)
   float mx1 = -INFINITY, mx2 = -INFINITY;
-  for (int j = tid; j < len; j += 512) { mx1 = fmaxf(mx1, e1[j]); if (A2 > 0) mx2 = fmaxf(mx2, e2[j]); }
+  for (int j = tid; j < len; j += 256) { mx1 = fmaxf(mx1, e1[j]); if (A2 > 0) mx2 = fmaxf(mx2, e2[j]); }
   mx1 = block_max(mx1, redbuf);
   if (A2 > 0) mx2 = block_max(mx2, redbuf);
   float s1 = 0.f, s2 = 0.f;
-  for (int j = tid; j < Tt; j += 512) {
-    const float p1 = (j < len) ? expf(e1[j] - mx1) : 0.f;
+  for (int j = tid; j < Tt; j += 256) {
+    const float p1 = (j < len) ? __expf(e1[j] - mx1) : 0.f;
     e1[j] = p1; s1 += p1;
-    if (A2 > 0) { const float p2 = (j < len) ? expf(e2[j] - mx2) : 0.f; e2[j] = p2; s2 += p2; }
+    if (A2 > 0) { const float p2 = (j < len) ? __expf(e2[j] - mx2) : 0.f; e2[j] = p2; s2 += p2; }
   }
   s1 = block_sum(s1, redbuf);
   if (A2 > 0) s2 = block_sum(s2, redbuf);
   __syncthreads();
-  const float u = (d.mode == 2) ? d.u[b] : 0.f;
   float sa = 0.f;
-  for (int j = tid; j < Tt; j += 512) {
+  for (int j = tid; j < Tt; j += 256) {
     const float a = e1[j] / s1;
     e1[j] = a;                                                     // softmax alignment a_t
     if (A2 > 0) e2[j] = e2[j] / s2;
@@ -193,44 +257,61 @@ __global__ void __launch_bounds__(512) attn_step_k(const satk_attn_step_desc d) 
   if (d.mode == 2) {
     sa = block_sum(sa, redbuf);
     __syncthreads();
-    for (int j = tid; j < Tt; j += 512) w1[j] = w1[j] / sa;        // :110
+    for (int j = tid; j < Tt; j += 256) w1[j] = w1[j] / sa;        // :110
   }
   __syncthreads();
-  // state + history
-  for (int j = tid; j < Tt; j += 512) {
-    if (loc) d.aprev[(long long)b * Tt + j] = d.cumulative ? (apv[j] + e1[j]) : e1[j];
-    if (d.mode == 2) d.alpha[(long long)b * Tt + j] = w1[j];
-    if (d.align1) d.align1[((long long)t * B + b) * Tt + j] = w1[j];
-    if (A2 > 0 && d.align2) d.align2[((long long)t * B + b) * Tt + j] = e2[j];
-  }
-  // context vectors: thread = (half of the positions, column)
-  const int MC = M1 + M2;
-  for (int c0 = 0; c0 < MC; c0 += 256) {
-    const int c = c0 + (tid & 255), hf = tid >> 8;
-    if (c < MC) {
-      const float* wS = (c < M1) ? w1 : e2;
-      float acc = 0.f;
-      const int jb = hf ? (len + 1) / 2 : 0, je = hf ? len : (len + 1) / 2;
-      if (c < M1) for (int j = jb; j < je; ++j) acc = fmaf(wS[j], __ldg(d.values1 + ((long long)j * B + b) * M1 + c), acc);
-      else for (int j = jb; j < je; ++j) acc = fmaf(wS[j], __ldg(d.values2 + ((long long)j * B + b) * M2 + (c - M1)), acc);
-      cpart[hf * MC + c] = acc;
+  if (rank == 0) {
+    // state + history
+    for (int j = tid; j < Tt; j += 256) {
+      if (loc) d.aprev[(long long)b * Tt + j] = d.cumulative ? (apv[j] + e1[j]) : e1[j];
+      if (d.mode == 2) d.alpha[(long long)b * Tt + j] = w1[j];
+      if (d.align1) d.align1[((long long)tt * B + b) * Tt + j] = w1[j];
+      if (A2 > 0 && d.align2) d.align2[((long long)tt * B + b) * Tt + j] = e2[j];
     }
   }
+  // my share of the context columns: thread = (position group, column)
+  const int MC = M1 + M2;
+  const int CP = (MC + ACS - 1) / ACS;           // columns per CTA
+  const int groups = 256 / CP;
+  const int cl = tid % CP, gq = tid / CP;
+  const int c = rank * CP + cl;
+  float agent_part = 0.f;
+  if (gq < groups && c < MC) {
+    const float* wS = (c < M1) ? w1 : e2;
+    const float* vb = (c < M1) ? (d.values1 + (long long)b * M1 + c) : (d.values2 + (long long)b * M2 + (c - M1));
+    const long long vs = (long long)B * ((c < M1) ? M1 : M2);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int j = gq;
+    for (; j + 3 * groups < len; j += 4 * groups) {
+      const float x0 = __ldg(vb + (long long)j * vs), x1 = __ldg(vb + (long long)(j + groups) * vs);
+      const float x2 = __ldg(vb + (long long)(j + 2 * groups) * vs), x3 = __ldg(vb + (long long)(j + 3 * groups) * vs);
+      a0 = fmaf(wS[j], x0, a0); a1 = fmaf(wS[j + groups], x1, a1);
+      a2 = fmaf(wS[j + 2 * groups], x2, a2); a3 = fmaf(wS[j + 3 * groups], x3, a3);
+    }
+    for (; j < len; j += groups) a0 = fmaf(wS[j], __ldg(vb + (long long)j * vs), a0);
+    cpart[gq * CP + cl] = (a0 + a1) + (a2 + a3);
+  }
   __syncthreads();
-  for (int c = tid; c < MC; c += 512) {
-    const float cx = cpart[c] + cpart[MC + c];
-    cpart[c] = cx;
-    if (d.ctx_dst0) d.ctx_dst0[(long long)b * d.ld0 + c] = cx;
-    if (d.ctx_dst1) d.ctx_dst1[(long long)b * d.ld1 + c] = cx;
+  if (tid < CP && rank * CP + tid < MC) {
+    const int cc = rank * CP + tid;
+    float cx = 0.f;
+    for (int g2 = 0; g2 < groups; ++g2) cx += cpart[g2 * CP + tid];
+    if (d.ctx_dst0) d.ctx_dst0[(long long)((tt + 1) & 1) * d.pstride0 + (long long)b * d.ld0 + cc] = cx;
+    if (d.ctx_dst1) d.ctx_dst1[(long long)(tt & 1) * d.pstride1 + (long long)b * d.ld1 + cc] = cx;
+    if (d.use_agent && cc < M1) agent_part = cx * __ldg(d.agent_w + cc);
   }
   if (d.mode == 2 && d.use_agent) {
     // transition agent: u = sigmoid([context1, processed_query1] . W + b)   (forward_attention.py:111-114)
-    __syncthreads();
-    float acc = 0.f;
-    for (int c = tid; c < M1; c += 512) acc = fmaf(cpart[c], __ldg(d.agent_w + c), acc);
-    for (int c = tid; c < A1; c += 512) acc = fmaf(qs[c], __ldg(d.agent_w + M1 + c), acc);
-    acc = block_sum(acc, redbuf);
-    if (tid == 0) d.u[b] = sigmoidf_(acc + __ldg(d.agent_b));
+    if (rank == 0)
+      for (int cq = tid; cq < A1; cq += 256) agent_part = fmaf(qs[cq], __ldg(d.agent_w + M1 + cq), agent_part);
+    agent_part = block_sum(agent_part, redbuf);
+    if (tid == 0) cluster.map_shared_rank(upart, 0)[rank] = agent_part;
+    cluster.sync();
+    if (rank == 0 && tid == 0) {
+      float s = 0.f;
+      for (int r = 0; r < ACS; ++r) s += upart[r];
+      d.u[b] = sigmoidf_(s + __ldg(d.agent_b));
+    }
   }
 }
 
@@ -297,26 +378,48 @@ __global__ void tick_k(int* t_ptr, const float* stop, int B, int min_iters, int*
 
 using namespace satk;
 
+template <int KS>
+static int launch_rowgemm(const satk_rowgemm_desc* d, int blocks, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks * KS);
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = KS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SATK_CUDA(cudaLaunchKernelEx(&cfg, dstep::rowgemm_k<KS>, *d));
+  return SATK_OK;
+}
+
 extern "C" int satk_rowgemm(const satk_rowgemm_desc* d, void* stream) {
   SATK_CHECK_ARG(d->nmat >= 1 && d->nmat <= 3, "satk_rowgemm: nmat=%d out of range (1..3)", d->nmat);
   SATK_CHECK_ARG(d->M >= 1 && d->K >= 1, "satk_rowgemm: M=%d K=%d", d->M, d->K);
   int blocks = 0;
-  for (int i = 0; i < d->nmat; ++i) {
-    SATK_CHECK_ARG(d->N[i] >= 1 && d->W[i] && d->C[i], "satk_rowgemm: matrix %d incomplete", i);
-    blocks += (d->N[i] + dstep::NC - 1) / dstep::NC;
+  if (d->lstm_H > 0) {
+    SATK_CHECK_ARG(d->nmat == 1 && d->N[0] == 4 * d->lstm_H && d->lstm_H % 8 == 0 && d->lstm_c && d->lstm_h && d->W[0],
+                   "satk_rowgemm: LSTM epilogue needs one [K,4H] matrix, H %% 8 == 0 and the c/h state (H=%d N=%d)", d->lstm_H, d->N[0]);
+    blocks = d->lstm_H / 8;
+  } else {
+    for (int i = 0; i < d->nmat; ++i) {
+      SATK_CHECK_ARG(d->N[i] >= 1 && d->W[i] && d->C[i], "satk_rowgemm: matrix %d incomplete", i);
+      blocks += (d->N[i] + dstep::NC - 1) / dstep::NC;
+    }
   }
-  dstep::rowgemm_k<<<blocks, 256, 0, (cudaStream_t)stream>>>(*d);
-  SATK_LAUNCH_CHECK();
-  return SATK_OK;
-}
-
-extern "C" int satk_lstm_point(const float* gates, float* c, float* h, int B, int H, float zc, float zh, float forget_bias,
-                               float* out, long long ld_out, float* hdst, long long ld_h, void* stream) {
-  SATK_CHECK_ARG(gates && c && h && B > 0 && H > 0, "satk_lstm_point: bad arguments");
-  const int n = B * H;
-  dstep::lstm_point_k<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(gates, c, h, B, H, zc, zh, forget_bias, out, ld_out, hdst, ld_h);
-  SATK_LAUNCH_CHECK();
-  return SATK_OK;
+  // split the reduction over a cluster so that ~128 CTAs stream the weights, each keeping >= 64 rows of K
+  int ks = 1;
+  while (ks < 8 && blocks * ks * 2 <= 160 && d->K / (ks * 2) >= 64) ks *= 2;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (ks) {
+    case 1: return launch_rowgemm<1>(d, blocks, st);
+    case 2: return launch_rowgemm<2>(d, blocks, st);
+    case 4: return launch_rowgemm<4>(d, blocks, st);
+    default: return launch_rowgemm<8>(d, blocks, st);
+  }
 }
 
 extern "C" int satk_attn_step(const satk_attn_step_desc* d, void* stream) {
@@ -326,10 +429,13 @@ extern "C" int satk_attn_step(const satk_attn_step_desc* d, void* stream) {
   SATK_CHECK_ARG(d->mode != 2 || (d->alpha && d->u), "satk_attn_step: forward attention needs alpha / u state");
   SATK_CHECK_ARG(!d->use_agent || (d->agent_w && d->agent_b), "satk_attn_step: transition agent weights missing");
   const int AF = d->att_filters > 0 ? d->att_filters : 1;
-  const size_t smem = sizeof(float) * ((size_t)d->A1 + d->A2 + (size_t)d->Tt * AF + (size_t)AF * d->A1 + 5 * (size_t)d->Tt + 2 * ((size_t)d->M1 + d->M2));
+  const int PP = (d->Tt + dstep::ACS - 1) / dstep::ACS;
+  const int CP = (d->M1 + d->M2 + dstep::ACS - 1) / dstep::ACS;
+  SATK_CHECK_ARG(CP <= 256, "satk_attn_step: memory depth %d too large", d->M1 + d->M2);
+  const size_t smem = sizeof(float) * ((size_t)d->A1 + d->A2 + (size_t)PP * AF + (size_t)AF * d->A1 + 5 * (size_t)d->Tt + (size_t)(256 / CP) * CP);
   SATK_CHECK_ARG(smem <= 200 * 1024, "satk_attn_step: Tt=%d needs %zu B of shared memory", d->Tt, smem);
   if (smem > 48 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::attn_step_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dstep::attn_step_k<<<d->B, 512, smem, (cudaStream_t)stream>>>(*d);
+  dstep::attn_step_k<<<d->B * dstep::ACS, 256, smem, (cudaStream_t)stream>>>(*d);
   SATK_LAUNCH_CHECK();
   return SATK_OK;
 }

@@ -597,17 +597,18 @@ class TacotronEngine:
         done = b_("pred.done", (1,), torch.int32)
         mel_hist = b_("pred.mel_hist", (Tmax + 1, B, OU))
         stop_hist = b_("pred.stop_hist", (Tmax, B))
-        cell_in, x2c, x3c = b_("pred.cell_in", (B, W1C)), b_("pred.x2cat", (B, W2C)), b_("pred.x3cat", (B, W3C))
-        g1, g2, g3 = b_("pred.g1", (B, 4 * H1)), b_("pred.g2", (B, 4 * HD)), b_("pred.g3", (B, 4 * HD))
+        # concatenated recurrent input rows, double-buffered on the parity of t (see satk_rowgemm_desc.a_pstride)
+        cell_in, x2c, x3c = b_("pred.cell_in", (2, B, W1C)), b_("pred.x2cat", (2, B, W2C)), b_("pred.x3cat", (2, B, W3C))
         st = {n: b_("pred." + n, (B, H1 if n.endswith("1") else HD)) for n in ("c1", "h1", "c2", "h2", "c3", "h3")}
         q = b_("pred.q", (B, d.att1 + d.att2))
         o3 = b_("pred.o3", (B, HD))
-        pp0, pp1 = b_("pred.pp0", (B, P0)), None
+        pp0 = b_("pred.pp0", (B, P0))
         aprev, alpha, u = b_("pred.aprev", (B, Tt)), b_("pred.alpha", (B, Tt)), b_("pred.u", (B,))
         al1 = b_("pred.align1", (Tmax, B, Tt))
         al2 = b_("pred.align2", (Tmax, B, Tt)) if d.dual else None
         lengths = b_("pred.lengths", (B,), torch.int64)
         loc = d.attention in ("forward", "location_sensitive")
+        zo = dict(zc=d.zc, zh=d.zh, forget_bias=FORGET_BIAS)
         steps = []
         # pre-net (module.py:1509-1511; speaker variant multi_speaker_modules.py:27-32); no dropout outside training
         a_in = dict(lda=OU, a_off=OU - d.dec_in, a_tstride=B * OU, t_ptr=t_dev)
@@ -620,14 +621,16 @@ class TacotronEngine:
         else:
             steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)],
                                         **a_in))
-        steps.append(O.rowgemm_desc(pp0, B, P0, [dict(W=p["dec.prenet1.W"], bias=p["dec.prenet1.b"], act="relu", C=cell_in, ldc=W1C)]))
-        # LSTM-1 on [prenet | attention | h] (AttentionWrapper concat, A.7)
-        steps.append(O.rowgemm_desc(cell_in, B, W1C, [dict(W=p["dec.lstm1.W"], bias=p["dec.lstm1.b"], C=g1)]))
-        steps.append(("lstm", g1, st["c1"], st["h1"], H1, dict(out=x2c, ld_out=W2C, hdst=cell_in, ld_h=W1C, h_off=P1 + CTX)))
+        steps.append(O.rowgemm_desc(pp0, B, P0, [dict(W=p["dec.prenet1.W"], bias=p["dec.prenet1.b"], act="relu", C=cell_in, ldc=W1C,
+                                                      c_pstride=B * W1C)], t_ptr=t_dev))
+        # LSTM-1 on [prenet | attention | h] (AttentionWrapper concat, A.7) with the cell update in the epilogue
+        steps.append(O.rowgemm_desc(cell_in, B, W1C, [dict(W=p["dec.lstm1.W"], bias=p["dec.lstm1.b"])], a_pstride=B * W1C, t_ptr=t_dev,
+                                    lstm=dict(H=H1, c=st["c1"], h=st["h1"], out=x2c, ld_out=W2C, out_pstride=B * W2C,
+                                              hdst=cell_in, ld_hdst=W1C, hdst_off=P1 + CTX, hdst_pstride=B * W1C, **zo)))
         qm = [dict(W=p["att1.query.W"], C=q, ldc=d.att1 + d.att2)]
         if d.dual:
             qm.append(dict(W=p["att2.query.W"], C=q, ldc=d.att1 + d.att2, c_off=d.att1))
-        steps.append(O.rowgemm_desc(x2c, B, H1, qm, lda=W2C))
+        steps.append(O.rowgemm_desc(x2c, B, H1, qm, lda=W2C, a_pstride=B * W2C, t_ptr=t_dev))
         bufs = self._bufs
         agent = d.attention == "forward" and d.transition_agent
         steps.append(O.attn_step_desc(
@@ -639,12 +642,15 @@ class TacotronEngine:
             keys2=bufs["dec.keys2"] if d.dual else None, values2=bufs["dec.values2"] if d.dual else None,
             v2=p["att2.v"] if d.dual else None, agent_w=p["att1.agent.W"] if agent else None,
             agent_b=p["att1.agent.b"] if agent else None, aprev=aprev, alpha=alpha, u=u,
-            ctx_dst0=cell_in.data_ptr() + 4 * P1, ld0=W1C, ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, align1=al1, align2=al2))
+            ctx_dst0=cell_in.data_ptr() + 4 * P1, ld0=W1C, pstride0=B * W1C,
+            ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, pstride1=B * W2C, align1=al1, align2=al2))
         # LSTM-2 / LSTM-3 (DecoderRNNV2 on ConcatOutputAndAttentionWrapper, module.py:1024,1525-1534)
-        steps.append(O.rowgemm_desc(x2c, B, W2C, [dict(W=p["dec.lstm2.W"], bias=p["dec.lstm2.b"], C=g2)]))
-        steps.append(("lstm", g2, st["c2"], st["h2"], HD, dict(out=x3c, ld_out=W3C, hdst=x2c, ld_h=W2C, h_off=X2W)))
-        steps.append(O.rowgemm_desc(x3c, B, W3C, [dict(W=p["dec.lstm3.W"], bias=p["dec.lstm3.b"], C=g3)]))
-        steps.append(("lstm", g3, st["c3"], st["h3"], HD, dict(out=o3, ld_out=HD, hdst=x3c, ld_h=W3C, h_off=HD)))
+        steps.append(O.rowgemm_desc(x2c, B, W2C, [dict(W=p["dec.lstm2.W"], bias=p["dec.lstm2.b"])], a_pstride=B * W2C, t_ptr=t_dev,
+                                    lstm=dict(H=HD, c=st["c2"], h=st["h2"], out=x3c, ld_out=W3C, out_pstride=B * W3C,
+                                              hdst=x2c, ld_hdst=W2C, hdst_off=X2W, hdst_pstride=B * W2C, **zo)))
+        steps.append(O.rowgemm_desc(x3c, B, W3C, [dict(W=p["dec.lstm3.W"], bias=p["dec.lstm3.b"])], a_pstride=B * W3C, t_ptr=t_dev,
+                                    lstm=dict(H=HD, c=st["c3"], h=st["h3"], out=o3, ld_out=HD, out_pstride=0,
+                                              hdst=x3c, ld_hdst=W3C, hdst_off=HD, hdst_pstride=B * W3C, **zo)))
         x = o3
         probs = []
         if d.dual:
@@ -670,14 +676,10 @@ class TacotronEngine:
         steps.append(O.rowgemm_desc(x, B, HD, [
             dict(W=p["dec.out_proj.W"], bias=p["dec.out_proj.b"], C=mel_hist, c_off=B * OU, c_tstride=B * OU),
             dict(W=p["dec.stop_proj.W"], bias=p["dec.stop_proj.b"], C=stop_hist, ldc=1, c_tstride=B)], t_ptr=t_dev))
-        zc, zh = d.zc, d.zh
 
         def run_step():
             for s_ in steps:
-                if isinstance(s_, tuple):
-                    _, g, c, h, H, kw = s_
-                    O.lstm_point(g, c, h, B, H, zc, zh, FORGET_BIAS, **kw)
-                elif isinstance(s_, O.RowGemmDesc):
+                if isinstance(s_, O.RowGemmDesc):
                     O.rowgemm(s_)
                 elif isinstance(s_, O.AttnStepDesc):
                     O.attn_step(s_)

@@ -84,6 +84,9 @@ class RowGemmDesc(C.Structure):
         ("M", i32), ("K", i32), ("A", fp), ("lda", i64), ("a_tstride", i64), ("t_ptr", fp), ("nmat", i32),
         ("W", fp * 3), ("bias", fp * 3), ("C", fp * 3), ("ldc", i64 * 3), ("c_tstride", i64 * 3),
         ("N", i32 * 3), ("act", i32 * 3), ("residual", fp * 3), ("ldres", i64 * 3), ("res_tstride", i64 * 3),
+        ("a_pstride", i64), ("c_pstride", i64 * 3),
+        ("lstm_H", i32), ("lstm_c", fp), ("lstm_h", fp), ("zc", f32), ("zh", f32), ("forget_bias", f32),
+        ("lstm_out", fp), ("ld_out", i64), ("out_pstride", i64), ("lstm_hdst", fp), ("ld_hdst", i64), ("hdst_pstride", i64),
     ]
 
 
@@ -96,7 +99,8 @@ class AttnStepDesc(C.Structure):
         ("loc_conv_w", fp), ("loc_conv_b", fp), ("loc_layer_w", fp),
         ("keys2", fp), ("values2", fp), ("v2", fp), ("agent_w", fp), ("agent_b", fp),
         ("aprev", fp), ("alpha", fp), ("u", fp),
-        ("ctx_dst0", fp), ("ld0", i64), ("ctx_dst1", fp), ("ld1", i64), ("align1", fp), ("align2", fp),
+        ("ctx_dst0", fp), ("ld0", i64), ("pstride0", i64), ("ctx_dst1", fp), ("ld1", i64), ("pstride1", i64),
+        ("align1", fp), ("align2", fp),
     ]
 
 
@@ -120,7 +124,7 @@ SYMBOLS = [
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
     "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_debug_phase_cycles",
-    "satk_struct_sizes_decode", "satk_rowgemm", "satk_lstm_point", "satk_attn_step", "satk_sa_step", "satk_decode_tick",
+    "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_decode_tick",
 ]
 
 

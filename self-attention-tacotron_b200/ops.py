@@ -357,26 +357,31 @@ def attn_rnn_bwd(f: AttnRnnFwdDesc, **kw):
 
 
 # ---------------------------------------------------------------------------------------------- free-running decode step
-def rowgemm_desc(A, M, K, mats, *, lda=None, a_off=0, a_tstride=0, t_ptr=None) -> RowGemmDesc:
+def rowgemm_desc(A, M, K, mats, *, lda=None, a_off=0, a_tstride=0, a_pstride=0, t_ptr=None, lstm=None) -> RowGemmDesc:
     """Descriptor of up to three skinny dense layers sharing the input rows ``A`` [M,K].
 
     ``mats``: list of dicts with W [K,N] (TF layout), optional bias / act / residual (+ ldres, res_off, res_tstride),
-    C (+ ldc, c_off, c_tstride).  Offsets are in elements.  The tensors must stay alive while the descriptor is used."""
+    C (+ ldc, c_off, c_tstride, c_pstride).  Offsets are in elements.  ``lstm``: dict(H, c, h, zc, zh, forget_bias, out, ld_out,
+    out_off, out_pstride, hdst, ld_hdst, hdst_off, hdst_pstride) turns the epilogue of the single [K,4H] matrix into the
+    ZoneoutLSTMCell pointwise update.  The tensors must stay alive while the descriptor is used."""
     _req(A)
     d = RowGemmDesc()
     d.M, d.K = M, K
-    d.A, d.lda, d.a_tstride = A.data_ptr() + 4 * a_off, lda or K, a_tstride
+    d.A, d.lda, d.a_tstride, d.a_pstride = A.data_ptr() + 4 * a_off, lda or K, a_tstride, a_pstride
     d.t_ptr = ptr(t_ptr)
     d.nmat = len(mats)
     for i, m in enumerate(mats):
         W = m["W"]
-        _req(W); _req(m["C"])
+        _req(W)
+        if lstm is None:
+            _req(m["C"])
         if W.shape[0] != K:
             raise L.SatkError(f"rowgemm: weight {tuple(W.shape)} does not match K={K}")
         N = W.shape[1]
         d.W[i] = W.data_ptr()
         d.bias[i] = ptr(m.get("bias"))
-        d.C[i] = m["C"].data_ptr() + 4 * m.get("c_off", 0)
+        d.C[i] = (m["C"].data_ptr() + 4 * m.get("c_off", 0)) if m.get("C") is not None else None
+        d.c_pstride[i] = m.get("c_pstride", 0)
         d.ldc[i] = m.get("ldc", N)
         d.c_tstride[i] = m.get("c_tstride", 0)
         d.N[i] = N
@@ -385,21 +390,21 @@ def rowgemm_desc(A, M, K, mats, *, lda=None, a_off=0, a_tstride=0, t_ptr=None) -
         d.residual[i] = (res.data_ptr() + 4 * m.get("res_off", 0)) if res is not None else None
         d.ldres[i] = m.get("ldres", N)
         d.res_tstride[i] = m.get("res_tstride", 0)
+    if lstm is not None:
+        _req(lstm["c"]); _req(lstm["h"])
+        d.lstm_H, d.lstm_c, d.lstm_h = lstm["H"], lstm["c"].data_ptr(), lstm["h"].data_ptr()
+        d.zc, d.zh, d.forget_bias = lstm["zc"], lstm["zh"], lstm["forget_bias"]
+        if lstm.get("out") is not None:
+            d.lstm_out = lstm["out"].data_ptr() + 4 * lstm.get("out_off", 0)
+            d.ld_out, d.out_pstride = lstm["ld_out"], lstm.get("out_pstride", 0)
+        if lstm.get("hdst") is not None:
+            d.lstm_hdst = lstm["hdst"].data_ptr() + 4 * lstm.get("hdst_off", 0)
+            d.ld_hdst, d.hdst_pstride = lstm["ld_hdst"], lstm.get("hdst_pstride", 0)
     return d
 
 
 def rowgemm(d: RowGemmDesc) -> None:
     check(load().satk_rowgemm(C.byref(d), C.c_void_p(stream_ptr())), "satk_rowgemm")
-    _count()
-
-
-def lstm_point(gates, c, h, B, H, zc, zh, forget_bias, out=None, ld_out=0, out_off=0, hdst=None, ld_h=0, h_off=0) -> None:
-    _req(gates); _req(c); _req(h)
-    o = (out.data_ptr() + 4 * out_off) if out is not None else None
-    hd = (hdst.data_ptr() + 4 * h_off) if hdst is not None else None
-    check(load().satk_lstm_point(C.c_void_p(ptr(gates)), C.c_void_p(ptr(c)), C.c_void_p(ptr(h)), B, H, C.c_float(zc), C.c_float(zh),
-                                 C.c_float(forget_bias), C.c_void_p(o), C.c_longlong(ld_out), C.c_void_p(hd), C.c_longlong(ld_h),
-                                 C.c_void_p(stream_ptr())), "satk_lstm_point")
     _count()
 
 

@@ -135,3 +135,35 @@ def test_rowgemm_unit(satk):
             N = r.shape[1]
             _close(m["C"][3, :, :N], r, 1e-5, f"rowgemm M={Mr} K={K} N={N}")
             assert m["C"][:3].abs().max().item() == 0 and m["C"][3, :, N:].abs().max().item() == 0
+
+
+def test_rowgemm_lstm_epilogue_unit(satk):
+    """Skinny GEMM with the ZoneoutLSTMCell epilogue (inference interpolation) against the oracle cell, parity buffers included."""
+    E, O, L, M = _mods()
+    g = torch.Generator().manual_seed(1)
+    for Mr, Kx, H in ((16, 416, 256), (5, 40, 64), (20, 256, 128)):
+        K = Kx + H
+        W = (torch.randn(K, 4 * H, generator=g) / K ** 0.5)
+        bias = torch.randn(4 * H, generator=g)
+        x = torch.randn(Mr, Kx, generator=g)
+        c0, h0 = torch.randn(Mr, H, generator=g), torch.randn(Mr, H, generator=g) * 0.5
+        zc, zh = 0.1, 0.2
+        out_ref, c_ref, h_ref = OR.zoneout_lstm_step(x, c0, h0, W, bias, None, None, zc, zh, False)
+        for t in (0, 1):
+            rows = torch.zeros(2, Mr, K)
+            rows[t & 1, :, :Kx] = x
+            rows[t & 1, :, Kx:] = h0
+            rows = rows.cuda()
+            outb = torch.zeros(2, Mr, H + 3, device="cuda")
+            c, h = c0.cuda().clone(), h0.cuda().clone()
+            tdev = torch.tensor([t], dtype=torch.int32, device="cuda")
+            dsc = O.rowgemm_desc(rows, Mr, K, [dict(W=W.cuda(), bias=bias.cuda())], a_pstride=Mr * K, t_ptr=tdev,
+                                 lstm=dict(H=H, c=c, h=h, zc=zc, zh=zh, forget_bias=1.0, out=outb, ld_out=H + 3, out_pstride=Mr * (H + 3),
+                                           hdst=rows, ld_hdst=K, hdst_off=Kx, hdst_pstride=Mr * K))
+            O.rowgemm(dsc)
+            torch.cuda.synchronize()
+            _close(outb[t & 1, :, :H], out_ref, 1e-5, "lstm out")
+            _close(c, c_ref, 1e-5, "lstm c")
+            _close(h, h_ref, 1e-5, "lstm h")
+            _close(rows[(t + 1) & 1, :, Kx:], h_ref, 1e-5, "next-step h rows")
+            assert outb[(t + 1) & 1].abs().max().item() == 0
