@@ -95,10 +95,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const uint32_t smem_base = (cl::smem_u32(smem) + 1023u) & ~1023u;
 
   const int kblocks_total = (p.K + BK - 1) / BK;
-  const int kb_per = (kblocks_total + p.split_k - 1) / p.split_k;
-  const int kb_beg = ks * kb_per, kb_end = min(kblocks_total, kb_beg + kb_per);
-  const int nkb = max(0, kb_end - kb_beg);
-  const int iters = nkb * p.taps;
+  // split-K partitions the flattened (tap, k-block) iteration space, so tapped (conv) products with a short K still split
+  const int it_total = kblocks_total * p.taps;
+  const int it_per = (it_total + p.split_k - 1) / p.split_k;
+  const int it_beg = ks * it_per;
+  const int iters = max(0, min(it_total, it_beg + it_per) - it_beg);
 #ifdef SATK_PHASE_TIMING
   const long long t_start = clock64();
 #endif
@@ -128,7 +129,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       if (use > 0) cl::mbar_wait(&empty_bar[s], (use - 1) & 1);
-      const int tap = it / nkb, kb = kb_beg + it % nkb;
+      const int tap = (it_beg + it) / kblocks_total, kb = (it_beg + it) % kblocks_total;
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
       TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
@@ -305,17 +306,18 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   p.split_k = d->split_k < 1 ? 1 : d->split_k;
   const int kblocks = (d->K + BK - 1) / BK;
   const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);
-  const bool linear_epi = !d->bias && d->act == 0 && !d->residual && !d->keep_mask && d->beta == 0.0f;
+  const bool linear_epi = !d->bias && d->act == 0 && !d->residual && !d->keep_mask && (d->beta == 0.0f || d->beta == 1.0f);
   if (p.split_k == 1 && linear_epi && tiles < 74 && kblocks * taps >= 16) {
     // too few tiles for 148 SMs: split K, accumulate with atomics into a zeroed C
     int sk = (148 + tiles - 1) / tiles;
-    if (sk > kblocks / 4) sk = kblocks / 4;
+    if (sk > kblocks * taps / 4) sk = kblocks * taps / 4;
     if (sk > 1) {
-      SATK_CUDA(cudaMemset2DAsync(d->C, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, st));
+      // beta == 1: the partial sums are added straight onto the existing C; beta == 0: onto a zeroed C
+      if (d->beta == 0.0f) SATK_CUDA(cudaMemset2DAsync(d->C, (size_t)d->ldc * 4, 0, (size_t)d->N * 4, (size_t)d->M, st));
       p.split_k = sk;
     }
   }
-  if (p.split_k > kblocks) p.split_k = kblocks;
+  if (p.split_k > kblocks * taps) p.split_k = kblocks * taps;
   if (d->split_k > 1 && p.split_k == 1) p.beta = 1.0f;   // split-K semantics = accumulate onto C
   const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
   static bool attr_set = false;

@@ -195,7 +195,7 @@ def test_full_size_batch_properties(satk, root):
 
 def test_estimator_surface(satk, root, tmp_path):
     E, O, L, M = _mods()
-    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"), "max_iters=12")
     model = M.tacotron_model_factory(hp, str(tmp_path), None)
     assert isinstance(model, M.DualSourceSelfAttentionTacotronModel)
     f, l = satk.synthetic_batch(hp, 4, 20, 24, seed=2)
@@ -207,8 +207,12 @@ def test_estimator_surface(satk, root, tmp_path):
     assert spec.train_op == 2 and torch.isfinite(spec.loss)
     ev = model.evaluate(input_fn, steps=1)
     assert {"loss_with_teacher", "mel_loss_with_teacher", "done_loss_with_teacher", "global_step"} <= set(ev)
-    pred = next(model.predict(input_fn))
-    assert pred["mel"].shape == (4, 24, 80) and pred["alignment"].shape == (4, 20, 12) and "alignment2" in pred
+    ev_spec = model.model_fn(f, l, M.ModeKeys.EVAL, hp)                      # teacher-forced decode keeps the target length
+    assert ev_spec.predictions["mel"].shape == (4, 24, 80) and ev_spec.predictions["alignment"].shape == (4, 20, 12)
+    pred = next(model.predict(input_fn))                                     # free-running (PREDICT mode), <= max_iters steps
+    T = pred["alignment"].shape[2]
+    assert 11 < T <= 12 and pred["mel"].shape == (4, 2 * T, 80) and pred["alignment"].shape == (4, 20, T)
+    assert {"alignment2", "alignment3", "alignment4", "alignment5", "ground_truth_mel", "stop_token"} <= set(pred)
     model2 = M.tacotron_model_factory(hp, str(tmp_path), None)           # resume from model_dir
     assert model2.engine.global_step == 2
     assert torch.equal(model2.engine.ps.flat, model.engine.ps.flat)
