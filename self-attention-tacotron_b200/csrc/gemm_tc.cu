@@ -27,10 +27,17 @@ constexpr int XFORM_THREADS = 192;              // warps 2..7
 constexpr int XFORM_WARPS = 6;
 constexpr int TMEM_COLS = 128;
 
-#ifdef SATK_PHASE_TIMING
+#if defined(SATK_PHASE_TIMING) && defined(SATK_TC_LIFE)
+// lifecycle marks of CTA (0,0,0): cycles since kernel entry at setup-done / first TMA issued / first tile landed / first split
+// done / first MMA issue / last commit issued / accumulator complete / epilogue done / teardown
+#define TC_TRACE(ev)
+#define TC_MARK(i) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) satk::g_phase[i] = clock64() - t_start;
+#elif defined(SATK_PHASE_TIMING)
+#define TC_MARK(i)
 #define TC_TRACE(ev) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && it >= 6 && it < 10) satk::g_phase[(it - 6) * 4 + (ev)] = clock64() - t_start;
 #else
 #define TC_TRACE(ev)
+#define TC_MARK(i)
 #endif
 
 struct Params {
@@ -82,6 +89,49 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return d;
 }
 
+// Epilogue of one 32-row x 32-column block held in shared memory (stg, row stride 33): lane = column.  Residual / accumulate
+// operands of all 32 rows are loaded before the first use so the loads overlap.
+template <int ACT, bool MASK, bool ADD>
+__device__ __forceinline__ void epi_rows(const Params& p, const float* stg, int lane, int mbase, int nrows, int n, float bias) {
+  const float alpha = p.alpha, beta = p.beta, keep_scale = p.keep_scale;
+  const long long ldc = p.ldc, ldres = p.ldres;
+  float* cp = p.C + (long long)mbase * ldc + n;
+  const float* rp = p.residual ? p.residual + (long long)mbase * ldres + n : nullptr;
+  const uint8_t* kp = MASK ? p.keep_mask + (long long)mbase * p.N + n : nullptr;
+  const int N = p.N;
+  float add[32];
+  if (ADD) {
+    if (rp) {
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) add[rr] = (rr < nrows) ? __ldg(rp + rr * ldres) : 0.f;
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) add[rr] = 0.f;
+    }
+    if (beta != 0.0f) {
+      float cv[32];
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) cv[rr] = (rr < nrows) ? cp[rr * ldc] : 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) add[rr] = fmaf(beta, cv[rr], add[rr]);
+    }
+  }
+  uint8_t keep[32];
+  if (MASK) {
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) keep[rr] = (rr < nrows) ? kp[(long long)rr * N] : (uint8_t)0;
+  }
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    if (rr < nrows) {
+      float v = apply_act(fmaf(alpha, stg[rr * 33 + lane], bias), ACT);
+      if (MASK) v = keep[rr] ? v * keep_scale : 0.0f;
+      if (ADD) v += add[rr];
+      cp[rr * ldc] = v;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p, const int b_rank3) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -123,6 +173,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
+  if (tid == 0) { TC_MARK(0) }
 
   if (warp == 0 && lane == 0) {
     // ===== TMA producer
@@ -136,6 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tma_load_2d(sa, &mapA, kb * BK, m0 + p.shift0 + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
       if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap, cl::smem_u32(&full_bar[s]));
       else tma_load_2d(sb, &mapB, kb * BK, n0, cl::smem_u32(&full_bar[s]));
+      if (it == 0) { TC_MARK(1) }
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer
@@ -143,6 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       cl::mbar_wait(&xform_bar[s], use & 1);
+      if (it == 0) { TC_MARK(4) }
       TC_TRACE(2)
       tc_fence_after();
       const uint32_t sa = smem_base + s * STAGE_BYTES;
@@ -159,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TC_TRACE(3)
     }
     tc_commit(&accum_bar);               // accumulator complete
+    TC_MARK(5)
   } else if (warp >= 2) {
     // ===== hi/lo split of both operand tiles (element-wise: the swizzled layout is untouched)
     const int xt = tid - 64;
@@ -166,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const int s = it % STAGES, use = it / STAGES;
       cl::mbar_wait(&full_bar[s], use & 1);
       if (tid == 64) { TC_TRACE(1) }
+      if (tid == 64 && it == 0) { TC_MARK(2) }
       uint8_t* base = smem + (smem_base - cl::smem_u32(smem)) + s * STAGE_BYTES;
 #pragma unroll 2
       for (int i = xt; i < 2 * (TILE_BYTES / 16); i += XFORM_THREADS) {
@@ -184,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       cl::fence_proxy_async();           // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&xform_bar[s]);
+      if (tid == 64 && it == 0) { TC_MARK(3) }
     }
   }
 
@@ -191,6 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp >= 4) {
     cl::mbar_wait(&accum_bar, 0);
     tc_fence_after();
+    if (tid == 128) { TC_MARK(6) }
     const int q = warp - 4;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -205,36 +262,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (tid == 128 && c0 == 0) { TC_MARK(9) }
       // stage the 32x32 block of this warp in shared memory (the operand ring is idle now), then write rows coalesced
       float* stg = reinterpret_cast<float*>(smem + (smem_base - cl::smem_u32(smem))) + q * (32 * 33);
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
       __syncwarp();
+      if (tid == 128 && c0 == 0) { TC_MARK(10) }
       const int n = n0 + c0 + lane;
       if (iters > 0 && n < p.N) {
         const float bias = (p.bias && p.split_k == 1) ? __ldg(p.bias + n) : 0.f;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int mm = m0 + q * 32 + rr;
-          if (mm >= p.M) break;
-          float v = p.alpha * stg[rr * 33 + lane];
-          float* cp = p.C + (long long)mm * p.ldc + n;
-          if (p.split_k > 1) {
-            atomicAdd(cp, v);
-          } else {
-            v = apply_act(v + bias, p.act);
-            if (p.keep_mask) v = p.keep_mask[(long long)mm * p.N + n] ? v * p.keep_scale : 0.0f;
-            if (p.residual) v += __ldg(p.residual + (long long)mm * p.ldres + n);
-            if (p.beta != 0.0f) v += p.beta * (*cp);
-            *cp = v;
+        const int mbase = m0 + q * 32;
+        const int nrows = min(32, p.M - mbase);
+        if (p.split_k > 1) {
+          float* cp = p.C + (long long)mbase * p.ldc + n;
+          const float alpha = p.alpha;
+          const long long ldc = p.ldc;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            if (rr < nrows) atomicAdd(cp + rr * ldc, alpha * stg[rr * 33 + lane]);
+        } else {
+          // every epilogue option is resolved OUTSIDE the row loop (a per-row switch on kernel parameters costs a chain of
+          // uniform-datapath loads and branches per row, ~270 cycles each with one warp per scheduler: measured 34 K cycles)
+          const bool has_add = p.residual != nullptr || p.beta != 0.0f, has_mask = p.keep_mask != nullptr;
+#define SATK_EPI(A)                                                                                   \
+  do {                                                                                                \
+    if (has_mask) { if (has_add) epi_rows<A, true, true>(p, stg, lane, mbase, nrows, n, bias); else epi_rows<A, true, false>(p, stg, lane, mbase, nrows, n, bias); } \
+    else { if (has_add) epi_rows<A, false, true>(p, stg, lane, mbase, nrows, n, bias); else epi_rows<A, false, false>(p, stg, lane, mbase, nrows, n, bias); } \
+  } while (0)
+          switch (p.act) {
+            case SATK_ACT_RELU: SATK_EPI(SATK_ACT_RELU); break;
+            case SATK_ACT_TANH: SATK_EPI(SATK_ACT_TANH); break;
+            case SATK_ACT_SIGMOID: SATK_EPI(SATK_ACT_SIGMOID); break;
+            default: SATK_EPI(SATK_ACT_NONE); break;
           }
+#undef SATK_EPI
         }
       }
+      if (tid == 128 && c0 == 0) { TC_MARK(11) }
+      if (tid == 128 && c0 == 32) { TC_MARK(12) }
     }
   }
+  if (tid == 128) { TC_MARK(7) }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) { TC_MARK(8) }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");

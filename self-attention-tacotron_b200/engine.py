@@ -571,8 +571,9 @@ class TacotronEngine:
         if d.use_speaker:
             spk = self.buf("spk_embed", (B, d.speaker_dim))
             O.embedding_fwd(features.speaker_id, self.ps.p["speaker_embedding"], spk, offset=d.speaker_offset)
-        mem1, mem2, enc_al = self.encoder(source, source_length, training, masks)
-        mel_tm, stop_tm, al1, al2, dec_sa = self.decoder(mem1, mem2, source_length, labels.mel, spk, training, masks)
+        mem1, mem2, enc_al = self._timed("sec.encoder_fwd", self.encoder, source, source_length, training, masks)
+        mel_tm, stop_tm, al1, al2, dec_sa = self._timed("sec.decoder_fwd", self.decoder, mem1, mem2, source_length, labels.mel, spk,
+                                                        training, masks)
         out3 = self.buf("loss3", (3,))
         dmel = self.buf("dec.dmel_tm", mel_tm.shape)
         dstop = self.buf("dec.dstop_tm", stop_tm.shape)
@@ -782,7 +783,8 @@ class TacotronEngine:
         """BPTT through decoder and encoder; gradients land in ``self.ps.grad`` (zeroed first)."""
         s = self.saved
         self.ps.grad.zero_()
-        dmem1, dmem2 = self.decoder_backward(s["dmel"], s["dstop"], s["B"], s["Tt"], s["Td"], s["source_length"])
+        dmem1, dmem2 = self._timed("sec.decoder_bwd", self.decoder_backward, s["dmel"], s["dstop"], s["B"], s["Tt"], s["Td"],
+                                   s["source_length"])
         if self.d.use_speaker:
             g, p = self.ps.g, self.ps.p
             dsp_pre = self._dspk_pre
@@ -792,7 +794,7 @@ class TacotronEngine:
             dspk = self.buf("dspk_embed", (s["B"], self.d.speaker_dim))
             O.linear_dx(dsp_pre, p["dec.prenet0.Ws"], dspk, s["B"])
             O.embedding_bwd(s["features"].speaker_id, dspk, g["speaker_embedding"], offset=self.d.speaker_offset)
-        self.encoder_backward(dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
+        self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
 
     def optimizer_step(self, world_size: int = 1):
         """clip_by_global_norm(1.0) + Adam + noam LR (models.py:485-498).  With world_size > 1 the caller has
@@ -812,5 +814,5 @@ class TacotronEngine:
         self.backward()
         if allreduce is not None:
             allreduce(self.ps.grad)
-        out["lr"] = self.optimizer_step(world_size)
+        out["lr"] = self._timed("sec.optimizer", self.optimizer_step, world_size)
         return out
