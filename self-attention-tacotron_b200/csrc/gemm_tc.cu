@@ -12,6 +12,7 @@
 // Convolution taps = extra iterations of the K loop with a row-shifted TMA coordinate for A (time-major rows:
 // a tap is a shift by B rows; out-of-range rows are zero-filled by TMA) and the tap index as third coordinate of B.
 #include <cuda.h>
+#include <stdlib.h>
 #include "cluster_sync.cuh"
 #include "common.cuh"
 
@@ -50,6 +51,7 @@ struct Params {
   const float* residual; long long ldres;
   const uint8_t* keep_mask; float keep_scale;
   int split_k;
+  int tma_store;            // 1: plain overwrite epilogue (bias + activation only) leaves through TMA bulk stores
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -133,7 +135,8 @@ __device__ __forceinline__ void epi_rows(const Params& p, const float* stg, int 
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const Params p, const int b_rank3) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapC,
+               const Params p, const int b_rank3) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[STAGES], xform_bar[STAGES], empty_bar[STAGES], accum_bar;
   __shared__ uint32_t tmem_base_sh;
@@ -249,6 +252,78 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     tc_fence_after();
     if (tid == 128) { TC_MARK(6) }
     const int q = warp - 4;
+    if (p.tma_store) {
+      // ---- fast path: all four 32-column blocks of this warp's 32 rows are read from TMEM at once (one TMEM round trip
+      // instead of four), bias + activation applied in registers (lane = row), written to shared memory in the 128-byte
+      // swizzle layout and handed to the TMA unit: the warps never wait on global stores (a plain STG row loop costs ~120
+      // cycles per 128-byte row when every SM drains its tile at the same time) and TMA clips rows / columns outside C.
+      uint32_t r[4][32];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+            "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[cb][0]), "=r"(r[cb][1]), "=r"(r[cb][2]), "=r"(r[cb][3]), "=r"(r[cb][4]), "=r"(r[cb][5]), "=r"(r[cb][6]), "=r"(r[cb][7]),
+              "=r"(r[cb][8]), "=r"(r[cb][9]), "=r"(r[cb][10]), "=r"(r[cb][11]), "=r"(r[cb][12]), "=r"(r[cb][13]), "=r"(r[cb][14]),
+              "=r"(r[cb][15]), "=r"(r[cb][16]), "=r"(r[cb][17]), "=r"(r[cb][18]), "=r"(r[cb][19]), "=r"(r[cb][20]), "=r"(r[cb][21]),
+              "=r"(r[cb][22]), "=r"(r[cb][23]), "=r"(r[cb][24]), "=r"(r[cb][25]), "=r"(r[cb][26]), "=r"(r[cb][27]), "=r"(r[cb][28]),
+              "=r"(r[cb][29]), "=r"(r[cb][30]), "=r"(r[cb][31])
+            : "r"(taddr));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (tid == 128) { TC_MARK(9) }
+      const float alpha = p.alpha;
+      const int act = p.split_k == 1 ? p.act : 0;
+      const bool has_bias = p.bias != nullptr && p.split_k == 1;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const int nb = n0 + cb * 32;
+        if (iters > 0 && nb < p.N && m0 + q * 32 < p.M) {
+          // staging block: 32 rows x 128 B, 1024-byte aligned, one per (warp, column block)
+          const uint32_t sblk = smem_base + (uint32_t)((q * 4 + cb) * 4096);
+          const float bl = (has_bias && nb + lane < p.N) ? __ldg(p.bias + nb + lane) : 0.f;   // lane j holds bias[nb + j]
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float b = __shfl_sync(0xffffffffu, bl, c * 4 + e);
+              v[e] = fmaf(alpha, __uint_as_float(r[cb][c * 4 + e]), b);
+            }
+            if (act == SATK_ACT_RELU) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (act == SATK_ACT_TANH) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = tanhf_(v[e]);
+            } else if (act == SATK_ACT_SIGMOID) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = sigmoidf_(v[e]);
+            }
+            const uint32_t addr = sblk + (uint32_t)(lane * 128) + (uint32_t)(((c ^ (lane & 7)) & 7) * 16);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          }
+          cl::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.tma_store == 2)   // split-K partial sums / accumulation onto C: the TMA unit adds into global memory
+              asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC),
+                           "r"(nb), "r"(m0 + q * 32), "r"(sblk)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC), "r"(nb),
+                           "r"(m0 + q * 32), "r"(sblk)
+                           : "memory");
+          }
+        }
+      }
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must stay valid until the TMA unit has read it
+      }
+      __syncwarp();
+    } else
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
@@ -330,6 +405,19 @@ static EncodeTiledFn get_encode() {
 }
 
 // rank-2 map over a K-contiguous matrix [rows, K] (row stride ld floats), box BK x BM, 128-byte swizzle
+// rank-2 map over the output C [M, N] (row stride ldc floats), box 32 columns x 32 rows, 128-byte swizzle (epilogue TMA stores)
+static bool make_map_c(CUtensorMap* map, float* base, long long M, long long N, long long ldc) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)ldc * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static bool make_map(CUtensorMap* map, const float* base, long long rows, long long K, long long ld, int rank3_taps, long long tap_stride) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
@@ -398,8 +486,19 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
     SATK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
+  // plain overwrite epilogues (bias + activation at most) leave through TMA stores when C is 16-byte addressable
+  CUtensorMap mapC = mapA;
+  p.tma_store = 0;
+  if ((d->ldc % 4) == 0 && ((uintptr_t)d->C % 16) == 0 && getenv("SATK_NO_TMA_STORE") == nullptr) {
+    int mode = 0;
+    if (p.split_k > 1) mode = 2;                                                          // atomically added partial sums
+    else if (!d->residual && !d->keep_mask && p.beta == 0.0f) mode = 1;                   // overwrite
+    else if (!d->residual && !d->keep_mask && p.beta == 1.0f && d->act == 0) mode = 2;    // C += alpha*A.B (+bias)
+    if (mode && make_map_c(&mapC, d->C, d->M, d->N, d->ldc)) p.tma_store = mode;
+    else mapC = mapA;
+  }
   dim3 grid(ceil_div(d->M, BM), ceil_div(d->N, BN), p.split_k);
-  gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, p, taps > 1 ? 1 : 0);
+  gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapC, p, taps > 1 ? 1 : 0);
   SATK_LAUNCH_CHECK();
   return SATK_OK;
 }
