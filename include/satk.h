@@ -83,6 +83,9 @@ typedef struct {
                               (C must hold the value to accumulate onto; beta ignored; no epilogue
                               other than alpha) */
   int causal_skip;         /* 1: batched QK^T / PV with causal structure — skip tiles fully above the diagonal */
+  /* weight gradient of a 1-D convolution on the tensor-core tile (operands already transposed, reduction index
+   * contiguous): batch entry z1 reads A[m, k + kshift0 + z1*kshift_per_batch1] (zero outside [0,K)); one output per tap. */
+  int kshift0, kshift_per_batch1;
 } satk_gemm_desc;
 
 /* engine: 0 = auto, 1 = fp32 SIMT tile, 2 = tcgen05 3xTF32 tile (TMA-fed; falls back with an

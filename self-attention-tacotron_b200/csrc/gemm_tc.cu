@@ -51,6 +51,8 @@ struct Params {
   const float* residual; long long ldres;
   const uint8_t* keep_mask; float keep_scale;
   int split_k;
+  int zbatch, kshift0, kshift_step;   // z-batches with a shifted reduction coordinate of A (conv weight gradients)
+  long long c_zstride;
   int tma_store;            // 1: plain overwrite epilogue (bias + activation only) leaves through TMA bulk stores
 };
 
@@ -94,10 +96,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // Epilogue of one 32-row x 32-column block held in shared memory (stg, row stride 33): lane = column.  Residual / accumulate
 // operands of all 32 rows are loaded before the first use so the loads overlap.
 template <int ACT, bool MASK, bool ADD>
-__device__ __forceinline__ void epi_rows(const Params& p, const float* stg, int lane, int mbase, int nrows, int n, float bias) {
+__device__ __forceinline__ void epi_rows(const Params& p, const float* stg, int lane, int mbase, int nrows, int n, float bias, long long zoff) {
   const float alpha = p.alpha, beta = p.beta, keep_scale = p.keep_scale;
   const long long ldc = p.ldc, ldres = p.ldres;
-  float* cp = p.C + (long long)mbase * ldc + n;
+  float* cp = p.C + zoff + (long long)mbase * ldc + n;
   const float* rp = p.residual ? p.residual + (long long)mbase * ldres + n : nullptr;
   const uint8_t* kp = MASK ? p.keep_mask + (long long)mbase * p.N + n : nullptr;
   const int N = p.N;
@@ -143,7 +145,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-  const int ks = blockIdx.z;
+  const int ks = blockIdx.z % p.split_k, zb = blockIdx.z / p.split_k;
+  const int a_kshift = p.kshift0 + zb * p.kshift_step;
   // carve: align the dynamic region to 1024 B (swizzle atom alignment)
   const uint32_t smem_base = (cl::smem_u32(smem) + 1023u) & ~1023u;
 
@@ -187,7 +190,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
       TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-      tma_load_2d(sa, &mapA, kb * BK, m0 + p.shift0 + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
+      tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + p.shift0 + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
       if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap, cl::smem_u32(&full_bar[s]));
       else tma_load_2d(sb, &mapB, kb * BK, n0, cl::smem_u32(&full_bar[s]));
       if (it == 0) { TC_MARK(1) }
@@ -309,11 +312,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (lane == 0) {
             if (p.tma_store == 2)   // split-K partial sums / accumulation onto C: the TMA unit adds into global memory
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC),
-                           "r"(nb), "r"(m0 + q * 32), "r"(sblk)
+                           "r"(nb), "r"(zb * p.M + m0 + q * 32), "r"(sblk)
                            : "memory");
             else
               asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC), "r"(nb),
-                           "r"(m0 + q * 32), "r"(sblk)
+                           "r"(zb * p.M + m0 + q * 32), "r"(sblk)
                            : "memory");
           }
         }
@@ -351,7 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int mbase = m0 + q * 32;
         const int nrows = min(32, p.M - mbase);
         if (p.split_k > 1) {
-          float* cp = p.C + (long long)mbase * p.ldc + n;
+          float* cp = p.C + zb * p.c_zstride + (long long)mbase * p.ldc + n;
           const float alpha = p.alpha;
           const long long ldc = p.ldc;
 #pragma unroll
@@ -363,8 +366,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const bool has_add = p.residual != nullptr || p.beta != 0.0f, has_mask = p.keep_mask != nullptr;
 #define SATK_EPI(A)                                                                                   \
   do {                                                                                                \
-    if (has_mask) { if (has_add) epi_rows<A, true, true>(p, stg, lane, mbase, nrows, n, bias); else epi_rows<A, true, false>(p, stg, lane, mbase, nrows, n, bias); } \
-    else { if (has_add) epi_rows<A, false, true>(p, stg, lane, mbase, nrows, n, bias); else epi_rows<A, false, false>(p, stg, lane, mbase, nrows, n, bias); } \
+    if (has_mask) { if (has_add) epi_rows<A, true, true>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); else epi_rows<A, true, false>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); } \
+    else { if (has_add) epi_rows<A, false, true>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); else epi_rows<A, false, false>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); } \
   } while (0)
           switch (p.act) {
             case SATK_ACT_RELU: SATK_EPI(SATK_ACT_RELU); break;
@@ -447,7 +450,11 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   *supported = false;
   const int batches = (d->batch1 < 1 ? 1 : d->batch1) * (d->batch2 < 1 ? 1 : d->batch2);
   const int taps = d->taps < 1 ? 1 : d->taps;
-  if (batches != 1 || d->transA != 0 || d->transB != 1 || d->causal_skip != 0 || d->seq_len != 0 || d->shift_per_batch1 != 0) return SATK_OK;
+  // z-batches are served in one form only: same A and B for every entry, A read with a per-entry shift of the reduction
+  // coordinate, one output per entry (conv weight gradients)
+  const bool zform = batches > 1 && (d->batch2 <= 1) && d->sA1 == 0 && d->sB1 == 0 && taps == 1 && !d->bias && d->act == 0 &&
+                     !d->residual && !d->keep_mask;
+  if ((batches != 1 && !zform) || d->transA != 0 || d->transB != 1 || d->causal_skip != 0 || d->seq_len != 0 || d->shift_per_batch1 != 0) return SATK_OK;
   if (d->M < 64 || d->N < 48 || d->K < 32) return SATK_OK;                       // tiny problems stay on the SIMT tile
   if ((d->lda % 4) || (d->ldb % 4) || (d->K % 4) || ((uintptr_t)d->A % 16) || ((uintptr_t)d->B % 16)) return SATK_OK;
   if (taps > 1 && (d->sBtap % 4)) return SATK_OK;
@@ -465,10 +472,11 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   p.residual = d->residual; p.ldres = d->ldres;
   p.keep_mask = d->keep_mask; p.keep_scale = d->keep_scale;
   p.split_k = d->split_k < 1 ? 1 : d->split_k;
+  p.zbatch = batches; p.kshift0 = d->kshift0; p.kshift_step = d->kshift_per_batch1; p.c_zstride = d->sC1;
   const int kblocks = (d->K + BK - 1) / BK;
   const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);
   const bool linear_epi = !d->bias && d->act == 0 && !d->residual && !d->keep_mask && (d->beta == 0.0f || d->beta == 1.0f);
-  if (p.split_k == 1 && linear_epi && tiles < 74 && kblocks * taps >= 16) {
+  if (batches == 1 && p.split_k == 1 && linear_epi && tiles < 74 && kblocks * taps >= 16) {
     // too few tiles for 148 SMs: split K, accumulate with atomics into a zeroed C
     int sk = (148 + tiles - 1) / tiles;
     if (sk > kblocks * taps / 4) sk = kblocks * taps / 4;
@@ -494,10 +502,12 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
     if (p.split_k > 1) mode = 2;                                                          // atomically added partial sums
     else if (!d->residual && !d->keep_mask && p.beta == 0.0f) mode = 1;                   // overwrite
     else if (!d->residual && !d->keep_mask && p.beta == 1.0f && d->act == 0) mode = 2;    // C += alpha*A.B (+bias)
-    if (mode && make_map_c(&mapC, d->C, d->M, d->N, d->ldc)) p.tma_store = mode;
+    // z-batched outputs are addressed as extra rows of one map: needs whole tiles per entry and densely stacked outputs
+    if (batches > 1 && (d->M % BM != 0 || d->sC1 != (long long)d->M * d->ldc)) mode = 0;
+    if (mode && make_map_c(&mapC, d->C, (long long)d->M * batches, d->N, d->ldc)) p.tma_store = mode;
     else mapC = mapA;
   }
-  dim3 grid(ceil_div(d->M, BM), ceil_div(d->N, BN), p.split_k);
+  dim3 grid(ceil_div(d->M, BM), ceil_div(d->N, BN), p.split_k * batches);
   gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapC, p, taps > 1 ? 1 : 0);
   SATK_LAUNCH_CHECK();
   return SATK_OK;

@@ -307,11 +307,20 @@ class TacotronEngine:
             O.bn_bwd(s["x"], R, s["C"], s["mean"], s["var"], s["gamma"], s["beta"], dy, dx, dgamma, dbeta, scratch, eps=BN_EPS,
                      act=s["act"], maxpool_seq_len=Tt if s["maxpool"] else 0, pos_stride=B, use_batch_stats=training)
 
-        def conv_back(x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None):
+        def conv_back(x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None, xT=None,
+                      drawT=None, drawT_row0=0):
             """draw: gradient wrt the raw conv output [R, cout] (ld draw_ld); accumulates dW, writes/accumulates dx."""
             pl = (k - 1) // 2
-            O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True, b_off=draw_off,
-                   batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B, split_k=max(1, min(32, R // 512)), beta=1.0)
+            if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
+                # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
+                if xT is None:
+                    xT = O.transposed_rows(x, R, cin, x_ld)
+                if drawT is None:
+                    drawT, drawT_row0 = O.transposed_rows(draw, R, cout, draw_ld, draw_off), 0
+                O.conv_dw_tc(xT, drawT, g[Wname], R, cin, cout, k, B, drawT_row0)
+            else:
+                O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True, b_off=draw_off,
+                       batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B, split_k=max(1, min(32, R // 512)), beta=1.0)
             O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
                    taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
 
@@ -328,9 +337,13 @@ class TacotronEngine:
         bn_back(sv["bn_bank"], dmp, draw)
         cin = sv["inp"].shape[1]
         dinp = self.buf("enc.dinp", (R, cin))
+        bank_tc = R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and d.conv_ch >= 48
+        inpT = O.transposed_rows(sv["inp"], R, cin) if bank_tc else None          # shared by all bank widths
+        drawT = O.transposed_rows(draw, R, KC) if bank_tc else None
         for k in range(1, d.bank_k + 1):   # dinp = dhw (residual branch, module.py:86) + sum_k conv_k^T(d bank_k)
             conv_back(sv["inp"], f"cbhg.bank{k}.W", k, cin, d.conv_ch, draw, dinp, 0.0 if k == 1 else 1.0, draw_ld=KC,
-                      draw_off=(k - 1) * d.conv_ch, residual=dhw if k == 1 else None)
+                      draw_off=(k - 1) * d.conv_ch, residual=dhw if k == 1 else None, xT=inpT, drawT=drawT,
+                      drawT_row0=(k - 1) * d.conv_ch)
         # encoder pre-net
         dy = dinp
         n = len(d.enc_prenet)

@@ -40,7 +40,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
          transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=None, residual=None, ldres=0,
          keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0),
          taps=1, shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0,
-         a_off=0, b_off=0, c_off=0, engine=None) -> None:
+         a_off=0, b_off=0, c_off=0, engine=None, kshift0=0, kshift_per_batch1=0) -> None:
     """C = epi(alpha * sum_taps op(A) op(B)) (+beta*C).  ``*_off`` are element offsets into the tensors."""
     _req(A); _req(B); _req(C_)
     d = GemmDesc()
@@ -60,6 +60,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
     d.sC1, d.sC2 = sC
     d.taps, d.shift0, d.tap_dir, d.seq_len, d.sBtap = taps, shift0, tap_dir, seq_len, sBtap
     d.shift_per_batch1, d.split_k, d.causal_skip = shift_per_batch1, split_k, causal_skip
+    d.kshift0, d.kshift_per_batch1 = kshift0, kshift_per_batch1
     check(load().satk_gemm(C.byref(d), GEMM_ENGINE if engine is None else engine, C.c_void_p(stream_ptr())), "satk_gemm")
     _count()
 
@@ -97,6 +98,22 @@ def transposed_rows(x: torch.Tensor, rows: int, cols: int, ldx=None, x_off=0, fr
           "satk_transpose_strided")
     _count()
     return y
+
+
+def conv_dw_tc(xT: torch.Tensor, drawT: torch.Tensor, dW: torch.Tensor, rows: int, cin: int, cout: int, taps: int, B: int,
+               drawT_row0: int = 0) -> None:
+    """dW[tap, cin, cout] += sum_r x[r + (tap - (taps-1)//2) * B, :]^T draw[r, :] for every tap in ONE tcgen05 launch.
+    ``xT`` [cin, ld] and ``drawT`` [*, ld] are row-contiguous transposes (``transposed_rows``); the tap shift is a shift of the
+    reduction coordinate of xT (TMA zero-fills outside the sequence), the taps are the z-batches of the launch, split-K partial
+    sums are added by the TMA unit.  (tf Conv1D SAME gradient, module.py:46-68)"""
+    ld = xT.shape[1]
+    assert drawT.shape[1] == ld
+    pl = (taps - 1) // 2
+    tiles = ((cin + 127) // 128) * ((cout + 127) // 128) * taps
+    kblocks = (rows + 31) // 32
+    sk = max(1, min(kblocks // 4, 148 // tiles))
+    gemm(xT, drawT, dW, cin, cout, rows, lda=ld, ldb=ld, ldc=cout, transB=True, b_off=drawT_row0 * ld, batch1=taps,
+         sC=(cin * cout, 0), kshift0=-pl * B, kshift_per_batch1=B, split_k=sk, beta=1.0, engine=2)
 
 
 DW_TC_MIN_ROWS = 2048      # below this the two transposes cost more than the SIMT split-K product saves

@@ -87,6 +87,28 @@ def test_weight_gradient_products_tensor_core_path():
         _close(dW, ref, 1e-7 * rows, f"dW tc shared yT {rows}x{K}x{N}")
 
 
+def test_conv_weight_gradient_all_taps_one_tensor_core_launch():
+    """dW[tap] += x_shifted(tap)^T draw for every tap of a SAME conv as z-batches of one tcgen05 launch (K-shifted TMA
+    coordinate, TMA reduce-add epilogue) against fp64 autograd of the oracle conv; shared transposes for a bank slice."""
+    O = _O()
+    g = torch.Generator().manual_seed(5)
+    T, Bb = 80, 32
+    R = T * Bb
+    for (k, cin, cout, ld_draw, off) in ((1, 128, 128, 128, 0), (4, 128, 128, 384, 256), (3, 256, 128, 128, 0), (16, 128, 64, 64, 0)):
+        x = torch.randn(T, Bb, cin, generator=g)
+        draw_full = torch.randn(R, ld_draw, generator=g)
+        draw = draw_full[:, off:off + cout]
+        W = torch.randn(k, cin, cout, generator=g).double().requires_grad_(True)
+        y = OR.conv1d_same(x.transpose(0, 1).double(), W).transpose(0, 1).reshape(R, cout)
+        (y * draw.double()).sum().backward()
+        dW0 = torch.randn(k, cin, cout, generator=g)
+        dW = dW0.clone().cuda()
+        xT = O.transposed_rows(x.cuda(), R, cin)
+        drawT = O.transposed_rows(draw_full.cuda(), R, ld_draw)
+        O.conv_dw_tc(xT, drawT, dW, R, cin, cout, k, Bb, drawT_row0=off)
+        _close(dW, (dW0.double() + W.grad).float(), 1e-7 * R, f"conv dW tc k={k} cin={cin} cout={cout}")
+
+
 def test_gemm_time_major_conv_and_grads():
     O = _O()
     g = torch.Generator().manual_seed(1)

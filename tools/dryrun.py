@@ -27,7 +27,8 @@ def _extent(t, off, need, what):
 
 def gemm(A, B, C_, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=None,
          residual=None, ldres=0, keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0), taps=1,
-         shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0, a_off=0, b_off=0, c_off=0, engine=None):
+         shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0, a_off=0, b_off=0, c_off=0, engine=None,
+         kshift0=0, kshift_per_batch1=0):
     zA = (batch1 - 1) * sA[0] + (batch2 - 1) * sA[1]
     zB = (batch1 - 1) * sB[0] + (batch2 - 1) * sB[1] + (taps - 1) * sBtap
     zC = (batch1 - 1) * sC[0] + (batch2 - 1) * sC[1]
