@@ -12,7 +12,9 @@ uses strides (row stride B*D) instead of transposes.
 """
 from __future__ import annotations
 
+import contextlib
 import math
+import os
 from typing import Dict, Optional
 
 import torch
@@ -49,6 +51,9 @@ class TacotronEngine:
         self.global_step = 0
         self._sumsq = torch.zeros(1, device=self.device)
         self.refresh_transposed()
+        # weight-gradient products have no consumer before the optimiser: they run on a second stream beside the critical path
+        # (dX chain + recurrent kernels, which leave most SMs idle); SATK_WGRAD_STREAM=0 keeps everything on one stream
+        self._side = torch.cuda.Stream(device=self.device) if os.environ.get("SATK_WGRAD_STREAM", "1") != "0" else None
         self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
 
     def _timed(self, name, fn, *a, **k):
@@ -62,6 +67,17 @@ class TacotronEngine:
         return r
 
     # ------------------------------------------------------------------ helpers
+    @contextlib.contextmanager
+    def _wg(self):
+        """Weight-gradient section: launches inside run on the side stream, ordered after everything issued so far on the main
+        stream.  Only tensors that the main stream does not write again during this backward pass may be read here."""
+        if self._side is None:
+            yield
+            return
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            yield
+
     def refresh_transposed(self):
         """K-contiguous copies of all matrices (ps.flat -> ps.flat_t), one batched launch."""
         O.transpose_batched(self.ps.flat, self.ps.flat_t, self.ps.t_desc, self.ps.t_count)
@@ -135,12 +151,14 @@ class TacotronEngine:
         scale = 1.0 / math.sqrt(dh)
         dz = self.buf(key + ".dz", (R, D))
         O.act_bwd(sv["tr"], dy, dz, "tanh")
-        O.linear_dw(sv["ao"], dz, g[name + ".transform.W"], R, D, D)
-        O.colsum_acc(dz, R, D, g[name + ".transform.b"])
+        with self._wg():
+            O.linear_dw(sv["ao"], dz, g[name + ".transform.W"], R, D, D)
+            O.colsum_acc(dz, R, D, g[name + ".transform.b"])
         dao = self.buf(key + ".dao", (R, D))
         O.linear_dx(dz, p[name + ".transform.W"], dao, R)
-        O.linear_dw(sv["O"], dao, g[name + ".output.W"], R, D, D)
-        O.colsum_acc(dao, R, D, g[name + ".output.b"])
+        with self._wg():
+            O.linear_dw(sv["O"], dao, g[name + ".output.W"], R, D, D)
+            O.colsum_acc(dao, R, D, g[name + ".output.b"])
         dO = self.buf(key + ".dO", (R, D))
         O.linear_dx(dao, p[name + ".output.W"], dO, R)
         bs = dict(batch1=B, batch2=heads)
@@ -159,9 +177,11 @@ class TacotronEngine:
         O.gemm(dS, sv["Q"], dK, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, alpha=scale, sA=sP, sB=sX, sC=sX, **bs)
         dx = self.buf(key + ".dx", (R, D))
         first = True
+        with self._wg():
+            for nm, dt in (("query", dQ), ("key", dK), ("value", dV)):
+                O.linear_dw(x, dt, g[f"{name}.{nm}.W"], R, D, D)
+                O.colsum_acc(dt, R, D, g[f"{name}.{nm}.b"])
         for nm, dt in (("query", dQ), ("key", dK), ("value", dV)):
-            O.linear_dw(x, dt, g[f"{name}.{nm}.W"], R, D, D)
-            O.colsum_acc(dt, R, D, g[f"{name}.{nm}.b"])
             if first:   # dx = dy (residual branch) + dQ.Wq^T
                 O.gemm(dt, p[f"{name}.{nm}.W"], dx, R, D, D, lda=D, ldb=D, ldc=D, transB=True, residual=dy, ldres=D)
                 first = False
@@ -269,8 +289,9 @@ class TacotronEngine:
             for h in reversed(range(d.enc_sa_hops)):
                 dx = self._sa_backward(sv["sa"][h], dx, B)
             mem1 = self._bufs["enc.mem1"]
-            O.linear_dw(mem1, dx, g["enc.sa_proj.W"], R, 2 * Hn, d.enc_sa)
-            O.colsum_acc(dx, R, d.enc_sa, g["enc.sa_proj.b"])
+            with self._wg():
+                O.linear_dw(mem1, dx, g["enc.sa_proj.W"], R, 2 * Hn, d.enc_sa)
+                O.colsum_acc(dx, R, d.enc_sa, g["enc.sa_proj.b"])
             O.linear_dx(dx, p["enc.sa_proj.W"], dmem1, R, beta=1.0)
         dhw = self.buf("enc.dhw", (R, Hn))
         for j, dr in enumerate(("fw", "bw")):
@@ -280,19 +301,22 @@ class TacotronEngine:
             O.lstm_seq_bwd(W[Hn:], s["gates"], s["c_prev"], dmem1, dg, Tt, B, Hn, reverse=(j == 1), lengths=source_length,
                            mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh, ld_dout=2 * Hn, dout_off=j * Hn)
             gW = g[f"cbhg.lstm_{dr}.W"]
-            O.linear_dw(sv["lstm_in"], dg, gW, R, Hn, 4 * Hn)
-            O.linear_dw(s["h_prev"], dg, gW, R, Hn, 4 * Hn, w_off=Hn * 4 * Hn)
-            O.colsum_acc(dg, R, 4 * Hn, g[f"cbhg.lstm_{dr}.b"])
+            with self._wg():
+                O.linear_dw(sv["lstm_in"], dg, gW, R, Hn, 4 * Hn)
+                O.linear_dw(s["h_prev"], dg, gW, R, Hn, 4 * Hn, w_off=Hn * 4 * Hn)
+                O.colsum_acc(dg, R, 4 * Hn, g[f"cbhg.lstm_{dr}.b"])
             O.linear_dx(dg, W[:Hn], dhw, R, beta=0.0 if j == 0 else 1.0)
-        dH, dT = self.buf("enc.dH", (R, Hn)), self.buf("enc.dT", (R, Hn))
         for i in reversed(range(d.n_highway)):
             Hb, Tb, x = sv["hwy"][i]
+            # per-layer gradient buffers: the weight-gradient stream still reads them while the next layer is computed
+            dH, dT = self.buf(f"enc.dH{i}", (R, Hn)), self.buf(f"enc.dT{i}", (R, Hn))
             dxd = self.buf(f"enc.dhw_in{i % 2}", (R, Hn))
             O.highway_bwd(Hb, Tb, x, dhw, dH, dT, dxd)
-            O.linear_dw(x, dH, g[f"cbhg.highway{i}.WH"], R, Hn, Hn)
-            O.colsum_acc(dH, R, Hn, g[f"cbhg.highway{i}.bH"])
-            O.linear_dw(x, dT, g[f"cbhg.highway{i}.WT"], R, Hn, Hn)
-            O.colsum_acc(dT, R, Hn, g[f"cbhg.highway{i}.bT"])
+            with self._wg():
+                O.linear_dw(x, dH, g[f"cbhg.highway{i}.WH"], R, Hn, Hn)
+                O.colsum_acc(dH, R, Hn, g[f"cbhg.highway{i}.bH"])
+                O.linear_dw(x, dT, g[f"cbhg.highway{i}.WT"], R, Hn, Hn)
+                O.colsum_acc(dT, R, Hn, g[f"cbhg.highway{i}.bT"])
             O.linear_dx(dH, p[f"cbhg.highway{i}.WH"], dxd, R, beta=1.0)
             O.linear_dx(dT, p[f"cbhg.highway{i}.WT"], dxd, R, beta=1.0)
             dhw = dxd
@@ -311,16 +335,18 @@ class TacotronEngine:
                       drawT=None, drawT_row0=0):
             """draw: gradient wrt the raw conv output [R, cout] (ld draw_ld); accumulates dW, writes/accumulates dx."""
             pl = (k - 1) // 2
-            if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
-                # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
-                if xT is None:
-                    xT = O.transposed_rows(x, R, cin, x_ld)
-                if drawT is None:
-                    drawT, drawT_row0 = O.transposed_rows(draw, R, cout, draw_ld, draw_off), 0
-                O.conv_dw_tc(xT, drawT, g[Wname], R, cin, cout, k, B, drawT_row0)
-            else:
-                O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True, b_off=draw_off,
-                       batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B, split_k=max(1, min(32, R // 512)), beta=1.0)
+            with self._wg():
+                if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
+                    # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
+                    if xT is None:
+                        xT = O.transposed_rows(x, R, cin, x_ld)
+                    if drawT is None:
+                        drawT, drawT_row0 = O.transposed_rows(draw, R, cout, draw_ld, draw_off), 0
+                    O.conv_dw_tc(xT, drawT, g[Wname], R, cin, cout, k, B, drawT_row0)
+                else:
+                    O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True,
+                           b_off=draw_off, batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B,
+                           split_k=max(1, min(32, R // 512)), beta=1.0)
             O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
                    taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
 
@@ -338,8 +364,9 @@ class TacotronEngine:
         cin = sv["inp"].shape[1]
         dinp = self.buf("enc.dinp", (R, cin))
         bank_tc = R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and d.conv_ch >= 48
-        inpT = O.transposed_rows(sv["inp"], R, cin) if bank_tc else None          # shared by all bank widths
-        drawT = O.transposed_rows(draw, R, KC) if bank_tc else None
+        with self._wg():
+            inpT = O.transposed_rows(sv["inp"], R, cin) if bank_tc else None      # shared by all bank widths
+            drawT = O.transposed_rows(draw, R, KC) if bank_tc else None
         for k in range(1, d.bank_k + 1):   # dinp = dhw (residual branch, module.py:86) + sum_k conv_k^T(d bank_k)
             conv_back(sv["inp"], f"cbhg.bank{k}.W", k, cin, d.conv_ch, draw, dinp, 0.0 if k == 1 else 1.0, draw_ld=KC,
                       draw_off=(k - 1) * d.conv_ch, residual=dhw if k == 1 else None, xT=inpT, drawT=drawT,
@@ -353,8 +380,9 @@ class TacotronEngine:
             u, cin_i = y.shape[1], x.shape[1]
             dz = self.buf(f"enc.dz{i}", (R, u))
             O.act_bwd(y, dy, dz, "relu", None, 1.0 / (1.0 - d.enc_prenet_drop) if training else 1.0)
-            O.linear_dw(x, dz, g[f"enc.prenet{i}.W"], R, cin_i, u)
-            O.colsum_acc(dz, R, u, g[f"enc.prenet{i}.b"])
+            with self._wg():
+                O.linear_dw(x, dz, g[f"enc.prenet{i}.W"], R, cin_i, u)
+                O.colsum_acc(dz, R, u, g[f"enc.prenet{i}.b"])
             dxp = self.buf(f"enc.dpx{i}", (R, cin_i))
             O.linear_dx(dz, p[f"enc.prenet{i}.W"], dxp, R)
             dy = dxp
@@ -458,10 +486,11 @@ class TacotronEngine:
         H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
         x = sv["proj_in"]
         Dp = x.shape[1]
-        O.linear_dw(x, dmel_tm, g["dec.out_proj.W"], Rd, Dp, d.out_units)
-        O.colsum_acc(dmel_tm, Rd, d.out_units, g["dec.out_proj.b"])
-        O.linear_dw(x, dstop_tm, g["dec.stop_proj.W"], Rd, Dp, 1)
-        O.colsum_acc(dstop_tm, Rd, 1, g["dec.stop_proj.b"])
+        with self._wg():
+            O.linear_dw(x, dmel_tm, g["dec.out_proj.W"], Rd, Dp, d.out_units)
+            O.colsum_acc(dmel_tm, Rd, d.out_units, g["dec.out_proj.b"])
+            O.linear_dw(x, dstop_tm, g["dec.stop_proj.W"], Rd, Dp, 1)
+            O.colsum_acc(dstop_tm, Rd, 1, g["dec.stop_proj.b"])
         dx = self.buf("dec.dproj_in", (Rd, Dp))
         O.linear_dx(dmel_tm, p["dec.out_proj.W"], dx, Rd)
         O.linear_dx(dstop_tm, p["dec.stop_proj.W"], dx, Rd, beta=1.0)
@@ -474,11 +503,12 @@ class TacotronEngine:
             dg = self.buf(f"dec.dgates{li}", (Rd, 4 * HD))
             O.lstm_seq_bwd(W[kin:], s["gates"], s["c_prev"], dout, dg, Td, B, HD, mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh)
             gW = g[f"dec.lstm{li}.W"]
-            dgT = O.transposed_rows(dg, Rd, 4 * HD) if Rd >= O.DW_TC_MIN_ROWS else None
-            O.linear_dw(s["x"], dg, gW, Rd, kin, 4 * HD, yT=dgT)
-            O.linear_dw(s["h_prev"], dg, gW, Rd, HD, 4 * HD, w_off=kin * 4 * HD, yT=dgT)
-            del dgT
-            O.colsum_acc(dg, Rd, 4 * HD, g[f"dec.lstm{li}.b"])
+            with self._wg():
+                dgT = O.transposed_rows(dg, Rd, 4 * HD) if Rd >= O.DW_TC_MIN_ROWS else None
+                O.linear_dw(s["x"], dg, gW, Rd, kin, 4 * HD, yT=dgT)
+                O.linear_dw(s["h_prev"], dg, gW, Rd, HD, 4 * HD, w_off=kin * 4 * HD, yT=dgT)
+                del dgT
+                O.colsum_acc(dg, Rd, 4 * HD, g[f"dec.lstm{li}.b"])
             dxl = self.buf(f"dec.dx_lstm{li}", (Rd, kin))
             O.linear_dx(dg, W[:kin], dxl, Rd)
             dout = dxl
@@ -499,27 +529,31 @@ class TacotronEngine:
         gW1 = g["dec.lstm1.W"]
         N4 = 4 * H1
         tc_dw = Rd >= O.DW_TC_MIN_ROWS
-        dg1T = O.transposed_rows(dg1, Rd, N4) if tc_dw else None     # shared by the three row blocks of dec.lstm1.W
-        O.linear_dw(sv["dp1"], dg1, gW1, Rd, P1, N4, yT=dg1T)
-        # context rows: input of step t is the context of step t-1 (zero at t=0) -> shift by one time step (B rows)
-        O.linear_dw(sv["x2"], dg1, gW1, Rd, d.ctx, N4, ldx=X2W, x_off=H1, w_off=P1 * N4, shift0=-B, yT=dg1T)
-        O.linear_dw(self._bufs["dec.hprev1"], dg1, gW1, Rd, H1, N4, w_off=(P1 + d.ctx) * N4, yT=dg1T)
-        del dg1T
-        O.colsum_acc(dg1, Rd, N4, g["dec.lstm1.b"])
+        with self._wg():
+            dg1T = O.transposed_rows(dg1, Rd, N4) if tc_dw else None     # shared by the three row blocks of dec.lstm1.W
+            O.linear_dw(sv["dp1"], dg1, gW1, Rd, P1, N4, yT=dg1T)
+            # context rows: input of step t is the context of step t-1 (zero at t=0) -> shift by one time step (B rows)
+            O.linear_dw(sv["x2"], dg1, gW1, Rd, d.ctx, N4, ldx=X2W, x_off=H1, w_off=P1 * N4, shift0=-B, yT=dg1T)
+            O.linear_dw(self._bufs["dec.hprev1"], dg1, gW1, Rd, H1, N4, w_off=(P1 + d.ctx) * N4, yT=dg1T)
+            del dg1T
+            O.colsum_acc(dg1, Rd, N4, g["dec.lstm1.b"])
+            # query layers: q = out1 . Wq  (out1 = x2[:, :H1])
+            O.linear_dw(sv["x2"], dq, g["att1.query.W"], Rd, H1, d.att1, ldx=X2W, ldy=QT)
+            if d.dual:
+                O.linear_dw(sv["x2"], dq, g["att2.query.W"], Rd, H1, d.att2, ldx=X2W, ldy=QT, y_off=d.att1)
         ddp1 = self.buf("dec.ddp1", (Rd, P1))
         O.linear_dx(dg1, p["dec.lstm1.W"][:P1], ddp1, Rd)
-        # query layers: q = out1 . Wq  (out1 = x2[:, :H1])
-        O.linear_dw(sv["x2"], dq, g["att1.query.W"], Rd, H1, d.att1, ldx=X2W, ldy=QT)
-        if d.dual:
-            O.linear_dw(sv["x2"], dq, g["att2.query.W"], Rd, H1, d.att2, ldx=X2W, ldy=QT, y_off=d.att1)
         # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]   (dx2[:, H1:] now holds dctx_total)
         dval1 = self.buf("dec.dvalues1", (R, d.mem1))
         O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
                b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
         # keys = values . W_mem ; attention bias folded into the keys
-        if loc:
-            O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
-        O.linear_dw(sv["values1"], dkeys1, g["att1.memory.W"], R, d.mem1, d.att1)
+        with self._wg():
+            if loc:
+                O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
+            O.linear_dw(sv["values1"], dkeys1, g["att1.memory.W"], R, d.mem1, d.att1)
+            if d.dual:
+                O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
         O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
         dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
         O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
@@ -528,7 +562,6 @@ class TacotronEngine:
             dval2 = self.buf("dec.dvalues2", (R, d.mem2))
             O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
                    b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
-            O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
             O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
             dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
             O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
@@ -537,16 +570,18 @@ class TacotronEngine:
         dz1 = self.buf("dec.dz1", (Rd, P1))
         O.act_bwd(sv["dp1"], ddp1, dz1, "relu", None, keep_scale)
         P0 = d.dec_prenet[0]
-        O.linear_dw(sv["dp0"], dz1, g["dec.prenet1.W"], Rd, P0, P1)
-        O.colsum_acc(dz1, Rd, P1, g["dec.prenet1.b"])
+        with self._wg():
+            O.linear_dw(sv["dp0"], dz1, g["dec.prenet1.W"], Rd, P0, P1)
+            O.colsum_acc(dz1, Rd, P1, g["dec.prenet1.b"])
         ddp0 = self.buf("dec.ddp0", (Rd, P0))
         O.linear_dx(dz1, p["dec.prenet1.W"], ddp0, Rd)
         dz0 = self.buf("dec.dz0", (Rd, P0))
         O.act_bwd(sv["dp0"], ddp0, dz0, "relu", None, keep_scale)
         if d.use_speaker:
             h0 = sv["h0"]
-            O.linear_dw(h0, dz0, g["dec.prenet0.W"], Rd, P0, P0)
-            O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
+            with self._wg():
+                O.linear_dw(h0, dz0, g["dec.prenet0.W"], Rd, P0, P0)
+                O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
             dh0 = self.buf("dec.dh0", (Rd, P0))
             O.linear_dx(dz0, p["dec.prenet0.W"], dh0, Rd)
             # h0 = relu(in.W0+b0) + softsign(spk.Ws+bs): the relu output is h0 - sp, recomputed on the fly
@@ -559,11 +594,13 @@ class TacotronEngine:
             self.lin(sv["dec_in"], "dec.prenet0.W0", relu0, bias=p["dec.prenet0.b0"], act="relu")
             dz00 = self.buf("dec.dz00", (Rd, P0))
             O.act_bwd(relu0, dh0, dz00, "relu")
-            O.linear_dw(sv["dec_in"], dz00, g["dec.prenet0.W0"], Rd, d.dec_in, P0)
-            O.colsum_acc(dz00, Rd, P0, g["dec.prenet0.b0"])
+            with self._wg():
+                O.linear_dw(sv["dec_in"], dz00, g["dec.prenet0.W0"], Rd, d.dec_in, P0)
+                O.colsum_acc(dz00, Rd, P0, g["dec.prenet0.b0"])
         else:
-            O.linear_dw(sv["dec_in"], dz0, g["dec.prenet0.W"], Rd, d.dec_in, P0)
-            O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
+            with self._wg():
+                O.linear_dw(sv["dec_in"], dz0, g["dec.prenet0.W"], Rd, d.dec_in, P0)
+                O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
         return dmem1, dmem2
 
     # ------------------------------------------------------------------ model_fn body
@@ -808,6 +845,8 @@ class TacotronEngine:
             O.linear_dx(dsp_pre, p["dec.prenet0.Ws"], dspk, s["B"])
             O.embedding_bwd(s["features"].speaker_id, dspk, g["speaker_embedding"], offset=self.d.speaker_offset)
         self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)      # every weight gradient is in before all-reduce / Adam
 
     def optimizer_step(self, world_size: int = 1):
         """clip_by_global_norm(1.0) + Adam + noam LR (models.py:485-498).  With world_size > 1 the caller has
