@@ -54,6 +54,8 @@ class TacotronEngine:
         # weight-gradient products have no consumer before the optimiser: they run on a second stream beside the critical path
         # (dX chain + recurrent kernels, which leave most SMs idle); SATK_WGRAD_STREAM=0 keeps everything on one stream
         self._side = torch.cuda.Stream(device=self.device) if os.environ.get("SATK_WGRAD_STREAM", "1") != "0" else None
+        # independent branches of the graph (decoder pre-net beside the encoder, the two BiLSTM directions) fork onto a third stream
+        self._aux = torch.cuda.Stream(device=self.device) if self._side is not None else None
         self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
 
     def _timed(self, name, fn, *a, **k):
@@ -115,6 +117,20 @@ class TacotronEngine:
             out[name] = m
         self._mask_seed += 1
         return out
+
+    @contextlib.contextmanager
+    def _fork(self):
+        """Independent branch: runs on the auxiliary stream after everything issued so far; `_join` merges it back."""
+        if getattr(self, "_aux", None) is None:
+            yield
+            return
+        self._aux.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._aux):
+            yield
+
+    def _join(self):
+        if getattr(self, "_aux", None) is not None:
+            torch.cuda.current_stream().wait_stream(self._aux)
 
     # ------------------------------------------------------------------ self-attention block
     def _sa_forward(self, x, T, B, name, heads, causal, mask, keep, key):
@@ -256,17 +272,20 @@ class TacotronEngine:
         mem1 = self.buf("enc.mem1", (Tt, B, 2 * Hn))
         sv["lstm"] = {}
         for j, dr in enumerate(("fw", "bw")):
-            W = p[f"cbhg.lstm_{dr}.W"]
-            xg = self.lin(hw, f"cbhg.lstm_{dr}.W", self.buf(f"enc.xg_{dr}", (R, 4 * Hn)), K=Hn, bias=p[f"cbhg.lstm_{dr}.b"])
-            gates = self.buf(f"enc.gates_{dr}", (R, 4 * Hn))
-            cp = self.buf(f"enc.cprev_{dr}", (R, Hn))
-            hp_ = self.buf(f"enc.hprev_{dr}", (R, Hn))
-            mc = masks[f"cbhg.lstm_{dr}.c"] if training else None
-            mh = masks[f"cbhg.lstm_{dr}.h"] if training else None
-            O.lstm_seq_fwd(xg, W[Hn:], mem1, Tt, B, Hn, reverse=(j == 1), lengths=source_length, mask_c=mc, mask_h=mh,
-                           zc=d.zc, zh=d.zh, forget_bias=FORGET_BIAS, gates=gates, c_prev=cp, h_prev=hp_,
-                           ld_out=2 * Hn, out_off=j * Hn)
-            sv["lstm"][dr] = dict(gates=gates, c_prev=cp, h_prev=hp_, mc=mc, mh=mh)
+            # the two directions are independent (disjoint column halves of mem1): the backward one runs on the auxiliary stream
+            with (self._fork() if j == 1 else contextlib.nullcontext()):
+                W = p[f"cbhg.lstm_{dr}.W"]
+                xg = self.lin(hw, f"cbhg.lstm_{dr}.W", self.buf(f"enc.xg_{dr}", (R, 4 * Hn)), K=Hn, bias=p[f"cbhg.lstm_{dr}.b"])
+                gates = self.buf(f"enc.gates_{dr}", (R, 4 * Hn))
+                cp = self.buf(f"enc.cprev_{dr}", (R, Hn))
+                hp_ = self.buf(f"enc.hprev_{dr}", (R, Hn))
+                mc = masks[f"cbhg.lstm_{dr}.c"] if training else None
+                mh = masks[f"cbhg.lstm_{dr}.h"] if training else None
+                O.lstm_seq_fwd(xg, W[Hn:], mem1, Tt, B, Hn, reverse=(j == 1), lengths=source_length, mask_c=mc, mask_h=mh,
+                               zc=d.zc, zh=d.zh, forget_bias=FORGET_BIAS, gates=gates, c_prev=cp, h_prev=hp_,
+                               ld_out=2 * Hn, out_off=j * Hn)
+                sv["lstm"][dr] = dict(gates=gates, c_prev=cp, h_prev=hp_, mc=mc, mh=mh)
+        self._join()
         mem2, aligns = None, []
         if d.dual:
             x2 = self.lin(mem1, "enc.sa_proj.W", self.buf("enc.sa_in", (R, d.enc_sa)), bias=p["enc.sa_proj.b"])
@@ -294,18 +313,22 @@ class TacotronEngine:
                 O.colsum_acc(dx, R, d.enc_sa, g["enc.sa_proj.b"])
             O.linear_dx(dx, p["enc.sa_proj.W"], dmem1, R, beta=1.0)
         dhw = self.buf("enc.dhw", (R, Hn))
-        for j, dr in enumerate(("fw", "bw")):
-            s = sv["lstm"][dr]
-            W = p[f"cbhg.lstm_{dr}.W"]
-            dg = self.buf(f"enc.dgates_{dr}", (R, 4 * Hn))
-            O.lstm_seq_bwd(W[Hn:], s["gates"], s["c_prev"], dmem1, dg, Tt, B, Hn, reverse=(j == 1), lengths=source_length,
-                           mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh, ld_dout=2 * Hn, dout_off=j * Hn)
-            gW = g[f"cbhg.lstm_{dr}.W"]
-            with self._wg():
-                O.linear_dw(sv["lstm_in"], dg, gW, R, Hn, 4 * Hn)
-                O.linear_dw(s["h_prev"], dg, gW, R, Hn, 4 * Hn, w_off=Hn * 4 * Hn)
-                O.colsum_acc(dg, R, 4 * Hn, g[f"cbhg.lstm_{dr}.b"])
-            O.linear_dx(dg, W[:Hn], dhw, R, beta=0.0 if j == 0 else 1.0)
+        dgs = {}
+        for j, dr in ((1, "bw"), (0, "fw")):     # backward direction forked first, forward direction on the main stream
+            with (self._fork() if j == 1 else contextlib.nullcontext()):
+                s = sv["lstm"][dr]
+                W = p[f"cbhg.lstm_{dr}.W"]
+                dg = dgs[dr] = self.buf(f"enc.dgates_{dr}", (R, 4 * Hn))
+                O.lstm_seq_bwd(W[Hn:], s["gates"], s["c_prev"], dmem1, dg, Tt, B, Hn, reverse=(j == 1), lengths=source_length,
+                               mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh, ld_dout=2 * Hn, dout_off=j * Hn)
+                gW = g[f"cbhg.lstm_{dr}.W"]
+                with self._wg():
+                    O.linear_dw(sv["lstm_in"], dg, gW, R, Hn, 4 * Hn)
+                    O.linear_dw(s["h_prev"], dg, gW, R, Hn, 4 * Hn, w_off=Hn * 4 * Hn)
+                    O.colsum_acc(dg, R, 4 * Hn, g[f"cbhg.lstm_{dr}.b"])
+        O.linear_dx(dgs["fw"], p["cbhg.lstm_fw.W"][:Hn], dhw, R, beta=0.0)
+        self._join()
+        O.linear_dx(dgs["bw"], p["cbhg.lstm_bw.W"][:Hn], dhw, R, beta=1.0)
         for i in reversed(range(d.n_highway)):
             Hb, Tb, x = sv["hwy"][i]
             # per-layer gradient buffers: the weight-gradient stream still reads them while the next layer is computed
@@ -389,13 +412,13 @@ class TacotronEngine:
         O.embedding_bwd(sv["ids_tm"], dy, g["embedding"])
 
     # ------------------------------------------------------------------ decoder
-    def decoder(self, mem1, mem2, source_length, target, speaker_embed, training, masks):
-        """Teacher-forced decoder.  -> (mel_tm [Td,B,r*n_mels], stop_tm [Td,B], align1, align2, dec self-attn P)."""
+    def decoder_pre(self, target, speaker_embed, training, masks):
+        """Teacher inputs, decoder pre-net and the input projection of LSTM-1: dense over all steps and independent of the encoder
+        (helpers.py:13-55; module.py:1509-1511; multi_speaker_modules.py:27-32), so `forward` runs it beside the encoder."""
         d, p = self.d, self.ps.p
-        Tt, B, _ = mem1.shape
-        Tm = target.shape[1]
+        B, Tm = target.shape[0], target.shape[1]
         Td = Tm // d.r
-        R, Rd = Tt * B, Td * B
+        Rd = Td * B
         sv = {}
         dec_in = self.buf("dec.in", (Rd, d.dec_in))
         O.teacher_inputs(target, B, Tm, d.n_mels, d.r, d.n_feed, dec_in)
@@ -416,9 +439,21 @@ class TacotronEngine:
                            keep_mask=m0, keep_scale=1.0 / keep)
         dp1 = self.lin(dp0, "dec.prenet1.W", self.buf("dec.p1", (Rd, d.dec_prenet[1])), bias=p["dec.prenet1.b"], act="relu",
                        keep_mask=m1, keep_scale=1.0 / keep)
+        xg1 = self.lin(dp1, "dec.lstm1.W", self.buf("dec.xg1", (Rd, 4 * d.att_rnn)), K=d.dec_prenet[1], bias=p["dec.lstm1.b"])
+        sv.update(dec_in=dec_in, dp0=dp0, dp1=dp1, xg1=xg1)
+        return sv
+
+    def decoder(self, mem1, mem2, source_length, target, speaker_embed, training, masks, pre=None):
+        """Teacher-forced decoder.  -> (mel_tm [Td,B,r*n_mels], stop_tm [Td,B], align1, align2, dec self-attn P)."""
+        d, p = self.d, self.ps.p
+        Tt, B, _ = mem1.shape
+        Tm = target.shape[1]
+        Td = Tm // d.r
+        R, Rd = Tt * B, Td * B
+        sv = dict(pre if pre is not None else self.decoder_pre(target, speaker_embed, training, masks))
+        dec_in, dp0, dp1, xg1 = sv["dec_in"], sv["dp0"], sv["dp1"], sv.pop("xg1")
         H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
         W1 = p["dec.lstm1.W"]
-        xg1 = self.lin(dp1, "dec.lstm1.W", self.buf("dec.xg1", (Rd, 4 * H1)), K=P1, bias=p["dec.lstm1.b"])
         # attention memories (BahdanauAttention.__init__, A.8): values masked past length, keys = values.W_mem
         values1 = self.buf("dec.values1", (R, d.mem1))
         O.mask_rows(mem1, source_length, B, Tt, d.mem1, True, values1)
@@ -621,9 +656,13 @@ class TacotronEngine:
         if d.use_speaker:
             spk = self.buf("spk_embed", (B, d.speaker_dim))
             O.embedding_fwd(features.speaker_id, self.ps.p["speaker_embedding"], spk, offset=d.speaker_offset)
+        with self._fork():      # pre-net + LSTM-1 input projection do not depend on the encoder
+            pre = self.decoder_pre(labels.mel, spk, training, masks)
         mem1, mem2, enc_al = self._timed("sec.encoder_fwd", self.encoder, source, source_length, training, masks)
+        # (the encoder forks / joins the auxiliary stream itself for the BiLSTM directions, which also orders `pre` before here)
+        self._join()
         mel_tm, stop_tm, al1, al2, dec_sa = self._timed("sec.decoder_fwd", self.decoder, mem1, mem2, source_length, labels.mel, spk,
-                                                        training, masks)
+                                                        training, masks, pre)
         out3 = self.buf("loss3", (3,))
         dmel = self.buf("dec.dmel_tm", mel_tm.shape)
         dstop = self.buf("dec.dstop_tm", stop_tm.shape)
