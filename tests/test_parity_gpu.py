@@ -193,6 +193,24 @@ def test_full_size_batch_properties(satk, root):
     assert l1 == l1 and l1 < l0 + 0.05
 
 
+def test_vctk_config3_per_replica_batch_runs_full_size(satk, root):
+    """BASELINE configs[2]: examples/vctk/self-attention-tacotron.json at its per-replica batch (64 utterances, T_text=148,
+    T_mel=800): 16 attention clusters = 3 waves.  One train step: finite loss, alignments are distributions, weights move."""
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "vctk_self-attention-tacotron.json"))
+    eng = E.TacotronEngine(hp, "cuda", seed=3)
+    f, l = satk.synthetic_batch(hp, 64, 148, 800, seed=21, device="cuda")
+    w0 = eng.ps.flat.clone()
+    out = eng.train_step(f, l)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["losses"]).all() and out["losses"][2].item() > 0
+    a = out["align1_tm"]                                            # [Td, B, Tt]
+    assert (a.sum(-1) - 1).abs().max().item() < 1e-4
+    pos = torch.arange(148, device="cuda")[None, None, :]
+    assert a.masked_select(pos >= f.source_length[None, :, None]).abs().max().item() == 0      # zero past the source length
+    assert torch.isfinite(eng.ps.grad).all() and (eng.ps.flat - w0).abs().max().item() > 0
+
+
 def test_estimator_surface(satk, root, tmp_path):
     E, O, L, M = _mods()
     hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"), "max_iters=12")
