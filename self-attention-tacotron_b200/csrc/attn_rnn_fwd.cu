@@ -289,6 +289,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         }
       }
     }
+    else if (d.att_kernel > 0) {
+      // warps 2..15 are idle while the two pointwise warps run the cell update and the exchange: they compute the location
+      // features f = conv1d(a_{t-1}) of this step now (a_{t-1} is final since the previous step's softmax)
+      location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, Tt, d.att_kernel, pl, tid - 64, NT - 64);
+    }
     PT(3)
     __syncthreads();
     PT(4)
@@ -313,10 +318,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
 
     // ======================= P2: query slice, location features, partial energies
     {
-      // location features f[j][.] = conv1d(a_prev) (forward_attention.py:98-100)
-      if (d.att_kernel > 0) {
-        location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, Tt, d.att_kernel, pl, tid, NT);
-      }
+      // (location features f[j][.] = conv1d(a_prev), forward_attention.py:98-100, were computed beside the pointwise phase)
       // query slice partials
       const int c = tid & 63, uq = tid >> 6;
       float acc = 0.f;
