@@ -118,3 +118,100 @@ def make_masks(d, B: int, Tt: int, Td: int, seed: int = 99, device="cpu") -> Dic
     for name, shape in mask_shapes(d, B, Tt, Td).items():
         out[name] = (torch.rand(shape, generator=g) < mask_keep_prob(d, name)).to(torch.uint8).to(device)
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's input pipeline on TFRecord files (datasets/ljspeech/dataset.py:74-281, datasets/vctk/dataset.py) restated on numpy /
+# torch.  Reading and parsing is in tfrecord.py; this part is `_prepare_target`, `group_by_batch` and `merge_target_to_source`.
+# ------------------------------------------------------------------------------------------------------------------
+def prepare_target(rec, hp):
+    """`DatasetSource._prepare_target.convert` (datasets/ljspeech/dataset.py:127-167) for one utterance: normalise the mel by the
+    corpus mean / stddev, add r silence frames at both ends, pad the tail with silence to a multiple of r, build done / masks.
+    -> dict(mel [L,num_mels] float32, target_length L, done [L/r], spec_loss_mask [L], binary_loss_mask [L/r])."""
+    import numpy as np
+    r = hp.outputs_per_step
+    mel = (np.asarray(rec.mel, np.float32) - np.asarray(hp.average_mel_level_db, np.float32)) / np.asarray(hp.stddev_mel_level_db,
+                                                                                                        np.float32)
+    sil = np.float32(hp.silence_mel_level_db)
+    mel = np.pad(mel, ((r, r), (0, 0)), constant_values=sil)
+    L = int(rec.target_length) + 2 * r                       # +2r for head and tail silence
+    if L % r != 0:
+        padded = (L // r + 1) * r
+        mel = np.pad(mel, ((0, padded - L), (0, 0)), constant_values=sil)
+        L = padded
+    done = np.concatenate([np.zeros(L // r - 1, np.float32), np.ones(1, np.float32)])
+    return dict(mel=mel.astype(np.float32), target_length=L, done=done, spec_loss_mask=np.ones(L, np.float32),
+                binary_loss_mask=np.ones(L // r, np.float32))
+
+
+def padded_batch(sources, targets, hp, device="cpu"):
+    """`window.padded_batch` of datasets/ljspeech/dataset.py:247-281: pad every field to the longest item of the batch with the
+    reference's padding values (source 0, mel = silence level, done 1, masks 0).  -> (SourceData, MelData) of torch tensors."""
+    B = len(sources)
+    Tt = max(len(s.source) for s in sources)
+    Tm = max(t["target_length"] for t in targets)
+    r = hp.outputs_per_step
+    source = torch.zeros(B, Tt, dtype=torch.int64)
+    mel = torch.full((B, Tm, hp.num_mels), float(hp.silence_mel_level_db))
+    done = torch.ones(B, Tm // r)
+    smask, bmask = torch.zeros(B, Tm), torch.zeros(B, Tm // r)
+    for i, (s, t) in enumerate(zip(sources, targets)):
+        source[i, :len(s.source)] = torch.from_numpy(s.source.astype("int64"))
+        L = t["target_length"]
+        mel[i, :L] = torch.from_numpy(t["mel"])
+        done[i, :L // r] = torch.from_numpy(t["done"])
+        smask[i, :L] = 1.0
+        bmask[i, :L // r] = 1.0
+    ids = torch.tensor([s.id for s in sources], dtype=torch.int64)
+    keys = [s.key for s in sources]
+    spk = None
+    if getattr(hp, "use_speaker_embedding", False) and sources[0].speaker_id is not None:
+        spk = torch.tensor([s.speaker_id for s in sources], dtype=torch.int64)
+    dev = torch.device(device)
+    mv = lambda x: x.to(dev) if x is not None else None      # noqa: E731
+    feats = SourceData(mv(ids), keys, mv(source), mv(torch.tensor([s.source_length for s in sources], dtype=torch.int64)),
+                       [s.text for s in sources], mv(spk))
+    labels = MelData(mv(ids), keys, mv(mel), mv(torch.full((B,), hp.num_mels, dtype=torch.int64)),
+                     mv(torch.tensor([t["target_length"] for t in targets], dtype=torch.int64)), mv(done), mv(smask), mv(bmask))
+    return feats, labels
+
+
+def group_by_batch(pairs, hp, batch_size=None):
+    """`ZippedDataset.group_by_batch` (datasets/ljspeech/dataset.py:225-283): tf `group_by_window` with the reference's key function
+    — bucket = min(num_buckets, min(target_length - approx_min_target_length, 0) // bucket_width), restated literally — and windows of
+    5 batches; a full window is emitted as padded batches, the remaining windows are flushed at the end of the input."""
+    bs = batch_size if batch_size is not None else hp.batch_size
+    windows: Dict[int, list] = {}
+    for src, tgt in pairs:
+        key = min(hp.batch_num_buckets, min(tgt["target_length"] - hp.approx_min_target_length, 0) // hp.batch_bucket_width)
+        w = windows.setdefault(key, [])
+        w.append((src, tgt))
+        if len(w) == bs * 5:
+            for i in range(0, len(w), bs):
+                yield padded_batch([x[0] for x in w[i:i + bs]], [x[1] for x in w[i:i + bs]], hp)
+            windows[key] = []
+    for key in list(windows):
+        w = windows[key]
+        for i in range(0, len(w), bs):
+            yield padded_batch([x[0] for x in w[i:i + bs]], [x[1] for x in w[i:i + bs]], hp)
+
+
+def tfrecord_input_fn(source_files, target_files, hp, batch_size=None, for_prediction=False):
+    """input_fn over the reference's pre-processed TFRecord files (train.py:40-66 / predict_mel.py:39-45): source and target files
+    are read in the given order and zipped record by record.  `for_prediction` applies `merge_target_to_source`
+    (datasets/ljspeech/dataset.py:309-322): features become SourceDataForPrediction carrying the ground-truth mel."""
+    from . import tfrecord as TF
+
+    def gen():
+        def pairs():
+            for sf, tf_ in zip(source_files, target_files):
+                for s, t in zip(TF.read_source_file(sf), TF.read_mel_file(tf_)):
+                    if s.key != t.key:
+                        raise ValueError(f"source / target records out of step: {s.key} vs {t.key}")
+                    yield s, prepare_target(t, hp)
+        for feats, labels in group_by_batch(pairs(), hp, batch_size):
+            if for_prediction:
+                feats = SourceDataForPrediction(feats.id, feats.key, feats.source, feats.source_length, feats.text, feats.speaker_id,
+                                                labels.mel, labels.mel_width, labels.target_length)
+            yield feats, labels
+    return gen

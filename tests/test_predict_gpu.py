@@ -167,3 +167,36 @@ def test_rowgemm_lstm_epilogue_unit(satk):
             _close(h, h_ref, 1e-5, "lstm h")
             _close(rows[(t + 1) & 1, :, Kx:], h_ref, 1e-5, "next-step h rows")
             assert outb[(t + 1) & 1].abs().max().item() == 0
+
+
+def test_tfrecord_files_to_prediction_files(satk, root, tmp_path):
+    """The callers either side of the path (train.py:40-88, predict_mel.py:36-74) on the reference's own file formats: TFRecord
+    source / target files -> input_fn -> train two steps -> free-running predict -> <key>.mfbsp + <key>.tfrecord outputs."""
+    import numpy as np
+    E, O, L, M = _mods()
+    TF = satk.tfrecord
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"), "batch_size=3,max_iters=9")
+    rs = np.random.RandomState(0)
+    srcs, mels = [], []
+    for i in range(6):
+        n, Lm = 9 + i, 11 + 3 * i
+        srcs.append(TF.PreprocessedSourceData(i, f"LJ{i:03d}", np.concatenate([[0], rs.randint(1, 68, n - 2), [0]]).astype(np.int64), n,
+                                              f"text {i}", None, None, None))
+        mels.append(TF.PreprocessedMelData(i, f"LJ{i:03d}", (rs.randn(Lm, hp.num_mels) * 8 - 40).astype(np.float32), hp.num_mels, Lm))
+    sp, mp = str(tmp_path / "source.tfrecord"), str(tmp_path / "target.tfrecord")
+    TF.write_records(sp, [TF.encode_source_record(s) for s in srcs])
+    TF.write_records(mp, [TF.encode_mel_record(m) for m in mels])
+    model = M.tacotron_model_factory(hp, str(tmp_path / "ckpt"), None)
+    spec = model.train(satk.tfrecord_input_fn([sp], [mp], hp), steps=2)
+    assert spec.train_op == 2 and torch.isfinite(spec.loss)
+    out_dir = str(tmp_path / "pred")
+    keys = TF.write_predictions(model.predict(satk.tfrecord_input_fn([sp], [mp], hp, batch_size=1, for_prediction=True)), out_dir)
+    assert keys == [f"LJ{i:03d}" for i in range(6)]
+    for i, k in enumerate(keys):
+        mel = np.fromfile(os.path.join(out_dir, k + ".mfbsp"), dtype="<f4").reshape(-1, hp.num_mels)
+        assert mel.shape[0] == 9 * hp.outputs_per_step and np.isfinite(mel).all()
+        ex = TF.decode_example(next(TF.read_records(os.path.join(out_dir, k + ".tfrecord"), verify_data_crc=True)))
+        assert ex["key"] == [k.encode()] and ex["mel_length"].tolist() == [mel.shape[0]] and len(ex["alignment"]) >= 2
+        assert np.array_equal(np.frombuffer(ex["source"][0], "<i8"), srcs[i].source)
+        gt = np.frombuffer(ex["ground_truth_mel"][0], "<f4").reshape(-1, hp.num_mels)
+        assert gt.shape[0] == int(ex["ground_truth_mel_length"][0]) == (mels[i].target_length + 2 * hp.outputs_per_step + 1) // 2 * 2
