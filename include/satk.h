@@ -269,6 +269,11 @@ typedef struct {
   float* h_prev;               /* [Td,B,H] */
   float* soft1;                /* [Td,B,Tt] softmax alignments a_t (forward attention: state field 0) */
   float* q_save;               /* [Td,B,A1+A2] processed queries (query_layer outputs) */
+  /* forward attention with the transition agent (forward_attention.py:111-114): u_t = sigmoid([ctx1_t, q1_t] . agent_w + agent_b)
+   * replaces the constant 0.5 in the recursion of step t+1.  agent_w NULL: no agent. */
+  const float* agent_w;        /* [M1+A1] transition_factor_projection kernel */
+  const float* agent_b;        /* [1] */
+  float* u_save;               /* [Td,B] transition factor USED by step t (u_{t-1}; 0.5 at t=0); saved for backward, may be NULL */
 } satk_attn_rnn_fwd_desc;
 int satk_attn_rnn_fwd(const satk_attn_rnn_fwd_desc* d, void* stream);
 
@@ -287,6 +292,8 @@ typedef struct {
   float* dloc_conv_w;          /* [att_kernel, att_filters] (+=) */
   float* dloc_conv_b;          /* [att_filters] (+=) */
   float* dloc_layer_w;         /* [att_filters, A1] (+=) */
+  float* dagent_w;             /* [M1+A1] (+=, atomics); required when f.agent_w is set */
+  float* dagent_b;             /* [1] (+=) */
 } satk_attn_rnn_bwd_desc;
 int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
 

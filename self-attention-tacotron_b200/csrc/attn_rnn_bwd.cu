@@ -83,7 +83,7 @@ struct BwdSmem {
 
 using cl::group_sum2;
 
-template <bool HAS2, int AFT, int NP>
+template <bool HAS2, int AFT, int NP, bool AGENT>
 __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn_bwd_desc dd) {
   using D = Dims<HAS2>;
   constexpr int A1Q = D::A1Q, NI1 = D::NI1, X2W = D::X2W, M2 = D::M2;
@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
   const bool arow_ok = arow < B;
   const int alen = arow_ok ? (int)d.lengths[arow] : 0;
   const int pl = d.att_kernel > 0 ? (d.att_kernel - 1) / 2 : 0;
-  const float u_tr = 0.5f;
   const bool loc = d.att_kernel > 0;
 
   // ---------------- one-time loads
@@ -209,6 +208,14 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
 #pragma unroll
   for (int i = 0; i < NCH; ++i) dv_acc[i] = 0.f;
   float dWf_acc = 0.f;     // tid < NI1*8*AFT owns one (channel, filter) entry of d(location_features_layer)
+  // transition agent (forward_attention.py:111-114): thread tid < 64 owns context column cq*64+tid and thread tid < A1Q score channel
+  // cq*A1Q+tid of [ctx1, q1] . W; S.red[40] carries d(u_t) from the step that used it, S.red[41] = d(pre-sigmoid) of step t
+  float wa = 0.f, waq = 0.f, dwa_acc = 0.f, dwaq_acc = 0.f, db_acc = 0.f;
+  if (AGENT) {
+    if (tid < 64) wa = __ldg(d.agent_w + cq * 64 + tid);
+    if (tid < A1Q) waq = __ldg(d.agent_w + M1 + cq * A1Q + tid);
+    if (tid == 0) { S.red[40] = 0.f; S.red[41] = 0.f; }
+  }
 
   cluster.sync();
 
@@ -274,6 +281,16 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     const float* alphaS = rA + TtP;
     const float* a2S = rA + 2 * TtP;
     const float* qs = rB;
+    // u used by the recursion of step t (u_{t-1}); u_t = the factor produced by step t, used by step t+1
+    const float u_tr = (AGENT && arow_ok) ? __ldg(d.u_save + (long long)t * B + arow) : 0.5f;
+    float ctx_own = 0.f;
+    if (AGENT) {
+      if (tid == 0) {
+        const float u_t = (t + 1 < Td && arow_ok) ? __ldg(d.u_save + (long long)(t + 1) * B + arow) : 0.5f;
+        S.red[41] = S.red[40] * u_t * (1.f - u_t);         // d(pre-sigmoid) of the agent output of step t
+      }
+      if (tid < 64 && arow_ok) ctx_own = __ldg(d.x2 + ((long long)t * B + arow) * X2W + H + cq * 64 + tid);
+    }
     for (int j = tid; j < TtP; j += NT) {
       const bool in = j < Tt && t > 0;
       S.aprev[HALO + j] = in ? rAp[j] : 0.f;
@@ -294,7 +311,13 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
 
     // ======================= BA1
     if (tid < VCW) {
-      const float v = S.dctx_in[tid] + rB[QC + tid];
+      float v = S.dctx_in[tid] + rB[QC + tid];
+      if (AGENT && tid < 64) {
+        const float dpre = S.red[41];
+        v = fmaf(dpre, wa, v);                   // u_t = sigmoid([ctx1_t, q1_t] . W + b): d(ctx1_t) += d(pre) W_ctx
+        dwa_acc = fmaf(dpre, ctx_own, dwa_acc);
+        if (tid == 0 && cq == 0) db_acc += dpre;
+      }
       S.dctxS[tid] = v;                          // total d(ctx); saved for the dense dvalues GEMM by the saver warps
     }
     __syncthreads();
@@ -365,6 +388,12 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         const float dau = (in && j < alen) ? (dal - s2) / s1 : 0.f;
         da = dau * mix + dst;
         if (in) S.dmixS[j] = dau * a;
+        if (AGENT) {
+          // d(u_{t-1}) = sum_j d(mix_j) (alpha_{t-1}[j-1] - alpha_{t-1}[j])      (forward_attention.py:109)
+          float s3 = in ? dau * a * (apm1 - S.alphaPrevS[j]) : 0.f, dummy3 = 0.f;
+          group_sum2(s3, dummy3, S.red, warp & 7, lane, 2);
+          if (tid == 256) S.red[40] = (t > 0) ? s3 : 0.f;
+        }
       } else {
         da = dw + dst;
       }
@@ -489,6 +518,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         if (tid < A1Q || HAS2) {
 #pragma unroll
           for (int w_ = 0; w_ < 16; ++w_) q += S.stageQ[w_ * QC + tid];
+        }
+        if (AGENT && tid < A1Q) {
+          const float dpre = S.red[41];                   // d(q1_t) += d(pre) W_q ; d(W_q) += d(pre) q1_t
+          dwaq_acc = fmaf(dpre, qs[tid], dwaq_acc);
+          q = fmaf(dpre, waq, q);
         }
         S.dqS[tid] = q;
         const int qcol = (tid < A1Q) ? (cq * A1Q + tid) : (d.A1 + cq * 8 + (tid - A1Q));
@@ -757,6 +791,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         else atomicAdd(dd.dv2 + cq * 8 + cl_, v);
       }
     }
+    if (AGENT) {
+      if (tid < 64) atomicAdd(dd.dagent_w + cq * 64 + tid, dwa_acc);
+      if (tid < A1Q) atomicAdd(dd.dagent_w + M1 + cq * A1Q + tid, dwaq_acc);
+      if (tid == 0 && cq == 0) atomicAdd(dd.dagent_b, db_acc);
+    }
     if (loc) {
       if (tid < NI1 * 8 * AFT) {
         const int c8 = tid / SW, rem = tid % SW;
@@ -826,9 +865,14 @@ extern "C" int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   const int np = (d->f.Tt + 63) / 64;
   const bool af5 = d->f.att_filters == 5 || d->f.att_kernel == 0;
+  const bool agent = d->f.agent_w != nullptr;
+  SATK_CHECK_ARG(!agent || (d->f.mode == 2 && d->f.u_save && d->dagent_w && d->dagent_b),
+                 "attn_rnn_bwd: the transition agent needs forward attention, the saved factors and its gradient buffers");
   size_t smem = has2 ? bwd_smem_bytes<true>(d->f.Tt, af5 ? 5 : 8) : bwd_smem_bytes<false>(d->f.Tt, af5 ? 5 : 8);
   SATK_CHECK_ARG(smem <= 227 * 1024, "attn_rnn_bwd: Tt=%d needs %zu B of shared memory (> 227 KB)", d->f.Tt, smem);
-#define SATK_ARNN_DISPATCH(H2, AF, NPV) return launch16b(attn_rnn_bwd_kernel<H2, AF, NPV>, *d, smem, st)
+#define SATK_ARNN_DISPATCH(H2, AF, NPV) \
+  do { if (agent) return launch16b(attn_rnn_bwd_kernel<H2, AF, NPV, true>, *d, smem, st); \
+       return launch16b(attn_rnn_bwd_kernel<H2, AF, NPV, false>, *d, smem, st); } while (0)
   if (has2) {
     if (af5) { if (np <= 3) SATK_ARNN_DISPATCH(true, 5, 3); else SATK_ARNN_DISPATCH(true, 5, 4); }
     else { if (np <= 3) SATK_ARNN_DISPATCH(true, 8, 3); else SATK_ARNN_DISPATCH(true, 8, 4); }

@@ -34,7 +34,7 @@ struct FwdSmem {
   using D = Dims<HAS2>;
   int TtP, Tt4;
   float *xrec, *gsm, *out1buf, *Wqs, *keyS, *valS, *fS, *Wfs, *wconv, *bconv, *vs, *qs, *qpart, *epart, *aprev, *alphaS,
-      *w1S, *w2S, *softS, *cpart, *ctxS, *save1, *xg_ring, *red;
+      *w1S, *w2S, *softS, *cpart, *ctxS, *save1, *xg_ring, *red, *upart;
   uint8_t* mk_ring;
   uint64_t* bars;   // [0..1] X, [2..3] O, [4..5] E
   __host__ __device__ size_t carve(float* base, int Tt) {
@@ -64,6 +64,7 @@ struct FwdSmem {
     ctxS = p; p += VC + 8;
     save1 = p; p += 7 * 64;
     red = p; p += 32;
+    upart = p; p += 2 * 4 + 4;                       // transition agent: [parity][source CTA of the quad] partial sums, [8] = u
     xg_ring = p; p += RING * 256;
     mk_ring = reinterpret_cast<uint8_t*>(p); p += RING * 2 * BG * UH / 4;
     bars = reinterpret_cast<uint64_t*>(p); p += 2 * 6;
@@ -71,14 +72,15 @@ struct FwdSmem {
   }
 };
 
-template <bool HAS2, int AFT, int NP>
+template <bool HAS2, int AFT, int NP, bool AGENT>
 __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn_fwd_desc d) {
   using D = Dims<HAS2>;
   constexpr int KREC = D::KREC, A1Q = D::A1Q, NI1 = D::NI1, M2 = D::M2, X2W = D::X2W;
   constexpr int KPT = KREC / 32;                       // k's per lane in the gate GEMM (17 / 16)
   constexpr int VCW = HAS2 ? VC : 64;                  // context columns produced per CTA
   constexpr int NATT = HAS2 ? 2 : 1;
-  constexpr uint32_t RX_X = (uint32_t)((CS - 1) * UH * BG + (BG * (M1 + M2) - VCW)) * 4u;
+  // bytes landing on barX per step: h slices of the 15 peers + context slices of every other CTA (+ 3 agent partial sums)
+  constexpr uint32_t RX_X = (uint32_t)((CS - 1) * UH * BG + (BG * (M1 + M2) - VCW) + (AGENT ? 3 : 0)) * 4u;
   constexpr uint32_t RX_O = (uint32_t)(CS - 1) * UH * 4u;
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
@@ -153,6 +155,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
   for (int i = tid; i < RING * 2 * BG * UH; i += NT) S.mk_ring[i] = 0;
   if (tid < H) S.out1buf[tid] = 0.f;
   if (tid < VC + 8) S.ctxS[tid] = 0.f;
+  if (tid < 12) S.upart[tid] = (tid == 8) ? 0.5f : 0.f;       // u_0 = 0.5 (forward_attention.py:135)
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) cl::mbar_init(&S.bars[i], 1);
     cl::fence_mbar_init();
@@ -187,6 +190,13 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
   // P2 role: position group / channel lane
   const int pg = warp * 4 + (lane >> 3), cl_ = lane & 7;
 
+  float wa = 0.f;
+  if (AGENT) {
+    if (tid < 64) wa = __ldg(d.agent_w + cq * 64 + tid);
+    else if (tid < 64 + A1Q) wa = __ldg(d.agent_w + M1 + cq * A1Q + (tid - 64));
+  }
+  const float agent_b = AGENT ? __ldg(d.agent_b) : 0.f;
+
   cluster.sync();
 
   auto prefetch = [&](int t) {
@@ -214,6 +224,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
     prefetch(t + PFD);
     cp_async_wait<PFD>();
     if (t > 0) cl::mbar_wait(&barX[cur], (uint32_t)((t - 1) >> 1) & 1u);    // h(t), ctx(t-1) of every peer have landed
+    if (AGENT && t > 0 && tid == 32) {
+      // transition factor of the previous step from the four partial sums of this utterance's CTAs (forward_attention.py:111-114)
+      const float* up = S.upart + cur * 4;
+      S.upart[8] = fsigmoid(((up[0] + up[1]) + (up[2] + up[3])) + agent_b);
+    }
     if (tid == 0) {
       if (!last) cl::mbar_arrive_expect_tx(&barX[nxt], RX_X);
       cl::mbar_arrive_expect_tx(&barO[cur], RX_O);
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         e = S.epart[(0 * 4 + 0) * TtP + j] + S.epart[(0 * 4 + 1) * TtP + j] + S.epart[(0 * 4 + 2) * TtP + j] + S.epart[(0 * 4 + 3) * TtP + j];
       const float mx = cl::group_max(e, S.red, warp & 7, lane, 2);
       const float pexp = (in && j < alen) ? __expf(e - mx) : 0.f;
-      const float u = 0.5f;  // transition factor stays at its initial value without the agent (forward_attention.py:116,135)
+      const float u = AGENT ? S.upart[8] : 0.5f;  // without the agent the factor stays at its initial value (forward_attention.py:116,135)
       float mixp = 0.f;
       if (d.mode == 2 && in) {
         const float apm1 = (j > 0) ? S.alphaS[j - 1] : 0.f;
@@ -496,6 +511,23 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
     }
     PT(14)
     __syncthreads();
+    if (AGENT && tid < 128 && !last) {
+      // partial sum of [context1, processed_query1] . W over this CTA's context columns and score channels -> the quad
+      float part = 0.f;
+      if (tid < 64) part = S.ctxS[tid] * wa;
+      else if (tid < 64 + A1Q) part = S.qs[tid - 64] * wa;
+      part = warp_sum(part);
+      if (lane == 0) S.red[16 + warp] = part;
+      asm volatile("bar.sync 5, 128;" ::: "memory");
+      if (tid == 0) {
+        const float v = (S.red[16] + S.red[17]) + (S.red[18] + S.red[19]);
+        S.upart[nxt * 4 + cq] = v;
+        const uint32_t dsta = cl::smem_u32(&S.upart[nxt * 4 + cq]), bara = cl::smem_u32(&barX[nxt]);
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4)
+          if (r4 != cq) cl::st_async_f32(cl::mapa(dsta, ab * 4 + r4), v, cl::mapa(bara, ab * 4 + r4));
+      }
+    }
     if (arow_ok && tid >= 256) {
       // saver B: context and alignments of step t -> global
       const int e = tid - 256;
@@ -503,6 +535,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         const int k = (e < 64) ? (cq * 64 + e) : (M1 + cq * 8 + (e - 64));
         d.x2[((long long)t * B + arow) * X2W + H + k] = S.ctxS[e];
       }
+      if (AGENT && cq == 0 && e == 0 && d.u_save) d.u_save[(long long)t * B + arow] = S.upart[8];
       if (cq == 0) {
         const long long oa = ((long long)t * B + arow) * Tt;
         for (int j = e; j < Tt; j += 256) {
@@ -559,7 +592,7 @@ int attn_rnn_check(const satk_attn_rnn_fwd_desc* d, bool& has2) {
 }
 
 int attn_rnn_max_clusters() {
-  auto kern = attn_rnn_fwd_kernel<true, 5, 3>;
+  auto kern = attn_rnn_fwd_kernel<true, 5, 3, false>;
   size_t smem = fwd_smem_bytes<true>(148);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return -1; }
   cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
@@ -601,9 +634,13 @@ extern "C" int satk_attn_rnn_fwd(const satk_attn_rnn_fwd_desc* d, void* stream) 
   cudaStream_t st = (cudaStream_t)stream;
   const int np = (d->Tt + 63) / 64;
   const bool af5 = d->att_filters == 5 || d->att_kernel == 0;
+  const bool agent = d->agent_w != nullptr;
+  SATK_CHECK_ARG(!agent || (d->mode == 2 && d->agent_b), "attn_rnn_fwd: the transition agent needs forward attention (mode 2) and its bias");
   size_t smem = has2 ? fwd_smem_bytes<true>(d->Tt) : fwd_smem_bytes<false>(d->Tt);
   SATK_CHECK_ARG(smem <= 227 * 1024, "attn_rnn_fwd: Tt=%d needs %zu B of shared memory (> 227 KB)", d->Tt, smem);
-#define SATK_ARNN_DISPATCH(H2, AF, NPV) return launch16(attn_rnn_fwd_kernel<H2, AF, NPV>, *d, smem, st)
+#define SATK_ARNN_DISPATCH(H2, AF, NPV) \
+  do { if (agent) return launch16(attn_rnn_fwd_kernel<H2, AF, NPV, true>, *d, smem, st); \
+       return launch16(attn_rnn_fwd_kernel<H2, AF, NPV, false>, *d, smem, st); } while (0)
   if (has2) {
     if (af5) { if (np <= 3) SATK_ARNN_DISPATCH(true, 5, 3); else SATK_ARNN_DISPATCH(true, 5, 4); }
     else { if (np <= 3) SATK_ARNN_DISPATCH(true, 8, 3); else SATK_ARNN_DISPATCH(true, 8, 4); }

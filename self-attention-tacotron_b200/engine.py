@@ -468,6 +468,7 @@ class TacotronEngine:
         al1 = self.buf("dec.align1", (Td, B, Tt))
         al2 = self.buf("dec.align2", (Td, B, Tt)) if d.dual else None
         loc = d.attention in ("forward", "location_sensitive")
+        agent = d.attention == "forward" and d.transition_agent          # forward_attention.py:111-114
         fd = O.attn_rnn_desc(
             Td=Td, B=B, Tt=Tt, H=H1, A1=d.att1, A2=d.att2, M1=d.mem1, M2=d.mem2,
             att_kernel=d.att_kernel if loc else 0, mode=_MODE[d.attention], cumulative=int(d.cumulative),
@@ -481,7 +482,9 @@ class TacotronEngine:
             x2=x2, align1=al1, align2=al2,
             gates=self.buf("dec.gates1", (Rd, 4 * H1)), c_prev=self.buf("dec.cprev1", (Rd, H1)),
             h_prev=self.buf("dec.hprev1", (Rd, H1)), soft1=self.buf("dec.soft1", (Td, B, Tt)),
-            q_save=self.buf("dec.qsave", (Rd, d.att1 + d.att2)))
+            q_save=self.buf("dec.qsave", (Rd, d.att1 + d.att2)),
+            agent_w=p["att1.agent.W"] if agent else None, agent_b=p["att1.agent.b"] if agent else None,
+            u_save=self.buf("dec.usave", (Td, B)) if agent else None)
         self._timed("attn_rnn_fwd", O.attn_rnn_fwd, fd)
         sv.update(fd=fd, dec_in=dec_in, dp0=dp0, dp1=dp1, x2=x2, values1=values1, values2=values2, keys1=keys1, keys2=keys2)
         # LSTM-2, LSTM-3 (DecoderRNNV2)
@@ -559,7 +562,9 @@ class TacotronEngine:
         self._timed("attn_rnn_bwd", O.attn_rnn_bwd, fd, dx2=dx2, dgates=dg1, dq=dq, dkeys1=dkeys1, dkeys2=dkeys2,
                        dv1=g["att1.v"], dv2=g["att2.v"] if d.dual else None,
                        dloc_conv_w=g["att1.loc_conv.W"] if loc else None, dloc_conv_b=g["att1.loc_conv.b"] if loc else None,
-                       dloc_layer_w=g["att1.loc_layer.W"] if loc else None)
+                       dloc_layer_w=g["att1.loc_layer.W"] if loc else None,
+                       dagent_w=g["att1.agent.W"] if (d.attention == "forward" and d.transition_agent) else None,
+                       dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None)
         # LSTM-1 weight gradients (dense over time)
         gW1 = g["dec.lstm1.W"]
         N4 = 4 * H1
@@ -646,9 +651,6 @@ class TacotronEngine:
         B, Tt = source.shape
         Tm = labels.mel.shape[1]
         Td = Tm // d.r
-        if d.transition_agent:
-            raise NotImplementedError("use_forward_attention_transition_agent=True: only the free-running decode (predict) "
-                                      "implements the transition agent; the teacher-forced attention-RNN kernels do not yet")
         if training and masks is None:
             masks = self.device_masks(B, Tt, Td)
         self._training = training

@@ -68,6 +68,7 @@ class AttnRnnFwdDesc(C.Structure):
         ("keys2", fp), ("values2", fp), ("Wq2", fp), ("v2", fp),
         ("x2", fp), ("align1", fp), ("align2", fp),
         ("gates", fp), ("c_prev", fp), ("h_prev", fp), ("soft1", fp), ("q_save", fp),
+        ("agent_w", fp), ("agent_b", fp), ("u_save", fp),
     ]
 
 
@@ -76,6 +77,7 @@ class AttnRnnBwdDesc(C.Structure):
         ("f", AttnRnnFwdDesc),
         ("dx2", fp), ("dgates", fp), ("dq", fp), ("dkeys1", fp), ("dkeys2", fp),
         ("dv1", fp), ("dv2", fp), ("dloc_conv_w", fp), ("dloc_conv_b", fp), ("dloc_layer_w", fp),
+        ("dagent_w", fp), ("dagent_b", fp),
     ]
 
 

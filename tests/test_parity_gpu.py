@@ -117,6 +117,18 @@ def test_variant_location_sensitive(satk, root):
     _case(satk, root, "ljspeech_self-attention-tacotron.json", 3, 20, 24, True, overrides="attention=location_sensitive")
 
 
+def test_variant_forward_attention_transition_agent(satk, root):
+    """use_forward_attention_transition_agent=True (forward_attention.py:111-114): the transition factor of the recursion is
+    produced by a sigmoid layer on [context, processed query]; forward tensors and every gradient (incl. the agent's own
+    kernel / bias) against the oracle, for the dual model (ragged batch, > one cluster) and the single-attention model."""
+    eng, tr, _, _ = _case(satk, root, "ljspeech_self-attention-tacotron.json", 6, 22, 28, True,
+                          overrides="use_forward_attention_transition_agent=True")
+    assert eng.ps.g["att1.agent.W"].abs().max().item() > 0 and eng.ps.g["att1.agent.b"].abs().max().item() > 0
+    _case(satk, root, "ljspeech_tacotron.json", 3, 17, 20, True, overrides="use_forward_attention_transition_agent=True")
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 3, 20, 16, False,
+          overrides="use_forward_attention_transition_agent=True")
+
+
 def test_variant_additive(satk, root):
     _case(satk, root, "ljspeech_tacotron.json", 3, 20, 24, True, overrides="attention=additive")
 
