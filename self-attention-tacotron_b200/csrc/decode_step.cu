@@ -23,6 +23,13 @@ constexpr int MR = 16;     // rows per pass
 constexpr int KC = 128;    // reduction chunk staged in shared memory
 constexpr int NC = 32;     // columns per CTA (one per lane)
 
+// Programmatic dependent launch: the step's kernels are launched with programmaticStreamSerialization, so kernel N+1 is scheduled
+// while kernel N drains; `pdl_wait` blocks until kernel N has completed and its writes are visible, `pdl_launch` lets N+1 start early.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ float ftanh_(float x) {
   x = fminf(fmaxf(x, -15.f), 15.f);
   const float e = __expf(2.0f * x);
@@ -41,6 +48,7 @@ __global__ void __launch_bounds__(256) rowgemm_k(const satk_rowgemm_desc d) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = KS > 1 ? (int)cluster.block_rank() : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_enter();
   int i = 0, cb = blockIdx.x / KS;
   const bool lstm = d.lstm_H > 0;
   if (!lstm)
@@ -164,6 +172,7 @@ __global__ void __cluster_dims__(ACS, 1, 1) __launch_bounds__(256) attn_step_k(c
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.x / ACS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_enter();
   const int Tt = d.Tt, B = d.B, A1 = d.A1, A2 = d.A2, M1 = d.M1, M2 = d.M2, AF = d.att_filters;
   const int tt = d.t_ptr ? *d.t_ptr : 0;
   const int len = (int)d.lengths[b];
@@ -320,6 +329,7 @@ __global__ void __launch_bounds__(256) sa_step_k(const satk_sa_step_desc d) {
   extern __shared__ float ps[];            // [Tmax] scores / probabilities, then [2][dh] partial outputs
   __shared__ float redbuf[32];
   const int b = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_enter();
   const int D = d.D, dh = D / d.heads, B = d.B;
   const int t = *d.t_ptr;
   const int n = t + 1;
@@ -362,6 +372,7 @@ __global__ void __launch_bounds__(256) sa_step_k(const satk_sa_step_desc d) {
 
 __global__ void tick_k(int* t_ptr, const float* stop, int B, int min_iters, int* done_step) {
   // StopTokenBasedInferenceHelper.is_finished: sigmoid(stop) > 0.5 for EVERY utterance and time > min_iters (helpers.py:103-107)
+  pdl_enter();
   const int t = *t_ptr;
   bool all = true;
   if (stop)
@@ -378,22 +389,35 @@ __global__ void tick_k(int* t_ptr, const float* stop, int B, int min_iters, int*
 
 using namespace satk;
 
+// every decode-step kernel is launched with programmatic stream serialization (see pdl_enter) and, where it uses one, its cluster shape
+template <typename Kern, typename... Args>
+static int launch_step(Kern kern, dim3 grid, int threads, size_t smem, cudaStream_t st, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  SATK_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+  return SATK_OK;
+}
+
 template <int KS>
 static int launch_rowgemm(const satk_rowgemm_desc* d, int blocks, cudaStream_t st) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(blocks * KS);
-  cfg.blockDim = dim3(256);
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = KS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  SATK_CUDA(cudaLaunchKernelEx(&cfg, dstep::rowgemm_k<KS>, *d));
-  return SATK_OK;
+  return launch_step(dstep::rowgemm_k<KS>, dim3(blocks * KS), 256, 0, st, KS, *d);
 }
 
 extern "C" int satk_rowgemm(const satk_rowgemm_desc* d, void* stream) {
@@ -435,9 +459,7 @@ extern "C" int satk_attn_step(const satk_attn_step_desc* d, void* stream) {
   const size_t smem = sizeof(float) * ((size_t)d->A1 + d->A2 + (size_t)PP * AF + (size_t)AF * d->A1 + 5 * (size_t)d->Tt + (size_t)(256 / CP) * CP);
   SATK_CHECK_ARG(smem <= 200 * 1024, "satk_attn_step: Tt=%d needs %zu B of shared memory", d->Tt, smem);
   if (smem > 48 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::attn_step_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dstep::attn_step_k<<<d->B * dstep::ACS, 256, smem, (cudaStream_t)stream>>>(*d);
-  SATK_LAUNCH_CHECK();
-  return SATK_OK;
+  return launch_step(dstep::attn_step_k, dim3(d->B * dstep::ACS), 256, smem, (cudaStream_t)stream, 1, *d);   // cluster dims are compiled in
 }
 
 extern "C" int satk_sa_step(const satk_sa_step_desc* d, void* stream) {
@@ -449,14 +471,10 @@ extern "C" int satk_sa_step(const satk_sa_step_desc* d, void* stream) {
   const size_t smem = sizeof(float) * ((size_t)d->Tmax + (size_t)groups * dh);
   SATK_CHECK_ARG(smem <= 200 * 1024, "satk_sa_step: Tmax=%d too large", d->Tmax);
   if (smem > 48 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::sa_step_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dstep::sa_step_k<<<dim3(d->B, d->heads), 256, smem, (cudaStream_t)stream>>>(*d);
-  SATK_LAUNCH_CHECK();
-  return SATK_OK;
+  return launch_step(dstep::sa_step_k, dim3(d->B, d->heads), 256, smem, (cudaStream_t)stream, 1, *d);
 }
 
 extern "C" int satk_decode_tick(int* t_ptr, const float* stop, int B, int min_iters, int* done_step, void* stream) {
   SATK_CHECK_ARG(t_ptr && done_step, "satk_decode_tick: null pointer");
-  dstep::tick_k<<<1, 32, 0, (cudaStream_t)stream>>>(t_ptr, stop, B, min_iters, done_step);
-  SATK_LAUNCH_CHECK();
-  return SATK_OK;
+  return launch_step(dstep::tick_k, dim3(1), 32, 0, (cudaStream_t)stream, 1, t_ptr, stop, B, min_iters, done_step);
 }
