@@ -42,8 +42,8 @@ int satk_device_info(int* out5);
 /* sizeof() of the descriptor structs, in declaration order (gemm, lstm_fwd, lstm_bwd, attn_fwd, attn_bwd):
  * lets a foreign-language binding verify its struct layout */
 int satk_struct_sizes(int* out5);
-/* same for the decode-step descriptors (rowgemm, attn_step, sa_step) */
-int satk_struct_sizes_decode(int* out3);
+/* same for the decode-step descriptors (rowgemm, attn_step, sa_step, sa_tail) */
+int satk_struct_sizes_decode(int* out4);
 
 /* ------------------------------------------------------------------------------------------
  * Dense tile: C = epilogue( alpha * sum_tap op(A_tap) * op(B_tap) ) (+ beta*C)
@@ -368,6 +368,25 @@ typedef struct {
   float* probs;                    /* [B,heads,Tmax,Tmax] row t receives the alignment, or NULL */
 } satk_sa_step_desc;
 int satk_sa_step(const satk_sa_step_desc* d, void* stream);
+
+/* Fused tail of a decoder step, one cluster of 8 CTAs per utterance: for each self-attention hop the K/V/Q projections of the newest
+ * decoder output (K, V appended to the caches), causal attention over rows 0..t, output projection, tanh transform + residual
+ * (TransformerWrapper, rnn_wrappers.py:111-124; SelfAttentionTransformer.call, module.py:363-371), then the mel and stop projections
+ * (OutputAndStopTokenTransparentWrapper, rnn_wrappers.py:188-214).  hops = 0: projections only (single-attention model). */
+typedef struct {
+  int B, D, heads, Tmax, hops;
+  const int* t_ptr;
+  const float* x; long long ldx;       /* [B, D] LSTM-3 output of this step */
+  const float* Wk[4]; const float* bk[4]; const float* Wv[4]; const float* bv[4]; const float* Wq[4]; const float* bq[4];
+  const float* Wo[4]; const float* bo[4]; const float* Wt[4]; const float* bt[4];     /* [D,D] kernels (TF layout), [D] biases */
+  float* Kc[4]; float* Vc[4];          /* [Tmax,B,D] caches; row t is written here */
+  float* probs[4];                     /* [B,heads,Tmax,Tmax] row t receives the alignment, or NULL */
+  const float* W_out; const float* b_out; int n_out;    /* [D, n_out] mel projection */
+  const float* W_stop; const float* b_stop;             /* [D, 1] */
+  float* mel_dst; long long mel_tstride;                /* mel_dst[(t+1)*mel_tstride + b*n_out + c] (row 0 = go frame) */
+  float* stop_dst;                                      /* [Tmax, B] */
+} satk_sa_tail_desc;
+int satk_sa_tail(const satk_sa_tail_desc* d, void* stream);
 
 /* End of a step: records the first step at which sigmoid(stop[t,b]) > 0.5 for all b and t > min_iters into *done_step
  * (initialised to -1 by the caller; stop may be NULL), then *t_ptr += 1. */

@@ -48,10 +48,11 @@ int satk_struct_sizes(int* out5) {
   return 0;
 }
 
-int satk_struct_sizes_decode(int* out3) {
-  out3[0] = (int)sizeof(satk_rowgemm_desc);
-  out3[1] = (int)sizeof(satk_attn_step_desc);
-  out3[2] = (int)sizeof(satk_sa_step_desc);
+int satk_struct_sizes_decode(int* out4) {
+  out4[0] = (int)sizeof(satk_rowgemm_desc);
+  out4[1] = (int)sizeof(satk_attn_step_desc);
+  out4[2] = (int)sizeof(satk_sa_step_desc);
+  out4[3] = (int)sizeof(satk_sa_tail_desc);
   return 0;
 }
 

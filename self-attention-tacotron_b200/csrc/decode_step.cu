@@ -370,6 +370,219 @@ __global__ void __launch_bounds__(256) sa_step_k(const satk_sa_step_desc d) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused tail of a decoder step for ONE utterance per cluster of 8 CTAs: everything after LSTM-3 only couples the vectors of one
+// utterance (TransformerWrapper over the cached history, rnn_wrappers.py:111-124; OutputAndStopTokenTransparentWrapper, :188-214):
+//   hop h:  K/V/Q projections of the newest row (K, V appended to the caches) -> causal attention of the newest query over rows
+//           0..t (rows split over the 64 warps of the cluster, online softmax, flash-style combine through DSMEM) -> output
+//           projection -> tanh transform + residual;   then the mel and stop projections.
+// Every dense layer gives each CTA 32 output columns x 8 reduction slices; the full vector is re-assembled in every CTA's shared
+// memory by DSMEM stores + one cluster barrier per layer.  Replaces 5 launches (13 -> 9 per step) and their global round trips.
+constexpr int TCS = 8;
+constexpr int TMAXD = 256;
+
+// y[col] (+)= sum_k x[k] W[k, col] for this CTA's columns [c0, c0+nc) (nc <= 32); thread = (column lane, 1/8 of the reduction);
+// returns the full sums for tid < nc through shared memory `part` [8][32]
+__device__ __forceinline__ float tail_matvec(const float* __restrict__ W, int ldw, int K, const float* xs, int c0, int nc, float (*part)[33],
+                                             int tid) {
+  const int cl = tid & 31, ks = tid >> 5;
+  const int kper = (K + 7) / 8, k0 = ks * kper, k1 = min(K, k0 + kper);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  if (cl < nc) {
+    const float* wp = W + (long long)k0 * ldw + c0 + cl;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+      const float w0 = __ldg(wp), w1 = __ldg(wp + ldw), w2 = __ldg(wp + 2 * ldw), w3 = __ldg(wp + 3 * ldw);
+      acc0 = fmaf(xs[k], w0, acc0); acc1 = fmaf(xs[k + 1], w1, acc1);
+      acc2 = fmaf(xs[k + 2], w2, acc2); acc3 = fmaf(xs[k + 3], w3, acc3);
+      wp += 4 * ldw;
+    }
+    for (; k < k1; ++k) { acc0 = fmaf(xs[k], __ldg(wp), acc0); wp += ldw; }
+  }
+  __syncthreads();                       // previous use of `part` is over
+  part[ks][cl] = (acc0 + acc1) + (acc2 + acc3);
+  __syncthreads();
+  float v = 0.f;
+  if (tid < nc) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][tid];
+  }
+  return v;
+}
+
+__global__ void __cluster_dims__(TCS, 1, 1) __launch_bounds__(256) sa_tail_k(const satk_sa_tail_desc d) {
+  extern __shared__ float dyn[];           // scores of this CTA's rows: [heads][rows per CTA]
+  __shared__ float xin[TMAXD], qv[TMAXD], att[TMAXD], ao[TMAXD], ybuf[TMAXD];
+  __shared__ float part[8][33];
+  __shared__ float comb[TCS][TMAXD + 16];  // per source CTA: partial attention output [D] + (m, l) per head
+  __shared__ float wcomb[8][TMAXD + 16];   // per warp of this CTA
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / TCS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_enter();
+  const int D = d.D, heads = d.heads, dh = D / heads, B = d.B;
+  const int t = *d.t_ptr;
+  const int n = t + 1;
+  const int CP = D / TCS;                   // columns of a D-wide layer per CTA (32 for D = 256)
+  const int c0 = rank * CP;
+  const int rows_cap = (d.Tmax + TCS - 1) / TCS;
+  for (int i = tid; i < D; i += 256) xin[i] = d.x[(long long)b * d.ldx + i];
+  __syncthreads();
+  for (int h = 0; h < d.hops; ++h) {
+    // ---- K / V / Q projections of the newest row
+    float* Kc = d.Kc[h];
+    float* Vc = d.Vc[h];
+    const long long rowoff = ((long long)t * B + b) * D;
+    float v = tail_matvec(d.Wk[h], D, D, xin, c0, CP, part, tid);
+    if (tid < CP) Kc[rowoff + c0 + tid] = v + __ldg(d.bk[h] + c0 + tid);
+    v = tail_matvec(d.Wv[h], D, D, xin, c0, CP, part, tid);
+    if (tid < CP) Vc[rowoff + c0 + tid] = v + __ldg(d.bv[h] + c0 + tid);
+    v = tail_matvec(d.Wq[h], D, D, xin, c0, CP, part, tid);
+    if (tid < CP) {
+      v += __ldg(d.bq[h] + c0 + tid);
+#pragma unroll
+      for (int r = 0; r < TCS; ++r) cluster.map_shared_rank(qv, r)[c0 + tid] = v;
+    }
+    __threadfence();                        // the newest K / V row is read by the other CTAs of the cluster below
+    cluster.sync();
+    // ---- causal attention of the newest query over rows 0..t: row j belongs to CTA j % 8, warp (j / 8) % 8
+    {
+      const float scale = rsqrtf((float)dh);
+      const int EPL = D / 32;               // elements per lane (8 for D = 256); a lane never straddles two heads (dh % EPL == 0)
+      const int hd = (lane * EPL) / dh;
+      const int lanes_per_head = dh / EPL;
+      float m = -INFINITY, l = 0.f, acc[TMAXD / 32];
+#pragma unroll
+      for (int e = 0; e < TMAXD / 32; ++e) acc[e] = 0.f;
+      float qreg[TMAXD / 32];
+#pragma unroll
+      for (int e = 0; e < TMAXD / 32; ++e) qreg[e] = (e < EPL) ? qv[lane * EPL + e] : 0.f;
+      for (int j = rank + TCS * warp; j < n; j += TCS * 8) {
+        const float* kr = Kc + ((long long)j * B + b) * D + lane * EPL;
+        const float* vr = Vc + ((long long)j * B + b) * D + lane * EPL;
+        float s = 0.f, vv[TMAXD / 32];
+#pragma unroll
+        for (int e = 0; e < TMAXD / 32; ++e)
+          if (e < EPL) { s = fmaf(qreg[e], kr[e], s); vv[e] = vr[e]; }
+        for (int o = 1; o < lanes_per_head; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        s *= scale;
+        if ((lane % lanes_per_head) == 0) dyn[hd * rows_cap + j / TCS] = s;       // kept for the alignment output
+        const float mn = fmaxf(m, s);
+        const float corr = __expf(m - mn), pj = __expf(s - mn);
+        l = l * corr + pj;
+#pragma unroll
+        for (int e = 0; e < TMAXD / 32; ++e)
+          if (e < EPL) acc[e] = fmaf(pj, vv[e], acc[e] * corr);
+        m = mn;
+      }
+      // combine the 8 warps of this CTA, then the 8 CTAs of the cluster (each lane carries the (m, l) of its head)
+#pragma unroll
+      for (int e = 0; e < TMAXD / 32; ++e)
+        if (e < EPL) wcomb[warp][lane * EPL + e] = acc[e];
+      if ((lane % lanes_per_head) == 0) { wcomb[warp][TMAXD + 2 * hd] = m; wcomb[warp][TMAXD + 2 * hd + 1] = l; }
+      __syncthreads();
+      for (int i = tid; i < D; i += 256) {
+        const int hh = i / dh;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, wcomb[w][TMAXD + 2 * hh]);
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float mw = wcomb[w][TMAXD + 2 * hh];
+          if (mw > -INFINITY) o = fmaf(__expf(mw - M), wcomb[w][i], o);
+        }
+#pragma unroll
+        for (int r = 0; r < TCS; ++r) cluster.map_shared_rank(&comb[0][0], r)[rank * (TMAXD + 16) + i] = o;
+      }
+      if (tid < heads) {
+        float M = -INFINITY, L = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) M = fmaxf(M, wcomb[w][TMAXD + 2 * tid]);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float mw = wcomb[w][TMAXD + 2 * tid];
+          if (mw > -INFINITY) L = fmaf(__expf(mw - M), wcomb[w][TMAXD + 2 * tid + 1], L);
+        }
+#pragma unroll
+        for (int r = 0; r < TCS; ++r) {
+          float* cr = cluster.map_shared_rank(&comb[0][0], r) + rank * (TMAXD + 16) + TMAXD;
+          cr[2 * tid] = M;
+          cr[2 * tid + 1] = L;
+        }
+      }
+      cluster.sync();
+      __shared__ float ML[2 * 16];          // final (max, sum) per head
+      if (tid < heads) {
+        float M = -INFINITY, L = 0.f;
+#pragma unroll
+        for (int r = 0; r < TCS; ++r) M = fmaxf(M, comb[r][TMAXD + 2 * tid]);
+#pragma unroll
+        for (int r = 0; r < TCS; ++r) {
+          const float mr = comb[r][TMAXD + 2 * tid];
+          if (mr > -INFINITY) L = fmaf(__expf(mr - M), comb[r][TMAXD + 2 * tid + 1], L);
+        }
+        ML[2 * tid] = M;
+        ML[2 * tid + 1] = L;
+      }
+      __syncthreads();
+      for (int i = tid; i < D; i += 256) {
+        const int hh = i / dh;
+        const float M = ML[2 * hh], L = ML[2 * hh + 1];
+        float o = 0.f;
+#pragma unroll
+        for (int r = 0; r < TCS; ++r) {
+          const float mr = comb[r][TMAXD + 2 * hh];
+          if (mr > -INFINITY) o = fmaf(__expf(mr - M), comb[r][i], o);
+        }
+        att[i] = o / L;
+      }
+      if (d.probs[h]) {
+        // alignment row t (self_attention.py:45-65): this CTA's rows j = rank + 8 i
+        float* pr = d.probs[h];
+        for (int idx = tid; idx < heads * rows_cap; idx += 256) {
+          const int hh = idx / rows_cap, i = idx % rows_cap, j = rank + TCS * i;
+          if (j < n) pr[(((long long)b * heads + hh) * d.Tmax + t) * d.Tmax + j] = __expf(dyn[hh * rows_cap + i] - ML[2 * hh]) / ML[2 * hh + 1];
+        }
+      }
+      __syncthreads();
+    }
+    // ---- output projection, then tanh transform + residual (SelfAttentionTransformer.call, module.py:363-371)
+    v = tail_matvec(d.Wo[h], D, D, att, c0, CP, part, tid);
+    if (tid < CP) {
+      v += __ldg(d.bo[h] + c0 + tid);
+#pragma unroll
+      for (int r = 0; r < TCS; ++r) cluster.map_shared_rank(ao, r)[c0 + tid] = v;
+    }
+    cluster.sync();
+    v = tail_matvec(d.Wt[h], D, D, ao, c0, CP, part, tid);
+    if (tid < CP) {
+      v = xin[c0 + tid] + tanhf_(v + __ldg(d.bt[h] + c0 + tid));
+#pragma unroll
+      for (int r = 0; r < TCS; ++r) cluster.map_shared_rank(ybuf, r)[c0 + tid] = v;
+    }
+    cluster.sync();
+    for (int i = tid; i < D; i += 256) xin[i] = ybuf[i];
+    __syncthreads();
+    // buffer reuse across hops: a peer writes my qv again before the next hop's first barrier (my last read of qv was before this hop's
+    // second barrier), my ybuf only after three more barriers, my comb / ao after at least one — all later than my reads above
+  }
+  // ---- mel and stop projections (module.py:639-643): NO columns split over the cluster
+  {
+    const int NO = d.n_out + 1;
+    const int CPo = (NO + TCS - 1) / TCS;
+    const int o0 = rank * CPo, nc = max(0, min(CPo, NO - o0));
+    // columns [0, n_out) come from W_out, column n_out from W_stop (a [D,1] matrix): handled as two matvecs
+    const int nc_mel = max(0, min(nc, d.n_out - o0));
+    float v = tail_matvec(d.W_out, d.n_out, D, xin, o0, nc_mel, part, tid);
+    if (tid < nc_mel) d.mel_dst[(long long)(t + 1) * d.mel_tstride + (long long)b * d.n_out + o0 + tid] = v + __ldg(d.b_out + o0 + tid);
+    const bool has_stop = (o0 + nc == NO) && nc > 0;       // the CTA that owns the last column
+    v = tail_matvec(d.W_stop, 1, D, xin, 0, has_stop ? 1 : 0, part, tid);
+    if (has_stop && tid == 0) d.stop_dst[(long long)t * B + b] = v + __ldg(d.b_stop);
+  }
+  cluster.sync();     // peers may still be writing into this CTA's shared memory until their last remote store has landed
+}
+
 __global__ void tick_k(int* t_ptr, const float* stop, int B, int min_iters, int* done_step) {
   // StopTokenBasedInferenceHelper.is_finished: sigmoid(stop) > 0.5 for EVERY utterance and time > min_iters (helpers.py:103-107)
   pdl_enter();
@@ -472,6 +685,19 @@ extern "C" int satk_sa_step(const satk_sa_step_desc* d, void* stream) {
   SATK_CHECK_ARG(smem <= 200 * 1024, "satk_sa_step: Tmax=%d too large", d->Tmax);
   if (smem > 48 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::sa_step_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_step(dstep::sa_step_k, dim3(d->B, d->heads), 256, smem, (cudaStream_t)stream, 1, *d);
+}
+
+extern "C" int satk_sa_tail(const satk_sa_tail_desc* d, void* stream) {
+  SATK_CHECK_ARG(d->hops >= 0 && d->hops <= 4, "satk_sa_tail: hops=%d out of range (0..4)", d->hops);
+  SATK_CHECK_ARG(d->D == dstep::TMAXD, "satk_sa_tail: D=%d unsupported (the fused tail is built for %d units)", d->D, dstep::TMAXD);
+  SATK_CHECK_ARG(d->n_out + 1 <= 32 * dstep::TCS, "satk_sa_tail: n_out=%d too wide", d->n_out);
+  SATK_CHECK_ARG(d->heads > 0 && d->heads <= 16 && d->D % d->heads == 0 && (d->D / d->heads) % (d->D / 32) == 0,
+                 "satk_sa_tail: heads=%d does not divide D=%d into lane-aligned heads", d->heads, d->D);
+  SATK_CHECK_ARG(d->t_ptr && d->x && d->W_out && d->W_stop && d->mel_dst && d->stop_dst && d->n_out > 0, "satk_sa_tail: null pointer");
+  const size_t smem = sizeof(float) * (size_t)d->heads * ((d->Tmax + dstep::TCS - 1) / dstep::TCS);
+  SATK_CHECK_ARG(smem <= 64 * 1024, "satk_sa_tail: Tmax=%d too large", d->Tmax);
+  if (smem > 8 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::sa_tail_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem + 1024));
+  return launch_step(dstep::sa_tail_k, dim3(d->B * dstep::TCS), 256, smem, (cudaStream_t)stream, 1, *d);
 }
 
 extern "C" int satk_decode_tick(int* t_ptr, const float* stop, int B, int min_iters, int* done_step, void* stream) {

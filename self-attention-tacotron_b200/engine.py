@@ -745,29 +745,44 @@ class TacotronEngine:
                                               hdst=x3c, ld_hdst=W3C, hdst_off=HD, hdst_pstride=B * W3C, **zo)))
         x = o3
         probs = []
-        if d.dual:
-            # TransformerWrapper (rnn_wrappers.py:111-124) with cached keys / values: row t of the causal attention
-            for h in range(d.dec_sa_hops):
+        if getattr(self, "fused_decode_tail", True) and HD == 256 and OU + 1 <= 256:
+            # fused tail: self-attention hops over the KV cache + mel / stop projections, one cluster per utterance (satk_sa_tail)
+            hops = []
+            for h in range(d.dec_sa_hops if d.dual else 0):
                 n = f"dec.sa{h}"
-                D = HD
-                Kc, Vc = b_(f"pred.K{h}", (Tmax, B, D)), b_(f"pred.V{h}", (Tmax, B, D))
-                Qb, Ob, ao, y = b_(f"pred.Q{h}", (B, D)), b_(f"pred.O{h}", (B, D)), b_(f"pred.ao{h}", (B, D)), b_(f"pred.y{h}", (B, D))
                 pr = b_(f"pred.P{h}", (B, d.dec_sa_heads, Tmax, Tmax), zero=True)
                 probs.append(pr)
-                steps.append(O.rowgemm_desc(x, B, D, [
-                    dict(W=p[n + ".key.W"], bias=p[n + ".key.b"], C=Kc, c_tstride=B * D),
-                    dict(W=p[n + ".value.W"], bias=p[n + ".value.b"], C=Vc, c_tstride=B * D),
-                    dict(W=p[n + ".query.W"], bias=p[n + ".query.b"], C=Qb)], t_ptr=t_dev))
-                steps.append(O.sa_step_desc(B=B, D=D, heads=d.dec_sa_heads, Tmax=Tmax, t_ptr=t_dev, q=Qb, ldq=D, Kc=Kc, Vc=Vc, out=Ob,
-                                            ldo=D, probs=pr))
-                steps.append(O.rowgemm_desc(Ob, B, D, [dict(W=p[n + ".output.W"], bias=p[n + ".output.b"], C=ao)]))
-                steps.append(O.rowgemm_desc(ao, B, D, [dict(W=p[n + ".transform.W"], bias=p[n + ".transform.b"], act="tanh", C=y,
-                                                            residual=x)]))
-                x = y
-        # OutputAndStopTokenTransparentWrapper (rnn_wrappers.py:188-214): mel frames of step t -> row t+1 (row 0 = go frame)
-        steps.append(O.rowgemm_desc(x, B, HD, [
-            dict(W=p["dec.out_proj.W"], bias=p["dec.out_proj.b"], C=mel_hist, c_off=B * OU, c_tstride=B * OU),
-            dict(W=p["dec.stop_proj.W"], bias=p["dec.stop_proj.b"], C=stop_hist, ldc=1, c_tstride=B)], t_ptr=t_dev))
+                hops.append(dict(Wk=p[n + ".key.W"], bk=p[n + ".key.b"], Wv=p[n + ".value.W"], bv=p[n + ".value.b"],
+                                 Wq=p[n + ".query.W"], bq=p[n + ".query.b"], Wo=p[n + ".output.W"], bo=p[n + ".output.b"],
+                                 Wt=p[n + ".transform.W"], bt=p[n + ".transform.b"], Kc=b_(f"pred.K{h}", (Tmax, B, HD)),
+                                 Vc=b_(f"pred.V{h}", (Tmax, B, HD)), probs=pr))
+            steps.append(O.sa_tail_desc(B=B, D=HD, heads=d.dec_sa_heads if d.dual else 1, Tmax=Tmax, t_ptr=t_dev, x=o3, ldx=HD, hops=hops,
+                                        W_out=p["dec.out_proj.W"], b_out=p["dec.out_proj.b"], W_stop=p["dec.stop_proj.W"],
+                                        b_stop=p["dec.stop_proj.b"], mel_dst=mel_hist, mel_tstride=B * OU, stop_dst=stop_hist))
+        else:
+            if d.dual:
+                # TransformerWrapper (rnn_wrappers.py:111-124) with cached keys / values: row t of the causal attention
+                for h in range(d.dec_sa_hops):
+                    n = f"dec.sa{h}"
+                    D = HD
+                    Kc, Vc = b_(f"pred.K{h}", (Tmax, B, D)), b_(f"pred.V{h}", (Tmax, B, D))
+                    Qb, Ob, ao, y = b_(f"pred.Q{h}", (B, D)), b_(f"pred.O{h}", (B, D)), b_(f"pred.ao{h}", (B, D)), b_(f"pred.y{h}", (B, D))
+                    pr = b_(f"pred.P{h}", (B, d.dec_sa_heads, Tmax, Tmax), zero=True)
+                    probs.append(pr)
+                    steps.append(O.rowgemm_desc(x, B, D, [
+                        dict(W=p[n + ".key.W"], bias=p[n + ".key.b"], C=Kc, c_tstride=B * D),
+                        dict(W=p[n + ".value.W"], bias=p[n + ".value.b"], C=Vc, c_tstride=B * D),
+                        dict(W=p[n + ".query.W"], bias=p[n + ".query.b"], C=Qb)], t_ptr=t_dev))
+                    steps.append(O.sa_step_desc(B=B, D=D, heads=d.dec_sa_heads, Tmax=Tmax, t_ptr=t_dev, q=Qb, ldq=D, Kc=Kc, Vc=Vc,
+                                                out=Ob, ldo=D, probs=pr))
+                    steps.append(O.rowgemm_desc(Ob, B, D, [dict(W=p[n + ".output.W"], bias=p[n + ".output.b"], C=ao)]))
+                    steps.append(O.rowgemm_desc(ao, B, D, [dict(W=p[n + ".transform.W"], bias=p[n + ".transform.b"], act="tanh", C=y,
+                                                                residual=x)]))
+                    x = y
+            # OutputAndStopTokenTransparentWrapper (rnn_wrappers.py:188-214): mel frames of step t -> row t+1 (row 0 = go frame)
+            steps.append(O.rowgemm_desc(x, B, HD, [
+                dict(W=p["dec.out_proj.W"], bias=p["dec.out_proj.b"], C=mel_hist, c_off=B * OU, c_tstride=B * OU),
+                dict(W=p["dec.stop_proj.W"], bias=p["dec.stop_proj.b"], C=stop_hist, ldc=1, c_tstride=B)], t_ptr=t_dev))
 
         def run_step():
             for s_ in steps:
@@ -775,6 +790,8 @@ class TacotronEngine:
                     O.rowgemm(s_)
                 elif isinstance(s_, O.AttnStepDesc):
                     O.attn_step(s_)
+                elif isinstance(s_, O.SaTailDesc):
+                    O.sa_tail(s_)
                 else:
                     O.sa_step(s_)
             O.decode_tick(t_dev, stop_hist if use_stop_token else None, B, min_iters, done)
@@ -811,7 +828,7 @@ class TacotronEngine:
         if d.use_speaker:
             sp_pre = self.lin(spk, "dec.prenet0.Ws", self.buf("dec.sp_pre", (B, d.dec_prenet[0])), bias=p["dec.prenet0.bs"])
             O.softsign_fwd(sp_pre, self.buf("dec.sp", (B, d.dec_prenet[0])))
-        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters))
+        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters), bool(getattr(self, "fused_decode_tail", True)))
         cache = getattr(self, "_decode_cache", None)
         if cache is None or cache["key"] != key:
             run_step, stt = self._build_decode_step(B, Tt, Tmax, use_stop_token, min_iters)

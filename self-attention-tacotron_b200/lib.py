@@ -113,6 +113,16 @@ class SaStepDesc(C.Structure):
     ]
 
 
+class SaTailDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("D", i32), ("heads", i32), ("Tmax", i32), ("hops", i32), ("t_ptr", fp), ("x", fp), ("ldx", i64),
+        ("Wk", fp * 4), ("bk", fp * 4), ("Wv", fp * 4), ("bv", fp * 4), ("Wq", fp * 4), ("bq", fp * 4),
+        ("Wo", fp * 4), ("bo", fp * 4), ("Wt", fp * 4), ("bt", fp * 4), ("Kc", fp * 4), ("Vc", fp * 4), ("probs", fp * 4),
+        ("W_out", fp), ("b_out", fp), ("n_out", i32), ("W_stop", fp), ("b_stop", fp),
+        ("mel_dst", fp), ("mel_tstride", i64), ("stop_dst", fp),
+    ]
+
+
 ACT = {"none": 0, None: 0, "relu": 1, "tanh": 2, "sigmoid": 3}
 
 _lib: Optional[C.CDLL] = None
@@ -126,7 +136,7 @@ SYMBOLS = [
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
     "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_debug_phase_cycles",
-    "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_decode_tick",
+    "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_sa_tail", "satk_decode_tick",
 ]
 
 

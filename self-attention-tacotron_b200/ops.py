@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import lib as L
-from .lib import (ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, AttnStepDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, RowGemmDesc, SaStepDesc,
+from .lib import (ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, AttnStepDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, RowGemmDesc, SaStepDesc, SaTailDesc,
                   check, load, ptr, stream_ptr)
 
 # GEMM engine: 0 auto (tcgen05 tile when the shape allows, else SIMT), 1 SIMT fp32, 2 tcgen05 only
@@ -454,6 +454,30 @@ def sa_step_desc(**kw) -> SaStepDesc:
 
 def sa_step(d: SaStepDesc) -> None:
     check(load().satk_sa_step(C.byref(d), C.c_void_p(stream_ptr())), "satk_sa_step")
+    _count()
+
+
+def sa_tail_desc(*, B, D, heads, Tmax, t_ptr, x, ldx, hops, W_out, b_out, W_stop, b_stop, mel_dst, mel_tstride, stop_dst) -> SaTailDesc:
+    """``hops``: list of dicts with Wk,bk,Wv,bv,Wq,bq,Wo,bo,Wt,bt (weights), Kc,Vc (caches) and probs (or None)."""
+    d = SaTailDesc()
+    d.B, d.D, d.heads, d.Tmax, d.hops = B, D, heads, Tmax, len(hops)
+    d.t_ptr, d.x, d.ldx = t_ptr.data_ptr(), x.data_ptr(), ldx
+    for i, hp_ in enumerate(hops):
+        for k in ("Wk", "bk", "Wv", "bv", "Wq", "bq", "Wo", "bo", "Wt", "bt", "Kc", "Vc", "probs"):
+            v = hp_.get(k)
+            if v is not None:
+                _req(v)
+            getattr(d, k)[i] = ptr(v)
+    for t_ in (W_out, b_out, W_stop, b_stop, mel_dst, stop_dst):
+        _req(t_)
+    d.W_out, d.b_out, d.n_out = W_out.data_ptr(), b_out.data_ptr(), W_out.shape[1]
+    d.W_stop, d.b_stop = W_stop.data_ptr(), b_stop.data_ptr()
+    d.mel_dst, d.mel_tstride, d.stop_dst = mel_dst.data_ptr(), mel_tstride, stop_dst.data_ptr()
+    return d
+
+
+def sa_tail(d: SaTailDesc) -> None:
+    check(load().satk_sa_tail(C.byref(d), C.c_void_p(stream_ptr())), "satk_sa_tail")
     _count()
 
 

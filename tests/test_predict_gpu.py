@@ -66,6 +66,12 @@ def test_free_running_matches_oracle(satk, root, cfg, overrides, B, Tt, T):
         out = eng.predict(fd, max_iters=T, use_stop_token=False, use_graph=use_graph)
         torch.cuda.synchronize()
         _compare(out, ref, d, T)
+    probs = [p_.clone() for p_ in out["dec_self_P"]]
+    eng.fused_decode_tail = False                          # per-layer launches (rowgemm + sa_step) instead of the fused tail kernel
+    out = eng.predict(fd, max_iters=T, use_stop_token=False, use_graph=False)
+    _compare(out, ref, d, T)
+    for a, b_ in zip(probs, out["dec_self_P"]):            # decoder self-attention alignments of both paths agree
+        _close(a, b_, RTOL, "decoder self-attention alignment", 1e-6)
 
 
 def test_stop_token_terminates_like_the_helper(satk, root):
