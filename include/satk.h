@@ -42,8 +42,8 @@ int satk_device_info(int* out5);
 /* sizeof() of the descriptor structs, in declaration order (gemm, lstm_fwd, lstm_bwd, attn_fwd, attn_bwd):
  * lets a foreign-language binding verify its struct layout */
 int satk_struct_sizes(int* out5);
-/* same for the decode-step descriptors (rowgemm, attn_step, sa_step, sa_tail) */
-int satk_struct_sizes_decode(int* out4);
+/* same for the decode-step descriptors (rowgemm, attn_step, sa_step, sa_tail, mlp_chain) */
+int satk_struct_sizes_decode(int* out5);
 
 /* ------------------------------------------------------------------------------------------
  * Dense tile: C = epilogue( alpha * sum_tap op(A_tap) * op(B_tap) ) (+ beta*C)
@@ -342,7 +342,11 @@ typedef struct {
   int cumulative, use_agent;
   const int* t_ptr;            /* device step index (row of align1/align2), NULL: 0 */
   const long long* lengths;    /* [B] */
-  const float* q; long long ldq;               /* [B, A1+A2] processed queries (query_layer outputs) */
+  const float* q; long long ldq;               /* [B, A1+A2] processed queries (query_layer outputs); unused when Wq1 is set */
+  /* optional fused query layers: q = q_x[b] . [Wq1 | Wq2] computed by the cluster (Wq1 NULL: read q).  q_x rows are double-buffered
+   * on the parity of t like the recurrent input rows of satk_rowgemm. */
+  const float* Wq1; const float* Wq2;          /* [q_in, A1], [q_in, A2] */
+  const float* q_x; long long q_x_ld; long long q_x_pstride; int q_in;
   const float* keys1; const float* values1;    /* [Tt,B,A1], [Tt,B,M1] time-major */
   const float* v1; const float* b1;            /* [A1]; b1 may be NULL */
   const float* loc_conv_w; const float* loc_conv_b; const float* loc_layer_w;
@@ -368,6 +372,19 @@ typedef struct {
   float* probs;                    /* [B,heads,Tmax,Tmax] row t receives the alignment, or NULL */
 } satk_sa_step_desc;
 int satk_sa_step(const satk_sa_step_desc* d, void* stream);
+
+/* Chain of up to three dense layers on one row per cluster (decoder pre-net of a free-running step, module.py:1509-1511,
+ * multi_speaker_modules.py:27-32): h_{l+1} = act_l(h_l . W_l + bias_l) (+ residual_l[b]); widths <= 256.  Input row b is
+ * x[t*x_tstride + b*x_ld ...], the last layer is written to out[(t&1)*out_pstride + b*out_ld ...]. */
+typedef struct {
+  int B, K0, nlayers;
+  const int* t_ptr;
+  const float* x; long long x_ld, x_tstride;
+  const float* W[3]; const float* bias[3]; int N[3]; int act[3];
+  const float* residual[3]; long long ldres[3];
+  float* out; long long out_ld, out_pstride;
+} satk_mlp_chain_desc;
+int satk_mlp_chain(const satk_mlp_chain_desc* d, void* stream);
 
 /* Fused tail of a decoder step, one cluster of 8 CTAs per utterance: for each self-attention hop the K/V/Q projections of the newest
  * decoder output (K, V appended to the caches), causal attention over rows 0..t, output projection, tanh transform + residual

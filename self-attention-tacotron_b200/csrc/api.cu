@@ -49,6 +49,7 @@ int satk_struct_sizes(int* out5) {
 }
 
 int satk_struct_sizes_decode(int* out4) {
+  out4[4] = (int)sizeof(satk_mlp_chain_desc);
   out4[0] = (int)sizeof(satk_rowgemm_desc);
   out4[1] = (int)sizeof(satk_attn_step_desc);
   out4[2] = (int)sizeof(satk_sa_step_desc);

@@ -22,6 +22,7 @@ namespace cg = cooperative_groups;
 constexpr int MR = 16;     // rows per pass
 constexpr int KC = 128;    // reduction chunk staged in shared memory
 constexpr int NC = 32;     // columns per CTA (one per lane)
+constexpr int TCS = 8;     // CTAs per cluster of the one-utterance-per-cluster kernels
 
 // Programmatic dependent launch: the step's kernels are launched with programmaticStreamSerialization, so kernel N+1 is scheduled
 // while kernel N drains; `pdl_wait` blocks until kernel N has completed and its writes are visible, `pdl_launch` lets N+1 start early.
@@ -161,6 +162,35 @@ __global__ void __launch_bounds__(256) rowgemm_k(const satk_rowgemm_desc d) {
   }
 }
 
+// y[col] (+)= sum_k x[k] W[k, col] for this CTA's columns [c0, c0+nc) (nc <= 32); thread = (column lane, 1/8 of the reduction);
+// returns the full sums for tid < nc through shared memory `part` [8][32]
+__device__ __forceinline__ float tail_matvec(const float* __restrict__ W, int ldw, int K, const float* xs, int c0, int nc, float (*part)[33],
+                                             int tid) {
+  const int cl = tid & 31, ks = tid >> 5;
+  const int kper = (K + 7) / 8, k0 = ks * kper, k1 = min(K, k0 + kper);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  if (cl < nc) {
+    const float* wp = W + (long long)k0 * ldw + c0 + cl;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+      const float w0 = __ldg(wp), w1 = __ldg(wp + ldw), w2 = __ldg(wp + 2 * ldw), w3 = __ldg(wp + 3 * ldw);
+      acc0 = fmaf(xs[k], w0, acc0); acc1 = fmaf(xs[k + 1], w1, acc1);
+      acc2 = fmaf(xs[k + 2], w2, acc2); acc3 = fmaf(xs[k + 3], w3, acc3);
+      wp += 4 * ldw;
+    }
+    for (; k < k1; ++k) { acc0 = fmaf(xs[k], __ldg(wp), acc0); wp += ldw; }
+  }
+  __syncthreads();                       // previous use of `part` is over
+  part[ks][cl] = (acc0 + acc1) + (acc2 + acc3);
+  __syncthreads();
+  float v = 0.f;
+  if (tid < nc) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][tid];
+  }
+  return v;
+}
+
 // Attention step: a cluster of 8 CTAs per utterance.  Each CTA computes the energies of 1/8 of the source positions and
 // scatters them into every peer's shared memory (DSMEM); after one cluster barrier each CTA holds all energies, repeats the
 // (tiny) softmax / forward recursion locally and produces 1/8 of the context columns.
@@ -189,7 +219,26 @@ __global__ void __cluster_dims__(ACS, 1, 1) __launch_bounds__(256) attn_step_k(c
   float* alo = apv + Tt;                  // [Tt] previous alpha
   float* cpart = alo + Tt;                // [groups][cols per CTA]
   const bool loc = d.att_kernel > 0;
-  for (int i = tid; i < A1 + A2; i += 256) qs[i] = d.q[(long long)b * d.ldq + i];
+  __shared__ float part[8][33];
+  if (d.Wq1) {
+    // processed queries q = out1 . Wq (query_layer of both mechanisms): each CTA computes 1/8 of the A1+A2 columns and stores its
+    // slice into every peer's shared memory; the cluster barrier below (state reads) also publishes it
+    float* xq = cpart + (256 / ((M1 + M2 + ACS - 1) / ACS)) * ((M1 + M2 + ACS - 1) / ACS);   // staging for out1 [q_in], behind cpart
+    const float* xr = d.q_x + (long long)(tt & 1) * d.q_x_pstride + (long long)b * d.q_x_ld;
+    for (int i = tid; i < d.q_in; i += 256) xq[i] = xr[i];
+    __syncthreads();
+    const int QP = (A1 + A2 + ACS - 1) / ACS;           // host guarantees QP <= 32 and A1 % QP == 0: a block never straddles the layers
+    const int c0 = rank * QP, nc = max(0, min(QP, A1 + A2 - c0));
+    const bool second = c0 >= A1;
+    const float v = tail_matvec(second ? d.Wq2 : d.Wq1, second ? A2 : A1, d.q_in, xq, second ? (c0 - A1) : c0, nc, part, tid);
+    cluster.sync();                         // every peer is running: its shared memory may be written
+    if (tid < nc) {
+#pragma unroll
+      for (int r = 0; r < ACS; ++r) cluster.map_shared_rank(qs, r)[c0 + tid] = v;
+    }
+  } else {
+    for (int i = tid; i < A1 + A2; i += 256) qs[i] = d.q[(long long)b * d.ldq + i];
+  }
   for (int i = tid; i < Tt; i += 256) {
     apv[i] = loc ? d.aprev[(long long)b * Tt + i] : 0.f;
     alo[i] = (d.mode == 2) ? d.alpha[(long long)b * Tt + i] : 0.f;
@@ -370,6 +419,45 @@ __global__ void __launch_bounds__(256) sa_step_k(const satk_sa_step_desc d) {
   }
 }
 
+// Chain of up to three small dense layers for ONE row per cluster of 8 CTAs (decoder pre-net, module.py:1509-1511; speaker variant
+// multi_speaker_modules.py:27-32): each layer gives every CTA <= 32 output columns, the layer output is re-assembled in every CTA's
+// shared memory through DSMEM, the last layer goes to global memory.  Replaces 2-3 launches of the step.
+constexpr int MLP_MAXW = 256;
+__global__ void __cluster_dims__(TCS, 1, 1) __launch_bounds__(256) mlp_chain_k(const satk_mlp_chain_desc d) {
+  __shared__ float bufs[2][MLP_MAXW];
+  __shared__ float part[8][33];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / TCS, tid = threadIdx.x;
+  pdl_enter();
+  const int tt = d.t_ptr ? *d.t_ptr : 0;
+  const float* xr = d.x + (long long)tt * d.x_tstride + (long long)b * d.x_ld;
+  for (int i = tid; i < d.K0; i += 256) bufs[0][i] = xr[i];
+  __syncthreads();
+  int K = d.K0, cur = 0;
+  for (int l = 0; l < d.nlayers; ++l) {
+    const int N = d.N[l];
+    const int CPn = (N + TCS - 1) / TCS;
+    const int c0 = rank * CPn, nc = max(0, min(CPn, N - c0));
+    float v = tail_matvec(d.W[l], N, K, bufs[cur], c0, nc, part, tid);
+    if (l == 0) cluster.sync();               // every peer is running before the first remote store
+    if (tid < nc) {
+      if (d.bias[l]) v += __ldg(d.bias[l] + c0 + tid);
+      v = apply_act(v, d.act[l]);
+      if (d.residual[l]) v += d.residual[l][(long long)b * d.ldres[l] + c0 + tid];
+      if (l + 1 < d.nlayers) {
+#pragma unroll
+        for (int r = 0; r < TCS; ++r) cluster.map_shared_rank(&bufs[0][0], r)[(cur ^ 1) * MLP_MAXW + c0 + tid] = v;
+      } else {
+        d.out[(long long)(tt & 1) * d.out_pstride + (long long)b * d.out_ld + c0 + tid] = v;
+      }
+    }
+    cluster.sync();                           // layer output complete everywhere (and nobody still reads the buffer written next)
+    K = N;
+    cur ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Fused tail of a decoder step for ONE utterance per cluster of 8 CTAs: everything after LSTM-3 only couples the vectors of one
 // utterance (TransformerWrapper over the cached history, rnn_wrappers.py:111-124; OutputAndStopTokenTransparentWrapper, :188-214):
@@ -378,37 +466,7 @@ __global__ void __launch_bounds__(256) sa_step_k(const satk_sa_step_desc d) {
 //           projection -> tanh transform + residual;   then the mel and stop projections.
 // Every dense layer gives each CTA 32 output columns x 8 reduction slices; the full vector is re-assembled in every CTA's shared
 // memory by DSMEM stores + one cluster barrier per layer.  Replaces 5 launches (13 -> 9 per step) and their global round trips.
-constexpr int TCS = 8;
 constexpr int TMAXD = 256;
-
-// y[col] (+)= sum_k x[k] W[k, col] for this CTA's columns [c0, c0+nc) (nc <= 32); thread = (column lane, 1/8 of the reduction);
-// returns the full sums for tid < nc through shared memory `part` [8][32]
-__device__ __forceinline__ float tail_matvec(const float* __restrict__ W, int ldw, int K, const float* xs, int c0, int nc, float (*part)[33],
-                                             int tid) {
-  const int cl = tid & 31, ks = tid >> 5;
-  const int kper = (K + 7) / 8, k0 = ks * kper, k1 = min(K, k0 + kper);
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-  if (cl < nc) {
-    const float* wp = W + (long long)k0 * ldw + c0 + cl;
-    int k = k0;
-    for (; k + 3 < k1; k += 4) {
-      const float w0 = __ldg(wp), w1 = __ldg(wp + ldw), w2 = __ldg(wp + 2 * ldw), w3 = __ldg(wp + 3 * ldw);
-      acc0 = fmaf(xs[k], w0, acc0); acc1 = fmaf(xs[k + 1], w1, acc1);
-      acc2 = fmaf(xs[k + 2], w2, acc2); acc3 = fmaf(xs[k + 3], w3, acc3);
-      wp += 4 * ldw;
-    }
-    for (; k < k1; ++k) { acc0 = fmaf(xs[k], __ldg(wp), acc0); wp += ldw; }
-  }
-  __syncthreads();                       // previous use of `part` is over
-  part[ks][cl] = (acc0 + acc1) + (acc2 + acc3);
-  __syncthreads();
-  float v = 0.f;
-  if (tid < nc) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) v += part[q][tid];
-  }
-  return v;
-}
 
 __global__ void __cluster_dims__(TCS, 1, 1) __launch_bounds__(256) sa_tail_k(const satk_sa_tail_desc d) {
   extern __shared__ float dyn[];           // scores of this CTA's rows: [heads][rows per CTA]
@@ -669,7 +727,15 @@ extern "C" int satk_attn_step(const satk_attn_step_desc* d, void* stream) {
   const int PP = (d->Tt + dstep::ACS - 1) / dstep::ACS;
   const int CP = (d->M1 + d->M2 + dstep::ACS - 1) / dstep::ACS;
   SATK_CHECK_ARG(CP <= 256, "satk_attn_step: memory depth %d too large", d->M1 + d->M2);
-  const size_t smem = sizeof(float) * ((size_t)d->A1 + d->A2 + (size_t)PP * AF + (size_t)AF * d->A1 + 5 * (size_t)d->Tt + (size_t)(256 / CP) * CP);
+  if (d->Wq1) {
+    const int QP = (d->A1 + d->A2 + dstep::ACS - 1) / dstep::ACS;
+    SATK_CHECK_ARG(QP <= 32 && d->A1 % QP == 0 && (d->A2 == 0 || d->Wq2) && d->q_x && d->q_in > 0,
+                   "satk_attn_step: fused query projection needs (A1+A2)/8 <= 32 columns per CTA and A1 a multiple of it (A1=%d A2=%d)", d->A1, d->A2);
+  } else {
+    SATK_CHECK_ARG(d->q != nullptr, "satk_attn_step: processed queries missing");
+  }
+  const size_t smem = sizeof(float) * ((size_t)d->A1 + d->A2 + (size_t)PP * AF + (size_t)AF * d->A1 + 5 * (size_t)d->Tt + (size_t)(256 / CP) * CP +
+                                       (d->Wq1 ? (size_t)d->q_in : 0));
   SATK_CHECK_ARG(smem <= 200 * 1024, "satk_attn_step: Tt=%d needs %zu B of shared memory", d->Tt, smem);
   if (smem > 48 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::attn_step_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_step(dstep::attn_step_k, dim3(d->B * dstep::ACS), 256, smem, (cudaStream_t)stream, 1, *d);   // cluster dims are compiled in
@@ -685,6 +751,15 @@ extern "C" int satk_sa_step(const satk_sa_step_desc* d, void* stream) {
   SATK_CHECK_ARG(smem <= 200 * 1024, "satk_sa_step: Tmax=%d too large", d->Tmax);
   if (smem > 48 * 1024) SATK_CUDA(cudaFuncSetAttribute(dstep::sa_step_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return launch_step(dstep::sa_step_k, dim3(d->B, d->heads), 256, smem, (cudaStream_t)stream, 1, *d);
+}
+
+extern "C" int satk_mlp_chain(const satk_mlp_chain_desc* d, void* stream) {
+  SATK_CHECK_ARG(d->nlayers >= 1 && d->nlayers <= 3 && d->B > 0 && d->x && d->out, "satk_mlp_chain: bad arguments");
+  SATK_CHECK_ARG(d->K0 > 0 && d->K0 <= dstep::MLP_MAXW, "satk_mlp_chain: input width %d unsupported (<= %d)", d->K0, dstep::MLP_MAXW);
+  for (int l = 0; l < d->nlayers; ++l)
+    SATK_CHECK_ARG(d->W[l] && d->N[l] > 0 && d->N[l] <= dstep::MLP_MAXW, "satk_mlp_chain: layer %d width %d unsupported (<= %d)", l, d->N[l],
+                   dstep::MLP_MAXW);
+  return launch_step(dstep::mlp_chain_k, dim3(d->B * dstep::TCS), 256, 0, (cudaStream_t)stream, 1, *d);
 }
 
 extern "C" int satk_sa_tail(const satk_sa_tail_desc* d, void* stream) {

@@ -704,25 +704,41 @@ class TacotronEngine:
         steps = []
         # pre-net (module.py:1509-1511; speaker variant multi_speaker_modules.py:27-32); no dropout outside training
         a_in = dict(lda=OU, a_off=OU - d.dec_in, a_tstride=B * OU, t_ptr=t_dev)
-        if d.use_speaker:
-            h0 = b_("pred.h0", (B, P0))
-            sp = b_("dec.sp", (B, P0))
-            steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W0"], bias=p["dec.prenet0.b0"], act="relu", C=h0,
-                                                                      residual=sp)], **a_in))
-            steps.append(O.rowgemm_desc(h0, B, P0, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)]))
+        if getattr(self, "fused_decode_tail", True) and max(d.dec_in, P0, P1) <= 256:
+            # the whole pre-net in one cluster-per-utterance launch (satk_mlp_chain)
+            if d.use_speaker:
+                layers = [dict(W=p["dec.prenet0.W0"], bias=p["dec.prenet0.b0"], act="relu", residual=b_("dec.sp", (B, P0))),
+                          dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu")]
+            else:
+                layers = [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu")]
+            layers.append(dict(W=p["dec.prenet1.W"], bias=p["dec.prenet1.b"], act="relu"))
+            steps.append(O.mlp_chain_desc(mel_hist, B, d.dec_in, layers, cell_in, x_ld=OU, x_off=OU - d.dec_in, x_tstride=B * OU,
+                                          out_ld=W1C, out_pstride=B * W1C, t_ptr=t_dev))
         else:
-            steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)],
-                                        **a_in))
-        steps.append(O.rowgemm_desc(pp0, B, P0, [dict(W=p["dec.prenet1.W"], bias=p["dec.prenet1.b"], act="relu", C=cell_in, ldc=W1C,
-                                                      c_pstride=B * W1C)], t_ptr=t_dev))
+            if d.use_speaker:
+                h0 = b_("pred.h0", (B, P0))
+                sp = b_("dec.sp", (B, P0))
+                steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W0"], bias=p["dec.prenet0.b0"], act="relu", C=h0,
+                                                                          residual=sp)], **a_in))
+                steps.append(O.rowgemm_desc(h0, B, P0, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)]))
+            else:
+                steps.append(O.rowgemm_desc(mel_hist, B, d.dec_in, [dict(W=p["dec.prenet0.W"], bias=p["dec.prenet0.b"], act="relu", C=pp0)],
+                                            **a_in))
+            steps.append(O.rowgemm_desc(pp0, B, P0, [dict(W=p["dec.prenet1.W"], bias=p["dec.prenet1.b"], act="relu", C=cell_in, ldc=W1C,
+                                                          c_pstride=B * W1C)], t_ptr=t_dev))
         # LSTM-1 on [prenet | attention | h] (AttentionWrapper concat, A.7) with the cell update in the epilogue
         steps.append(O.rowgemm_desc(cell_in, B, W1C, [dict(W=p["dec.lstm1.W"], bias=p["dec.lstm1.b"])], a_pstride=B * W1C, t_ptr=t_dev,
                                     lstm=dict(H=H1, c=st["c1"], h=st["h1"], out=x2c, ld_out=W2C, out_pstride=B * W2C,
                                               hdst=cell_in, ld_hdst=W1C, hdst_off=P1 + CTX, hdst_pstride=B * W1C, **zo)))
-        qm = [dict(W=p["att1.query.W"], C=q, ldc=d.att1 + d.att2)]
-        if d.dual:
-            qm.append(dict(W=p["att2.query.W"], C=q, ldc=d.att1 + d.att2, c_off=d.att1))
-        steps.append(O.rowgemm_desc(x2c, B, H1, qm, lda=W2C, a_pstride=B * W2C, t_ptr=t_dev))
+        QP = (d.att1 + d.att2 + 7) // 8
+        fused_q = getattr(self, "fused_decode_tail", True) and QP <= 32 and d.att1 % QP == 0     # query layers inside satk_attn_step
+        if not fused_q:
+            qm = [dict(W=p["att1.query.W"], C=q, ldc=d.att1 + d.att2)]
+            if d.dual:
+                qm.append(dict(W=p["att2.query.W"], C=q, ldc=d.att1 + d.att2, c_off=d.att1))
+            steps.append(O.rowgemm_desc(x2c, B, H1, qm, lda=W2C, a_pstride=B * W2C, t_ptr=t_dev))
+        qkw = dict(Wq1=p["att1.query.W"], Wq2=p["att2.query.W"] if d.dual else None, q_x=x2c, q_x_ld=W2C, q_x_pstride=B * W2C,
+                   q_in=H1) if fused_q else {}
         bufs = self._bufs
         agent = d.attention == "forward" and d.transition_agent
         steps.append(O.attn_step_desc(
@@ -735,7 +751,7 @@ class TacotronEngine:
             v2=p["att2.v"] if d.dual else None, agent_w=p["att1.agent.W"] if agent else None,
             agent_b=p["att1.agent.b"] if agent else None, aprev=aprev, alpha=alpha, u=u,
             ctx_dst0=cell_in.data_ptr() + 4 * P1, ld0=W1C, pstride0=B * W1C,
-            ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, pstride1=B * W2C, align1=al1, align2=al2))
+            ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, pstride1=B * W2C, align1=al1, align2=al2, **qkw))
         # LSTM-2 / LSTM-3 (DecoderRNNV2 on ConcatOutputAndAttentionWrapper, module.py:1024,1525-1534)
         steps.append(O.rowgemm_desc(x2c, B, W2C, [dict(W=p["dec.lstm2.W"], bias=p["dec.lstm2.b"])], a_pstride=B * W2C, t_ptr=t_dev,
                                     lstm=dict(H=HD, c=st["c2"], h=st["h2"], out=x3c, ld_out=W3C, out_pstride=B * W3C,
@@ -792,6 +808,8 @@ class TacotronEngine:
                     O.attn_step(s_)
                 elif isinstance(s_, O.SaTailDesc):
                     O.sa_tail(s_)
+                elif isinstance(s_, O.MlpChainDesc):
+                    O.mlp_chain(s_)
                 else:
                     O.sa_step(s_)
             O.decode_tick(t_dev, stop_hist if use_stop_token else None, B, min_iters, done)

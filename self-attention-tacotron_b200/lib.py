@@ -97,6 +97,7 @@ class AttnStepDesc(C.Structure):
         ("B", i32), ("Tt", i32), ("A1", i32), ("A2", i32), ("M1", i32), ("M2", i32),
         ("att_kernel", i32), ("att_filters", i32), ("mode", i32), ("cumulative", i32), ("use_agent", i32),
         ("t_ptr", fp), ("lengths", fp), ("q", fp), ("ldq", i64),
+        ("Wq1", fp), ("Wq2", fp), ("q_x", fp), ("q_x_ld", i64), ("q_x_pstride", i64), ("q_in", i32),
         ("keys1", fp), ("values1", fp), ("v1", fp), ("b1", fp),
         ("loc_conv_w", fp), ("loc_conv_b", fp), ("loc_layer_w", fp),
         ("keys2", fp), ("values2", fp), ("v2", fp), ("agent_w", fp), ("agent_b", fp),
@@ -110,6 +111,14 @@ class SaStepDesc(C.Structure):
     _fields_ = [
         ("B", i32), ("D", i32), ("heads", i32), ("Tmax", i32), ("t_ptr", fp), ("q", fp), ("ldq", i64),
         ("Kc", fp), ("Vc", fp), ("out", fp), ("ldo", i64), ("probs", fp),
+    ]
+
+
+class MlpChainDesc(C.Structure):
+    _fields_ = [
+        ("B", i32), ("K0", i32), ("nlayers", i32), ("t_ptr", fp), ("x", fp), ("x_ld", i64), ("x_tstride", i64),
+        ("W", fp * 3), ("bias", fp * 3), ("N", i32 * 3), ("act", i32 * 3), ("residual", fp * 3), ("ldres", i64 * 3),
+        ("out", fp), ("out_ld", i64), ("out_pstride", i64),
     ]
 
 
@@ -136,7 +145,7 @@ SYMBOLS = [
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
     "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_debug_phase_cycles",
-    "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_sa_tail", "satk_decode_tick",
+    "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_sa_tail", "satk_mlp_chain", "satk_decode_tick",
 ]
 
 

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import lib as L
-from .lib import (ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, AttnStepDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, RowGemmDesc, SaStepDesc, SaTailDesc,
+from .lib import (ACT, AttnRnnBwdDesc, AttnRnnFwdDesc, AttnStepDesc, GemmDesc, LstmBwdDesc, LstmFwdDesc, MlpChainDesc, RowGemmDesc, SaStepDesc, SaTailDesc,
                   check, load, ptr, stream_ptr)
 
 # GEMM engine: 0 auto (tcgen05 tile when the shape allows, else SIMT), 1 SIMT fp32, 2 tcgen05 only
@@ -454,6 +454,32 @@ def sa_step_desc(**kw) -> SaStepDesc:
 
 def sa_step(d: SaStepDesc) -> None:
     check(load().satk_sa_step(C.byref(d), C.c_void_p(stream_ptr())), "satk_sa_step")
+    _count()
+
+
+def mlp_chain_desc(x, B, K0, layers, out, *, x_ld, x_off=0, x_tstride=0, out_ld, out_off=0, out_pstride=0, t_ptr=None) -> MlpChainDesc:
+    """``layers``: list of dicts W [K,N], bias, act, residual ([B,N], optional).  Offsets in elements."""
+    _req(x); _req(out)
+    d = MlpChainDesc()
+    d.B, d.K0, d.nlayers = B, K0, len(layers)
+    d.t_ptr = ptr(t_ptr)
+    d.x, d.x_ld, d.x_tstride = x.data_ptr() + 4 * x_off, x_ld, x_tstride
+    K = K0
+    for i, m in enumerate(layers):
+        W = m["W"]
+        _req(W)
+        if W.shape[0] != K:
+            raise L.SatkError(f"mlp_chain: layer {i} weight {tuple(W.shape)} does not match input width {K}")
+        d.W[i], d.bias[i], d.N[i], d.act[i] = W.data_ptr(), ptr(m.get("bias")), W.shape[1], ACT[m.get("act")]
+        res = m.get("residual")
+        d.residual[i], d.ldres[i] = ptr(res), (res.shape[-1] if res is not None else 0)
+        K = W.shape[1]
+    d.out, d.out_ld, d.out_pstride = out.data_ptr() + 4 * out_off, out_ld, out_pstride
+    return d
+
+
+def mlp_chain(d: MlpChainDesc) -> None:
+    check(load().satk_mlp_chain(C.byref(d), C.c_void_p(stream_ptr())), "satk_mlp_chain")
     _count()
 
 

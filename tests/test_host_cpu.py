@@ -68,9 +68,9 @@ def test_abi_symbols_and_struct_sizes(satk, root):
     out = (ctypes.c_int * 5)()
     assert lib.satk_struct_sizes(out) == 0
     assert list(out) == [ctypes.sizeof(x) for x in (L.GemmDesc, L.LstmFwdDesc, L.LstmBwdDesc, L.AttnRnnFwdDesc, L.AttnRnnBwdDesc)]
-    out4 = (ctypes.c_int * 4)()
-    assert lib.satk_struct_sizes_decode(out4) == 0
-    assert list(out4) == [ctypes.sizeof(x) for x in (L.RowGemmDesc, L.AttnStepDesc, L.SaStepDesc, L.SaTailDesc)]
+    out5 = (ctypes.c_int * 5)()
+    assert lib.satk_struct_sizes_decode(out5) == 0
+    assert list(out5) == [ctypes.sizeof(x) for x in (L.RowGemmDesc, L.AttnStepDesc, L.SaStepDesc, L.SaTailDesc, L.MlpChainDesc)]
     assert lib.satk_version() >= 100
 
 
