@@ -402,6 +402,9 @@ typedef struct {
   const float* W_stop; const float* b_stop;             /* [D, 1] */
   float* mel_dst; long long mel_tstride;                /* mel_dst[(t+1)*mel_tstride + b*n_out + c] (row 0 = go frame) */
   float* stop_dst;                                      /* [Tmax, B] */
+  /* optional end-of-step bookkeeping (replaces satk_decode_tick): the last CTA to finish records the first finished step in
+   * *done_step (see satk_decode_tick) and increments *tick_t; tick_counter is a zero-initialised device word.  NULL: disabled. */
+  unsigned int* tick_counter; int* tick_t; int* done_step; int min_iters; int use_stop;
 } satk_sa_tail_desc;
 int satk_sa_tail(const satk_sa_tail_desc* d, void* stream);
 

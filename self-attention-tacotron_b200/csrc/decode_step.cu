@@ -639,6 +639,21 @@ __global__ void __cluster_dims__(TCS, 1, 1) __launch_bounds__(256) sa_tail_k(con
     if (has_stop && tid == 0) d.stop_dst[(long long)t * B + b] = v + __ldg(d.b_stop);
   }
   cluster.sync();     // peers may still be writing into this CTA's shared memory until their last remote store has landed
+  if (d.tick_counter && tid == 0) {
+    // end-of-step bookkeeping by the LAST CTA of the grid to get here (every CTA read t at its start, so the increment cannot race):
+    // StopTokenBasedInferenceHelper.is_finished (sigmoid(stop) > 0.5 for every utterance and t > min_iters), then t += 1
+    __threadfence();
+    const unsigned prev = atomicAdd(d.tick_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence();
+      bool all = d.use_stop != 0;
+      if (all)
+        for (int bb = 0; bb < B; ++bb) all = all && (((volatile float*)d.stop_dst)[(long long)t * B + bb] > 0.f);
+      if (all && t > d.min_iters && *d.done_step < 0) *d.done_step = t;
+      *d.tick_counter = 0u;
+      *d.tick_t = t + 1;
+    }
+  }
 }
 
 __global__ void tick_k(int* t_ptr, const float* stop, int B, int min_iters, int* done_step) {

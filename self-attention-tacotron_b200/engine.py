@@ -761,6 +761,7 @@ class TacotronEngine:
                                               hdst=x3c, ld_hdst=W3C, hdst_off=HD, hdst_pstride=B * W3C, **zo)))
         x = o3
         probs = []
+        tick_fused = False
         if getattr(self, "fused_decode_tail", True) and HD == 256 and OU + 1 <= 256:
             # fused tail: self-attention hops over the KV cache + mel / stop projections, one cluster per utterance (satk_sa_tail)
             hops = []
@@ -774,7 +775,10 @@ class TacotronEngine:
                                  Vc=b_(f"pred.V{h}", (Tmax, B, HD)), probs=pr))
             steps.append(O.sa_tail_desc(B=B, D=HD, heads=d.dec_sa_heads if d.dual else 1, Tmax=Tmax, t_ptr=t_dev, x=o3, ldx=HD, hops=hops,
                                         W_out=p["dec.out_proj.W"], b_out=p["dec.out_proj.b"], W_stop=p["dec.stop_proj.W"],
-                                        b_stop=p["dec.stop_proj.b"], mel_dst=mel_hist, mel_tstride=B * OU, stop_dst=stop_hist))
+                                        b_stop=p["dec.stop_proj.b"], mel_dst=mel_hist, mel_tstride=B * OU, stop_dst=stop_hist,
+                                        tick=dict(counter=b_("pred.tick_counter", (1,), torch.int32, zero=True), done_step=done,
+                                                  min_iters=min_iters, use_stop=use_stop_token)))
+            tick_fused = True
         else:
             if d.dual:
                 # TransformerWrapper (rnn_wrappers.py:111-124) with cached keys / values: row t of the causal attention
@@ -812,7 +816,8 @@ class TacotronEngine:
                     O.mlp_chain(s_)
                 else:
                     O.sa_step(s_)
-            O.decode_tick(t_dev, stop_hist if use_stop_token else None, B, min_iters, done)
+            if not tick_fused:
+                O.decode_tick(t_dev, stop_hist if use_stop_token else None, B, min_iters, done)
 
         state = dict(t_dev=t_dev, done=done, mel_hist=mel_hist, stop_hist=stop_hist, cell_in=cell_in, x2c=x2c, x3c=x3c, st=st,
                      aprev=aprev, alpha=alpha, u=u, al1=al1, al2=al2, lengths=lengths, probs=probs, steps=steps)

@@ -129,6 +129,7 @@ class SaTailDesc(C.Structure):
         ("Wo", fp * 4), ("bo", fp * 4), ("Wt", fp * 4), ("bt", fp * 4), ("Kc", fp * 4), ("Vc", fp * 4), ("probs", fp * 4),
         ("W_out", fp), ("b_out", fp), ("n_out", i32), ("W_stop", fp), ("b_stop", fp),
         ("mel_dst", fp), ("mel_tstride", i64), ("stop_dst", fp),
+        ("tick_counter", fp), ("tick_t", fp), ("done_step", fp), ("min_iters", i32), ("use_stop", i32),
     ]
 
 

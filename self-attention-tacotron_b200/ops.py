@@ -483,7 +483,8 @@ def mlp_chain(d: MlpChainDesc) -> None:
     _count()
 
 
-def sa_tail_desc(*, B, D, heads, Tmax, t_ptr, x, ldx, hops, W_out, b_out, W_stop, b_stop, mel_dst, mel_tstride, stop_dst) -> SaTailDesc:
+def sa_tail_desc(*, B, D, heads, Tmax, t_ptr, x, ldx, hops, W_out, b_out, W_stop, b_stop, mel_dst, mel_tstride, stop_dst,
+                 tick=None) -> SaTailDesc:
     """``hops``: list of dicts with Wk,bk,Wv,bv,Wq,bq,Wo,bo,Wt,bt (weights), Kc,Vc (caches) and probs (or None)."""
     d = SaTailDesc()
     d.B, d.D, d.heads, d.Tmax, d.hops = B, D, heads, Tmax, len(hops)
@@ -499,6 +500,9 @@ def sa_tail_desc(*, B, D, heads, Tmax, t_ptr, x, ldx, hops, W_out, b_out, W_stop
     d.W_out, d.b_out, d.n_out = W_out.data_ptr(), b_out.data_ptr(), W_out.shape[1]
     d.W_stop, d.b_stop = W_stop.data_ptr(), b_stop.data_ptr()
     d.mel_dst, d.mel_tstride, d.stop_dst = mel_dst.data_ptr(), mel_tstride, stop_dst.data_ptr()
+    if tick is not None:      # dict(counter=int32[1] zeroed, done_step=int32[1], min_iters, use_stop)
+        d.tick_counter, d.tick_t, d.done_step = tick["counter"].data_ptr(), t_ptr.data_ptr(), tick["done_step"].data_ptr()
+        d.min_iters, d.use_stop = int(tick["min_iters"]), int(bool(tick["use_stop"]))
     return d
 
 
