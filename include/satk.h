@@ -274,6 +274,8 @@ typedef struct {
   const float* agent_w;        /* [M1+A1] transition_factor_projection kernel */
   const float* agent_b;        /* [1] */
   float* u_save;               /* [Td,B] transition factor USED by step t (u_{t-1}; 0.5 at t=0); saved for backward, may be NULL */
+  float* state_final;          /* [B,Tt] location-attention state after the last step (sum of all alignments when cumulative);
+                                  required by the backward pass when cumulative != 0, else may be NULL */
 } satk_attn_rnn_fwd_desc;
 int satk_attn_rnn_fwd(const satk_attn_rnn_fwd_desc* d, void* stream);
 

@@ -164,7 +164,11 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     S.vs[tid] = v;
     S.dqS[tid] = 0.f;
   }
-  for (int i = tid; i < TtP + 2 * HALO; i += NT) S.aprev[i] = 0.f;
+  for (int i = tid; i < TtP + 2 * HALO; i += NT) {
+    // cumulative_weights: the location input of step t is the sum of all earlier alignments; start from the final state
+    const int j = i - HALO;
+    S.aprev[i] = (d.cumulative && loc && arow_ok && j >= 0 && j < Tt) ? __ldg(d.state_final + (long long)arow * Tt + j) : 0.f;
+  }
   for (int i = tid; i < (TtP + 2 * HALO) * MAXF; i += NT) S.dfS[i] = 0.f;
   for (int i = tid; i < TtP * MAXF; i += NT) S.fS[i] = 0.f;
   for (int i = tid; i < 2 * 4 * TtP; i += NT) { S.dstate_part[i] = 0.f; S.dwpart[i] = 0.f; }
@@ -208,6 +212,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
 #pragma unroll
   for (int i = 0; i < NCH; ++i) dv_acc[i] = 0.f;
   float dWf_acc = 0.f;     // tid < NI1*8*AFT owns one (channel, filter) entry of d(location_features_layer)
+  float Gacc = 0.f;        // cumulative_weights: running sum of d(state) over the later steps (thread 256 + j owns position j)
   // transition agent (forward_attention.py:111-114): thread tid < 64 owns context column cq*64+tid and thread tid < A1Q score channel
   // cq*A1Q+tid of [ctx1, q1] . W; S.red[40] carries d(u_t) from the step that used it, S.red[41] = d(pre-sigmoid) of step t
   float wa = 0.f, waq = 0.f, dwa_acc = 0.f, dwaq_acc = 0.f, db_acc = 0.f;
@@ -293,7 +298,8 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     }
     for (int j = tid; j < TtP; j += NT) {
       const bool in = j < Tt && t > 0;
-      S.aprev[HALO + j] = in ? rAp[j] : 0.f;
+      // state of step t: a_{t-1}, or with cumulative weights state_{t+1} - a_t (walked back from the saved final state)
+      S.aprev[HALO + j] = in ? (d.cumulative ? S.aprev[HALO + j] - rA[j] : rAp[j]) : 0.f;
       S.alphaPrevS[j] = in ? rAp[TtP + j] : ((j == 0 && d.mode == 2) ? 1.f : 0.f);
     }
     __syncthreads();
@@ -378,6 +384,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           dst = S.dstate_part[(cur * 4 + 0) * TtP + j] + S.dstate_part[(cur * 4 + 1) * TtP + j] + S.dstate_part[(cur * 4 + 2) * TtP + j] +
                 S.dstate_part[(cur * 4 + 3) * TtP + j];
       }
+      if (d.cumulative) { Gacc += dst; dst = Gacc; }     // a_t feeds the state of EVERY later step
       float da;
       if (d.mode == 2) {
         const float dal = in ? dw + S.dalpha_carry[j] : 0.f;
@@ -859,7 +866,7 @@ extern "C" int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream) 
   bool has2;
   int rc = attn_rnn_check(&d->f, has2);
   if (rc) return rc;
-  SATK_CHECK_ARG(!d->f.cumulative, "attn_rnn_bwd: cumulative_weights=True is not supported in the backward pass");
+  SATK_CHECK_ARG(!d->f.cumulative || d->f.att_kernel == 0 || d->f.state_final, "attn_rnn_bwd: cumulative_weights needs the final state saved by forward");
   SATK_CHECK_ARG(d->f.gates && d->f.c_prev && d->f.q_save && d->f.soft1,
                  "attn_rnn_bwd: forward must have saved gates/c_prev/q_save/soft1");
   cudaStream_t st = (cudaStream_t)stream;

@@ -548,6 +548,8 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
   }
   PT_FLUSH(d.Td)
   cp_async_wait<0>();
+  if (d.state_final && d.att_kernel > 0 && cq == 0 && arow_ok)
+    for (int j = tid; j < Tt; j += NT) d.state_final[(long long)arow * Tt + j] = S.aprev[HALO + j];
   cluster.sync();
 }
 

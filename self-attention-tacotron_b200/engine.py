@@ -484,7 +484,8 @@ class TacotronEngine:
             h_prev=self.buf("dec.hprev1", (Rd, H1)), soft1=self.buf("dec.soft1", (Td, B, Tt)),
             q_save=self.buf("dec.qsave", (Rd, d.att1 + d.att2)),
             agent_w=p["att1.agent.W"] if agent else None, agent_b=p["att1.agent.b"] if agent else None,
-            u_save=self.buf("dec.usave", (Td, B)) if agent else None)
+            u_save=self.buf("dec.usave", (Td, B)) if agent else None,
+            state_final=self.buf("dec.state_final", (B, Tt)) if (loc and d.cumulative) else None)
         self._timed("attn_rnn_fwd", O.attn_rnn_fwd, fd)
         sv.update(fd=fd, dec_in=dec_in, dp0=dp0, dp1=dp1, x2=x2, values1=values1, values2=values2, keys1=keys1, keys2=keys2)
         # LSTM-2, LSTM-3 (DecoderRNNV2)

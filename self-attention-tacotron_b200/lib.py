@@ -68,7 +68,7 @@ class AttnRnnFwdDesc(C.Structure):
         ("keys2", fp), ("values2", fp), ("Wq2", fp), ("v2", fp),
         ("x2", fp), ("align1", fp), ("align2", fp),
         ("gates", fp), ("c_prev", fp), ("h_prev", fp), ("soft1", fp), ("q_save", fp),
-        ("agent_w", fp), ("agent_b", fp), ("u_save", fp),
+        ("agent_w", fp), ("agent_b", fp), ("u_save", fp), ("state_final", fp),
     ]
 
 

@@ -129,6 +129,13 @@ def test_variant_forward_attention_transition_agent(satk, root):
           overrides="use_forward_attention_transition_agent=True")
 
 
+def test_variant_cumulative_weights(satk, root):
+    """cumulative_weights=True (forward_attention.py:118-119; tacotron2 LocationSensitiveAttention): the location input is the SUM of
+    all earlier alignments, so every alignment feeds the state of every later step; forward and all gradients, both mechanisms."""
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 5, 21, 26, True, overrides="cumulative_weights=True")
+    _case(satk, root, "ljspeech_tacotron.json", 3, 19, 22, True, overrides="attention=location_sensitive,cumulative_weights=True")
+
+
 def test_variant_additive(satk, root):
     _case(satk, root, "ljspeech_tacotron.json", 3, 20, 24, True, overrides="attention=additive")
 
