@@ -105,6 +105,17 @@ def dims_from_hparams(hp) -> ModelDims:
         raise ValueError("attention2 must be 'additive' on the hot path")
     if not hp.use_zoneout_at_encoder:
         raise ValueError("use_zoneout_at_encoder=False (plain CBHG with GRU) is out of scope")
+    # switches of the reference's model_fn that this implementation does not build (SURVEY §8 f3 / out of scope): refuse loudly
+    for flag, what in (("use_postnet_v2", "PostNetV2 (models/models.py:440-462)"),
+                       ("use_l2_regularization", "l2_regularization_loss (models/models.py:471-478)"),
+                       ("use_forced_alignment_mode", "forced-alignment attention (teacher_forcing_attention.py)"),
+                       ("use_external_speaker_embedding", "external speaker embeddings (multi_speaker_tacotron)"),
+                       ("use_language_embedding", "language embeddings (multi_speaker_tacotron)"),
+                       ("speaker_embedd_to_postnet", "speaker embedding into the post-net"),
+                       ("channel_id_to_postnet", "channel labels into the post-net"),
+                       ("use_accent_type", "accent-type inputs")):
+        if bool(getattr(hp, flag, False)):
+            raise NotImplementedError(f"{flag}=True: {what} is not built in this implementation")
     return ModelDims(
         dual=dual, num_symbols=hp.num_symbols, embed=hp.embedding_dim,
         enc_prenet=tuple(hp.encoder_prenet_out_units), conv_ch=hp.conv_channels, bank_k=hp.max_filter_width,
