@@ -208,6 +208,8 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
 
   // ---------------- energy role
   const int pg = warp * 4 + (lane >> 3), cl_ = lane & 7;
+  // position passes of this warp that touch the utterance (see attn_rnn_fwd.cu): gradients of positions past the source length are zero
+  const int nact = min(NP, max(0, (alen - 4 * warp + 63) / 64));
   float dv_acc[NCH];
 #pragma unroll
   for (int i = 0; i < NCH; ++i) dv_acc[i] = 0.f;
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       for (int i = 0; i < 8; ++i) dcx[i] = S.dctxS[cl_ + 8 * i];
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
+        if (m >= nact) continue;                 // d(weights) of positions past the source length is never used
         const int j = pg + 64 * m;
         const float* vr = S.valS + (j < Tt ? j : 0) * KS + cl_;
         float a1 = 0.f, a1b = 0.f;
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         float dq = 0.f;
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
+          if (m >= nact) continue;
           float s = S.keyS[jm[m] * KS + c] + qc;
 #pragma unroll
           for (int f = 0; f < AFT; ++f) s = fmaf(fv[m][f], wf[f], s);
@@ -489,6 +493,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
         float dq = 0.f;
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
+          if (m >= nact) continue;
           const float th = ftanh(S.keyS[jm[m] * KS + c] + qc);
           const float dsv = de2[m] * vc * (1.f - th * th);
           dv_acc[NI1] = fmaf(de2[m], th, dv_acc[NI1]);
@@ -507,6 +512,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
       // d(location features): reduce over the 8 channel lanes
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
+        if (m >= nact) continue;                 // dfS of those positions stays at its initial zero
 #pragma unroll
         for (int f = 0; f < AFT; ++f) {
           float v = dfp[m][f];
@@ -571,7 +577,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
           const bool ok = e < d.att_kernel * AFT;
           const int k = ok ? e / AFT : 0, f = ok ? e % AFT : 0;
           float acc = 0.f;
-          for (int j = lane & 7; j < Tt; j += 8) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[f * DFW + HALO + j], acc);
+          for (int j = lane & 7; j < alen; j += 8) acc = fmaf(S.aprev[HALO + j + k - pl], S.dfS[f * DFW + HALO + j], acc);
           acc += __shfl_xor_sync(0xffffffffu, acc, 1);
           acc += __shfl_xor_sync(0xffffffffu, acc, 2);
           acc += __shfl_xor_sync(0xffffffffu, acc, 4);

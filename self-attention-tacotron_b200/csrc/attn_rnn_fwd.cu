@@ -189,6 +189,9 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
   const bool srow_ok = (tid >= 128 && tid < 192) && srow < B;
   // P2 role: position group / channel lane
   const int pg = warp * 4 + (lane >> 3), cl_ = lane & 7;
+  // passes m = 0..nact-1 of this warp touch a position inside the utterance (j = pg + 64 m < alen); positions past the source length
+  // have zero attention weight, so the other passes are skipped (warp-uniform)
+  const int nact = min(NP, max(0, (alen - 4 * warp + 63) / 64));
 
   float wa = 0.f;
   if (AGENT) {
@@ -372,17 +375,20 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         const float qc = S.qs[c], vc = S.vs[c];
 #pragma unroll
         for (int m = 0; m < NP; ++m) {
-          float s = S.keyS[jm[m] * KS + c] + qc;
+          if (m < nact) {
+            float s = S.keyS[jm[m] * KS + c] + qc;
 #pragma unroll
-          for (int f = 0; f < AFT; ++f) s = fmaf(fv[m][f], wf[f], s);
-          e1[m] = fmaf(vc, ftanh(s), e1[m]);
+            for (int f = 0; f < AFT; ++f) s = fmaf(fv[m][f], wf[f], s);
+            e1[m] = fmaf(vc, ftanh(s), e1[m]);
+          }
         }
       }
       if (HAS2) {
         const int c = A1Q + cl_;
         const float qc = S.qs[c], vc = S.vs[c];
 #pragma unroll
-        for (int m = 0; m < NP; ++m) e2[m] = vc * ftanh(S.keyS[jm[m] * KS + c] + qc);
+        for (int m = 0; m < NP; ++m)
+          if (m < nact) e2[m] = vc * ftanh(S.keyS[jm[m] * KS + c] + qc);
       }
 #pragma unroll
       for (int m = 0; m < NP; ++m) {
@@ -474,13 +480,13 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_fwd_kernel(const satk_attn_rnn
         const float* wS = (c < 64) ? S.w1S : S.w2S;
         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
         int j = jg;
-        for (; j + 21 < Tt; j += 28) {
+        for (; j + 21 < alen; j += 28) {        // weights past the source length are exactly zero
           acc0 = fmaf(wS[j], S.valS[j * KS + c], acc0);
           acc1 = fmaf(wS[j + 7], S.valS[(j + 7) * KS + c], acc1);
           acc2 = fmaf(wS[j + 14], S.valS[(j + 14) * KS + c], acc2);
           acc3 = fmaf(wS[j + 21], S.valS[(j + 21) * KS + c], acc3);
         }
-        for (; j < Tt; j += 7) acc0 = fmaf(wS[j], S.valS[j * KS + c], acc0);
+        for (; j < alen; j += 7) acc0 = fmaf(wS[j], S.valS[j * KS + c], acc0);
         S.cpart[jg * VC + c] = (acc0 + acc1) + (acc2 + acc3);
       }
     }

@@ -59,6 +59,23 @@ def _check_grads(eng, tr, rg, cuda=None, l2_tol=1e-3):
     assert (num / den) ** 0.5 <= l2_tol, f"whole-gradient relative L2 error {(num / den) ** 0.5:.3e}"
 
 
+def _unsort(out, B):
+    """TRAIN-mode steps sort the batch by source length (engine.forward): put the per-utterance outputs back into the caller's order."""
+    perm = out.get("perm")
+    if perm is None:
+        return out
+    inv = torch.argsort(perm)
+    o = dict(out)
+    for k in ("memory1_tm", "memory2_tm", "align1_tm", "align2_tm"):
+        if o.get(k) is not None:
+            o[k] = o[k].reshape(-1, B, o[k].shape[-1]).index_select(1, inv)
+    for k in ("mel_tm", "stop_tm"):
+        o[k] = o[k].view(-1, B, o[k].shape[-1] if k == "mel_tm" else 1).index_select(1, inv)
+    for k in ("enc_self_P", "dec_self_P"):
+        o[k] = [a.index_select(0, inv) for a in o[k]]
+    return o
+
+
 def _case(satk, root, cfg, B, Tt, Tm, training, overrides=None, grads=True, seed=7):
     E, O, L, M = _mods()
     hp = satk.load_hparams(os.path.join(root, "examples", cfg), overrides)
@@ -72,7 +89,7 @@ def _case(satk, root, cfg, B, Tt, Tm, training, overrides=None, grads=True, seed
     fd = satk.SourceData(*[x.cuda() if torch.is_tensor(x) else x for x in f])
     ld = satk.MelData(*[x.cuda() if torch.is_tensor(x) else x for x in l])
     md = {k: v.cuda() for k, v in masks.items()} if masks else None
-    out = eng.forward(fd, ld, training, md)
+    out = _unsort(eng.forward(fd, ld, training, md), B)
     Td = Tm // d.r
     _close(out["memory1_tm"].view(Tt, B, -1).transpose(0, 1), ref["memory1"], RTOL_OUT, "encoder lstm_output")
     _close(out["align1_tm"].permute(1, 2, 0), ref["alignment"], RTOL_OUT, "alignment", 1e-6)
@@ -220,7 +237,7 @@ def test_vctk_config3_per_replica_batch_runs_full_size(satk, root):
     eng = E.TacotronEngine(hp, "cuda", seed=3)
     f, l = satk.synthetic_batch(hp, 64, 148, 800, seed=21, device="cuda")
     w0 = eng.ps.flat.clone()
-    out = eng.train_step(f, l)
+    out = _unsort(eng.train_step(f, l), 64)
     torch.cuda.synchronize()
     assert torch.isfinite(out["losses"]).all() and out["losses"][2].item() > 0
     a = out["align1_tm"]                                            # [Td, B, Tt]
