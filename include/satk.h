@@ -86,6 +86,11 @@ typedef struct {
   /* weight gradient of a 1-D convolution on the tensor-core tile (operands already transposed, reduction index
    * contiguous): batch entry z1 reads A[m, k + kshift0 + z1*kshift_per_batch1] (zero outside [0,K)); one output per tap. */
   int kshift0, kshift_per_batch1;
+  /* convolution BANK in one launch (module.py:46-53 and its input gradient): bank_widths = W > 0 makes z-batch entry w = 0..W-1 the
+   * SAME-padded conv of width w+1 over the same A: taps = w+1, first tap at row shift -(w/2)*tap_dir, weights = entries
+   * [w(w+1)/2 + tap] of B's tap dimension (stride sBtap: the W kernels stored back to back), A read at reduction offset
+   * w*bank_a_kstep, result written (beta = 0) or added (beta = 1) at output column w*bank_c_nstep.  N is the width of one conv. */
+  int bank_widths, bank_a_kstep, bank_c_nstep;
 } satk_gemm_desc;
 
 /* engine: 0 = auto, 1 = fp32 SIMT tile, 2 = tcgen05 3xTF32 tile (TMA-fed; falls back with an

@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmArgs args) {
 }
 
 int gemm_simt_launch(const satk_gemm_desc* d, cudaStream_t st) {
-  SATK_CHECK_ARG(d->kshift0 == 0 && d->kshift_per_batch1 == 0, "satk_gemm: K-shifted batches are served by the tcgen05 tile only");
+  SATK_CHECK_ARG(d->kshift0 == 0 && d->kshift_per_batch1 == 0 && d->bank_widths == 0,
+                 "satk_gemm: K-shifted batches and conv banks are served by the tcgen05 tile only");
   GemmArgs a;
   a.d = *d;
   if (a.d.batch1 < 1) a.d.batch1 = 1;

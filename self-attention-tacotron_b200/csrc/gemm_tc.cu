@@ -53,6 +53,7 @@ struct Params {
   int split_k;
   int zbatch, kshift0, kshift_step;   // z-batches with a shifted reduction coordinate of A (conv weight gradients)
   long long c_zstride;
+  int bank, bank_a_kstep, bank_c_nstep;   // conv bank: z-batch entry = conv width (see satk_gemm_desc.bank_widths)
   int tma_store;            // 1: plain overwrite epilogue (bias + activation only) leaves through TMA bulk stores
 };
 
@@ -146,13 +147,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int ks = blockIdx.z % p.split_k, zb = blockIdx.z / p.split_k;
-  const int a_kshift = p.kshift0 + zb * p.kshift_step;
+  int a_kshift = p.kshift0 + zb * p.kshift_step;
+  int taps_eff = p.taps, shift0_eff = p.shift0, tap_base = 0, c_noff = 0, c_rowz = zb * p.M;
+  long long c_zoff = zb * p.c_zstride;
+  if (p.bank) {
+    const int w = p.zbatch - 1 - zb;               // widest conv first: the long tiles are scheduled before the short ones
+    taps_eff = w + 1;
+    shift0_eff = -(w / 2) * p.tap_dir;             // SAME padding: (k-1)/2 taps to the left
+    tap_base = w * (w + 1) / 2;
+    a_kshift = w * p.bank_a_kstep;
+    c_noff = w * p.bank_c_nstep;
+    c_rowz = 0;
+    c_zoff = 0;
+  }
   // carve: align the dynamic region to 1024 B (swizzle atom alignment)
   const uint32_t smem_base = (cl::smem_u32(smem) + 1023u) & ~1023u;
 
   const int kblocks_total = (p.K + BK - 1) / BK;
   // split-K partitions the flattened (tap, k-block) iteration space, so tapped (conv) products with a short K still split
-  const int it_total = kblocks_total * p.taps;
+  const int it_total = kblocks_total * taps_eff;
   const int it_per = (it_total + p.split_k - 1) / p.split_k;
   const int it_beg = ks * it_per;
   const int iters = max(0, min(it_total, it_beg + it_per) - it_beg);
@@ -190,8 +203,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
       TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-      tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + p.shift0 + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
-      if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap, cl::smem_u32(&full_bar[s]));
+      tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + shift0_eff + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
+      if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap_base + tap, cl::smem_u32(&full_bar[s]));
       else tma_load_2d(sb, &mapB, kb * BK, n0, cl::smem_u32(&full_bar[s]));
       if (it == 0) { TC_MARK(1) }
     }
@@ -312,11 +325,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (lane == 0) {
             if (p.tma_store == 2)   // split-K partial sums / accumulation onto C: the TMA unit adds into global memory
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC),
-                           "r"(nb), "r"(zb * p.M + m0 + q * 32), "r"(sblk)
+                           "r"(c_noff + nb), "r"(c_rowz + m0 + q * 32), "r"(sblk)
                            : "memory");
             else
-              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC), "r"(nb),
-                           "r"(zb * p.M + m0 + q * 32), "r"(sblk)
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC), "r"(c_noff + nb),
+                           "r"(c_rowz + m0 + q * 32), "r"(sblk)
                            : "memory");
           }
         }
@@ -354,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int mbase = m0 + q * 32;
         const int nrows = min(32, p.M - mbase);
         if (p.split_k > 1) {
-          float* cp = p.C + zb * p.c_zstride + (long long)mbase * p.ldc + n;
+          float* cp = p.C + c_zoff + (long long)mbase * p.ldc + n;
           const float alpha = p.alpha;
           const long long ldc = p.ldc;
 #pragma unroll
@@ -366,8 +379,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const bool has_add = p.residual != nullptr || p.beta != 0.0f, has_mask = p.keep_mask != nullptr;
 #define SATK_EPI(A)                                                                                   \
   do {                                                                                                \
-    if (has_mask) { if (has_add) epi_rows<A, true, true>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); else epi_rows<A, true, false>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); } \
-    else { if (has_add) epi_rows<A, false, true>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); else epi_rows<A, false, false>(p, stg, lane, mbase, nrows, n, bias, zb * p.c_zstride); } \
+    if (has_mask) { if (has_add) epi_rows<A, true, true>(p, stg, lane, mbase, nrows, n, bias, c_zoff); else epi_rows<A, true, false>(p, stg, lane, mbase, nrows, n, bias, c_zoff); } \
+    else { if (has_add) epi_rows<A, false, true>(p, stg, lane, mbase, nrows, n, bias, c_zoff); else epi_rows<A, false, false>(p, stg, lane, mbase, nrows, n, bias, c_zoff); } \
   } while (0)
           switch (p.act) {
             case SATK_ACT_RELU: SATK_EPI(SATK_ACT_RELU); break;
@@ -444,6 +457,41 @@ int tc_trace(long long* out16) {
 
 }  // namespace tc
 
+// Convolution bank: every width of the bank as a z-batch of ONE launch (see satk_gemm_desc.bank_widths)
+static int gemm_tc_bank_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
+  using namespace tc;
+  const int W = d->bank_widths;
+  SATK_CHECK_ARG(W <= 64 && d->transA == 0 && d->transB == 1 && !d->bias && d->act == 0 && !d->residual && !d->keep_mask &&
+                     (d->beta == 0.0f || d->beta == 1.0f) && d->batch1 <= 1 && d->batch2 <= 1 && d->split_k <= 1 && d->seq_len == 0,
+                 "satk_gemm: a conv bank takes K-contiguous operands, no epilogue options and beta in {0, 1}");
+  SATK_CHECK_ARG((d->lda % 4) == 0 && (d->ldb % 4) == 0 && (d->K % 4) == 0 && ((uintptr_t)d->A % 16) == 0 && ((uintptr_t)d->B % 16) == 0 &&
+                     (d->sBtap % 4) == 0 && (d->ldc % 4) == 0 && ((uintptr_t)d->C % 16) == 0,
+                 "satk_gemm: conv bank operands must be 16-byte addressable");
+  const long long a_cols = (long long)d->K + (long long)(W - 1) * d->bank_a_kstep;       // widest reduction coordinate read from A
+  const long long c_cols = (long long)d->N + (long long)(W - 1) * d->bank_c_nstep;
+  CUtensorMap mapA, mapB, mapC;
+  if (!make_map(&mapA, d->A, d->M, a_cols, d->lda, 0, 0) || !make_map(&mapB, d->B, d->N, d->K, d->ldb, W * (W + 1) / 2, d->sBtap) ||
+      !make_map_c(&mapC, d->C, d->M, c_cols, d->ldc)) {
+    set_error("satk_gemm: cuTensorMapEncodeTiled failed for the conv bank");
+    return SATK_ERR_CUDA;
+  }
+  *supported = true;
+  Params p = {};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.taps = 1; p.shift0 = 0; p.tap_dir = d->tap_dir;
+  p.C = d->C; p.ldc = d->ldc;
+  p.alpha = d->alpha; p.beta = d->beta;
+  p.split_k = 1;
+  p.zbatch = W; p.bank = 1; p.bank_a_kstep = d->bank_a_kstep; p.bank_c_nstep = d->bank_c_nstep;
+  p.tma_store = d->beta == 0.0f ? 1 : 2;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  SATK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(d->M, BM), ceil_div(d->N, BN), W);
+  gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapC, p, 1);
+  SATK_LAUNCH_CHECK();
+  return SATK_OK;
+}
+
 // Shapes served by the tensor-core tile: plain or tapped (conv) products with K-contiguous operands.
 int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   using namespace tc;
@@ -452,6 +500,7 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   const int taps = d->taps < 1 ? 1 : d->taps;
   // z-batches are served in one form only: same A and B for every entry, A read with a per-entry shift of the reduction
   // coordinate, one output per entry (conv weight gradients)
+  if (d->bank_widths > 0) return gemm_tc_bank_launch(d, st, supported);
   const bool zform = batches > 1 && (d->batch2 <= 1) && d->sA1 == 0 && d->sB1 == 0 && taps == 1 && !d->bias && d->act == 0 &&
                      !d->residual && !d->keep_mask;
   if ((batches != 1 && !zform) || d->transA != 0 || d->transB != 1 || d->causal_skip != 0 || d->seq_len != 0 || d->shift_per_batch1 != 0) return SATK_OK;
@@ -472,6 +521,7 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   p.residual = d->residual; p.ldres = d->ldres;
   p.keep_mask = d->keep_mask; p.keep_scale = d->keep_scale;
   p.split_k = d->split_k < 1 ? 1 : d->split_k;
+  p.bank = 0; p.bank_a_kstep = 0; p.bank_c_nstep = 0;
   p.zbatch = batches; p.kshift0 = d->kshift0; p.kshift_step = d->kshift_per_batch1; p.c_zstride = d->sC1;
   const int kblocks = (d->K + BK - 1) / BK;
   const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);

@@ -206,6 +206,10 @@ class TacotronEngine:
                 O.linear_dx(dt, p[f"{name}.{nm}.W"], dx, R, beta=1.0)
         return dx
 
+    def _bank_one_launch(self, R, cin, C):
+        """The conv bank runs as one z-batched tcgen05 launch when its tiles are whole (128-wide convs over 128 channels)."""
+        return getattr(self, "bank_one_launch", True) and C == 128 and cin % 32 == 0 and R >= 64
+
     # ------------------------------------------------------------------ encoder
     def encoder(self, source, source_length, training, masks):
         """-> (lstm_output [Tt,B,2H], self_attention_output [Tt,B,32] | None, [alignments])."""
@@ -228,10 +232,17 @@ class TacotronEngine:
         C, K, cin = d.conv_ch, d.bank_k, inp.shape[1]
         KC = C * K
         raw = self.buf("enc.bank_raw", (R, KC))
-        for k in range(1, K + 1):
-            pl = (k - 1) // 2
-            O.gemm(inp, self.ps.pt[f"cbhg.bank{k}.W"], raw, R, C, cin, lda=cin, ldb=cin, ldc=KC, c_off=(k - 1) * C, transB=True,
-                   taps=k, shift0=-pl * B, tap_dir=B, sBtap=cin * C)
+        if self._bank_one_launch(R, cin, C):
+            # all K widths as z-batches of ONE tcgen05 launch: the K kernels are stored back to back ([K(K+1)/2 taps][C][cin])
+            o = self.ps.offsets["cbhg.bank1.W"][0]
+            Wt_all = self.ps.flat_t[o:o + (K * (K + 1) // 2) * C * cin]
+            O.gemm(inp, Wt_all, raw, R, C, cin, lda=cin, ldb=cin, ldc=KC, transB=True, tap_dir=B, sBtap=cin * C, bank_widths=K,
+                   bank_c_nstep=C, engine=2)
+        else:
+            for k in range(1, K + 1):
+                pl = (k - 1) // 2
+                O.gemm(inp, self.ps.pt[f"cbhg.bank{k}.W"], raw, R, C, cin, lda=cin, ldb=cin, ldc=KC, c_off=(k - 1) * C, transB=True,
+                       taps=k, shift0=-pl * B, tap_dir=B, sBtap=cin * C)
 
         def bn(xraw, Cc, first, gname, act, out, residual=None, maxpool=False):
             gamma = self._span(self.ps.p, gname + ".gamma", Cc)
@@ -356,7 +367,7 @@ class TacotronEngine:
                      act=s["act"], maxpool_seq_len=Tt if s["maxpool"] else 0, pos_stride=B, use_batch_stats=training)
 
         def conv_back(x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None, xT=None,
-                      drawT=None, drawT_row0=0):
+                      drawT=None, drawT_row0=0, skip_dx=False):
             """draw: gradient wrt the raw conv output [R, cout] (ld draw_ld); accumulates dW, writes/accumulates dx."""
             pl = (k - 1) // 2
             with self._wg():
@@ -371,8 +382,9 @@ class TacotronEngine:
                     O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True,
                            b_off=draw_off, batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B,
                            split_k=max(1, min(32, R // 512)), beta=1.0)
-            O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
-                   taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
+            if not skip_dx:
+                O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
+                       taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
 
         draw2 = self.buf("enc.draw2", (R, d.proj2))
         bn_back(sv["bn_p2"], dhw, draw2)
@@ -391,10 +403,19 @@ class TacotronEngine:
         with self._wg():
             inpT = O.transposed_rows(sv["inp"], R, cin) if bank_tc else None      # shared by all bank widths
             drawT = O.transposed_rows(draw, R, KC) if bank_tc else None
-        for k in range(1, d.bank_k + 1):   # dinp = dhw (residual branch, module.py:86) + sum_k conv_k^T(d bank_k)
+        one = bank_tc and self._bank_one_launch(R, cin, d.conv_ch)
+        if one:
+            # dinp = dhw (residual branch, module.py:86) + sum over widths and taps of the transposed convs: ONE launch, every width a
+            # z-batch that reads its 128-column block of `draw` and adds its partial sum through the TMA unit
+            dinp.copy_(dhw)
+            o = self.ps.offsets["cbhg.bank1.W"][0]
+            W_all = self.ps.flat[o:o + (d.bank_k * (d.bank_k + 1) // 2) * cin * d.conv_ch]
+            O.gemm(draw, W_all, dinp, R, cin, d.conv_ch, lda=KC, ldb=d.conv_ch, ldc=cin, transB=True, tap_dir=-B, sBtap=cin * d.conv_ch,
+                   beta=1.0, bank_widths=d.bank_k, bank_a_kstep=d.conv_ch, engine=2)
+        for k in range(1, d.bank_k + 1):   # weight gradients per width (+ the per-width input gradient when not fused above)
             conv_back(sv["inp"], f"cbhg.bank{k}.W", k, cin, d.conv_ch, draw, dinp, 0.0 if k == 1 else 1.0, draw_ld=KC,
                       draw_off=(k - 1) * d.conv_ch, residual=dhw if k == 1 else None, xT=inpT, drawT=drawT,
-                      drawT_row0=(k - 1) * d.conv_ch)
+                      drawT_row0=(k - 1) * d.conv_ch, skip_dx=one)
         # encoder pre-net
         dy = dinp
         n = len(d.enc_prenet)

@@ -36,6 +36,7 @@ class GemmDesc(C.Structure):
         ("sA1", i64), ("sA2", i64), ("sB1", i64), ("sB2", i64), ("sC1", i64), ("sC2", i64),
         ("taps", i32), ("shift0", i32), ("tap_dir", i32), ("seq_len", i32), ("sBtap", i64),
         ("shift_per_batch1", i32), ("split_k", i32), ("causal_skip", i32), ("kshift0", i32), ("kshift_per_batch1", i32),
+        ("bank_widths", i32), ("bank_a_kstep", i32), ("bank_c_nstep", i32),
     ]
 
 

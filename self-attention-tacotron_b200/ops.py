@@ -40,7 +40,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
          transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=None, residual=None, ldres=0,
          keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0),
          taps=1, shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0,
-         a_off=0, b_off=0, c_off=0, engine=None, kshift0=0, kshift_per_batch1=0) -> None:
+         a_off=0, b_off=0, c_off=0, engine=None, kshift0=0, kshift_per_batch1=0,
+         bank_widths=0, bank_a_kstep=0, bank_c_nstep=0) -> None:
     """C = epi(alpha * sum_taps op(A) op(B)) (+beta*C).  ``*_off`` are element offsets into the tensors."""
     _req(A); _req(B); _req(C_)
     d = GemmDesc()
@@ -61,6 +62,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
     d.taps, d.shift0, d.tap_dir, d.seq_len, d.sBtap = taps, shift0, tap_dir, seq_len, sBtap
     d.shift_per_batch1, d.split_k, d.causal_skip = shift_per_batch1, split_k, causal_skip
     d.kshift0, d.kshift_per_batch1 = kshift0, kshift_per_batch1
+    d.bank_widths, d.bank_a_kstep, d.bank_c_nstep = bank_widths, bank_a_kstep, bank_c_nstep
     check(load().satk_gemm(C.byref(d), GEMM_ENGINE if engine is None else engine, C.c_void_p(stream_ptr())), "satk_gemm")
     _count()
 

@@ -109,6 +109,38 @@ def test_conv_weight_gradient_all_taps_one_tensor_core_launch():
         _close(dW, (dW0.double() + W.grad).float(), 1e-7 * R, f"conv dW tc k={k} cin={cin} cout={cout}")
 
 
+def test_conv_bank_one_launch_forward_and_input_gradient():
+    """All widths of a SAME-padded conv bank as z-batches of one tcgen05 launch (satk_gemm_desc.bank_widths): forward into the
+    concatenated output and the summed input gradient (TMA reduce-add onto the residual), against fp64 convs."""
+    O = _O()
+    g = torch.Generator().manual_seed(9)
+    T, Bb, cin, C, W = 37, 8, 128, 128, 6
+    R = T * Bb
+    x = torch.randn(T, Bb, cin, generator=g)
+    Ws = [torch.randn(k, cin, C, generator=g) / (k * cin) ** 0.5 for k in range(1, W + 1)]
+    # forward: kernels stored back to back in the K-contiguous layout [tap][C][cin]
+    Wt_all = torch.cat([w.transpose(1, 2).contiguous().reshape(-1) for w in Ws]).cuda()
+    raw = torch.full((R, W * C + 4), 7.0, device="cuda")
+    O.gemm(x.cuda(), Wt_all, raw, R, C, cin, lda=cin, ldb=cin, ldc=W * C + 4, transB=True, tap_dir=Bb, sBtap=cin * C, bank_widths=W,
+           bank_c_nstep=C, engine=2)
+    for k in range(1, W + 1):
+        ref = OR.conv1d_same(x.transpose(0, 1).double(), Ws[k - 1].double()).transpose(0, 1).reshape(R, C).float()
+        _close(raw[:, (k - 1) * C:k * C], ref, 1e-6 * cin * k, f"bank forward width {k}")
+    assert (raw[:, W * C:] == 7.0).all()
+    # input gradient: dx = res + sum_k conv_k^T(draw_k)
+    draw = torch.randn(R, W * C, generator=g)
+    res = torch.randn(R, cin, generator=g)
+    xr = x.transpose(0, 1).double().clone().requires_grad_(True)
+    tot = sum((OR.conv1d_same(xr, Ws[k - 1].double()).transpose(0, 1).reshape(R, C) * draw[:, (k - 1) * C:k * C].double()).sum()
+              for k in range(1, W + 1))
+    tot.backward()
+    W_all = torch.cat([w.reshape(-1) for w in Ws]).cuda()
+    dx = res.clone().cuda()
+    O.gemm(draw.cuda(), W_all, dx, R, cin, C, lda=W * C, ldb=C, ldc=cin, transB=True, tap_dir=-Bb, sBtap=cin * C, beta=1.0,
+           bank_widths=W, bank_a_kstep=C, engine=2)
+    _close(dx, (res.double() + xr.grad.transpose(0, 1).reshape(R, cin)).float(), 2e-6 * C * W, "bank input gradient")
+
+
 def test_gemm_time_major_conv_and_grads():
     O = _O()
     g = torch.Generator().manual_seed(1)

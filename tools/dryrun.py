@@ -28,7 +28,9 @@ def _extent(t, off, need, what):
 def gemm(A, B, C_, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=None,
          residual=None, ldres=0, keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0), taps=1,
          shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0, a_off=0, b_off=0, c_off=0, engine=None,
-         kshift0=0, kshift_per_batch1=0):
+         kshift0=0, kshift_per_batch1=0, bank_widths=0, bank_a_kstep=0, bank_c_nstep=0):
+    if bank_widths:
+        taps = bank_widths * (bank_widths + 1) // 2      # all kernels of the bank, back to back
     zA = (batch1 - 1) * sA[0] + (batch2 - 1) * sA[1]
     zB = (batch1 - 1) * sB[0] + (batch2 - 1) * sB[1] + (taps - 1) * sBtap
     zC = (batch1 - 1) * sC[0] + (batch2 - 1) * sC[1]
