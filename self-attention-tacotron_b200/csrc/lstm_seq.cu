@@ -73,11 +73,13 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
 
   // --- pointwise role: tid < 64 -> (pb, pu).  These two warps touch NO global memory: stores issued by the warp
   // that also issues the st.async exchange would sit in front of it in the LSU and delay every peer.
-  const int pb = tid >> 4, pu = tid & 15;
+  // (unit-major: the 4 rows of a unit sit in 4 adjacent lanes, so one 16-byte st.async per peer carries them)
+  const int pb = tid & 3, pu = (tid >> 2) & 15;
   const int prow = b0 + pb;
   const bool prow_ok = (tid < 64) && prow < d.B;
   const int plen = prow_ok ? (d.lengths ? (int)d.lengths[prow] : d.T) : 0;
   const int pidx = rank * LUH + pu;
+  const int pslot = pb * 16 + pu;                           // index of (row, unit) in the staging arrays read by the saver warps
   float c_st = 0.f, h_st = 0.f;
 
   // --- saver / mask-prefetch role: tid in [64,128) -> (sb, su)
@@ -160,19 +162,24 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
         h_st = h_st + mh * (h_new - h_st);
       }
       if (s + 1 < d.T) {
-        // publish h(s+1): local store + one 4-byte st.async per peer (completes 4 bytes on the peer's barrier)
+        // publish h(s+1): local store + ONE 16-byte st.async per peer for the 4 rows of a unit (issued by the row-0 lane)
         hbuf[nxt][pidx][pb] = h_st;
-        const uint32_t dsta = cl::smem_u32(&hbuf[nxt][pidx][pb]);
-        const uint32_t bara = cl::smem_u32(&bars[nxt]);
+        const int l4 = lane & ~3;
+        const float h0 = __shfl_sync(0xffffffffu, h_st, l4), h1 = __shfl_sync(0xffffffffu, h_st, l4 + 1);
+        const float h2 = __shfl_sync(0xffffffffu, h_st, l4 + 2), h3 = __shfl_sync(0xffffffffu, h_st, l4 + 3);
+        if (pb == 0) {
+          const uint32_t dsta = cl::smem_u32(&hbuf[nxt][pidx][0]);
+          const uint32_t bara = cl::smem_u32(&bars[nxt]);
 #pragma unroll
-        for (int r = 0; r < CS; ++r)
-          if (r != rank) cl::st_async_f32(cl::mapa(dsta, r), h_st, cl::mapa(bara, r));
+          for (int r = 0; r < CS; ++r)
+            if (r != rank) st_async_v4(cl::mapa(dsta, r), h0, h1, h2, h3, cl::mapa(bara, r));
+        }
       }
       // stage what the backward pass needs; zero past the row's length (dynamic_rnn semantics)
-      save_st[0][tid] = gi; save_st[1][tid] = gj; save_st[2][tid] = gf; save_st[3][tid] = go;
-      save_st[4][tid] = valid ? c_old : 0.f;
-      save_st[5][tid] = valid ? h_old : 0.f;
-      save_st[6][tid] = h_new;
+      save_st[0][pslot] = gi; save_st[1][pslot] = gj; save_st[2][pslot] = gf; save_st[3][pslot] = go;
+      save_st[4][pslot] = valid ? c_old : 0.f;
+      save_st[5][pslot] = valid ? h_old : 0.f;
+      save_st[6][pslot] = h_new;
     }
     PT(3)
     __syncthreads();
