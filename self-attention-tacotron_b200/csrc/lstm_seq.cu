@@ -32,8 +32,14 @@ using cl::st_async_v4;
 using cl::RING;
 using cl::PFD;
 
-template <int H>
-__global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_desc d) {
+// UH = hidden units per CTA: 16 (cluster of H/16 CTAs x 256 threads, two CTAs per SM) or 32 (cluster of H/32 CTAs x 512 threads, one CTA
+// per SM: with H = 256 and 8 clusters this gives every cluster its own SMs — 15 clusters of 8 are co-resident, only 7 of 16)
+template <int H, int UH>
+__global__ void __launch_bounds__(UH * 16, UH == 16 ? 2 : 1) lstm_fwd_kernel(const satk_lstm_fwd_desc d) {
+  constexpr int LUH = UH;
+  constexpr int NT = UH * 16;          // threads: 16 reduction lanes x UH column groups of 4 gate columns
+  constexpr int PW = LBG * UH;         // pointwise threads (row, unit)
+  constexpr int GC = 4 * UH;           // gate columns of this CTA
   constexpr int CS = H / LUH;
   constexpr int KPT = H / 4;  // weights per thread
   constexpr uint32_t SLICE_BYTES = LUH * LBG * 4;          // one CTA's slice of the hidden state
@@ -45,11 +51,11 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
   const int tid = threadIdx.x;
 
   __shared__ __align__(16) float hbuf[2][H][LBG];
-  __shared__ float gsm[LBG][64];
+  __shared__ float gsm[LBG][GC];
   __shared__ __align__(8) uint64_t bars[2];
-  __shared__ float xg_ring[RING][256];                      // this thread's x-projection element, PFD steps ahead
+  __shared__ float xg_ring[RING][NT];                      // this thread's x-projection element, PFD steps ahead
   __shared__ __align__(4) uint8_t mk_ring[RING][2][LBG][LUH];  // zoneout keep masks (c, h) of this CTA's units
-  __shared__ float save_st[7][64];                          // activations saved for backward, staged for the saver warps
+  __shared__ float save_st[7][PW];                          // activations saved for backward, staged for the saver warps
 
   // --- gate-GEMM role: thread = (kq = lane & 15, column group cgp = tid >> 4): 4 gate columns x the k's
   // congruent to kq mod 16.  One LDS.128 of h[k][0..3] feeds 16 FMAs (4 columns x 4 rows); the 16 partial
@@ -61,12 +67,12 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
   for (int i = 0; i < KPT / 4; ++i)
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-      const int colc = cgp * 4 + c;                                  // CTA-local gate column = gate*16 + unit
-      const int gc = (colc >> 4) * H + rank * LUH + (colc & 15);     // column in the [.,4H] kernel
+      const int colc = cgp * 4 + c;                                  // CTA-local gate column = gate*UH + unit
+      const int gc = (colc / LUH) * H + rank * LUH + (colc % LUH);   // column in the [.,4H] kernel
       w[i][c] = __ldg(d.Wh + (long long)(kq + 16 * i) * (4 * H) + gc);
     }
   const int col = cgp * 4 + ((kq >> 2) & 3);                         // the column / row this lane finalises
-  const int gcol = (col >> 4) * H + rank * LUH + (col & 15);
+  const int gcol = (col / LUH) * H + rank * LUH + (col % LUH);
   const int myb = b0 + (kq & 3);
   const bool myb_ok = myb < d.B;
   const int mylen = myb_ok ? (d.lengths ? (int)d.lengths[myb] : d.T) : 0;
@@ -74,18 +80,18 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
   // --- pointwise role: tid < 64 -> (pb, pu).  These two warps touch NO global memory: stores issued by the warp
   // that also issues the st.async exchange would sit in front of it in the LSU and delay every peer.
   // (unit-major: the 4 rows of a unit sit in 4 adjacent lanes, so one 16-byte st.async per peer carries them)
-  const int pb = tid & 3, pu = (tid >> 2) & 15;
+  const int pb = tid & 3, pu = (tid >> 2) % LUH;
   const int prow = b0 + pb;
-  const bool prow_ok = (tid < 64) && prow < d.B;
+  const bool prow_ok = (tid < PW) && prow < d.B;
   const int plen = prow_ok ? (d.lengths ? (int)d.lengths[prow] : d.T) : 0;
   const int pidx = rank * LUH + pu;
-  const int pslot = pb * 16 + pu;                           // index of (row, unit) in the staging arrays read by the saver warps
+  const int pslot = pb * LUH + pu;                           // index of (row, unit) in the staging arrays read by the saver warps
   float c_st = 0.f, h_st = 0.f;
 
   // --- saver / mask-prefetch role: tid in [64,128) -> (sb, su)
-  const int sb = (tid - 64) >> 4, su = tid & 15;
+  const int sb = (tid - PW) / LUH, su = (tid - PW) % LUH;
   const int srow = b0 + sb;
-  const bool srow_ok = (tid >= 64 && tid < 128) && srow < d.B;
+  const bool srow_ok = (tid >= PW && tid < 2 * PW) && srow < d.B;
   const int slen = srow_ok ? (d.lengths ? (int)d.lengths[srow] : d.T) : 0;
 
   if (tid == 0) {
@@ -93,8 +99,8 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
     cl::mbar_init(&bars[1], 1);
     cl::fence_mbar_init();
   }
-  for (int i = tid; i < 2 * H * LBG; i += 256) (&hbuf[0][0][0])[i] = 0.f;
-  for (int i = tid; i < RING * 2 * LBG * LUH; i += 256) (&mk_ring[0][0][0][0])[i] = 0;
+  for (int i = tid; i < 2 * H * LBG; i += NT) (&hbuf[0][0][0])[i] = 0.f;
+  for (int i = tid; i < RING * 2 * LBG * LUH; i += NT) (&mk_ring[0][0][0][0])[i] = 0;
   cluster.sync();
 
   // issue the prefetch of processing step s into ring slot s % RING (always commits one group)
@@ -145,17 +151,17 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
     PT(1)
     __syncthreads();
     PT(2)
-    if (tid < 64) {
+    if (tid < PW) {
       const bool valid = prow_ok && (s < plen);
       float gi = 0.f, gj = 0.f, gf = 0.f, go = 0.f, h_new = 0.f;
       const float c_old = c_st, h_old = h_st;
       if (valid) {
         const float mc = d.mask_c ? (float)mk_ring[s % RING][0][pb][pu] : (1.f - d.zc);
         const float mh = d.mask_h ? (float)mk_ring[s % RING][1][pb][pu] : (1.f - d.zh);
-        gi = fast_sigmoid(gsm[pb][0 * 16 + pu]);
-        gj = fast_tanh(gsm[pb][1 * 16 + pu]);
-        gf = fast_sigmoid(gsm[pb][2 * 16 + pu] + d.forget_bias);
-        go = fast_sigmoid(gsm[pb][3 * 16 + pu]);
+        gi = fast_sigmoid(gsm[pb][0 * LUH + pu]);
+        gj = fast_tanh(gsm[pb][1 * LUH + pu]);
+        gf = fast_sigmoid(gsm[pb][2 * LUH + pu] + d.forget_bias);
+        go = fast_sigmoid(gsm[pb][3 * LUH + pu]);
         const float c_new = gf * c_st + gi * gj;
         h_new = go * fast_tanh(c_new);
         c_st = c_st + mc * (c_new - c_st);
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(256, 2) lstm_fwd_kernel(const satk_lstm_fwd_de
     PT(4)
     if (srow_ok) {
       // saver warps: staged activations -> global memory (position-indexed), off the exchange's critical path
-      const int e = tid - 64;
+      const int e = tid - PW;
       const bool valid = s < slen;
       const int p = valid ? (d.reverse ? (slen - 1 - s) : s) : s;
       const int sidx = rank * LUH + su;
@@ -370,12 +376,12 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_kernel(const satk_lstm_bwd_de
 }
 
 template <typename Kern, typename Desc>
-static int launch_cluster(Kern kern, const Desc& d, int H, int B, cudaStream_t st) {
-  const int CS = H / LUH;
+static int launch_cluster(Kern kern, const Desc& d, int H, int B, cudaStream_t st, int uh = LUH) {
+  const int CS = H / uh;
   const int groups = (B + LBG - 1) / LBG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * CS);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(uh * 16);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -394,18 +400,17 @@ static int launch_cluster(Kern kern, const Desc& d, int H, int B, cudaStream_t s
 
 int lstm_max_clusters_h256() {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(16 * 64);
-  cfg.blockDim = dim3(256);
+  cfg.gridDim = dim3(8 * 64);
+  cfg.blockDim = dim3(512);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 16;
+  attr[0].val.clusterDim.x = 8;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaFuncSetAttribute(lstm_fwd_kernel<256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, lstm_fwd_kernel<256>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_fwd_kernel<256, 32>, &cfg) != cudaSuccess) { cudaGetLastError(); return -1; }
   return n;
 }
 
@@ -437,8 +442,9 @@ int satk_lstm_seq_fwd(const satk_lstm_fwd_desc* d, void* stream) {
   SATK_CHECK_ARG(d->ld_out >= d->H, "lstm_seq_fwd: ld_out=%lld < H", d->ld_out);
   SATK_CHECK_ARG((d->gates == nullptr) == (d->c_prev == nullptr) && (d->gates == nullptr) == (d->h_prev == nullptr),
                  "lstm_seq_fwd: gates/c_prev/h_prev must be all set or all NULL");
-  if (d->H == 256) return launch_cluster(lstm_fwd_kernel<256>, *d, 256, d->B, (cudaStream_t)stream);
-  return launch_cluster(lstm_fwd_kernel<128>, *d, 128, d->B, (cudaStream_t)stream);
+  // H = 256: 32 units per CTA (clusters of 8 x 512 threads, one CTA per SM); H = 128: 16 units per CTA (clusters of 8 x 256 threads)
+  if (d->H == 256) return launch_cluster(lstm_fwd_kernel<256, 32>, *d, 256, d->B, (cudaStream_t)stream, 32);
+  return launch_cluster(lstm_fwd_kernel<128, 16>, *d, 128, d->B, (cudaStream_t)stream, 16);
 }
 
 int satk_lstm_seq_bwd(const satk_lstm_bwd_desc* d, void* stream) {
