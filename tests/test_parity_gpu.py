@@ -165,6 +165,19 @@ def test_single_utterance_and_minimum_lengths(satk, root):
     _case(satk, root, "ljspeech_self-attention-tacotron.json", 1, 5, 6, True)
 
 
+def test_maximum_text_length_and_loud_failure_beyond(satk, root):
+    """The attention-RNN backward kernel keeps an utterance's keys / values / key gradients in shared memory: T_text <= 152.  At the
+    limit everything matches the oracle; one position more is refused with an error (never silently rerouted)."""
+    E, O, L, M = _mods()
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 2, 152, 8, True)
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    eng = E.TacotronEngine(hp, "cuda", seed=1)
+    f, l = satk.synthetic_batch(hp, 2, 153, 8, seed=5, device="cuda")
+    eng.forward(f, l, True)                                   # forward fits (210 KB of shared memory at T_text = 148)
+    with pytest.raises(L.SatkError, match="shared memory"):
+        eng.backward()
+
+
 def test_train_step_matches_oracle_optimizer(satk, root):
     """Two full train steps (clip-by-global-norm + Adam + noam LR): parameters track the oracle's."""
     eng, tr, (fd, ld, md), (f, l, masks) = _case(satk, root, "ljspeech_self-attention-tacotron.json", 4, 16, 20, True, grads=False)
