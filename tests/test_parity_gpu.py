@@ -178,6 +178,29 @@ def test_maximum_text_length_and_loud_failure_beyond(satk, root):
         eng.backward()
 
 
+def test_multi_stream_backward_matches_single_stream_full_size(satk, root, monkeypatch):
+    """Weight gradients on the second stream, forked branches on the third: at full size the gradient buffer must agree with the
+    single-stream run to reduction-order noise (a buffer written again while another stream still reads it would show up here)."""
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(5, "glorot")
+    f, l = satk.synthetic_batch(hp, 32, 148, 800, seed=77, device="cuda")
+    masks = satk.make_masks(d, 32, 148, 400, seed=3, device="cuda")
+    grads = []
+    for mode in ("0", "1", "1"):
+        monkeypatch.setenv("SATK_WGRAD_STREAM", mode)
+        eng = E.TacotronEngine(hp, "cuda", params=ps)
+        assert (eng._side is None) == (mode == "0")
+        eng.forward(f, l, True, masks)
+        eng.backward()
+        torch.cuda.synchronize()
+        grads.append(eng.ps.grad.clone())
+    for g in grads[1:]:
+        rel = ((g - grads[0]).double().norm() / grads[0].double().norm()).item()
+        assert torch.isfinite(g).all() and rel < 1e-5, rel
+
+
 def test_train_step_matches_oracle_optimizer(satk, root):
     """Two full train steps (clip-by-global-norm + Adam + noam LR): parameters track the oracle's."""
     eng, tr, (fd, ld, md), (f, l, masks) = _case(satk, root, "ljspeech_self-attention-tacotron.json", 4, 16, 20, True, grads=False)
