@@ -18,6 +18,30 @@ def golden_case(satk, root):
     return out, grads
 
 
+def golden_predict_case(satk, root):
+    """Free-running decode (PREDICT branch) and the transition-agent + cumulative-weights variant, frozen in oracle_predict.npz."""
+    import torch
+    from oracle import model as OR
+    res = {}
+    for tag, ov in (("base", None), ("agent_cum", "use_forward_attention_transition_agent=True,cumulative_weights=True")):
+        hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"), ov)
+        d = satk.dims_from_hparams(hp)
+        ps = satk.ParamStore(d).init(2025, "random")
+        f, l = satk.synthetic_batch(hp, 2, 11, 16, seed=2025)
+        with torch.no_grad():
+            pr = OR.model_predict(ps.as_dict(), d, f, max_iters=7, use_stop_token=False)
+        res[tag + "_mel"] = pr["mel"].numpy()
+        res[tag + "_stop"] = pr["stop"].numpy()
+        res[tag + "_alignment"] = pr["alignment"].numpy()
+        if tag == "agent_cum":
+            masks = satk.make_masks(d, 2, 11, 8, seed=2025)
+            out, grads, _ = OR.OracleTrainer(d, hp, ps.as_dict()).loss_and_grads(f, l, masks, True)
+            res["agent_cum_train_loss"] = np.float64(float(out["loss"].detach()))
+            res["agent_cum_grad_agent_W"] = grads["att1.agent.W"].numpy()
+            res["agent_cum_grad_loc_conv_W"] = grads["att1.loc_conv.W"].numpy()
+    return res
+
+
 if __name__ == "__main__":
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -28,4 +52,5 @@ if __name__ == "__main__":
                         stop=out["stop"].detach().numpy(), alignment=out["alignment"].detach().numpy(),
                         alignment2=out["alignment2"].detach().numpy(), loss=float(out["loss"].detach()),
                         grad_dec_lstm1_W_slice=grads["dec.lstm1.W"].numpy()[100:164, :64], grad_att1_v=grads["att1.v"].numpy())
+    np.savez_compressed(os.path.join(root, "tests", "golden", "oracle_predict.npz"), **golden_predict_case(satk, root))
     print("written")

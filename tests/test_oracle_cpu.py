@@ -147,6 +147,17 @@ def test_golden_fixture(satk, root):
     assert np.allclose(grads["att1.v"].numpy(), z["grad_att1_v"], atol=1e-6)
 
 
+def test_golden_fixture_predict_and_variants(satk, root):
+    """tests/golden/oracle_predict.npz (oracle/make_golden.py): the free-running branch and the transition-agent + cumulative-weights
+    variant of the oracle, frozen against drift (self-generated, like oracle_small.npz)."""
+    z = np.load(os.path.join(root, "tests", "golden", "oracle_predict.npz"))
+    from oracle.make_golden import golden_predict_case
+    res = golden_predict_case(satk, root)
+    assert set(res) == set(z.files)
+    for k, v in res.items():
+        assert np.allclose(np.asarray(v), z[k], atol=2e-5, rtol=1e-5), k
+
+
 def test_free_running_oracle_is_consistent_with_teacher_forcing(satk, root):
     """PREDICT-branch restatement (oracle.decoder_free_running, module.py:762-778) vs the teacher-forced restatement: feeding
     the free-running output back as the target reproduces it (eval mode), for the dual and the single-attention model."""
