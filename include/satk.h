@@ -91,6 +91,18 @@ typedef struct {
    * [w(w+1)/2 + tap] of B's tap dimension (stride sBtap: the W kernels stored back to back), A read at reduction offset
    * w*bank_a_kstep, result written (beta = 0) or added (beta = 1) at output column w*bank_c_nstep.  N is the width of one conv. */
   int bank_widths, bank_a_kstep, bank_c_nstep;
+  /* batched products of the self-attention block (self_attention.py:45-65 and their gradients) on the tensor-core tile:
+   * zcoord = 1 makes the batch1*batch2 entries share ONE 2-D view of each operand — A is [a_rows, a_cols] (row stride lda),
+   * B is [b_rows, b_cols] (row stride ldb), both with the reduction index contiguous (transA = 0, transB = 1) — and entry z
+   * reads A at (row + z*za_row, k + z*za_k) and B at (row + z*zb_row, k + z*zb_k); coordinates outside a view read as zero.
+   * The result of entry z is slab z of a stacked output (sC1 = slab stride in elements, rows >= M / columns >= N clipped)
+   * when sC1 != 0, otherwise columns [z*zc_col, z*zc_col + N) of one [M, c_cols] matrix.  Heads of a time-major
+   * [T, B*D] activation are k-shifts (z*d_head) or, in its transpose, row shifts; stacked [z][T][T] score matrices are
+   * row shifts (z*T) or, transposed as a whole, k-shifts.  No epilogue other than alpha; beta = 0.
+   * causal_skip: 1 = skip tiles entirely above the diagonal (QK^T, dP), 2 = reduce over k < m0 + tile only (P.V, dS.K),
+   * 3 = reduce over k >= m0 only (P^T.dO, dS^T.Q). */
+  int zcoord, za_row, za_k, zb_row, zb_k, zc_col;
+  long long a_rows, a_cols, b_rows, b_cols, c_cols;
 } satk_gemm_desc;
 
 /* engine: 0 = auto, 1 = fp32 SIMT tile, 2 = tcgen05 3xTF32 tile (TMA-fed; falls back with an

@@ -59,11 +59,15 @@ int satk_struct_sizes_decode(int* out4) {
 
 int satk_gemm(const satk_gemm_desc* d, int engine, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->zcoord && engine == 1) {
+    satk::set_error("satk_gemm: the zcoord form exists on the tcgen05 tile only");
+    return SATK_ERR_UNSUPPORTED;
+  }
   if (engine == 1) return satk::gemm_simt_launch(d, st);
   bool supported = false;
   int rc = satk::gemm_tc_launch(d, st, &supported);
-  if (supported) return rc;
-  if (engine == 2) {
+  if (supported || rc != SATK_OK) return rc;
+  if (engine == 2 || d->zcoord) {
     satk::set_error("satk_gemm: shape not supported by the tcgen05 tile (M=%d N=%d K=%d tA=%d tB=%d taps=%d)", d->M, d->N, d->K,
                     d->transA, d->transB, d->taps);
     return SATK_ERR_UNSUPPORTED;

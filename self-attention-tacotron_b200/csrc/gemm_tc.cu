@@ -55,6 +55,10 @@ struct Params {
   long long c_zstride;
   int bank, bank_a_kstep, bank_c_nstep;   // conv bank: z-batch entry = conv width (see satk_gemm_desc.bank_widths)
   int tma_store;            // 1: plain overwrite epilogue (bias + activation only) leaves through TMA bulk stores
+  // batched self-attention products (satk_gemm_desc.zcoord): per-entry coordinate shifts into shared 2-D operand views
+  int zcoord, za_row, za_k, zb_row, zb_k, zc_col;
+  int causal;               // satk_gemm_desc.causal_skip (zcoord form only)
+  int c_rank3;              // output map is [z][M][N] (rank 3): rows / columns outside an entry's slab are clipped by the TMA unit
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -147,7 +151,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int ks = blockIdx.z % p.split_k, zb = blockIdx.z / p.split_k;
+  if (p.causal == 1 && n0 >= m0 + BM) return;       // QK^T / dP under a causal mask: the softmax never reads this tile
   int a_kshift = p.kshift0 + zb * p.kshift_step;
+  int a_rowoff = 0, b_rowoff = 0, b_kshift = 0;
   int taps_eff = p.taps, shift0_eff = p.shift0, tap_base = 0, c_noff = 0, c_rowz = zb * p.M;
   long long c_zoff = zb * p.c_zstride;
   if (p.bank) {
@@ -160,10 +166,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     c_rowz = 0;
     c_zoff = 0;
   }
+  if (p.zcoord) {
+    a_kshift = zb * p.za_k; a_rowoff = zb * p.za_row;
+    b_kshift = zb * p.zb_k; b_rowoff = zb * p.zb_row;
+    c_noff = zb * p.zc_col;
+    c_rowz = 0;
+  }
   // carve: align the dynamic region to 1024 B (swizzle atom alignment)
   const uint32_t smem_base = (cl::smem_u32(smem) + 1023u) & ~1023u;
 
-  const int kblocks_total = (p.K + BK - 1) / BK;
+  // causal structure of the attention products: P[m, k] = 0 for k > m, so P.V reduces over k < m0 + BM only (2) and
+  // P^T.dO over k >= m0 only (3)
+  const int k_eff = p.causal == 2 ? min(p.K, m0 + BM) : p.K;
+  const int kb_first = p.causal == 3 ? m0 / BK : 0;
+  const int kblocks_total = (k_eff + BK - 1) / BK - kb_first;
   // split-K partitions the flattened (tap, k-block) iteration space, so tapped (conv) products with a short K still split
   const int it_total = kblocks_total * taps_eff;
   const int it_per = (it_total + p.split_k - 1) / p.split_k;
@@ -199,13 +215,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       if (use > 0) cl::mbar_wait(&empty_bar[s], (use - 1) & 1);
-      const int tap = (it_beg + it) / kblocks_total, kb = (it_beg + it) % kblocks_total;
+      const int tap = (it_beg + it) / kblocks_total, kb = kb_first + (it_beg + it) % kblocks_total;
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
       TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-      tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + shift0_eff + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
+      tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + a_rowoff + shift0_eff + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
       if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap_base + tap, cl::smem_u32(&full_bar[s]));
-      else tma_load_2d(sb, &mapB, kb * BK, n0, cl::smem_u32(&full_bar[s]));
+      else tma_load_2d(sb, &mapB, kb * BK + b_kshift, n0 + b_rowoff, cl::smem_u32(&full_bar[s]));
       if (it == 0) { TC_MARK(1) }
     }
   } else if (warp == 1 && lane == 0) {
@@ -323,7 +339,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           cl::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (p.tma_store == 2)   // split-K partial sums / accumulation onto C: the TMA unit adds into global memory
+            if (p.c_rank3)          // stacked [z][M][N] output: the slab index is the third coordinate
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&mapC), "r"(nb),
+                           "r"(m0 + q * 32), "r"(zb), "r"(sblk)
+                           : "memory");
+            else if (p.tma_store == 2)   // split-K partial sums / accumulation onto C: the TMA unit adds into global memory
               asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&mapC),
                            "r"(c_noff + nb), "r"(c_rowz + m0 + q * 32), "r"(sblk)
                            : "memory");
@@ -492,6 +512,62 @@ static int gemm_tc_bank_launch(const satk_gemm_desc* d, cudaStream_t st, bool* s
   return SATK_OK;
 }
 
+// Batched self-attention products (see satk_gemm_desc.zcoord): QK^T, P.V and their four gradient products as z-batches over
+// shared 2-D operand views; outputs leave through TMA stores, which clip the ragged last tile of each entry.
+static int gemm_tc_zcoord_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
+  using namespace tc;
+  const int batches = (d->batch1 < 1 ? 1 : d->batch1) * (d->batch2 < 1 ? 1 : d->batch2);
+  const int taps = d->taps < 1 ? 1 : d->taps;
+  SATK_CHECK_ARG(d->transA == 0 && d->transB == 1 && taps == 1 && d->seq_len == 0 && !d->bias && d->act == 0 && !d->residual &&
+                     !d->keep_mask && d->beta == 0.0f && d->split_k <= 1 && d->causal_skip >= 0 && d->causal_skip <= 3,
+                 "satk_gemm: the zcoord form takes K-contiguous operands, no epilogue options, beta = 0");
+  SATK_CHECK_ARG(d->a_rows > 0 && d->a_cols > 0 && d->b_rows > 0 && d->b_cols > 0 && (d->sC1 != 0 || d->c_cols > 0),
+                 "satk_gemm: the zcoord form needs the extents of the operand views");
+  SATK_CHECK_ARG((d->lda % 4) == 0 && (d->ldb % 4) == 0 && (d->ldc % 4) == 0 && (d->sC1 % 4) == 0 && ((uintptr_t)d->A % 16) == 0 &&
+                     ((uintptr_t)d->B % 16) == 0 && ((uintptr_t)d->C % 16) == 0 && (d->za_k % 4) == 0 && (d->zb_k % 4) == 0 &&
+                     (d->zc_col % 4) == 0,
+                 "satk_gemm: zcoord operands must be 16-byte addressable");
+  SATK_CHECK_ARG(d->causal_skip == 0 || (d->causal_skip == 1 ? d->M == d->N : d->M == d->K),
+                 "satk_gemm: causal_skip needs a square (query, key) index pair");
+  CUtensorMap mapA, mapB, mapC;
+  bool ok = make_map(&mapA, d->A, d->a_rows, d->a_cols, d->lda, 0, 0) && make_map(&mapB, d->B, d->b_rows, d->b_cols, d->ldb, 0, 0);
+  if (ok) {
+    if (d->sC1 != 0) {
+      EncodeTiledFn enc = get_encode();
+      cuuint64_t dims[3] = {(cuuint64_t)d->N, (cuuint64_t)d->M, (cuuint64_t)batches};
+      cuuint64_t strides[2] = {(cuuint64_t)d->ldc * 4, (cuuint64_t)d->sC1 * 4};
+      cuuint32_t box[3] = {32, 32, 1};
+      cuuint32_t estr[3] = {1, 1, 1};
+      ok = enc && enc(&mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d->C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    } else {
+      ok = make_map_c(&mapC, d->C, d->M, d->c_cols, d->ldc);
+    }
+  }
+  if (!ok) {
+    set_error("satk_gemm: cuTensorMapEncodeTiled failed for the zcoord form");
+    return SATK_ERR_CUDA;
+  }
+  *supported = true;
+  Params p = {};
+  p.M = d->M; p.N = d->N; p.K = d->K;
+  p.taps = 1; p.shift0 = 0; p.tap_dir = 1;
+  p.C = d->C; p.ldc = d->ldc;
+  p.alpha = d->alpha; p.beta = 0.0f;
+  p.split_k = 1;
+  p.zbatch = batches;
+  p.zcoord = 1; p.za_row = d->za_row; p.za_k = d->za_k; p.zb_row = d->zb_row; p.zb_k = d->zb_k; p.zc_col = d->zc_col;
+  p.causal = d->causal_skip;
+  p.c_rank3 = d->sC1 != 0 ? 1 : 0;
+  p.tma_store = 1;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  SATK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(d->M, BM), ceil_div(d->N, BN), batches);
+  gemm_tc_kernel<<<grid, NTHREADS, smem, st>>>(mapA, mapB, mapC, p, 0);
+  SATK_LAUNCH_CHECK();
+  return SATK_OK;
+}
+
 // Shapes served by the tensor-core tile: plain or tapped (conv) products with K-contiguous operands.
 int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   using namespace tc;
@@ -501,6 +577,7 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   // z-batches are served in one form only: same A and B for every entry, A read with a per-entry shift of the reduction
   // coordinate, one output per entry (conv weight gradients)
   if (d->bank_widths > 0) return gemm_tc_bank_launch(d, st, supported);
+  if (d->zcoord) return gemm_tc_zcoord_launch(d, st, supported);
   const bool zform = batches > 1 && (d->batch2 <= 1) && d->sA1 == 0 && d->sB1 == 0 && taps == 1 && !d->bias && d->act == 0 &&
                      !d->residual && !d->keep_mask;
   if ((batches != 1 && !zform) || d->transA != 0 || d->transB != 1 || d->causal_skip != 0 || d->seq_len != 0 || d->shift_per_batch1 != 0) return SATK_OK;
@@ -522,6 +599,7 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   p.keep_mask = d->keep_mask; p.keep_scale = d->keep_scale;
   p.split_k = d->split_k < 1 ? 1 : d->split_k;
   p.bank = 0; p.bank_a_kstep = 0; p.bank_c_nstep = 0;
+  p.zcoord = 0; p.za_row = p.za_k = p.zb_row = p.zb_k = p.zc_col = 0; p.causal = 0; p.c_rank3 = 0;
   p.zbatch = batches; p.kshift0 = d->kshift0; p.kshift_step = d->kshift_per_batch1; p.c_zstride = d->sC1;
   const int kblocks = (d->K + BK - 1) / BK;
   const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);

@@ -144,14 +144,22 @@ class TacotronEngine:
         Vp = self.lin(x, name + ".value.W", self.buf(key + ".V", (R, D)), bias=p[name + ".value.b"])
         Qp = self.lin(x, name + ".query.W", self.buf(key + ".Q", (R, D)), bias=p[name + ".query.b"])
         S = self.buf(key + ".P", (B, heads, T, T))
-        O.gemm(Qp, Kp, S, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, alpha=1.0 / math.sqrt(dh),
-               batch1=B, batch2=heads, sA=(D, dh), sB=(D, dh), sC=(heads * T * T, T * T), causal_skip=1 if causal else 0)
+        # QK^T / P.V: z-batches of the tcgen05 tile when a head is whole k-blocks (decoder: d_head = 128), else the SIMT tile
+        tc = O.attn_tc_ok(T, dh)
+        if tc:
+            O.attn_scores_tc(Qp, Kp, S, T, B * heads, dh, alpha=1.0 / math.sqrt(dh), causal=causal)
+        else:
+            O.gemm(Qp, Kp, S, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, alpha=1.0 / math.sqrt(dh),
+                   batch1=B, batch2=heads, sA=(D, dh), sB=(D, dh), sC=(heads * T * T, T * T), causal_skip=1 if causal else 0)
         Pd = self.buf(key + ".Pd", (B, heads, T, T)) if mask is not None else None
         O.softmax_fwd(S, B * heads, T, causal, mask, 1.0 / keep, Pd)
         Pu = Pd if Pd is not None else S
         Oc = self.buf(key + ".O", (R, D))
-        O.gemm(Pu, Vp, Oc, T, dh, T, lda=T, ldb=B * D, ldc=B * D, batch1=B, batch2=heads,
-               sA=(heads * T * T, T * T), sB=(D, dh), sC=(D, dh), causal_skip=2 if causal else 0)
+        if tc:
+            O.attn_apply_tc(Pu, O.transposed_rows(Vp, T, B * D), Oc, T, B * heads, dh, causal=causal)
+        else:
+            O.gemm(Pu, Vp, Oc, T, dh, T, lda=T, ldb=B * D, ldc=B * D, batch1=B, batch2=heads,
+                   sA=(heads * T * T, T * T), sB=(D, dh), sC=(D, dh), causal_skip=2 if causal else 0)
         ao = self.lin(Oc, name + ".output.W", self.buf(key + ".ao", (R, D)), bias=p[name + ".output.b"])
         tr = self.lin(ao, name + ".transform.W", self.buf(key + ".tr", (R, D)), bias=p[name + ".transform.b"], act="tanh")
         y = self.buf(key + ".y", (R, D))
@@ -181,17 +189,29 @@ class TacotronEngine:
         bs = dict(batch1=B, batch2=heads)
         sP, sX = (heads * T * T, T * T), (D, dh)
         dPd = self.buf(key + ".dPd", (B, heads, T, T))
-        O.gemm(dO, sv["V"], dPd, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, sA=sX, sB=sX, sC=sP,
-               causal_skip=1 if causal else 0, **bs)
         dV = self.buf(key + ".dV", (R, D))
-        O.gemm(sv["Pd"], dO, dV, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, sA=sP, sB=sX, sC=sX, **bs)
         dS = self.buf(key + ".dS", (B, heads, T, T))
-        O.softmax_bwd(sv["P"], dPd, B * heads, T, causal, dS, sv["mask"], 1.0 / sv["keep"])
         dQ = self.buf(key + ".dQ", (R, D))
-        O.gemm(dS, sv["K"], dQ, T, dh, T, lda=T, ldb=B * D, ldc=B * D, alpha=scale, sA=sP, sB=sX, sC=sX,
-               causal_skip=2 if causal else 0, **bs)
         dK = self.buf(key + ".dK", (R, D))
-        O.gemm(dS, sv["Q"], dK, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, alpha=scale, sA=sP, sB=sX, sC=sX, **bs)
+        if O.attn_tc_ok(T, dh):
+            # the four gradient products on the tcgen05 tile: operands that are reduced over their row index are transposed once
+            # (the stacked [z][T][T] matrices as ONE [z*T, T] matrix, entry z = columns z*T.. of the transpose)
+            nz, W = B * heads, B * D
+            O.attn_scores_tc(dO, sv["V"], dPd, T, nz, dh, causal=causal)
+            dOT = O.transposed_rows(dO, T, W)
+            O.attn_apply_t_tc(O.transposed_rows(sv["Pd"], nz * T, T), dOT, dV, T, nz, dh, causal=causal)
+            O.softmax_bwd(sv["P"], dPd, nz, T, causal, dS, sv["mask"], 1.0 / sv["keep"])
+            O.attn_apply_tc(dS, O.transposed_rows(sv["K"], T, W), dQ, T, nz, dh, alpha=scale, causal=causal)
+            O.attn_apply_t_tc(O.transposed_rows(dS, nz * T, T), O.transposed_rows(sv["Q"], T, W), dK, T, nz, dh, alpha=scale,
+                              causal=causal)
+        else:
+            O.gemm(dO, sv["V"], dPd, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, sA=sX, sB=sX, sC=sP,
+                   causal_skip=1 if causal else 0, **bs)
+            O.gemm(sv["Pd"], dO, dV, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, sA=sP, sB=sX, sC=sX, **bs)
+            O.softmax_bwd(sv["P"], dPd, B * heads, T, causal, dS, sv["mask"], 1.0 / sv["keep"])
+            O.gemm(dS, sv["K"], dQ, T, dh, T, lda=T, ldb=B * D, ldc=B * D, alpha=scale, sA=sP, sB=sX, sC=sX,
+                   causal_skip=2 if causal else 0, **bs)
+            O.gemm(dS, sv["Q"], dK, T, dh, T, lda=T, ldb=B * D, ldc=B * D, transA=True, alpha=scale, sA=sP, sB=sX, sC=sX, **bs)
         dx = self.buf(key + ".dx", (R, D))
         first = True
         with self._wg():

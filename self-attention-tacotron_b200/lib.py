@@ -37,6 +37,8 @@ class GemmDesc(C.Structure):
         ("taps", i32), ("shift0", i32), ("tap_dir", i32), ("seq_len", i32), ("sBtap", i64),
         ("shift_per_batch1", i32), ("split_k", i32), ("causal_skip", i32), ("kshift0", i32), ("kshift_per_batch1", i32),
         ("bank_widths", i32), ("bank_a_kstep", i32), ("bank_c_nstep", i32),
+        ("zcoord", i32), ("za_row", i32), ("za_k", i32), ("zb_row", i32), ("zb_k", i32), ("zc_col", i32),
+        ("a_rows", i64), ("a_cols", i64), ("b_rows", i64), ("b_cols", i64), ("c_cols", i64),
     ]
 
 

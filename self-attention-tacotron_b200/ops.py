@@ -41,7 +41,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
          keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0),
          taps=1, shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0,
          a_off=0, b_off=0, c_off=0, engine=None, kshift0=0, kshift_per_batch1=0,
-         bank_widths=0, bank_a_kstep=0, bank_c_nstep=0) -> None:
+         bank_widths=0, bank_a_kstep=0, bank_c_nstep=0, zcoord=None) -> None:
     """C = epi(alpha * sum_taps op(A) op(B)) (+beta*C).  ``*_off`` are element offsets into the tensors."""
     _req(A); _req(B); _req(C_)
     d = GemmDesc()
@@ -63,6 +63,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
     d.shift_per_batch1, d.split_k, d.causal_skip = shift_per_batch1, split_k, causal_skip
     d.kshift0, d.kshift_per_batch1 = kshift0, kshift_per_batch1
     d.bank_widths, d.bank_a_kstep, d.bank_c_nstep = bank_widths, bank_a_kstep, bank_c_nstep
+    if zcoord is not None:   # batched self-attention products on the tcgen05 tile (satk_gemm_desc.zcoord)
+        d.zcoord = 1
+        d.za_row, d.za_k, d.zb_row, d.zb_k, d.zc_col = (zcoord.get(k, 0) for k in ("za_row", "za_k", "zb_row", "zb_k", "zc_col"))
+        d.a_rows, d.a_cols, d.b_rows, d.b_cols, d.c_cols = (zcoord.get(k, 0) for k in ("a_rows", "a_cols", "b_rows", "b_cols", "c_cols"))
     check(load().satk_gemm(C.byref(d), GEMM_ENGINE if engine is None else engine, C.c_void_p(stream_ptr())), "satk_gemm")
     _count()
 
@@ -87,6 +91,40 @@ def linear_dx(dy: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, rows: int, be
     N = N or Nw
     gemm(dy, W, dx, rows, K, N, lda=ldy or N, ldb=ldw or Nw, ldc=ldx or K, transB=True, beta=beta, a_off=y_off, c_off=x_off,
          b_off=w_off)
+
+
+def attn_tc_ok(T: int, dh: int) -> bool:
+    """Shapes of the batched self-attention products that the tcgen05 tile takes (``attn_scores_tc`` / ``attn_apply_tc`` /
+    ``attn_apply_t_tc``): a head is a k-shift of the time-major activation, so d_head must be whole 32-float k-blocks."""
+    return T >= 128 and T % 4 == 0 and dh % 32 == 0 and 32 <= dh <= 128
+
+
+def attn_scores_tc(X: torch.Tensor, Y: torch.Tensor, S: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
+    """S[z] = alpha * X_z @ Y_z^T for the nz = B*heads (utterance, head) pairs of time-major X, Y [T, nz*dh] (head z = columns
+    z*dh..): QK^T of ScaledDotProductAttentionMechanism (self_attention.py:52-53) and dP = dO V^T.  S is [nz, T, T]."""
+    W = nz * dh
+    gemm(X, Y, S, T, T, dh, lda=W, ldb=W, ldc=T, transB=True, alpha=alpha, batch1=nz, sC=(T * T, 0),
+         causal_skip=1 if causal else 0, engine=2,
+         zcoord=dict(za_k=dh, zb_k=dh, a_rows=T, a_cols=W, b_rows=T, b_cols=W))
+
+
+def attn_apply_tc(P: torch.Tensor, YT: torch.Tensor, Out: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
+    """Out[:, z*dh..] = alpha * P[z] @ Y_z with P [nz, T, T] and YT [nz*dh, T] the transpose of time-major Y (``transposed_rows``):
+    P.V (self_attention.py:63-65) and dQ = dS K."""
+    W = nz * dh
+    gemm(P, YT, Out, T, dh, T, lda=T, ldb=YT.shape[1], ldc=W, transB=True, alpha=alpha, batch1=nz,
+         causal_skip=2 if causal else 0, engine=2,
+         zcoord=dict(za_row=T, zb_row=dh, zc_col=dh, a_rows=nz * T, a_cols=T, b_rows=W, b_cols=T, c_cols=W))
+
+
+def attn_apply_t_tc(PT: torch.Tensor, YT: torch.Tensor, Out: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
+    """Out[:, z*dh..] = alpha * P[z]^T @ Y_z with PT [T, nz*T] the transpose of the stacked [nz*T, T] matrices as ONE matrix
+    (entry z = columns z*T..) and YT as above: dV = P^T dO and dK = dS^T Q.  The last k-block of an entry runs into the next
+    entry's columns of PT; YT reads as zero there."""
+    W = nz * dh
+    gemm(PT, YT, Out, T, dh, T, lda=PT.shape[1], ldb=YT.shape[1], ldc=W, transB=True, alpha=alpha, batch1=nz,
+         causal_skip=3 if causal else 0, engine=2,
+         zcoord=dict(za_k=T, zb_row=dh, zc_col=dh, a_rows=T, a_cols=nz * T, b_rows=W, b_cols=T, c_cols=W))
 
 
 def transposed_rows(x: torch.Tensor, rows: int, cols: int, ldx=None, x_off=0, front=0) -> torch.Tensor:

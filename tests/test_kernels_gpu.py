@@ -301,3 +301,49 @@ def test_bernoulli_mask_rate():
     m2 = torch.empty_like(m)
     O.bernoulli_mask(m2, 0.9, 12346)
     assert (m != m2).float().mean().item() > 0.1
+
+
+@pytest.mark.parametrize("T,nz,dh,causal", [(400, 6, 128, True), (200, 4, 64, False), (128, 3, 32, True), (148, 2, 128, False)])
+def test_self_attention_products_tensor_core_zbatches(T, nz, dh, causal):
+    """QK^T, P.V and the four gradient products of the self-attention block (self_attention.py:45-65) as z-batches of the
+    tcgen05 tile over shared 2-D operand views (satk_gemm_desc.zcoord): heads as k-shifts of the time-major activations, stacked
+    score matrices as row shifts / k-shifts of their transpose, ragged last tiles clipped by the TMA stores, causal tile /
+    k-range skipping.  Against fp64; entries the causal softmax never reads are not compared."""
+    O = _O()
+    g = torch.Generator().manual_seed(T + dh)
+    W = nz * dh
+    X, Y = torch.randn(T, W, generator=g), torch.randn(T, W, generator=g)
+    P = torch.randn(nz, T, T, generator=g)
+    if causal:
+        P = torch.tril(P)      # what the causal softmax leaves: zeros above the diagonal
+    Xz = X.double().view(T, nz, dh).transpose(0, 1)     # [nz, T, dh]
+    Yz = Y.double().view(T, nz, dh).transpose(0, 1)
+    tol = 3e-6 * max(T, dh) ** 0.5
+
+    S = torch.full((nz, T, T), float("nan"), device="cuda")
+    O.attn_scores_tc(X.cuda(), Y.cuda(), S, T, nz, dh, alpha=0.25, causal=causal)
+    ref = 0.25 * Xz @ Yz.transpose(1, 2)
+    S = S.cpu()
+    if causal:
+        keep = torch.tril(torch.ones(T, T, dtype=torch.bool))
+        S, ref = torch.where(keep, S, torch.zeros(())), torch.where(keep, ref, torch.zeros((), dtype=torch.float64))
+    _close(S, ref.float(), tol, "scores")
+
+    Out = torch.full((T, W), float("nan"), device="cuda")
+    O.attn_apply_tc(P.cuda(), O.transposed_rows(Y.cuda(), T, W), Out, T, nz, dh, alpha=0.5, causal=causal)
+    ref = 0.5 * (P.double() @ Yz).transpose(0, 1).reshape(T, W)
+    _close(Out, ref.float(), tol, "apply")
+
+    Out = torch.full((T, W), float("nan"), device="cuda")
+    O.attn_apply_t_tc(O.transposed_rows(P.cuda(), nz * T, T), O.transposed_rows(Y.cuda(), T, W), Out, T, nz, dh, alpha=2.0, causal=causal)
+    ref = 2.0 * (P.double().transpose(1, 2) @ Yz).transpose(0, 1).reshape(T, W)
+    _close(Out, ref.float(), tol, "apply_t")
+
+
+def test_self_attention_products_zcoord_refused_on_simt_tile():
+    O = _O()
+    x = torch.zeros(128, 128, device="cuda")
+    s = torch.zeros(1, 128, 128, device="cuda")
+    with pytest.raises(RuntimeError):
+        O.gemm(x, x, s, 128, 128, 128, lda=128, ldb=128, ldc=128, transB=True, batch1=1, sC=(128 * 128, 0), engine=1,
+               zcoord=dict(za_k=128, zb_k=128, a_rows=128, a_cols=128, b_rows=128, b_cols=128))

@@ -28,7 +28,24 @@ def _extent(t, off, need, what):
 def gemm(A, B, C_, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=1.0, beta=0.0, bias=None, act=None,
          residual=None, ldres=0, keep_mask=None, keep_scale=1.0, batch1=1, batch2=1, sA=(0, 0), sB=(0, 0), sC=(0, 0), taps=1,
          shift0=0, tap_dir=1, seq_len=0, sBtap=0, shift_per_batch1=0, split_k=1, causal_skip=0, a_off=0, b_off=0, c_off=0, engine=None,
-         kshift0=0, kshift_per_batch1=0, bank_widths=0, bank_a_kstep=0, bank_c_nstep=0):
+         kshift0=0, kshift_per_batch1=0, bank_widths=0, bank_a_kstep=0, bank_c_nstep=0, zcoord=None):
+    if zcoord is not None:
+        # batched self-attention products: shared 2-D operand views, per-entry coordinate shifts that must stay inside them
+        z = dict(za_row=0, za_k=0, zb_row=0, zb_k=0, zc_col=0, c_cols=0)
+        z.update(zcoord)
+        nz = batch1 * batch2
+        assert not transA and transB and taps == 1 and beta == 0.0 and bias is None and residual is None and keep_mask is None
+        _extent(A, a_off, (z["a_rows"] - 1) * lda + z["a_cols"], "zcoord A")
+        _extent(B, b_off, (z["b_rows"] - 1) * ldb + z["b_cols"], "zcoord B")
+        assert (nz - 1) * z["za_row"] + M <= z["a_rows"] and (nz - 1) * z["za_k"] + K <= z["a_cols"], "zcoord A shifts"
+        assert (nz - 1) * z["zb_row"] + N <= z["b_rows"] and (nz - 1) * z["zb_k"] + K <= z["b_cols"], "zcoord B shifts"
+        assert lda >= z["a_cols"] and ldb >= z["b_cols"] and lda % 4 == 0 and ldb % 4 == 0 and ldc % 4 == 0
+        if sC[0]:
+            _extent(C_, c_off, (nz - 1) * sC[0] + (M - 1) * ldc + N, "zcoord C")
+        else:
+            assert (nz - 1) * z["zc_col"] + N <= z["c_cols"] <= ldc, "zcoord C columns"
+            _extent(C_, c_off, (M - 1) * ldc + z["c_cols"], "zcoord C")
+        return
     if bank_widths:
         taps = bank_widths * (bank_widths + 1) // 2      # all kernels of the bank, back to back
     zA = (batch1 - 1) * sA[0] + (batch2 - 1) * sA[1]
