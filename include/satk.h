@@ -239,6 +239,10 @@ typedef struct {
   const float* dout;           /* [T,B,ld_dout] gradient wrt cell output */
   long long ld_dout;
   float* dgates;               /* [T,B,4H] gradient wrt pre-activation gates (position-indexed, 0 past length) */
+  /* optional [B] int32 (forward direction, lengths == NULL only): dout is exactly zero for the steps t >= step_end[b] of each
+   * utterance (masked losses behind a causal decoder, see satk_attn_rnn_bwd_desc.step_end), so a cluster starts its walk at
+   * the largest step_end of its rows and writes zeros to the dgates rows it skips.  NULL: all T steps. */
+  const int* step_end;
 } satk_lstm_bwd_desc;
 int satk_lstm_seq_bwd(const satk_lstm_bwd_desc* d, void* stream);
 
@@ -313,6 +317,13 @@ typedef struct {
   float* dloc_layer_w;         /* [att_filters, A1] (+=) */
   float* dagent_w;             /* [M1+A1] (+=, atomics); required when f.agent_w is set */
   float* dagent_b;             /* [1] (+=) */
+  /* optional [B] int32: number of decoder steps of each utterance that can carry a gradient (1 + the last step whose loss masks
+   * are non-zero, models.py:467-482).  The caller guarantees that dx2 is exactly zero for the steps t >= step_end[b] (the losses
+   * are masked there and every layer between the losses and x2 is causal in t), so their gradients are exactly zero: a cluster
+   * starts its walk at the largest step_end of its utterances instead of Td-1 and writes zeros to the dgates / dq rows it
+   * skips (dx2 is left as it is: zero).  Ignored with cumulative != 0 (the location state is walked back from the final state).
+   * NULL: all Td steps. */
+  const int* step_end;
 } satk_attn_rnn_bwd_desc;
 int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
 

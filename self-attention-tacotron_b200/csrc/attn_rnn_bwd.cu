@@ -102,6 +102,14 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tt = d.Tt, B = d.B, Td = d.Td;
   const int QT = d.A1 + d.A2;
+  // steps [Te, Td) of this cluster's utterances carry exactly zero gradient (satk_attn_rnn_bwd_desc.step_end): the walk starts at
+  // Te - 1.  With 8 clusters on 7 cluster slots a short cluster frees its slot early and the waiting cluster is short as well.
+  int Te = Td;
+  if (dd.step_end && !d.cumulative) {
+    Te = 1;
+    for (int r = 0; r < BG; ++r)
+      if (b0 + r < B) Te = max(Te, min(Td, __ldg(dd.step_end + b0 + r)));
+  }
 
   extern __shared__ __align__(16) float smem_raw[];
   BwdSmem<HAS2> S;
@@ -270,12 +278,24 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     cp_async_commit();
   };
 #pragma unroll 1
-  for (int i = 0; i <= PFDB; ++i) prefetch(Td - 1 - i);
+  for (int i = 0; i <= PFDB; ++i) prefetch(Te - 1 - i);
+  // rows of the skipped steps: zero gradients (round-robin over the CTAs of the cluster; plain stores, long before the first exchange)
+  for (int r = rank; r < (Td - Te) * BG; r += CS) {
+    const int tz = Te + r / BG, bz = b0 + r % BG;
+    if (bz < B) {
+      float* gz = dd.dgates + ((long long)tz * B + bz) * (4 * H);
+      for (int i = tid; i < 4 * H; i += NT) gz[i] = 0.f;
+      if (dd.dq) {
+        float* qz = dd.dq + ((long long)tz * B + bz) * QT;
+        for (int i = tid; i < QT; i += NT) qz[i] = 0.f;
+      }
+    }
+  }
 
   PT_DECL
 #pragma unroll 1
-  for (int t = Td - 1; t >= 0; --t) {
-    const int u = Td - 1 - t, cur = u & 1, nxt = cur ^ 1;
+  for (int t = Te - 1; t >= 0; --t) {
+    const int u = Te - 1 - t, cur = u & 1, nxt = cur ^ 1;
     const uint32_t par = (uint32_t)(u >> 1) & 1u;
     PT(15)
     prefetch(t - 1 - PFDB);
@@ -293,7 +313,7 @@ __global__ void __launch_bounds__(NT, 1) attn_rnn_bwd_kernel(const satk_attn_rnn
     float ctx_own = 0.f;
     if (AGENT) {
       if (tid == 0) {
-        const float u_t = (t + 1 < Td && arow_ok) ? __ldg(d.u_save + (long long)(t + 1) * B + arow) : 0.5f;
+        const float u_t = (t + 1 < Te && arow_ok) ? __ldg(d.u_save + (long long)(t + 1) * B + arow) : 0.5f;
         S.red[41] = S.red[40] * u_t * (1.f - u_t);         // d(pre-sigmoid) of the agent output of step t
       }
       if (tid < 64 && arow_ok) ctx_own = __ldg(d.x2 + ((long long)t * B + arow) * X2W + H + cq * 64 + tid);

@@ -268,9 +268,25 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_kernel(const satk_lstm_bwd_de
   for (int i = tid; i < RING * 2 * LBG * LUH; i += 256) (&mk_ring[0][0][0][0])[i] = 0;
   cluster.sync();
 
-  // prefetch of everything the pointwise step u (processing step s = T-1-u) reads from global memory
+  // steps [Te, T) of this cluster's rows carry exactly zero gradient (satk_lstm_bwd_desc.step_end): the walk starts at Te - 1 and
+  // their d(gates) rows are zero-filled here.  With 8 clusters on 7 cluster slots the clusters that share SMs finish earlier.
+  int Te = d.T;
+  if (d.step_end && !d.reverse && !d.lengths) {
+    Te = 1;
+    for (int r = 0; r < LBG; ++r)
+      if (b0 + r < d.B) Te = max(Te, min(d.T, __ldg(d.step_end + b0 + r)));
+    for (int r = rank; r < (d.T - Te) * LBG; r += CS) {
+      const int tz = Te + r / LBG, bz = b0 + r % LBG;
+      if (bz < d.B) {
+        float* gz = d.dgates + ((long long)tz * d.B + bz) * K4;
+        for (int i = tid; i < K4; i += 256) gz[i] = 0.f;
+      }
+    }
+  }
+
+  // prefetch of everything the pointwise step u (processing step s = Te-1-u) reads from global memory
   auto prefetch = [&](int u) {
-    const int s = d.T - 1 - u;
+    const int s = Te - 1 - u;
     if (s >= 0) {
       if (prow_ok && s < plen) {
         const int p = d.reverse ? (plen - 1 - s) : s;
@@ -296,8 +312,8 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_kernel(const satk_lstm_bwd_de
   for (int u = 0; u < PFD; ++u) prefetch(u);
 
 #pragma unroll 1
-  for (int s = d.T - 1; s >= 0; --s) {
-    const int u = d.T - 1 - s, cur = u & 1;
+  for (int s = Te - 1; s >= 0; --s) {
+    const int u = Te - 1 - s, cur = u & 1;
     prefetch(u + PFD);
     cp_async_wait<PFD>();
     // the 4-byte mask words are fetched by every 4th lane: make them visible to the other pointwise lanes

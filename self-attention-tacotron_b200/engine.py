@@ -56,7 +56,8 @@ class TacotronEngine:
         self._side = torch.cuda.Stream(device=self.device) if os.environ.get("SATK_WGRAD_STREAM", "1") != "0" else None
         # independent branches of the graph (decoder pre-net beside the encoder, the two BiLSTM directions) fork onto a third stream
         self._aux = torch.cuda.Stream(device=self.device) if self._side is not None else None
-        self.sort_batches = os.environ.get("SATK_SORT_BATCHES", "1") != "0"   # TRAIN steps sort the batch by source length
+        self.sort_batches = os.environ.get("SATK_SORT_BATCHES", "1") != "0"   # TRAIN steps sort the batch by target / source length
+        self.skip_masked_steps = os.environ.get("SATK_STEP_END", "1") != "0"  # attention-RNN backward starts at the last step with a loss
         self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
 
     def _timed(self, name, fn, *a, **k):
@@ -582,7 +583,8 @@ class TacotronEngine:
             li, kin = s["li"], s["kin"]
             W = p[f"dec.lstm{li}.W"]
             dg = self.buf(f"dec.dgates{li}", (Rd, 4 * HD))
-            O.lstm_seq_bwd(W[kin:], s["gates"], s["c_prev"], dout, dg, Td, B, HD, mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh)
+            O.lstm_seq_bwd(W[kin:], s["gates"], s["c_prev"], dout, dg, Td, B, HD, mask_c=s["mc"], mask_h=s["mh"], zc=d.zc, zh=d.zh,
+                           step_end=self.saved.get("step_end"))
             gW = g[f"dec.lstm{li}.W"]
             with self._wg():
                 dgT = O.transposed_rows(dg, Rd, 4 * HD) if Rd >= O.DW_TC_MIN_ROWS else None
@@ -607,7 +609,8 @@ class TacotronEngine:
                        dloc_conv_w=g["att1.loc_conv.W"] if loc else None, dloc_conv_b=g["att1.loc_conv.b"] if loc else None,
                        dloc_layer_w=g["att1.loc_layer.W"] if loc else None,
                        dagent_w=g["att1.agent.W"] if (d.attention == "forward" and d.transition_agent) else None,
-                       dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None)
+                       dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
+                       step_end=self.saved.get("step_end"))
         # LSTM-1 weight gradients (dense over time)
         gW1 = g["dec.lstm1.W"]
         N4 = 4 * H1
@@ -695,11 +698,20 @@ class TacotronEngine:
         Tm = labels.mel.shape[1]
         Td = Tm // d.r
         perm = None
+        # 1 + the last decoder step of each utterance whose loss masks are non-zero (models.py:467-482): later steps carry exactly
+        # zero gradient (masked losses, causal decoder), so the attention-RNN backward kernel starts its walk there
+        step_end = None
+        if training:
+            lm = (labels.binary_loss_mask != 0) | (labels.spec_loss_mask.reshape(B, Td, d.r) != 0).any(-1)
+            step_end = (lm * torch.arange(1, Td + 1, device=lm.device, dtype=torch.int32)).amax(1).clamp_(min=1).to(torch.int32)
         if training and getattr(self, "sort_batches", True) and B > 1:
-            # Utterances are independent, so the batch order is free: sort by source length (longest first).  The attention-RNN kernels
-            # skip positions past an utterance's length, a cluster of 4 short utterances finishes its 400 steps earlier, and with 8
-            # clusters on 7 cluster slots the last (shortest) cluster then starts earlier and runs faster.
-            perm = torch.argsort(source_length, descending=True, stable=True)
+            # Utterances are independent, so the batch order is free: sort by target length, then source length (longest first).  The
+            # attention-RNN kernels skip positions past an utterance's source length and (backward) steps past its last loss step, so
+            # a cluster of 4 short utterances finishes early, and with 8 clusters on 7 cluster slots the last (shortest) cluster
+            # then starts earlier and is short itself.
+            key = source_length if step_end is None else step_end.to(torch.int64) * (Tt + 1) + source_length
+            perm = torch.argsort(key, descending=True, stable=True)
+            step_end = step_end.index_select(0, perm) if step_end is not None else None
             sel = lambda x: x.index_select(0, perm) if torch.is_tensor(x) else x      # noqa: E731
             features = features._replace(source=sel(source), source_length=sel(source_length), speaker_id=sel(features.speaker_id))
             labels = labels._replace(mel=sel(labels.mel), target_length=sel(labels.target_length), done=sel(labels.done),
@@ -728,7 +740,8 @@ class TacotronEngine:
         dstop = self.buf("dec.dstop_tm", stop_tm.shape)
         O.losses(mel_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
                  out3, dmel, dstop, self.buf("loss_scratch", (4,)))
-        self.saved = dict(B=B, Tt=Tt, Td=Td, Tm=Tm, source_length=source_length, dmel=dmel, dstop=dstop, features=features)
+        self.saved = dict(B=B, Tt=Tt, Td=Td, Tm=Tm, source_length=source_length, dmel=dmel, dstop=dstop, features=features,
+                          step_end=step_end if getattr(self, "skip_masked_steps", True) else None)
         # with a sorted batch every per-utterance output is in SORTED order: row i belongs to utterance perm[i] of the caller's batch
         return dict(mel_tm=mel_tm, stop_tm=stop_tm, align1_tm=al1, align2_tm=al2, enc_self_P=enc_al, dec_self_P=dec_sa,
                     memory1_tm=mem1, memory2_tm=mem2, losses=out3, perm=perm)

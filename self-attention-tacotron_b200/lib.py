@@ -56,7 +56,7 @@ class LstmBwdDesc(C.Structure):
         ("T", i32), ("B", i32), ("H", i32), ("reverse", i32),
         ("Wh", fp), ("lengths", fp), ("mask_c", fp), ("mask_h", fp),
         ("zc", f32), ("zh", f32),
-        ("gates", fp), ("c_prev", fp), ("dout", fp), ("ld_dout", i64), ("dgates", fp),
+        ("gates", fp), ("c_prev", fp), ("dout", fp), ("ld_dout", i64), ("dgates", fp), ("step_end", fp),
     ]
 
 
@@ -80,7 +80,7 @@ class AttnRnnBwdDesc(C.Structure):
         ("f", AttnRnnFwdDesc),
         ("dx2", fp), ("dgates", fp), ("dq", fp), ("dkeys1", fp), ("dkeys2", fp),
         ("dv1", fp), ("dv2", fp), ("dloc_conv_w", fp), ("dloc_conv_b", fp), ("dloc_layer_w", fp),
-        ("dagent_w", fp), ("dagent_b", fp),
+        ("dagent_w", fp), ("dagent_b", fp), ("step_end", fp),
     ]
 
 

@@ -6,6 +6,7 @@ raw device pointers + the current CUDA stream; all arithmetic happens in libsatk
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -96,7 +97,7 @@ def linear_dx(dy: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, rows: int, be
 def attn_tc_ok(T: int, dh: int) -> bool:
     """Shapes of the batched self-attention products that the tcgen05 tile takes (``attn_scores_tc`` / ``attn_apply_tc`` /
     ``attn_apply_t_tc``): a head is a k-shift of the time-major activation, so d_head must be whole 32-float k-blocks."""
-    return T >= 128 and T % 4 == 0 and dh % 32 == 0 and 32 <= dh <= 128
+    return T >= 128 and T % 4 == 0 and dh % 32 == 0 and 32 <= dh <= 128 and os.environ.get("SATK_ATTN_TC", "1") != "0"
 
 
 def attn_scores_tc(X: torch.Tensor, Y: torch.Tensor, S: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
@@ -376,7 +377,7 @@ def lstm_seq_fwd(xg, Wh, out, T, B, H, *, reverse=False, lengths=None, mask_c=No
 
 
 def lstm_seq_bwd(Wh, gates, c_prev, dout, dgates, T, B, H, *, reverse=False, lengths=None, mask_c=None, mask_h=None,
-                 zc=0.0, zh=0.0, wh_off=0, ld_dout=None, dout_off=0):
+                 zc=0.0, zh=0.0, wh_off=0, ld_dout=None, dout_off=0, step_end=None):
     d = LstmBwdDesc()
     d.T, d.B, d.H, d.reverse = T, B, H, int(reverse)
     d.Wh = Wh.data_ptr() + 4 * wh_off
@@ -384,6 +385,7 @@ def lstm_seq_bwd(Wh, gates, c_prev, dout, dgates, T, B, H, *, reverse=False, len
     d.zc, d.zh = zc, zh
     d.gates, d.c_prev, d.dout, d.dgates = gates.data_ptr(), c_prev.data_ptr(), dout.data_ptr() + 4 * dout_off, dgates.data_ptr()
     d.ld_dout = ld_dout or H
+    d.step_end = ptr(step_end) if (step_end is not None and lengths is None and not reverse) else None
     check(load().satk_lstm_seq_bwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_lstm_seq_bwd")
     _count()
 

@@ -201,6 +201,44 @@ def test_multi_stream_backward_matches_single_stream_full_size(satk, root, monke
         assert torch.isfinite(g).all() and rel < 1e-5, rel
 
 
+def test_backward_skips_steps_without_loss_exactly(satk, root, monkeypatch):
+    """satk_attn_rnn_bwd_desc.step_end: decoder steps past an utterance's last loss step carry exactly zero gradient (masked losses,
+    causal decoder), so the attention-RNN backward kernel starts its walk there.  At full size, with ragged target lengths, the
+    gradient buffer must agree with the run over all Td steps (and with the unsorted batch order) to reduction-order noise, and
+    the kernel must have left zeros in the rows it skipped."""
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(5, "glorot")
+    f, l = satk.synthetic_batch(hp, 32, 148, 800, seed=77, device="cuda")
+    assert int(l.target_length.min()) < 800 * 0.8
+    masks = satk.make_masks(d, 32, 148, 400, seed=3, device="cuda")
+    grads = []
+    for skip, sort in (("0", "1"), ("1", "1"), ("1", "0")):
+        monkeypatch.setenv("SATK_STEP_END", skip)
+        monkeypatch.setenv("SATK_SORT_BATCHES", sort)
+        eng = E.TacotronEngine(hp, "cuda", params=ps)
+        assert eng.skip_masked_steps == (skip == "1")
+        eng.forward(f, l, True, masks)
+        # the kernel, not a stale buffer, must provide the zeros of the skipped rows
+        eng.buf("dec.dgates1", (400 * 32, 4 * d.att_rnn)).fill_(float("nan"))
+        eng.buf("dec.dq", (400 * 32, d.att1 + d.att2)).fill_(float("nan"))
+        eng.backward()
+        torch.cuda.synchronize()
+        assert torch.isfinite(eng.ps.grad).all()
+        if skip == "1":
+            se = eng.saved["step_end"]
+            assert int(se.min()) < 400 and int(se.max()) == 400
+            dg = eng._bufs["dec.dgates1"].view(400, 32, -1)
+            b = int(se.argmin())
+            assert float(dg[int(se[b]):, b].abs().max()) == 0.0 and float(dg[int(se[b]) - 1, b].abs().max()) > 0.0
+        grads.append(eng.ps.grad.clone())
+    # same batch order: only exactly-zero contributions were dropped; other batch order: fp32 reduction-order noise of the whole model
+    for g, tol in ((grads[1], 1e-5), (grads[2], 2e-4)):
+        rel = ((g - grads[0]).double().norm() / grads[0].double().norm()).item()
+        assert rel < tol, (rel, tol)
+
+
 def test_train_step_matches_oracle_optimizer(satk, root):
     """Two full train steps (clip-by-global-norm + Adam + noam LR): parameters track the oracle's."""
     eng, tr, (fd, ld, md), (f, l, masks) = _case(satk, root, "ljspeech_self-attention-tacotron.json", 4, 16, 20, True, grads=False)
