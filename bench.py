@@ -205,6 +205,12 @@ def run_satk(args, rank, world, local_rank):
         kt = {k: v for k, v in kt.items() if not k.startswith("sec.")}
         dom = max(kt, key=kt.get)
         alg = bytes_step * td * (2 if dom.endswith("bwd") else 1)
+        loss_frac = None
+        if dom.endswith("bwd") and getattr(eng, "skip_masked_steps", False):
+            # the backward walk only visits decoder steps that can carry a gradient (engine.forward: step_end); the keys / values
+            # of the skipped (utterance, step) pairs are not algorithmic work, the weights are (one utterance spans all Td steps)
+            loss_frac = statistics.mean(float((l_.binary_loss_mask != 0).sum()) / (B * td) for _, l_ in host)
+            alg = 2 * td * 2 * (w_seq + loss_frac * B * TT * (d.att1 + d.mem1 + d.att2 + d.mem2))
         ach = alg / (kt[dom] * 1e-3) / 1e9
         traffic = None
         try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same shapes only)
@@ -213,7 +219,7 @@ def run_satk(args, rank, world, local_rank):
             pass
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kt[dom], "us_per_decoder_step": kt[dom] * 1e3 / td,
+                "algorithmic_bytes_per_launch": alg, "steps_with_loss_frac": loss_frac, "avg_launch_ms": kt[dom], "us_per_decoder_step": kt[dom] * 1e3 / td,
                 "kernel_ms": kt, "section_ms": sections}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
