@@ -196,6 +196,11 @@ int satk_grad_sumsq(const float* g, long long n, float* sumsq, void* stream);
 int satk_adam_clip(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float grad_scale,
                    float clip_norm, float lr, float beta1, float beta2, float eps, int step, void* stream);
 
+/* l2_regularization_loss (modules/regularizers.py:11-18, models/models.py:470-478) on the flat parameter buffer:
+ * loss_acc[0] += scale * sum_i mask[i] * p[i]^2 / 2 (tf.nn.l2_loss) when loss_acc != NULL, and
+ * g[i] += scale * mask[i] * p[i] when g != NULL.  mask[i] in {0, 1} selects the variables that are not black-listed. */
+int satk_l2_reg(const float* p, const float* mask, long long n, float scale, float* g, float* loss_acc, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Recurrent core
  * ------------------------------------------------------------------------------------------ */

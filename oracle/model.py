@@ -507,11 +507,57 @@ def model_forward(P, d, features, labels, training, masks=None, stats_out=None):
                                                   training, masks)
     mel_loss = spec_loss_l1(mel, labels.mel.to(mel.dtype), labels.spec_loss_mask.to(mel.dtype))
     done_loss = binary_loss(stop, labels.done.to(mel.dtype), labels.binary_loss_mask.to(mel.dtype))
-    return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2,
+    reg_loss = l2_regularization_loss(P, d) if getattr(d, "l2_weight", 0.0) > 0 else torch.zeros((), dtype=mel.dtype)
+    return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2, regularization_loss=reg_loss,
                 enc_self_alignments=[a.transpose(1, 2) for a in enc_aligns],  # models.py:398 (B, T_mem, T_query)
                 dec_self_alignments=[a.transpose(1, 2) for a in dec_sa],
                 memory1=mem1, memory2=mem2,
-                mel_loss=mel_loss, done_loss=done_loss, loss=mel_loss + done_loss)
+                mel_loss=mel_loss, done_loss=done_loss, loss=mel_loss + done_loss + reg_loss)   # models.py:482 (no PostNetV2)
+
+
+# models/models.py:470-473
+L2_BLACKLIST = ["embedding", "bias", "batch_normalization", "output_projection_wrapper/kernel", "lstm_cell",
+                "output_and_stop_token_wrapper/dense/", "output_and_stop_token_wrapper/dense_1/", "stop_token_projection/kernel"]
+
+
+def tf_variable_name(n: str, d) -> str:
+    """The part of the reference's TF variable name that its black-list can match, for trainable tensor `n` of the parameter store.
+    In-tree names: forward_attention.py:17,21,73,78,86 (attention_variable / attention_bias / location_features_convolution /
+    location_features_layer / transition_factor_projection), module.py:718-723 (out_projection / stop_token_projection).
+    RECALLED (tacotron2 / TF layers): dense and conv layers own "kernel" and "bias", tf.layers.batch_normalization
+    owns "batch_normalization[_k]/gamma|beta", LSTMCell (inside ZoneoutLSTMCell) owns "lstm_cell/kernel|bias", Embedding owns
+    "embedding", the ExtendedDecoder projects through OutputAndStopTokenWrapper ("output_and_stop_token_wrapper/dense[_1]/")."""
+    leaf = n.rsplit(".", 1)[-1]
+    if n in ("embedding", "speaker_embedding"):
+        return n
+    if ".lstm" in n:
+        return "lstm_cell/" + ("kernel" if leaf == "W" else "bias")
+    if leaf in ("gamma", "beta"):
+        return "batch_normalization/" + leaf
+    if n == "att1.v" or n == "att2.v":
+        return "attention_variable" if n == "att1.v" and d.attention != "additive" else "attention_v"
+    if n == "att1.b":
+        return "attention_bias"
+    if n.startswith("dec.out_proj") or n.startswith("dec.stop_proj"):
+        kind = "kernel" if leaf == "W" else "bias"
+        if d.dual:
+            return ("out_projection/" if "out_proj" in n else "stop_token_projection/") + kind
+        return ("output_and_stop_token_wrapper/dense/" if "out_proj" in n else "output_and_stop_token_wrapper/dense_1/") + kind
+    return n + ("/kernel" if leaf.startswith("W") else "/bias")
+
+
+def l2_regularization_loss(P, d):
+    """modules/regularizers.py:11-18 with the black-list of models/models.py:470-478: scale * sum of tf.nn.l2_loss (= sum(w^2) / 2) over
+    the trainable variables whose name contains no black-listed substring."""
+    total = 0.0
+    for n, w in P.items():
+        if n.endswith(".mean") or n.endswith(".var"):      # BN moving statistics are not trainable
+            continue
+        name = tf_variable_name(n, d)
+        if any(black in name for black in L2_BLACKLIST):
+            continue
+        total = total + 0.5 * (w.double() ** 2).sum()
+    return (total * d.l2_weight).to(next(iter(P.values())).dtype)
 
 
 def noam_lr(init_rate, global_step, step_factor):

@@ -481,6 +481,20 @@ __global__ void sumsq_k(const float* __restrict__ g, long long n, float* __restr
   a = block_sum(a, sh);
   if (threadIdx.x == 0) atomicAdd(out, a);
 }
+__global__ void l2_reg_k(const float* __restrict__ p, const float* __restrict__ mask, long long n, float scale, float* __restrict__ g,
+                         float* __restrict__ loss_acc) {
+  __shared__ float sh[32];
+  float a = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float w = mask[i] * p[i];
+    a += w * w;
+    if (g) g[i] += scale * w;
+  }
+  if (loss_acc) {
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) atomicAdd(loss_acc, 0.5f * scale * a);
+  }
+}
 __global__ void adam_clip_k(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, const float* __restrict__ sumsq, float gscale, float clip, float lr_t, float b1,
                             float b2, float eps) {
@@ -673,6 +687,12 @@ int satk_losses(const float* pred_tm, const float* stop_tm, const float* mel, co
 int satk_grad_sumsq(const float* g, long long n, float* sumsq, void* stream) {
   SATK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float), ST));
   sumsq_k<<<kSMs * 4, 256, 0, ST>>>(g, n, sumsq);
+  SATK_LAUNCH_CHECK();
+  return 0;
+}
+int satk_l2_reg(const float* p, const float* mask, long long n, float scale, float* g, float* loss_acc, void* stream) {
+  SATK_CHECK_ARG(p && mask && n > 0 && (g || loss_acc), "l2_reg: needs parameters, a mask and at least one output");
+  l2_reg_k<<<kSMs * 4, 256, 0, ST>>>(p, mask, n, scale, g, loss_acc);
   SATK_LAUNCH_CHECK();
   return 0;
 }

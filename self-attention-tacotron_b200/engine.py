@@ -740,6 +740,10 @@ class TacotronEngine:
         dstop = self.buf("dec.dstop_tm", stop_tm.shape)
         O.losses(mel_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
                  out3, dmel, dstop, self.buf("loss_scratch", (4,)))
+        if d.l2_weight > 0:     # loss = mel_loss + done_loss + regularization_loss (models/models.py:482)
+            l2 = self.buf("l2_loss", (1,), zero=True)
+            O.l2_reg(self.ps.flat, self.ps.l2_mask(), d.l2_weight, loss_acc=l2)
+            O.add(out3[2:], l2, out3[2:])
         self.saved = dict(B=B, Tt=Tt, Td=Td, Tm=Tm, source_length=source_length, dmel=dmel, dstop=dstop, features=features,
                           step_end=step_end if getattr(self, "skip_masked_steps", True) else None)
         # with a sorted batch every per-utterance output is in SORTED order: row i belongs to utterance perm[i] of the caller's batch
@@ -1000,6 +1004,10 @@ class TacotronEngine:
         self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)      # every weight gradient is in before all-reduce / Adam
+        if self.d.l2_weight > 0:
+            # gradient of l2_regularization_loss (models/models.py:470-478): scale * w on the regularised tensors.  Every replica adds it
+            # (TF: each replica's loss carries the term, gradients are averaged), the 1/world_size after the all-reduce restores it.
+            O.l2_reg(self.ps.flat, self.ps.l2_mask(), self.d.l2_weight, g=self.ps.grad)
 
     def optimizer_step(self, world_size: int = 1):
         """clip_by_global_norm(1.0) + Adam + noam LR (models.py:485-498).  With world_size > 1 the caller has

@@ -355,6 +355,14 @@ def grad_sumsq(g, sumsq):
     _count()
 
 
+def l2_reg(p, mask, scale, g=None, loss_acc=None):
+    """l2_regularization_loss (regularizers.py:11-18): loss_acc[0] += scale * sum(mask * p^2) / 2 and / or g += scale * mask * p."""
+    _req(p); _req(mask)
+    check(load().satk_l2_reg(C.c_void_p(p.data_ptr()), C.c_void_p(mask.data_ptr()), C.c_longlong(p.numel()), C.c_float(scale),
+                             C.c_void_p(ptr(g)), C.c_void_p(ptr(loss_acc)), C.c_void_p(stream_ptr())), "satk_l2_reg")
+    _count()
+
+
 def adam_clip(p, g, m, v, sumsq, grad_scale, clip_norm, lr, b1, b2, eps, step):
     check(load().satk_adam_clip(C.c_void_p(p.data_ptr()), C.c_void_p(g.data_ptr()), C.c_void_p(m.data_ptr()),
                                 C.c_void_p(v.data_ptr()), C.c_longlong(p.numel()), C.c_void_p(sumsq.data_ptr()),

@@ -63,6 +63,7 @@ class ModelDims:
     speaker_dim: int
     speaker_offset: int
     max_iters: int
+    l2_weight: float = 0.0  # l2_regularization_weight when use_l2_regularization, else 0 (models/models.py:470-478)
 
     @property
     def mem1(self) -> int:      # depth of attention-1 memory (BiLSTM output)
@@ -107,7 +108,6 @@ def dims_from_hparams(hp) -> ModelDims:
         raise ValueError("use_zoneout_at_encoder=False (plain CBHG with GRU) is out of scope")
     # switches of the reference's model_fn that this implementation does not build (SURVEY §8 f3 / out of scope): refuse loudly
     for flag, what in (("use_postnet_v2", "PostNetV2 (models/models.py:440-462)"),
-                       ("use_l2_regularization", "l2_regularization_loss (models/models.py:471-478)"),
                        ("use_forced_alignment_mode", "forced-alignment attention (teacher_forcing_attention.py)"),
                        ("use_external_speaker_embedding", "external speaker embeddings (multi_speaker_tacotron)"),
                        ("use_language_embedding", "language embeddings (multi_speaker_tacotron)"),
@@ -137,7 +137,23 @@ def dims_from_hparams(hp) -> ModelDims:
         zc=hp.zoneout_factor_cell, zh=hp.zoneout_factor_output,
         use_speaker=bool(hp.use_speaker_embedding), num_speakers=hp.num_speakers,
         speaker_dim=hp.speaker_embedding_dim, speaker_offset=hp.speaker_embedding_offset,
-        max_iters=hp.max_iters)
+        max_iters=hp.max_iters,
+        l2_weight=float(hp.l2_regularization_weight) if bool(getattr(hp, "use_l2_regularization", False)) else 0.0)
+
+
+def l2_regularized(d: ModelDims, name: str) -> bool:
+    """Is trainable tensor `name` part of l2_regularization_loss (models/models.py:470-478, regularizers.py:11-18)?  The reference
+    black-lists TF variable names containing "embedding", "bias", "batch_normalization", "lstm_cell", the ExtendedDecoder's
+    output / stop-token dense layers ("output_and_stop_token_wrapper/dense[_1]/", "output_projection_wrapper/kernel") and
+    "stop_token_projection/kernel".  In this store's names: embeddings, every bias (`attention_bias` of forward_attention.py:21
+    included), BN gamma / beta, every LSTM kernel, the stop projection, and — single-attention model only — the mel projection
+    (the transformer decoder's "out_projection/kernel", module.py:718-720, matches no black-list entry and IS regularised)."""
+    leaf = name.rsplit(".", 1)[-1]
+    if "embedding" in name or leaf in ("gamma", "beta") or leaf.startswith("b") or ".lstm" in name:
+        return False
+    if name == "dec.stop_proj.W" or (name == "dec.out_proj.W" and not d.dual):
+        return False
+    return True
 
 
 # init kinds: "glorot" (fan_in, fan_out from the last two dims; conv receptive field included),
@@ -285,6 +301,16 @@ class ParamStore:
             self.bn_off[name] = o
             o += c
         self.step = 0
+
+    def l2_mask(self) -> torch.Tensor:
+        """Flat {0, 1} mask of the l2-regularised parameters (``l2_regularized``), built on first use."""
+        if getattr(self, "_l2_mask", None) is None:
+            m = torch.zeros_like(self.flat)
+            for n, (o, s) in self.offsets.items():
+                if l2_regularized(self.dims, n):
+                    m[o:o + _numel(s)] = 1.0
+            self._l2_mask = m
+        return self._l2_mask
 
     def _views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
         return {n: flat[o:o + _numel(s)].view(s) for n, (o, s) in self.offsets.items()}

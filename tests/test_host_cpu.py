@@ -146,8 +146,8 @@ def test_data_parallel_gradient_mean_gloo(root, tmp_path):
 def test_unbuilt_model_switches_are_refused(satk, root):
     """Options of the reference's model_fn that are not built must fail loudly, never be silently ignored."""
     cfg = os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json")
-    for flag in ("use_postnet_v2", "use_l2_regularization", "use_forced_alignment_mode", "use_external_speaker_embedding",
+    for flag in ("use_postnet_v2", "use_forced_alignment_mode", "use_external_speaker_embedding",
                  "use_language_embedding", "use_accent_type"):
         with pytest.raises(NotImplementedError, match=flag):
             satk.dims_from_hparams(satk.load_hparams(cfg, f"{flag}=True"))
-    satk.dims_from_hparams(satk.load_hparams(cfg, "cumulative_weights=True,use_forward_attention_transition_agent=True"))
+    satk.dims_from_hparams(satk.load_hparams(cfg, "cumulative_weights=True,use_forward_attention_transition_agent=True,use_l2_regularization=True"))

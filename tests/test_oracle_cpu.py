@@ -184,3 +184,32 @@ def test_free_running_oracle_stop_token(satk, root):
     with torch.no_grad():
         pr = OR.model_predict(P, d, f, max_iters=30, min_iters=3, use_stop_token=True)
     assert pr["stop"].shape == (2, 5)          # first t > min_iters is t = 4 -> 5 executed steps
+
+
+def test_l2_regularization_selection_and_value(satk, root):
+    """models/models.py:470-478 + regularizers.py:11-18: the oracle applies the reference's literal black-list to (recalled) TF
+    variable names, the parameter store selects by its own naming rules; both must pick the same tensors, and the oracle's loss
+    must be scale * sum(w^2) / 2 over them.  Embeddings, biases (attention_bias included), BN parameters, LSTM kernels and the stop
+    projection are never regularised; the mel projection only in the transformer decoder ("out_projection/kernel")."""
+    import os
+    from importlib import import_module
+    P = import_module("self-attention-tacotron_b200.params")
+    for cfg, ov in (("ljspeech_self-attention-tacotron.json", "use_forward_attention_transition_agent=True"),
+                    ("ljspeech_tacotron.json", "attention=additive"), ("vctk_self-attention-tacotron.json", None)):
+        ov = (ov + "," if ov else "") + "use_l2_regularization=True,l2_regularization_weight=1e-3"
+        hp = satk.load_hparams(os.path.join(root, "examples", cfg), ov)
+        d = satk.dims_from_hparams(hp)
+        assert d.l2_weight == 1e-3
+        ps = satk.ParamStore(d).init(3, "random")
+        mine = {n for n in ps.p if P.l2_regularized(d, n)}
+        theirs = {n for n in ps.p if not any(b in OR.tf_variable_name(n, d) for b in OR.L2_BLACKLIST)}
+        assert mine == theirs and len(mine) > 30
+        for n in ("embedding", "att1.b", "cbhg.proj1.gamma", "dec.lstm1.W", "cbhg.lstm_fw.W", "dec.stop_proj.W", "enc.prenet0.b"):
+            assert n not in mine
+        assert ("dec.out_proj.W" in mine) == d.dual and "att1.v" in mine and "cbhg.bank3.W" in mine
+        want = 1e-3 * sum(0.5 * float((ps.p[n].double() ** 2).sum()) for n in mine)
+        got = float(OR.l2_regularization_loss(ps.as_dict(), d))
+        assert abs(got - want) <= 1e-6 * want
+        assert float(ps.l2_mask().sum()) == sum(ps.p[n].numel() for n in mine)
+    d0 = satk.dims_from_hparams(satk.load_hparams(os.path.join(root, "examples", "ljspeech_tacotron.json")))
+    assert d0.l2_weight == 0.0

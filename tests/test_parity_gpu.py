@@ -153,6 +153,17 @@ def test_variant_cumulative_weights(satk, root):
     _case(satk, root, "ljspeech_tacotron.json", 3, 19, 22, True, overrides="attention=location_sensitive,cumulative_weights=True")
 
 
+def test_l2_regularization_loss_and_gradient(satk, root):
+    """use_l2_regularization (models/models.py:470-478, regularizers.py:11-18): the loss carries scale * sum l2_loss(w) over the
+    variables that are not black-listed and their gradients carry scale * w; a large weight makes the term visible (0.4 of the loss).
+    Dual model (mel projection regularised) and single-attention model (both output projections black-listed)."""
+    for cfg, B in (("ljspeech_self-attention-tacotron.json", 5), ("ljspeech_tacotron.json", 2)):
+        eng, tr, _, _ = _case(satk, root, cfg, B, 19, 24, True, overrides="use_l2_regularization=True,l2_regularization_weight=2e-4")
+        assert eng.d.l2_weight == 2e-4
+        l2 = float(eng._bufs["l2_loss"])
+        assert l2 > 0.05 * float(eng._bufs["loss3"][2]), (l2, eng._bufs["loss3"])
+
+
 def test_variant_additive(satk, root):
     _case(satk, root, "ljspeech_tacotron.json", 3, 20, 24, True, overrides="attention=additive")
 
