@@ -702,7 +702,7 @@ class TacotronEngine:
         # zero gradient (masked losses, causal decoder), so the attention-RNN backward kernel starts its walk there
         step_end = None
         if training:
-            lm = (labels.binary_loss_mask != 0) | (labels.spec_loss_mask.reshape(B, Td, d.r) != 0).any(-1)
+            lm = (labels.binary_loss_mask != 0) | (labels.spec_loss_mask[:, :Td * d.r].reshape(B, Td, d.r) != 0).any(-1)
             step_end = (lm * torch.arange(1, Td + 1, device=lm.device, dtype=torch.int32)).amax(1).clamp_(min=1).to(torch.int32)
         if training and getattr(self, "sort_batches", True) and B > 1:
             # Utterances are independent, so the batch order is free: sort by target length, then source length (longest first).  The
@@ -711,6 +711,15 @@ class TacotronEngine:
             # then starts earlier and is short itself.
             key = source_length if step_end is None else step_end.to(torch.int64) * (Tt + 1) + source_length
             perm = torch.argsort(key, descending=True, stable=True)
+            if step_end is not None and B > 28 and os.environ.get("SATK_SORT_TWO_LEVEL", "1") != "0":
+                # more clusters than cluster slots: the backward kernels only need the 8 shortest TARGETS in the last two clusters (the
+                # one that frees its slot first and the one that waits for it); inside that tail and inside the head the order is
+                # free, so both are ordered by SOURCE length — the forward kernel walks all Td steps of every utterance and its
+                # per-step time depends on the source length only: the waiting cluster and the head's last cluster get short sources.
+                head, tail = perm[:B - 8], perm[B - 8:]
+                head = head[torch.argsort(source_length[head], descending=True, stable=True)]
+                tail = tail[torch.argsort(source_length[tail], descending=True, stable=True)]
+                perm = torch.cat([head, tail])
             step_end = step_end.index_select(0, perm) if step_end is not None else None
             sel = lambda x: x.index_select(0, perm) if torch.is_tensor(x) else x      # noqa: E731
             features = features._replace(source=sel(source), source_length=sel(source_length), speaker_id=sel(features.speaker_id))
