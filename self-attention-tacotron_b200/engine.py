@@ -56,6 +56,13 @@ class TacotronEngine:
         self._side = torch.cuda.Stream(device=self.device) if os.environ.get("SATK_WGRAD_STREAM", "1") != "0" else None
         # independent branches of the graph (decoder pre-net beside the encoder, the two BiLSTM directions) fork onto a third stream
         self._aux = torch.cuda.Stream(device=self.device) if self._side is not None else None
+        # the critical path runs on a high-priority stream of its own, so that pending CTAs of the recurrent cluster kernels are
+        # placed before pending CTAs of the weight-gradient products (SATK_MAIN_PRIORITY=0 switches it off; the caller's stream is joined on both sides)
+        self._main = torch.cuda.Stream(device=self.device, priority=-1) \
+            if (self._side is not None and os.environ.get("SATK_MAIN_PRIORITY", "1") != "0") else None
+        if self._main is not None:
+            for name in ("forward", "backward", "optimizer_step"):
+                setattr(self, name, self._on_main(getattr(self, name)))
         self.sort_batches = os.environ.get("SATK_SORT_BATCHES", "1") != "0"   # TRAIN steps sort the batch by target / source length
         self.skip_masked_steps = os.environ.get("SATK_STEP_END", "1") != "0"  # attention-RNN backward starts at the last step with a loss
         self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
@@ -93,6 +100,18 @@ class TacotronEngine:
         K = K or Ktot
         return O.linear_t(x, Wt, out, x.numel() // K, K, N, ldw=Ktot, k_off=k0, bias=bias, act=act, residual=residual,
                           keep_mask=keep_mask, keep_scale=keep_scale)
+
+    def _on_main(self, fn):
+        def run(*a, **k):
+            cur = torch.cuda.current_stream()
+            if cur == self._main:
+                return fn(*a, **k)
+            self._main.wait_stream(cur)
+            with torch.cuda.stream(self._main):
+                r = fn(*a, **k)
+            cur.wait_stream(self._main)
+            return r
+        return run
 
     def buf(self, name: str, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
         shape = tuple(int(s) for s in shape)
