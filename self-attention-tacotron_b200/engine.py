@@ -36,6 +36,35 @@ def noam_lr(init_rate: float, global_step: int, step_factor: float) -> float:
     return init_rate * warm ** 0.5 * min(step * warm ** -1.5, step ** -0.5)
 
 
+def loss_step_end(labels, Td: int, r: int) -> torch.Tensor:
+    """[B] int32: 1 + the last decoder step of each utterance whose loss masks (``spec_loss_mask`` over its r frames, ``binary_loss_mask``;
+    models.py:467-482) are non-zero, at least 1.  No host synchronisation."""
+    B = labels.binary_loss_mask.shape[0]
+    lm = (labels.binary_loss_mask != 0) | (labels.spec_loss_mask[:, :Td * r].reshape(B, Td, r) != 0).any(-1)
+    return (lm * torch.arange(1, Td + 1, device=lm.device, dtype=torch.int32)).amax(1).clamp_(min=1).to(torch.int32)
+
+
+def train_batch_order(step_end: Optional[torch.Tensor], source_length: torch.Tensor, Tt: int, two_level: bool = True) -> torch.Tensor:
+    """Permutation of a TRAIN batch (utterances are independent, so the order is free): by target length (``step_end``), then source
+    length, longest first.  The attention-RNN kernels skip positions past an utterance's source length and (backward) steps past its
+    last loss step, so a cluster of 4 short utterances finishes early, and with 8 clusters on 7 cluster slots the last (shortest)
+    cluster then starts earlier and is short itself.
+
+    With more clusters than slots (B > 28) the order is two-level: the backward kernels only need the 8 shortest TARGETS in the last two
+    clusters (the one that frees its slot first and the one that waits for it); inside that tail and inside the head the order is
+    free, so both are ordered by SOURCE length — the forward kernel walks all Td steps of every utterance and its per-step time
+    depends on the source length only: the waiting cluster and the head's last cluster get short sources."""
+    B = source_length.shape[0]
+    key = source_length if step_end is None else step_end.to(torch.int64) * (Tt + 1) + source_length
+    perm = torch.argsort(key, descending=True, stable=True)
+    if step_end is not None and B > 28 and two_level:
+        head, tail = perm[:B - 8], perm[B - 8:]
+        head = head[torch.argsort(source_length[head], descending=True, stable=True)]
+        tail = tail[torch.argsort(source_length[tail], descending=True, stable=True)]
+        perm = torch.cat([head, tail])
+    return perm
+
+
 class TacotronEngine:
     def __init__(self, hp, device="cuda", params: Optional[ParamStore] = None, seed: int = 1234):
         self.hp = hp
@@ -719,26 +748,9 @@ class TacotronEngine:
         perm = None
         # 1 + the last decoder step of each utterance whose loss masks are non-zero (models.py:467-482): later steps carry exactly
         # zero gradient (masked losses, causal decoder), so the attention-RNN backward kernel starts its walk there
-        step_end = None
-        if training:
-            lm = (labels.binary_loss_mask != 0) | (labels.spec_loss_mask[:, :Td * d.r].reshape(B, Td, d.r) != 0).any(-1)
-            step_end = (lm * torch.arange(1, Td + 1, device=lm.device, dtype=torch.int32)).amax(1).clamp_(min=1).to(torch.int32)
+        step_end = loss_step_end(labels, Td, d.r) if training else None
         if training and getattr(self, "sort_batches", True) and B > 1:
-            # Utterances are independent, so the batch order is free: sort by target length, then source length (longest first).  The
-            # attention-RNN kernels skip positions past an utterance's source length and (backward) steps past its last loss step, so
-            # a cluster of 4 short utterances finishes early, and with 8 clusters on 7 cluster slots the last (shortest) cluster
-            # then starts earlier and is short itself.
-            key = source_length if step_end is None else step_end.to(torch.int64) * (Tt + 1) + source_length
-            perm = torch.argsort(key, descending=True, stable=True)
-            if step_end is not None and B > 28 and os.environ.get("SATK_SORT_TWO_LEVEL", "1") != "0":
-                # more clusters than cluster slots: the backward kernels only need the 8 shortest TARGETS in the last two clusters (the
-                # one that frees its slot first and the one that waits for it); inside that tail and inside the head the order is
-                # free, so both are ordered by SOURCE length — the forward kernel walks all Td steps of every utterance and its
-                # per-step time depends on the source length only: the waiting cluster and the head's last cluster get short sources.
-                head, tail = perm[:B - 8], perm[B - 8:]
-                head = head[torch.argsort(source_length[head], descending=True, stable=True)]
-                tail = tail[torch.argsort(source_length[tail], descending=True, stable=True)]
-                perm = torch.cat([head, tail])
+            perm = train_batch_order(step_end, source_length, Tt, os.environ.get("SATK_SORT_TWO_LEVEL", "1") != "0")
             step_end = step_end.index_select(0, perm) if step_end is not None else None
             sel = lambda x: x.index_select(0, perm) if torch.is_tensor(x) else x      # noqa: E731
             features = features._replace(source=sel(source), source_length=sel(source_length), speaker_id=sel(features.speaker_id))

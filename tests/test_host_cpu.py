@@ -151,3 +151,35 @@ def test_unbuilt_model_switches_are_refused(satk, root):
         with pytest.raises(NotImplementedError, match=flag):
             satk.dims_from_hparams(satk.load_hparams(cfg, f"{flag}=True"))
     satk.dims_from_hparams(satk.load_hparams(cfg, "cumulative_weights=True,use_forward_attention_transition_agent=True,use_l2_regularization=True"))
+
+
+def test_loss_step_end_and_train_batch_order(satk, root):
+    """Host logic of the step_end contract (satk_attn_rnn_bwd_desc / satk_lstm_bwd_desc): 1 + the last decoder step with a non-zero
+    loss mask, and the TRAIN batch order built from it — a permutation; the 8 shortest targets form the last two clusters; head and
+    tail are each ordered by source length (two-level), or the whole batch by (target, source) when one wave of clusters suffices."""
+    from importlib import import_module
+    E = import_module("self-attention-tacotron_b200.engine")
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    f, l = satk.synthetic_batch(hp, 32, 148, 800, seed=5)
+    se = E.loss_step_end(l, 400, 2)
+    assert se.dtype == torch.int32 and se.shape == (32,)
+    want = torch.tensor([max(1, -(-int(t) // 2)) for t in l.target_length], dtype=torch.int32)     # ceil(target_length / r)
+    assert torch.equal(se, want) and int(se.max()) == 400 and int(se.min()) < 320
+    # a mask with a hole and an all-zero mask: last non-zero step counts, never below 1
+    l2 = l._replace(binary_loss_mask=torch.zeros_like(l.binary_loss_mask), spec_loss_mask=torch.zeros_like(l.spec_loss_mask))
+    l2.spec_loss_mask[0, 10] = 1.0
+    l2.spec_loss_mask[0, 101] = 1.0
+    se2 = E.loss_step_end(l2, 400, 2)
+    assert int(se2[0]) == 51 and int(se2[1]) == 1
+    src = f.source_length
+    perm = E.train_batch_order(se, src, 148, True)
+    assert sorted(perm.tolist()) == list(range(32))
+    tail, head = perm[24:], perm[:24]
+    assert int(se[tail].max()) <= int(se[head].min())                      # the 8 shortest targets are last
+    assert (src[tail][1:] <= src[tail][:-1]).all() and (src[head][1:] <= src[head][:-1]).all()
+    flat = E.train_batch_order(se, src, 148, False)
+    key = se.to(torch.int64) * 149 + src
+    assert (key[flat][1:] <= key[flat][:-1]).all() and set(flat[24:].tolist()) == set(tail.tolist())
+    small = E.train_batch_order(se[:28], src[:28], 148, True)                # one wave of clusters: plain (target, source) order
+    assert (key[:28][small][1:] <= key[:28][small][:-1]).all()
+    assert (src[E.train_batch_order(None, src, 148)][1:] <= src[E.train_batch_order(None, src, 148)][:-1]).all()
