@@ -183,3 +183,13 @@ def test_loss_step_end_and_train_batch_order(satk, root):
     small = E.train_batch_order(se[:28], src[:28], 148, True)                # one wave of clusters: plain (target, source) order
     assert (key[:28][small][1:] <= key[:28][small][:-1]).all()
     assert (src[E.train_batch_order(None, src, 148)][1:] <= src[E.train_batch_order(None, src, 148)][:-1]).all()
+
+
+def test_header_is_plain_c(root, tmp_path):
+    """include/satk.h is the drop-in boundary: it must compile as C99 (no C++ types in the signatures), alone."""
+    src = tmp_path / "abi.c"
+    src.write_text('#include "satk.h"\nint main(void) { satk_gemm_desc g; satk_attn_rnn_bwd_desc a; satk_lstm_bwd_desc l; '
+                   '(void)g; (void)a; (void)l; return (int)sizeof(g) == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
