@@ -42,6 +42,21 @@ def golden_predict_case(satk, root):
     return res
 
 
+def golden_l2_case(satk, root):
+    """use_l2_regularization (models/models.py:470-478) on the single-attention model (BASELINE configs[0]), frozen in oracle_l2.npz."""
+    from oracle import model as OR
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_tacotron.json"), "use_l2_regularization=True,l2_regularization_weight=1e-4")
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(2026, "random")
+    f, l = satk.synthetic_batch(hp, 2, 10, 12, seed=2026)
+    masks = satk.make_masks(d, 2, 10, 6, seed=2026)
+    out, grads, _ = OR.OracleTrainer(d, hp, ps.as_dict()).loss_and_grads(f, l, masks, True)
+    return dict(loss=np.float64(float(out["loss"].detach())), regularization_loss=np.float64(float(out["regularization_loss"].detach())),
+                grad_enc_prenet0_W_slice=grads["enc.prenet0.W"].numpy()[:32, :32],      # regularised
+                grad_out_proj_W_slice=grads["dec.out_proj.W"].numpy()[:32, :32],        # black-listed in the ExtendedDecoder
+                grad_att1_v=grads["att1.v"].numpy())
+
+
 if __name__ == "__main__":
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -53,4 +68,5 @@ if __name__ == "__main__":
                         alignment2=out["alignment2"].detach().numpy(), loss=float(out["loss"].detach()),
                         grad_dec_lstm1_W_slice=grads["dec.lstm1.W"].numpy()[100:164, :64], grad_att1_v=grads["att1.v"].numpy())
     np.savez_compressed(os.path.join(root, "tests", "golden", "oracle_predict.npz"), **golden_predict_case(satk, root))
+    np.savez_compressed(os.path.join(root, "tests", "golden", "oracle_l2.npz"), **golden_l2_case(satk, root))
     print("written")

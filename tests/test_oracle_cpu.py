@@ -158,6 +158,18 @@ def test_golden_fixture_predict_and_variants(satk, root):
         assert np.allclose(np.asarray(v), z[k], atol=2e-5, rtol=1e-5), k
 
 
+def test_golden_fixture_l2_regularization(satk, root):
+    """tests/golden/oracle_l2.npz (oracle/make_golden.py): loss with the l2 term, the term itself and gradients of a regularised, a
+    black-listed and an attention tensor of the single-attention model, frozen against drift (self-generated)."""
+    z = np.load(os.path.join(root, "tests", "golden", "oracle_l2.npz"))
+    from oracle.make_golden import golden_l2_case
+    res = golden_l2_case(satk, root)
+    assert set(res) == set(z.files)
+    for k, v in res.items():
+        assert np.allclose(np.asarray(v), z[k], atol=2e-6, rtol=1e-5), k
+    assert 0.05 < float(z["regularization_loss"]) / float(z["loss"]) < 0.5
+
+
 def test_free_running_oracle_is_consistent_with_teacher_forcing(satk, root):
     """PREDICT-branch restatement (oracle.decoder_free_running, module.py:762-778) vs the teacher-forced restatement: feeding
     the free-running output back as the target reproduces it (eval mode), for the dual and the single-attention model."""
