@@ -635,11 +635,18 @@ int attn_fwd_phase_cycles(long long* out16) {
 using namespace satk;
 using namespace satk::arnn;
 
+namespace satk { namespace arnn2 {
+bool v2_eligible(const satk_attn_rnn_fwd_desc* d);
+int attn_rnn2_fwd_launch(const satk_attn_rnn_fwd_desc* d, cudaStream_t st);
+} }
+
 extern "C" int satk_attn_rnn_fwd(const satk_attn_rnn_fwd_desc* d, void* stream) {
   bool has2;
   int rc = attn_rnn_check(d, has2);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  // dual-source decoder of the shipped configurations: second-generation kernel (one wave at B = 32), attn_rnn2_fwd.cu
+  if (arnn2::v2_eligible(d)) return arnn2::attn_rnn2_fwd_launch(d, st);
   const int np = (d->Tt + 63) / 64;
   const bool af5 = d->att_filters == 5 || d->att_kernel == 0;
   const bool agent = d->agent_w != nullptr;

@@ -434,6 +434,7 @@ int lstm_max_clusters_h256() {
 
 namespace satk { namespace tc { int tc_trace(long long* out16); } }
 namespace satk { namespace arnn { int attn_fwd_phase_cycles(long long* out16); int attn_bwd_phase_cycles(long long* out16); } }
+namespace satk { namespace arnn2 { int attn2_fwd_phase_cycles(long long* out16); int attn2_bwd_phase_cycles(long long* out16); } }
 using namespace satk;
 
 extern "C" {
@@ -443,6 +444,8 @@ int satk_debug_phase_cycles(int which, long long* out16) {
   if (which == 1) return satk::arnn::attn_fwd_phase_cycles(out16);
   if (which == 2) return satk::arnn::attn_bwd_phase_cycles(out16);
   if (which == 3) return satk::tc::tc_trace(out16);
+  if (which == 4) return satk::arnn2::attn2_fwd_phase_cycles(out16);
+  if (which == 5) return satk::arnn2::attn2_bwd_phase_cycles(out16);
   SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
   return 0;
 #else

@@ -13,7 +13,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsatk.so")
+LIB_PATH = os.environ.get("SATK_LIB_PATH") or os.path.join(_HERE, "libsatk.so")   # override: developer builds (make pt)
 
 
 class SatkError(RuntimeError):
