@@ -329,8 +329,21 @@ typedef struct {
    * skips (dx2 is left as it is: zero).  Ignored with cumulative != 0 (the location state is walked back from the final state).
    * NULL: all Td steps. */
   const int* step_end;
+  /* optional workspace [Td,B,2,Tt] floats.  When it is set and the configuration is the dual-source decoder of the shipped
+   * models (forward / location-sensitive first mechanism without cumulative weights or transition agent, <= 5 location
+   * filters, Tt <= 192), the second-generation kernels run: the sequential kernel (one wave of 16-CTA clusters at B = 32)
+   * only walks the recurrence and leaves d(energies) of both mechanisms here, and dkeys / dv / d(location layer / conv),
+   * which do not feed the recurrence, come from a second, fully parallel launch over all (step, utterance) pairs
+   * (forward_attention.py:13-26,98-100).  NULL: first-generation kernel, everything in one launch. */
+  float* de_ws;
 } satk_attn_rnn_bwd_desc;
 int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
+/* The two launches of the second-generation path separately (satk_attn_rnn_bwd issues both on one stream): the sequential
+ * recurrence (fills dx2[:, H:], dgates, dq, de_ws) and the parallel energy gradients (reads de_ws; fills dkeys1/2 and adds
+ * onto dv1/2, dloc_*), so that a caller can overlap the second one with whatever does not consume dkeys.
+ * Both return SATK_ERR_UNSUPPORTED when the configuration is not covered (see de_ws). */
+int satk_attn_rnn_bwd_recurrence(const satk_attn_rnn_bwd_desc* d, void* stream);
+int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Free-running decoder step (PREDICT mode, predict_mel.py:36-74): the inference-branch cells of

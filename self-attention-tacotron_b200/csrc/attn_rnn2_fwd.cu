@@ -721,5 +721,3 @@ int attn2_fwd_phase_cycles(long long* out16) {
 }  // namespace arnn2
 }  // namespace satk
 
-// (temporary until attn_rnn2_bwd.cu lands)
-namespace satk { namespace arnn2 { int attn2_bwd_phase_cycles(long long* out16) { for (int i = 0; i < 16; ++i) out16[i] = 0; return 0; } } }

@@ -888,10 +888,47 @@ int attn_bwd_phase_cycles(long long* out16) {
 using namespace satk;
 using namespace satk::arnn;
 
+namespace satk { namespace arnn2 {
+bool v2_eligible(const satk_attn_rnn_fwd_desc* d);
+int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, cudaStream_t st);
+int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, cudaStream_t st);
+} }
+
+static int bwd2_check(const satk_attn_rnn_bwd_desc* d) {
+  bool has2;
+  int rc = attn_rnn_check(&d->f, has2);
+  if (rc) return rc;
+  if (!d->de_ws || !arnn2::v2_eligible(&d->f)) {
+    satk::set_error("attn_rnn_bwd: configuration not covered by the second-generation kernels (or de_ws missing)");
+    return SATK_ERR_UNSUPPORTED;
+  }
+  SATK_CHECK_ARG(d->f.gates && d->f.c_prev && d->f.q_save && d->f.soft1 && d->dkeys1 && d->dkeys2 && d->dv1 && d->dv2 &&
+                 d->dloc_conv_w && d->dloc_conv_b && d->dloc_layer_w,
+                 "attn_rnn_bwd: forward must have saved gates/c_prev/q_save/soft1 and every gradient buffer must be set");
+  return SATK_OK;
+}
+
+extern "C" int satk_attn_rnn_bwd_recurrence(const satk_attn_rnn_bwd_desc* d, void* stream) {
+  int rc = bwd2_check(d);
+  if (rc) return rc;
+  return arnn2::attn_rnn2_bwd_launch(d, d->de_ws, (cudaStream_t)stream);
+}
+
+extern "C" int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream) {
+  int rc = bwd2_check(d);
+  if (rc) return rc;
+  return arnn2::attn_energy_grad_launch(d, d->de_ws, (cudaStream_t)stream);
+}
+
 extern "C" int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream) {
   bool has2;
   int rc = attn_rnn_check(&d->f, has2);
   if (rc) return rc;
+  if (d->de_ws && arnn2::v2_eligible(&d->f)) {
+    rc = satk_attn_rnn_bwd_recurrence(d, stream);
+    if (rc) return rc;
+    return satk_attn_energy_grad(d, stream);
+  }
   SATK_CHECK_ARG(!d->f.cumulative || d->f.att_kernel == 0 || d->f.state_final, "attn_rnn_bwd: cumulative_weights needs the final state saved by forward");
   SATK_CHECK_ARG(d->f.gates && d->f.c_prev && d->f.q_save && d->f.soft1,
                  "attn_rnn_bwd: forward must have saved gates/c_prev/q_save/soft1");

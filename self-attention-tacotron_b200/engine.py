@@ -652,13 +652,22 @@ class TacotronEngine:
         dq = self.buf("dec.dq", (Rd, QT))
         dkeys1 = self.buf("dec.dkeys1", (R, d.att1))
         dkeys2 = self.buf("dec.dkeys2", (R, d.att2)) if d.dual else None
-        self._timed("attn_rnn_bwd", O.attn_rnn_bwd, fd, dx2=dx2, dgates=dg1, dq=dq, dkeys1=dkeys1, dkeys2=dkeys2,
-                       dv1=g["att1.v"], dv2=g["att2.v"] if d.dual else None,
-                       dloc_conv_w=g["att1.loc_conv.W"] if loc else None, dloc_conv_b=g["att1.loc_conv.b"] if loc else None,
-                       dloc_layer_w=g["att1.loc_layer.W"] if loc else None,
-                       dagent_w=g["att1.agent.W"] if (d.attention == "forward" and d.transition_agent) else None,
-                       dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
-                       step_end=self.saved.get("step_end"))
+        bd = O.attn_rnn_bwd_desc(
+            fd, dx2=dx2, dgates=dg1, dq=dq, dkeys1=dkeys1, dkeys2=dkeys2,
+            dv1=g["att1.v"], dv2=g["att2.v"] if d.dual else None,
+            dloc_conv_w=g["att1.loc_conv.W"] if loc else None, dloc_conv_b=g["att1.loc_conv.b"] if loc else None,
+            dloc_layer_w=g["att1.loc_layer.W"] if loc else None,
+            dagent_w=g["att1.agent.W"] if (d.attention == "forward" and d.transition_agent) else None,
+            dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
+            step_end=self.saved.get("step_end"),
+            # workspace of the second-generation kernels (d(energies) of both mechanisms, include/satk.h)
+            de_ws=self.buf("dec.de_ws", (Td, B, 2, Tt)) if d.dual else None)
+        # second generation: the recurrence, then the energy gradients (dkeys, dv, location layer / conv) as a parallel launch of
+        # their own; configurations it does not cover run the first-generation kernel (everything in one launch)
+        if d.dual and self._timed("attn_rnn_bwd", O.attn_rnn_bwd_recurrence, bd):
+            self._timed("attn_energy_grad", O.attn_energy_grad, bd)
+        else:
+            self._timed("attn_rnn_bwd", O.attn_rnn_bwd_launch, bd)
         # LSTM-1 weight gradients (dense over time)
         gW1 = g["dec.lstm1.W"]
         N4 = 4 * H1

@@ -412,15 +412,43 @@ def attn_rnn_fwd(d: AttnRnnFwdDesc):
     _count()
 
 
-def attn_rnn_bwd(f: AttnRnnFwdDesc, **kw):
+def attn_rnn_bwd_desc(f: AttnRnnFwdDesc, **kw) -> AttnRnnBwdDesc:
     d = AttnRnnBwdDesc()
     d.f = f
     for k, v in kw.items():
         if isinstance(v, torch.Tensor):
             v = v.data_ptr()
         setattr(d, k, v)
+    return d
+
+
+def attn_rnn_bwd(f: AttnRnnFwdDesc, **kw):
+    d = attn_rnn_bwd_desc(f, **kw)
     check(load().satk_attn_rnn_bwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_rnn_bwd")
     _count()
+
+
+def attn_rnn_bwd_launch(d: AttnRnnBwdDesc):
+    check(load().satk_attn_rnn_bwd(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_rnn_bwd")
+    _count()
+
+
+SATK_ERR_UNSUPPORTED = -3
+
+
+def attn_rnn_bwd_recurrence(d: AttnRnnBwdDesc) -> bool:
+    """Sequential half of the second-generation backward (include/satk.h).  False: configuration not covered, nothing launched."""
+    rc = load().satk_attn_rnn_bwd_recurrence(C.byref(d), C.c_void_p(stream_ptr()))
+    if rc == SATK_ERR_UNSUPPORTED:
+        return False
+    check(rc, "satk_attn_rnn_bwd_recurrence")
+    _count()
+    return True
+
+
+def attn_energy_grad(d: AttnRnnBwdDesc):
+    check(load().satk_attn_energy_grad(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_energy_grad")
+    _count(2)
 
 
 # ---------------------------------------------------------------------------------------------- free-running decode step

@@ -4,6 +4,7 @@ Tolerance (BASELINE.json north_star: "within 1e-3 rel fp32"): for every compared
 max|cuda - oracle| <= 1e-3 * max|oracle| (outputs) and <= 2e-3 * max|oracle| (gradients; parameters whose
 true gradient is exactly zero, e.g. the key bias under softmax shift invariance, are compared absolutely).
 """
+import json
 import os
 
 import pytest
@@ -14,6 +15,7 @@ pytestmark = pytest.mark.gpu
 from oracle import model as OR  # noqa: E402
 
 RTOL_OUT, RTOL_GRAD = 1e-3, 2e-3
+_GRAD_LOG = []      # one entry per _check_grads call: how many tensors took the loose branch, whole-gradient relative L2
 
 
 def _mods():
@@ -55,8 +57,19 @@ def _check_grads(eng, tr, rg, cuda=None, l2_tol=1e-3):
         if d > RTOL_GRAD * s + 5e-5 * gmax:
             assert d <= 0.1 * s + 5e-5 * gmax, f"grad {n}: max abs err {d:.3e} vs scale {s:.3e}"
             loose.append((n, d, s))
+    l2 = (num / den) ** 0.5
+    # measured record of how many tensors needed the loose branch (kept under gpurun_out/ and copied to profiles/)
+    _GRAD_LOG.append(dict(test=os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0], tensors=len(tr.names), loose=len(loose),
+                          loose_names=[n for n, _, _ in loose], worst_loose_rel=max([dd / max(ss, 1e-30) for _, dd, ss in loose], default=0.0),
+                          rel_l2=l2))
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open(os.path.join("gpurun_out", "parity_grad_log.json"), "w") as fh:
+            json.dump(_GRAD_LOG, fh, indent=1)
+    except OSError:
+        pass
     assert len(loose) <= max(3, len(tr.names) // 10), f"too many gradient tensors outside {RTOL_GRAD}: {loose}"
-    assert (num / den) ** 0.5 <= l2_tol, f"whole-gradient relative L2 error {(num / den) ** 0.5:.3e}"
+    assert l2 <= l2_tol, f"whole-gradient relative L2 error {l2:.3e}"
 
 
 def _unsort(out, B):
@@ -176,17 +189,37 @@ def test_single_utterance_and_minimum_lengths(satk, root):
     _case(satk, root, "ljspeech_self-attention-tacotron.json", 1, 5, 6, True)
 
 
-def test_maximum_text_length_and_loud_failure_beyond(satk, root):
-    """The attention-RNN backward kernel keeps an utterance's keys / values / key gradients in shared memory: T_text <= 152.  At the
-    limit everything matches the oracle; one position more is refused with an error (never silently rerouted)."""
+def test_maximum_text_length_and_loud_failure_beyond(satk, root, monkeypatch):
+    """The attention-RNN kernels keep an utterance's keys / values in shared memory.  The second-generation kernels take
+    T_text <= 192 (one softmax position per thread of a 6-warp group; groups of 4 CTAs above 156 positions), the first-generation
+    backward kernel T_text <= 152.  At each limit everything matches the oracle; one position more is refused with an error
+    (never silently rerouted)."""
     E, O, L, M = _mods()
-    _case(satk, root, "ljspeech_self-attention-tacotron.json", 2, 152, 8, True)
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 2, 192, 8, True)
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 3, 157, 12, True)
     hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
     eng = E.TacotronEngine(hp, "cuda", seed=1)
+    f, l = satk.synthetic_batch(hp, 2, 193, 8, seed=5, device="cuda")
+    with pytest.raises(L.SatkError, match="shared memory"):
+        eng.forward(f, l, True)
+    monkeypatch.setenv("SATK_ATTN_GEN", "1")                  # first-generation kernels: limit 152
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 2, 152, 8, True)
+    eng = E.TacotronEngine(hp, "cuda", seed=1)
     f, l = satk.synthetic_batch(hp, 2, 153, 8, seed=5, device="cuda")
-    eng.forward(f, l, True)                                   # forward fits (210 KB of shared memory at T_text = 148)
+    eng.forward(f, l, True)
     with pytest.raises(L.SatkError, match="shared memory"):
         eng.backward()
+
+
+@pytest.mark.parametrize("nb,gen", [("5", "2"), ("4", "2"), ("", "1")])
+def test_attention_rnn_kernel_generations_and_cluster_geometries(satk, root, monkeypatch, nb, gen):
+    """Both geometries of the second-generation attention-RNN kernels (5 utterances per cluster in groups of 3 CTAs, 4 in groups
+    of 4; the last cluster partly filled) and the first-generation kernels against the oracle, all gradients included."""
+    monkeypatch.setenv("SATK_ATTN_GEN", gen)
+    if nb:
+        monkeypatch.setenv("SATK_ATTN_NB", nb)
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 7, 61, 40, True)
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 6, 33, 24, True, overrides="attention=location_sensitive")
 
 
 def test_multi_stream_backward_matches_single_stream_full_size(satk, root, monkeypatch):
@@ -312,6 +345,21 @@ def test_full_size_batch_properties(satk, root):
     for _ in range(3):
         l1 = eng.train_step(fd, ld)["losses"][2].item()
     assert l1 == l1 and l1 < l0 + 0.05
+
+
+def test_full_size_gradient_parity_config2(satk, root):
+    """BASELINE.json configs[1] at FULL size (B=32, T_text=148, T_mel=800), TRAIN mode with injected masks, the default path
+    (batch sort, step_end walk, side streams, second-generation attention-RNN kernels in one wave): every output and EVERY
+    gradient tensor against the oracle's fp64-free autograd (400-step BPTT)."""
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 32, 148, 800, True, seed=3)
+    assert _GRAD_LOG[-1]["loose"] <= 3, _GRAD_LOG[-1]
+
+
+def test_full_size_gradient_parity_config3_vctk(satk, root):
+    """BASELINE.json configs[2] at its per-replica size (B=64, multi-speaker pre-net): outputs and every gradient tensor
+    against the oracle (13 attention clusters of 5 utterances = two waves)."""
+    _case(satk, root, "vctk_self-attention-tacotron.json", 64, 148, 800, True, seed=5)
+    assert _GRAD_LOG[-1]["loose"] <= 3, _GRAD_LOG[-1]
 
 
 def test_vctk_config3_per_replica_batch_runs_full_size(satk, root):

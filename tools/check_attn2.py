@@ -55,6 +55,8 @@ def main():
     shapes = [(5, 30, 40), (7, 148, 120), (3, 61, 64), (32, 148, 800)]
     if "big" in sys.argv:
         shapes = [(32, 148, 800), (64, 148, 800)]
+    if "small" in sys.argv:
+        shapes = [(5, 30, 40)]
     for (B, Tt, Tm) in shapes:
         ps = satk.ParamStore(d).init(7, "random")
         eng = E.TacotronEngine(hp, "cuda", params=ps)

@@ -77,7 +77,8 @@ def install():
     for name in ["colsum_acc", "embedding_fwd", "embedding_bwd", "bn_stats", "bn_apply", "bn_bwd", "highway_fwd", "highway_bwd",
                  "act_bwd", "add", "axpy", "transpose", "mask_rows", "softsign_fwd", "softsign_bwd", "add_rowvec_tb",
                  "sum_over_t", "bernoulli_mask", "softmax_fwd", "softmax_bwd", "teacher_inputs", "losses", "grad_sumsq",
-                 "adam_clip", "l2_reg", "transpose_batched", "lstm_seq_fwd", "lstm_seq_bwd", "attn_rnn_fwd", "attn_rnn_bwd"]:
+                 "adam_clip", "l2_reg", "transpose_batched", "lstm_seq_fwd", "lstm_seq_bwd", "attn_rnn_fwd", "attn_rnn_bwd",
+                 "attn_rnn_bwd_recurrence", "attn_energy_grad", "attn_rnn_bwd_launch"]:
         setattr(O, name, any_ok)
 
     def transposed_rows(x, rows, cols, ldx=None, x_off=0, front=0):
