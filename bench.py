@@ -22,10 +22,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-CFG = "ljspeech_self-attention-tacotron.json"
-B, TT, TM = 32, 148, 800
 METRIC = "teacher_forced_mel_frames_per_sec"
 UNIT = "mel-frames/s"
+# BASELINE.json configs: name -> (example json, hparams overrides, per-GPU batch, T_text, T_mel, mode)
+WORKLOADS = {
+    "ljspeech": ("ljspeech_self-attention-tacotron.json", None, 32, 148, 800, "train"),                      # configs[1]: headline
+    "vctk": ("vctk_self-attention-tacotron.json", None, 64, 148, 800, "train"),                              # configs[2]: per-replica 64
+    "location_sensitive": ("ljspeech_self-attention-tacotron.json", "attention=location_sensitive", 32, 148, 800, "train"),   # configs[3]
+    "transition_agent": ("ljspeech_self-attention-tacotron.json", "use_forward_attention_transition_agent=True", 32, 148, 800, "train"),
+    "predict": ("ljspeech_self-attention-tacotron.json", None, 16, 148, 1000, "predict"),                    # configs[4]: free-running
+}
+CFG, OVR, B, TT, TM, MODE = WORKLOADS["ljspeech"]
+
+
+def select_workload(name):
+    global CFG, OVR, B, TT, TM, MODE
+    CFG, OVR, B, TT, TM, MODE = WORKLOADS[name]
+
+
+def workload_name():
+    return f"{CFG}{' ' + OVR if OVR else ''} B={B}/GPU T_text={TT} T_mel={TM} n_mels=80"
 
 
 class ClockSampler(threading.Thread):
@@ -81,22 +97,85 @@ def oracle_sample(hp, satk, steps, warmup, sample_b):
 
 
 def run_reference(args, rank):
+    """CPU arm (rank 0 only; ONE replica however many GPUs the other arm uses): the oracle's full train step on the SAME
+    configuration and batch size as the GPU arm, with the requested warm-up."""
     if rank != 0:
         return
     import satk_path
     satk = satk_path.load()
-    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG))
-    sample_b = 8
-    value, dt, cores = oracle_sample(hp, satk, args.steps, min(args.warmup, 1), sample_b)
-    sample = (f"{sample_b} of the {B} utterances of the batch (same T_text={TT}, T_mel={TM}), full train step per step; "
-              "torch-CPU fp32 restatement of the TF1 graph (TF1 itself cannot run here)")
+    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG), OVR)
+    if MODE != "train":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU arm times the teacher-forced train step only"}), flush=True)
+        return
+    value, dt, cores = oracle_sample(hp, satk, args.steps, args.warmup, B)
+    sample = (f"the full per-replica batch ({B} utterances, T_text={TT}, T_mel={TM}), full train step per step, {args.warmup} warm-up steps; "
+              "torch-CPU fp32 restatement of the TF1 graph (TF1 itself cannot run here); one CPU replica regardless of --gpus")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{CFG} B={B}/GPU T_text={TT} T_mel={TM} n_mels=80 teacher-forced train step"},
+        "dtype": "f32", "data": "synthetic", "n_cpu_replicas": 1,
+        "config": {"workload": f"{workload_name()} teacher-forced train step"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_predict(args, rank, world, local_rank):
+    """BASELINE.json configs[4]: free-running inference (predict_mel.py path), B=16, <= 1000 mel frames (500 decoder steps), stop
+    token disabled for timing; every rank decodes its own batch (replicas, no collective)."""
+    import torch
+    import satk_path
+    satk = satk_path.load()
+    from importlib import import_module
+    E = import_module("self-attention-tacotron_b200.engine")
+    O = import_module("self-attention-tacotron_b200.ops")
+    torch.cuda.set_device(local_rank)
+    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG), OVR)
+    eng = E.TacotronEngine(hp, f"cuda:{local_rank}", seed=1)
+    d = eng.d
+    T = TM // d.r
+    host = [satk.synthetic_batch(hp, B, TT, 8 * d.r, seed=50 + i)[0] for i in range(3)]
+    host = [satk.SourceData(*[x.pin_memory() if torch.is_tensor(x) else x for x in f]) for f in host]
+    devb = [satk.SourceData(*[x.cuda() if torch.is_tensor(x) else x for x in f]) for f in host]
+    for i in range(max(args.warmup, 3)):
+        eng.predict(devb[i % 3], max_iters=T, use_stop_token=False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    n = max(1, min(args.steps, 5))
+    l0 = O.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        out = eng.predict(devb[i % 3], max_iters=T, use_stop_token=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    launches = O.launches() - l0
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    d2h = 0
+    for i in range(n):
+        f = satk.SourceData(*[x.cuda(non_blocking=True) if torch.is_tensor(x) else x for x in host[i % 3]])
+        mel = eng.predict(f, max_iters=T, use_stop_token=False)["mel"].cpu()       # the mel frames are the result
+        d2h = mel.numel() * 4
+    e3.record()
+    torch.cuda.synchronize()
+    ms_e2e = e2.elapsed_time(e3) / n
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    h2d = sum(x.numel() * x.element_size() for x in host[0] if torch.is_tensor(x))
+    print(json.dumps({
+        "metric": "free_running_mel_frames_per_sec", "value": world * B * T * d.r / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": n,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{workload_name()} free-running decode, {T} decoder steps (r={d.r}), stop token off; "
+                                                    "a step = one batch of utterances decoded", "parallelism": f"replicas x{world}"},
+        "e2e": {"value": world * B * T * d.r / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches, "clocks": clocks, "us_per_decoder_step": ms * 1e3 / T, "finite": bool(torch.isfinite(out["mel"]).all()),
+        "roofline": None,
     }), flush=True)
 
 
@@ -113,10 +192,13 @@ def run_satk(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG))
+    hp = satk.load_hparams(os.path.join(ROOT, "examples", CFG), OVR)
 
-    def allreduce(flat):
-        dist.all_reduce(flat)      # ONE ncclAllReduce(sum) over the flat fp32 gradient buffer
+    def allreduce(flat, async_op=False):
+        # ncclAllReduce(sum) over (a bucket of) the flat fp32 gradient buffer; the engine sends the decoder bucket while the
+        # encoder's backward pass runs (engine.backward)
+        return dist.all_reduce(flat, async_op=async_op)
+    allreduce.supports_async = True
 
     model = M.tacotron_model_factory(hp, None, None, device=str(dev), allreduce=allreduce if world > 1 else None, world_size=world)
     eng = model.engine
@@ -190,10 +272,24 @@ def run_satk(args, rank, world, local_rank):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- timed region 3: the same step with EVERY target at full length (all Td decoder steps carry a loss: nothing for the
+    # backward walk to skip): the length distribution of the synthetic batch does not flatter `value`
+    nfl = max(1, min(args.steps, 5))
+    full = [tuple(satk.synthetic_batch(hp, B, TT, TM, seed=4321 + 100 * rank + i, device=dev, full_length=True)) for i in range(2)]
+    for i in range(2):
+        eng.train_step(full[i][0], full[i][1], None, allreduce=allreduce if world > 1 else None, world_size=world)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record()
+    for i in range(nfl):
+        eng.train_step(full[i % 2][0], full[i % 2][1], None, allreduce=allreduce if world > 1 else None, world_size=world)
+    e5.record()
+    barrier()
+    ms_full = e4.elapsed_time(e5) / nfl
+    t = torch.tensor([ms, ms_e2e, ms_full], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_full = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -218,44 +314,57 @@ def run_satk(args, rank, world, local_rank):
         torch.cuda.synchronize()
         kt[name] = statistics.mean(a.elapsed_time(b) for a, b in evs)
     roof = None
+    # fraction of the (utterance, decoder step) pairs that carry a loss: the backward walk skips the others (engine.forward: step_end)
+    loss_frac = statistics.mean(float((l_.binary_loss_mask != 0).sum()) / (B * td) for _, l_ in host)
+    frames_with_loss = world * args.steps * statistics.mean(float((l_.spec_loss_mask != 0).sum()) for _, l_ in host)
     if kt:
         sections = {k[4:]: v for k, v in kt.items() if k.startswith("sec.")}
         kt = {k: v for k, v in kt.items() if not k.startswith("sec.")}
-        dom = max(kt, key=kt.get)
-        alg = bytes_step * td * (2 if dom.endswith("bwd") else 1)
-        loss_frac = None
-        if dom.endswith("bwd") and getattr(eng, "skip_masked_steps", False):
-            # the backward walk only visits decoder steps that can carry a gradient (engine.forward: step_end); the keys / values
-            # of the skipped (utterance, step) pairs are not algorithmic work, the weights are (one utterance spans all Td steps)
-            loss_frac = statistics.mean(float((l_.binary_loss_mask != 0).sum()) / (B * td) for _, l_ in host)
-            alg = 2 * td * 2 * (w_seq + loss_frac * B * TT * (d.att1 + d.mem1 + d.att2 + d.mem2))
-        ach = alg / (kt[dom] * 1e-3) / 1e9
+        kv = B * TT * (d.att1 + d.mem1 + d.att2 + d.mem2)
+
+        def kernel_roof(name):
+            # algorithmic bytes per launch: forward = bytes_step * Td; backward = 2x that, its key / value
+            # term counted only for the pairs that are walked (the weights are algorithmic work for all Td steps)
+            if name.endswith("bwd"):
+                lf = loss_frac if getattr(eng, "skip_masked_steps", False) else 1.0
+                alg = 2 * td * 2 * (w_seq + lf * kv)
+            else:
+                alg = bytes_step * td
+            ach = alg / (kt[name] * 1e-3) / 1e9
+            return {"achieved": ach, "frac": ach / hbm, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": kt[name],
+                    "us_per_decoder_step": kt[name] * 1e3 / td}
+        rk = {n: kernel_roof(n) for n in ("attn_rnn_fwd", "attn_rnn_bwd") if n in kt}
+        dom = max(rk, key=lambda n: kt[n]) if rk else max(kt, key=kt.get)
         traffic = None
         try:   # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (same shapes only)
             traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
         except Exception:
             pass
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+        r0 = rk.get(dom, {"achieved": None, "frac": None})
+        roof = {"kernel": dom, "bound": "hbm", "achieved": r0["achieved"], "peak": hbm, "unit": "GB/s", "frac": r0["frac"], "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                "algorithmic_bytes_per_launch": alg, "steps_with_loss_frac": loss_frac, "avg_launch_ms": kt[dom], "us_per_decoder_step": kt[dom] * 1e3 / td,
-                "kernel_ms": kt, "section_ms": sections}
+                "algorithmic_bytes_per_launch": r0.get("algorithmic_bytes_per_launch"), "steps_with_loss_frac": loss_frac,
+                "avg_launch_ms": kt[dom], "us_per_decoder_step": kt[dom] * 1e3 / td,
+                "kernels": rk, "kernel_ms": kt, "section_ms": sections}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{CFG} B={B}/GPU T_text={TT} T_mel={TM} n_mels=80 teacher-forced train step "
-                               "(fwd+bwd+allreduce+clip+Adam)", "parallelism": f"dp{world}",
+        "config": {"workload": f"{workload_name()} teacher-forced train step (fwd+bwd+allreduce+clip+Adam)", "parallelism": f"dp{world}",
                    "l2": "working set per step (>1 GB of activations) exceeds the 126 MB L2; 4 distinct batches rotated"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
                 "last_loss": loss,
                 "loss_readback": "blocking float(loss) per step" if blocking else
                 "every step's loss copied to pinned memory behind the step and read after the next step is enqueued"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        # the same step with all targets at full length (no masked decoder steps to skip), and the padded-frame-free variant of `value`
+        "value_full_length": world * B * TM / (ms_full * 1e-3), "ms_per_step_full_length": ms_full,
+        "frames_with_loss_per_sec": frames_with_loss / (ms * 1e-3),
     }
     if world == 1 and not args.no_cpu_baseline:
-        v, dt, cores = oracle_sample(hp, satk, 1, 1, 8)
+        v, dt, cores = oracle_sample(hp, satk, 1, 1, B)
         out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": f"1 timed train step (after 1 warm-up) on 8 of the {B} utterances, T_text={TT}, T_mel={TM}; "
+                               "sample": f"1 timed train step (after 1 warm-up) on the full batch ({B} utterances, T_text={TT}, T_mel={TM}); "
                                          "oracle = torch-CPU fp32 restatement of the TF1 graph"}
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -269,12 +378,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="satk", choices=["satk", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="ljspeech", choices=sorted(WORKLOADS),
+                    help="BASELINE.json workload: ljspeech = configs[1] (headline, default), vctk = configs[2], location_sensitive / "
+                         "transition_agent = configs[3] variants, predict = configs[4]")
     args = ap.parse_args()
+    select_workload(args.config)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif MODE == "predict":
+        run_predict(args, rank, world, local_rank)
     else:
         run_satk(args, rank, world, local_rank)
 

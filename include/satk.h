@@ -191,7 +191,9 @@ int satk_losses(const float* pred_tm, const float* stop_tm, const float* mel, co
 
 /* Optimiser step on the flat buffer (models.py:485-498,595-598): global-norm clip (1.0),
  * Adam (eps outside the sqrt), gradient pre-scale (1/world_size after the all-reduce).
- * sumsq: 1 float scratch. */
+ * sumsq: scratch of SATK_SUMSQ_SCRATCH floats; [0] receives the sum of squares (deterministic: per-block partials are added
+ * in a fixed order, so data-parallel replicas clip identically). */
+#define SATK_SUMSQ_SCRATCH 640
 int satk_grad_sumsq(const float* g, long long n, float* sumsq, void* stream);
 int satk_adam_clip(float* p, const float* g, float* m, float* v, long long n, const float* sumsq, float grad_scale,
                    float clip_norm, float lr, float beta1, float beta2, float eps, int step, void* stream);

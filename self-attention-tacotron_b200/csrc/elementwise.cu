@@ -468,8 +468,12 @@ __global__ void loss_grad_k(const float* __restrict__ pred, const float* __restr
 }
 
 // ---------------------------------------------------------------- optimiser
+// Deterministic global sum of squares: every block leaves its partial in the scratch, the last block to finish adds them in
+// a fixed order (data-parallel replicas must derive bit-identical clip factors from bit-identical all-reduced gradients, or
+// their weights drift apart).  scratch: [0] result, [1] ticket counter, [2 ..] one partial per block.
 __global__ void sumsq_k(const float* __restrict__ g, long long n, float* __restrict__ out) {
   __shared__ float sh[32];
+  __shared__ bool last;
   float a = 0.f;
   long long n4 = n >> 2;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -479,7 +483,19 @@ __global__ void sumsq_k(const float* __restrict__ g, long long n, float* __restr
   }
   for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a += g[i] * g[i];
   a = block_sum(a, sh);
-  if (threadIdx.x == 0) atomicAdd(out, a);
+  if (threadIdx.x == 0) {
+    out[2 + blockIdx.x] = a;
+    __threadfence();
+    last = atomicAdd(reinterpret_cast<unsigned*>(out + 1), 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    float t = 0.f;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(out + 2 + i);
+    t = block_sum(t, sh);
+    if (threadIdx.x == 0) out[0] = t;
+  }
 }
 __global__ void l2_reg_k(const float* __restrict__ p, const float* __restrict__ mask, long long n, float scale, float* __restrict__ g,
                          float* __restrict__ loss_acc) {
@@ -685,8 +701,8 @@ int satk_losses(const float* pred_tm, const float* stop_tm, const float* mel, co
   return 0;
 }
 int satk_grad_sumsq(const float* g, long long n, float* sumsq, void* stream) {
-  SATK_CUDA(cudaMemsetAsync(sumsq, 0, sizeof(float), ST));
-  sumsq_k<<<kSMs * 4, 256, 0, ST>>>(g, n, sumsq);
+  SATK_CUDA(cudaMemsetAsync(sumsq, 0, 2 * sizeof(float), ST));
+  sumsq_k<<<kSMs * 4, 256, 0, ST>>>(g, n, sumsq);      // SATK_SUMSQ_SCRATCH = 2 + 4 * 148 floats
   SATK_LAUNCH_CHECK();
   return 0;
 }

@@ -78,7 +78,7 @@ class TacotronEngine:
         self._mask_seed = 0x5A7C + seed
         self.saved = None
         self.global_step = 0
-        self._sumsq = torch.zeros(1, device=self.device)
+        self._sumsq = torch.zeros(O.SUMSQ_SCRATCH, device=self.device)   # include/satk.h: SATK_SUMSQ_SCRATCH
         self.refresh_transposed()
         # weight-gradient products have no consumer before the optimiser: they run on a second stream beside the critical path
         # (dX chain + recurrent kernels, which leave most SMs idle); SATK_WGRAD_STREAM=0 keeps everything on one stream
@@ -93,6 +93,8 @@ class TacotronEngine:
             for name in ("forward", "backward", "optimizer_step"):
                 setattr(self, name, self._on_main(getattr(self, name)))
         self.sort_batches = os.environ.get("SATK_SORT_BATCHES", "1") != "0"   # TRAIN steps sort the batch by target / source length
+        # first element of the decoder / attention suffix of the flat parameter buffer (ParamStore lays the tensors out in forward order)
+        self._dec_off = min(off for n, (off, _) in self.ps.offsets.items() if n.startswith(("att1.", "att2.", "dec.")))
         self.skip_masked_steps = os.environ.get("SATK_STEP_END", "1") != "0"  # attention-RNN backward starts at the last step with a loss
         self.timers = None     # dict name -> [(start_event, end_event)] when bench.py wants per-kernel device times
 
@@ -976,7 +978,11 @@ class TacotronEngine:
         if d.use_speaker:
             sp_pre = self.lin(spk, "dec.prenet0.Ws", self.buf("dec.sp_pre", (B, d.dec_prenet[0])), bias=p["dec.prenet0.bs"])
             O.softsign_fwd(sp_pre, self.buf("dec.sp", (B, d.dec_prenet[0])))
-        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters), bool(getattr(self, "fused_decode_tail", True)))
+        # the step descriptors (and the captured graph) hold raw pointers of the shared memory / key buffers: `buf` re-allocates a
+        # buffer when another (B, Tt) passed through forward / train_step in between, so the pointers are part of the key
+        shared = ("dec.values1", "dec.keys1", "dec.values2", "dec.keys2", "dec.sp", "spk_embed", "enc.mem1", "enc.mem2")
+        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters), bool(getattr(self, "fused_decode_tail", True)),
+               tuple(self._bufs[k].data_ptr() for k in shared if k in self._bufs), mem1.data_ptr(), 0 if mem2 is None else mem2.data_ptr())
         cache = getattr(self, "_decode_cache", None)
         if cache is None or cache["key"] != key:
             run_step, stt = self._build_decode_step(B, Tt, Tmax, use_stop_token, min_iters)
@@ -1029,14 +1035,35 @@ class TacotronEngine:
             if ds >= 0:
                 T = ds + 1
         mel = stt["mel_hist"][1:T + 1].view(T, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, T * d.r, d.n_mels)
-        out = dict(mel=mel, stop=stt["stop_hist"][:T].t(), alignment=stt["al1"][:T].permute(1, 2, 0),
+        out = dict(mel=mel, stop=stt["stop_hist"][:T].t(), mel_tm=stt["mel_hist"][1:T + 1], stop_tm=stt["stop_hist"][:T],
+                   alignment=stt["al1"][:T].permute(1, 2, 0),
                    alignment2=stt["al2"][:T].permute(1, 2, 0) if d.dual else None,
                    dec_self_P=[pr[:, i, :T, :T] for pr in stt["probs"] for i in range(d.dec_sa_heads)],
                    enc_self_P=enc_al, steps=T, steps_executed=n_run)
         return out
 
-    def backward(self):
-        """BPTT through decoder and encoder; gradients land in ``self.ps.grad`` (zeroed first)."""
+    def validate(self, features, labels):
+        """EVAL-mode decode WITHOUT teacher forcing (tacotron2 ValidationHelper(teacher_forcing=False), models/models.py:384-395,
+        467-482): the decoder feeds back its own output for exactly Tm / r steps (no stop token) and the losses are taken against
+        the labels.  -> (losses [3] = mel, done, total; the free-running outputs of `predict`)."""
+        d = self.d
+        B, Tm = labels.mel.shape[0], labels.mel.shape[1]
+        Td = Tm // d.r
+        out = self.predict(features, max_iters=Td, use_stop_token=False)
+        out3 = self.buf("val.loss3", (3,))
+        mel_tm = out["mel_tm"].reshape(Td * B, d.r * d.n_mels)
+        stop_tm = out["stop_tm"].reshape(Td * B, 1)
+        O.losses(mel_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
+                 out3, self.buf("val.dmel", mel_tm.shape), self.buf("val.dstop", stop_tm.shape), self.buf("val.scratch", (4,)))
+        return out3, out
+
+    def backward(self, allreduce=None):
+        """BPTT through decoder and encoder; gradients land in ``self.ps.grad`` (zeroed first).
+
+        ``allreduce(flat, async_op=False)``: the data-parallel gradient sum (train.py:68 MirroredStrategy).  When the
+        callable advertises ``supports_async`` the flat buffer goes out as TWO buckets: the decoder / attention suffix is reduced
+        (asynchronously, on the collective's own stream) while the encoder's backward pass still runs, the encoder prefix
+        right after it."""
         s = self.saved
         self.ps.grad.zero_()
         dmem1, dmem2 = self._timed("sec.decoder_bwd", self.decoder_backward, s["dmel"], s["dstop"], s["B"], s["Tt"], s["Td"],
@@ -1050,6 +1077,13 @@ class TacotronEngine:
             dspk = self.buf("dspk_embed", (s["B"], self.d.speaker_dim))
             O.linear_dx(dsp_pre, p["dec.prenet0.Ws"], dspk, s["B"])
             O.embedding_bwd(s["features"].speaker_id, dspk, g["speaker_embedding"], offset=self.d.speaker_offset)
+        handle = None
+        overlapped = (allreduce is not None and getattr(allreduce, "supports_async", False) and self.d.l2_weight == 0
+                      and os.environ.get("SATK_AR_OVERLAP", "1") != "0")
+        if overlapped:
+            if self._side is not None:
+                torch.cuda.current_stream().wait_stream(self._side)  # the decoder's weight gradients are in
+            handle = allreduce(self.ps.grad[self._dec_off:], async_op=True)
         self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)      # every weight gradient is in before all-reduce / Adam
@@ -1057,6 +1091,12 @@ class TacotronEngine:
             # gradient of l2_regularization_loss (models/models.py:470-478): scale * w on the regularised tensors.  Every replica adds it
             # (TF: each replica's loss carries the term, gradients are averaged), the 1/world_size after the all-reduce restores it.
             O.l2_reg(self.ps.flat, self.ps.l2_mask(), self.d.l2_weight, g=self.ps.grad)
+        if overlapped:
+            allreduce(self.ps.grad[:self._dec_off])
+            if handle is not None:
+                handle.wait()                                        # orders the current stream behind the asynchronous bucket
+        elif allreduce is not None:
+            allreduce(self.ps.grad)
 
     def optimizer_step(self, world_size: int = 1):
         """clip_by_global_norm(1.0) + Adam + noam LR (models.py:485-498).  With world_size > 1 the caller has
@@ -1073,8 +1113,6 @@ class TacotronEngine:
 
     def train_step(self, features, labels, masks=None, allreduce=None, world_size: int = 1):
         out = self.forward(features, labels, True, masks)
-        self.backward()
-        if allreduce is not None:
-            allreduce(self.ps.grad)
+        self.backward(allreduce)
         out["lr"] = self._timed("sec.optimizer", self.optimizer_step, world_size)
         return out

@@ -104,32 +104,31 @@ class _TacotronEstimator:
             return EstimatorSpec(mode=mode, predictions=preds)
         labels = _to_device(labels, self.device)
         training = mode == ModeKeys.TRAIN
-        if training:
-            out = eng.train_step(features, labels, masks, allreduce=self._allreduce, world_size=self._world_size)
-        else:
-            out = eng.forward(features, labels, False)
         B, Tm = labels.mel.shape[0], labels.mel.shape[1]
         Td = Tm // d.r
-        losses = out["losses"]
-        preds = None
-        if not training:
-            mel = out["mel_tm"].view(Td, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, Tm, d.n_mels)
-            preds = {"id": features.id, "key": features.key, "mel": mel, "ground_truth_mel": labels.mel,
-                     "stop_token": out["stop_tm"].view(Td, B).t(),
-                     "alignment": out["align1_tm"].permute(1, 2, 0),             # (B, Tt, Td), models.py:406
-                     "source": features.source, "text": features.text}
-            if d.dual:
-                preds["alignment2"] = out["align2_tm"].permute(1, 2, 0)          # models.py:407
-                for i, a in enumerate(out["dec_self_P"]):                        # alignment3/4, models.py:403-404
-                    preds[f"alignment{3 + i}"] = a.transpose(1, 2)
-                for i, a in enumerate(out["enc_self_P"]):                        # alignment5.., models.py:398
-                    preds[f"alignment{5 + i}"] = a.transpose(1, 2)
-        scalars = {"loss_with_teacher": losses[2], "mel_loss_with_teacher": losses[0], "done_loss_with_teacher": losses[1],
-                   "mel_loss": losses[0], "done_loss": losses[1]}
         if training:
-            scalars["learning_rate"] = out["lr"]
-        return EstimatorSpec(mode=mode, loss=losses[2], train_op=eng.global_step if training else None, predictions=preds,
-                             eval_metric_ops=None if training else dict(scalars), scalars=scalars)
+            out = eng.train_step(features, labels, masks, allreduce=self._allreduce, world_size=self._world_size)
+            losses = out["losses"]
+            scalars = {"mel_loss": losses[0], "done_loss": losses[1], "learning_rate": out["lr"]}
+            return EstimatorSpec(mode=mode, loss=losses[2], train_op=eng.global_step, predictions=None, eval_metric_ops=None, scalars=scalars)
+        # EVAL (models/models.py:384-395,500-545): `loss` / `mel_loss` / `done_loss` and the mel + alignments handed to MetricsSaver come
+        # from a decode WITHOUT teacher forcing over the target length (ValidationHelper(teacher_forcing=False)); a second, teacher-forced
+        # decode gives the `*_with_teacher` metrics
+        tf_out = eng.forward(features, labels, False)
+        with_teacher = tf_out["losses"].clone()
+        losses, out = eng.validate(features, labels)
+        preds = {"id": features.id, "key": features.key, "mel": out["mel"], "ground_truth_mel": labels.mel, "stop_token": out["stop"],
+                 "alignment": out["alignment"],                                  # (B, Tt, Td), models.py:406
+                 "source": features.source, "text": features.text}
+        if d.dual:
+            preds["alignment2"] = out["alignment2"]                              # models.py:407
+            for i, a in enumerate(out["dec_self_P"]):                            # alignment3/4, models.py:403-404
+                preds[f"alignment{3 + i}"] = a.transpose(1, 2)
+            for i, a in enumerate(out["enc_self_P"]):                            # alignment5.., models.py:398
+                preds[f"alignment{5 + i}"] = a.transpose(1, 2)
+        scalars = {"loss": losses[2], "mel_loss": losses[0], "done_loss": losses[1],
+                   "loss_with_teacher": with_teacher[2], "mel_loss_with_teacher": with_teacher[0], "done_loss_with_teacher": with_teacher[1]}
+        return EstimatorSpec(mode=mode, loss=losses[2], train_op=None, predictions=preds, eval_metric_ops=dict(scalars), scalars=scalars)
 
     # ---- drivers (tf.estimator.Estimator.train / evaluate / predict)
     def train(self, input_fn: Callable[[], Iterable], steps: Optional[int] = None, max_steps: Optional[int] = None, hooks=None):

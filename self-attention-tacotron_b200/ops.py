@@ -349,7 +349,12 @@ def losses(pred_tm, stop_tm, mel, done, spec_mask, bin_mask, B, Tm, n_mels, r, o
     _count(2)
 
 
+SUMSQ_SCRATCH = 640     # include/satk.h: SATK_SUMSQ_SCRATCH
+
+
 def grad_sumsq(g, sumsq):
+    if sumsq.numel() < SUMSQ_SCRATCH:
+        raise L.SatkError(f"grad_sumsq: the scratch needs {SUMSQ_SCRATCH} floats")
     check(load().satk_grad_sumsq(C.c_void_p(g.data_ptr()), C.c_longlong(g.numel()), C.c_void_p(sumsq.data_ptr()),
                                  C.c_void_p(stream_ptr())), "satk_grad_sumsq")
     _count()

@@ -116,6 +116,28 @@ def dims_from_hparams(hp) -> ModelDims:
                        ("use_accent_type", "accent-type inputs")):
         if bool(getattr(hp, flag, False)):
             raise NotImplementedError(f"{flag}=True: {what} is not built in this implementation")
+    # switches with a built default and an unbuilt alternative: the non-default value would train / predict a different model
+    if bool(hp.use_speaker_embedding) and not bool(getattr(hp, "speaker_embedd_to_prenet", True)):
+        raise NotImplementedError("speaker_embedd_to_prenet=False: the speaker embedding always feeds MultiSpeakerPreNet here "
+                                  "(models/models.py:387, multi_speaker_modules.py:27-32)")
+    for flag, what in (("speaker_embedd_to_decoder", "speaker embedding concatenated onto the encoder memories (models/models.py:366-372)"),
+                       ("apply_dropout_on_inference", "pre-net dropout at inference time"),
+                       ("language_embedd_to_input", "language embedding into the encoder input"),
+                       ("language_embedd_to_decoder", "language embedding into the decoder")):
+        if bool(getattr(hp, flag, False)):
+            raise NotImplementedError(f"{flag}=True: {what} is not built in this implementation")
+    if int(getattr(hp, "speaker_for_synthesis", -1)) > -1:
+        raise NotImplementedError("speaker_for_synthesis > -1: overriding the speaker id at synthesis time is not built")
+    # limits of the attention-RNN / LSTM sequence kernels (csrc/attn_rnn*.cu, lstm_seq.cu): fail at construction, not at the first step
+    if hp.attention in ("forward", "location_sensitive") and (hp.attention_filters > 8 or hp.attention_kernel > 32):
+        raise NotImplementedError(f"attention_filters={hp.attention_filters} / attention_kernel={hp.attention_kernel}: the location "
+                                  "convolution of the attention kernels holds at most 8 filters of 32 taps (the shipped configurations use 5 x 10)")
+    if hp.attention_out_units != 256 or hp.cbhg_out_units != 256 or hp.decoder_out_units != 256:
+        raise NotImplementedError("attention_out_units / cbhg_out_units / decoder_out_units must be 256 (recurrent kernels are built for "
+                                  "LSTM widths 128 (encoder) and 256)")
+    if dual and (hp.attention1_out_units, hp.attention2_out_units, hp.self_attention_out_units) != (224, 32, 32):
+        raise NotImplementedError("dual-source decoder: attention1_out_units / attention2_out_units / self_attention_out_units must be "
+                                  "224 / 32 / 32")
     return ModelDims(
         dual=dual, num_symbols=hp.num_symbols, embed=hp.embedding_dim,
         enc_prenet=tuple(hp.encoder_prenet_out_units), conv_ch=hp.conv_channels, bank_k=hp.max_filter_width,

@@ -264,7 +264,7 @@ def test_adam_clip_and_losses():
     n = 1003
     p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 3
     m, v = torch.zeros(n), torch.zeros(n)
-    pd, gd, md, vd, ss = p.cuda(), gr.cuda(), m.cuda(), v.cuda(), torch.zeros(1, device="cuda")
+    pd, gd, md, vd, ss = p.cuda(), gr.cuda(), m.cuda(), v.cuda(), torch.zeros(O.SUMSQ_SCRATCH, device="cuda")
     O.grad_sumsq(gd, ss)
     O.adam_clip(pd, gd, md, vd, ss, 0.5, 1.0, 1e-3, 0.9, 0.999, 1e-8, 3)
     cl, _ = OR.clip_by_global_norm([gr * 0.5], 1.0)

@@ -393,9 +393,25 @@ def test_estimator_surface(satk, root, tmp_path):
     spec = model.train(input_fn, steps=2)
     assert spec.train_op == 2 and torch.isfinite(spec.loss)
     ev = model.evaluate(input_fn, steps=1)
-    assert {"loss_with_teacher", "mel_loss_with_teacher", "done_loss_with_teacher", "global_step"} <= set(ev)
-    ev_spec = model.model_fn(f, l, M.ModeKeys.EVAL, hp)                      # teacher-forced decode keeps the target length
+    assert {"loss", "mel_loss", "done_loss", "loss_with_teacher", "mel_loss_with_teacher", "done_loss_with_teacher", "global_step"} <= set(ev)
+    # EVAL (models/models.py:384-395,500-545): plain metrics and predictions come from a decode WITHOUT teacher forcing over the target
+    # length (ValidationHelper(teacher_forcing=False)), the *_with_teacher metrics from a second, teacher-forced decode
+    ev_spec = model.model_fn(f, l, M.ModeKeys.EVAL, hp)
     assert ev_spec.predictions["mel"].shape == (4, 24, 80) and ev_spec.predictions["alignment"].shape == (4, 20, 12)
+    fd = satk.SourceData(*[x.cuda() if torch.is_tensor(x) else x for x in f])
+    ld = satk.MelData(*[x.cuda() if torch.is_tensor(x) else x for x in l])
+    tf_losses = model.engine.forward(fd, ld, False)["losses"].clone()
+    free = model.engine.predict(fd, max_iters=12, use_stop_token=False)
+    assert torch.allclose(ev_spec.scalars["loss_with_teacher"], tf_losses[2])
+    _close(ev_spec.predictions["mel"], free["mel"], 1e-5, "EVAL predictions = free-running decode over the target length")
+    want = torch.stack([OR.spec_loss_l1(free["mel"].cpu(), l.mel, l.spec_loss_mask), OR.binary_loss(free["stop"].cpu(), l.done, l.binary_loss_mask)])
+    _close(torch.stack([ev_spec.scalars["mel_loss"], ev_spec.scalars["done_loss"]]), want, 1e-4, "validation losses")
+    assert abs(float(ev_spec.scalars["loss"]) - float(ev_spec.scalars["loss_with_teacher"])) > 1e-6      # two different decodes
+    # the free-running step cache survives a teacher-forced pass of another shape in between (it re-keys on the buffer pointers)
+    f2, l2 = satk.synthetic_batch(hp, 3, 33, 16, seed=9, device="cuda")
+    a0 = model.engine.predict(fd, max_iters=12, use_stop_token=False)["mel"].clone()
+    model.engine.forward(f2, l2, False)
+    _close(model.engine.predict(fd, max_iters=12, use_stop_token=False)["mel"], a0, 1e-5, "free-running decode after a re-keyed step cache")
     pred = next(model.predict(input_fn))                                     # free-running (PREDICT mode), <= max_iters steps
     T = pred["alignment"].shape[2]
     assert 11 < T <= 12 and pred["mel"].shape == (4, 2 * T, 80) and pred["alignment"].shape == (4, 20, T)

@@ -159,7 +159,7 @@ def t_softmax_loss_adam():
     p, gr = torch.randn(n, generator=g), torch.randn(n, generator=g) * 3
     m, v = torch.zeros(n), torch.zeros(n)
     pd, gd, md, vd = p.to(dev), gr.to(dev), m.to(dev), v.to(dev)
-    ss = torch.zeros(1, device=dev)
+    ss = torch.zeros(O.SUMSQ_SCRATCH, device=dev)
     O.grad_sumsq(gd, ss)
     O.adam_clip(pd, gd, md, vd, ss, 0.5, 1.0, 1e-3, 0.9, 0.999, 1e-8, 3)
     cl, norm = OR.clip_by_global_norm([gr * 0.5], 1.0)
