@@ -12,35 +12,60 @@ namespace satk {
 namespace arnn2 {
 
 constexpr int EG_NT = 256;
-constexpr int EG_CB = 32;          // score channels per CTA
-constexpr int EG_KS = 40;          // key row stride (4 rows x 8 channel lanes -> 32 distinct banks)
-constexpr int EG_MP = 6;           // position passes of 32 slots: Tt <= 192
+constexpr int EG_CB = 16;          // score channels per CTA: lane = (position lane ep = lane >> 2, channel lane ecl = lane & 3), 4 channels per lane
+constexpr int EG_KS = 20;          // key row stride (8 rows x 4 channel lanes -> 32 distinct banks)
+constexpr int EG_MP = 3;           // position passes of 64 slots: Tt <= 192
 constexpr int EG_TB = 4;           // decoder steps per iteration (amortises the barriers, hides the global loads)
+constexpr int EG_JC = 8;           // positions per thread of the conv-gradient stage
 
 struct EgSmem {
   int TtP, DFW;
-  float *keyS, *fS, *dfS, *aprev, *deS, *qS, *wconv, *bconv;
+  float *keyS, *fS, *dfS, *aprev, *deS, *qS;
   __host__ __device__ size_t carve(float* base, int Tt) {
-    TtP = (Tt + 31) / 32 * 32;
+    TtP = (Tt + 63) / 64 * 64;
     DFW = TtP + 2 * HALO;
     float* p = base;
     keyS = p; p += (size_t)TtP * EG_KS;
-    fS = p; p += (size_t)EG_TB * TtP * MAXF;
+    fS = p; p += (size_t)2 * EG_TB * TtP * MAXF;   // [buffer][step][j][8] location features (precomputed, asynchronous copies)
     dfS = p; p += (size_t)EG_TB * AFT * DFW;
     aprev = p; p += 2 * EG_TB * DFW;           // [buffer][step][HALO + j]
     deS = p; p += 2 * EG_TB * TtP;
     qS = p; p += 2 * EG_TB * EG_CB;
-    wconv = p; p += MAXK * MAXF;
-    bconv = p; p += MAXF;
     return (size_t)(p - base) * sizeof(float);
   }
 };
 
+// location features f_t[j][0..AFT) = conv1d(a_{t-1}) + bias for every (step, utterance): [Td][B][Tt][MAXF] (forward_attention.py:98-100)
+__global__ void __launch_bounds__(256) loc_features_all_kernel(const satk_attn_rnn_fwd_desc d, float* __restrict__ fws) {
+  __shared__ float ap[256 + 2 * HALO + MAXK];
+  __shared__ float wc[MAXK * MAXF + MAXF];
+  const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, Tt = d.Tt;
+  const int pl = (d.att_kernel - 1) / 2;
+  for (int i = tid; i < MAXK * MAXF; i += 256) {
+    const int k = i / MAXF, f = i % MAXF;
+    wc[i] = (k < d.att_kernel && f < d.att_filters) ? __ldg(d.loc_conv_w + k * d.att_filters + f) : 0.f;
+  }
+  if (tid < MAXF) wc[MAXK * MAXF + tid] = (tid < d.att_filters) ? __ldg(d.loc_conv_b + tid) : 0.f;
+  for (int i = tid; i < Tt + 2 * HALO + MAXK; i += 256) {
+    const int j = i - HALO;
+    ap[i] = (t > 0 && j >= 0 && j < Tt) ? __ldg(d.soft1 + ((long long)(t - 1) * d.B + b) * Tt + j) : 0.f;
+  }
+  __syncthreads();
+  float* out = fws + ((long long)t * d.B + b) * Tt * MAXF;
+  for (int idx = tid; idx < Tt * MAXF; idx += 256) {
+    const int j = idx / MAXF, f = idx % MAXF;
+    float acc = wc[MAXK * MAXF + f];
+    for (int k = 0; k < d.att_kernel; ++k) acc = fmaf(ap[HALO + j - pl + k], wc[k * MAXF + f], acc);
+    out[idx] = (f < AFT) ? acc : 0.f;
+  }
+}
+
 template <bool LOC>
-__global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_attn_rnn_bwd_desc dd, const float* __restrict__ de) {
+__global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_attn_rnn_bwd_desc dd, const float* __restrict__ de,
+                                                                    const float* __restrict__ fws) {
   const satk_attn_rnn_fwd_desc& d = dd.f;
   const int b = blockIdx.y;
-  const int cb = LOC ? blockIdx.x : 0;             // channel block inside the mechanism
+  const int cb = blockIdx.x;                       // channel block inside the mechanism
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tt = d.Tt, B = d.B, Td = d.Td;
   const int alen = min((int)d.lengths[b], Tt);
@@ -48,16 +73,16 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
   const int pl = (d.att_kernel - 1) / 2;
   const int AW = LOC ? A1 : A2;                    // width of the mechanism's key rows
   const float* keys = LOC ? d.keys1 : d.keys2;
-  const int qoff = LOC ? cb * EG_CB : A1;          // column of my channels inside the saved query rows
+  const int qoff = (LOC ? 0 : A1) + cb * EG_CB;    // column of my channels inside the saved query rows
 
   extern __shared__ __align__(16) float smem_raw[];
   EgSmem S;
   S.carve(smem_raw, Tt);
   const int TtP = S.TtP, DFW = S.DFW;
 
-  const int ep = lane >> 3, ecl = lane & 7;
-  const int slot0 = warp * 4 + ep;                 // positions slot0 + 32 m
-  const int npass = min(EG_MP, (alen - 4 * warp + 31) / 32);   // passes of this warp that touch the utterance (warp-uniform)
+  const int ep = lane >> 2, ecl = lane & 3;
+  const int slot0 = warp * 8 + ep;                 // positions slot0 + 64 m
+  const int npass = min(EG_MP, (alen - 8 * warp + 63) / 64);   // passes of this warp that touch the utterance (warp-uniform)
 
   for (int i = tid; i < TtP * EG_KS; i += EG_NT) {
     const int j = i / EG_KS, c = i % EG_KS;
@@ -65,27 +90,22 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
     if (j < Tt && c < EG_CB) kv = (__ldg(keys + ((long long)j * B + b) * AW + cb * EG_CB + c) + ((LOC && d.b1) ? __ldg(d.b1 + cb * EG_CB + c) : 0.f)) * K2LOG2E;
     S.keyS[i] = kv;
   }
-  for (int i = tid; i < MAXK * MAXF; i += EG_NT) {
-    const int k = i / MAXF, f = i % MAXF;
-    S.wconv[i] = (LOC && k < d.att_kernel && f < d.att_filters) ? __ldg(d.loc_conv_w + k * d.att_filters + f) : 0.f;
-  }
-  if (tid < MAXF) S.bconv[tid] = (LOC && tid < d.att_filters) ? __ldg(d.loc_conv_b + tid) : 0.f;
   for (int i = tid; i < 2 * EG_TB * DFW; i += EG_NT) S.aprev[i] = 0.f;
   for (int i = tid; i < EG_TB * AFT * DFW; i += EG_NT) S.dfS[i] = 0.f;
-  for (int i = tid; i < EG_TB * TtP * MAXF; i += EG_NT) S.fS[i] = 0.f;
+  for (int i = tid; i < 2 * EG_TB * TtP * MAXF; i += EG_NT) S.fS[i] = 0.f;
   for (int i = tid; i < 2 * EG_TB * TtP; i += EG_NT) S.deS[i] = 0.f;
   for (int i = tid; i < 2 * EG_TB * EG_CB; i += EG_NT) S.qS[i] = 0.f;
 
-  // per-channel constants of my 4 channels (ecl + 8 i)
+  // per-channel constants of my 4 channels (ecl + 4 i)
   float v4c[4], wf[4][AFT];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int c = cb * EG_CB + ecl + 8 * i;
+    const int c = cb * EG_CB + ecl + 4 * i;
     v4c[i] = 4.f * __ldg((LOC ? d.v1 : d.v2) + c);
 #pragma unroll
     for (int f = 0; f < AFT; ++f) wf[i][f] = (LOC && f < d.att_filters) ? __ldg(d.loc_layer_w + (long long)f * A1 + c) * K2LOG2E : 0.f;
   }
-  // accumulators: dkeys tile, sum de*r per channel (dv = v-free: sum de*tanh = sum de - 2 sum de*r), d(location layer)
+  // accumulators: dkeys tile, sum de*r per channel (sum de*tanh = sum de - 2 sum de*r), d(location layer)
   float dk[EG_MP][4], dvr[4], dWf[4][AFT], sum_de = 0.f;
 #pragma unroll
   for (int m = 0; m < EG_MP; ++m)
@@ -97,13 +117,21 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
 #pragma unroll
     for (int f = 0; f < AFT; ++f) dWf[i][f] = 0.f;
   }
-  // d(location convolution): thread = (tap k, filter f, quarter of the positions); tap index att_kernel = the bias
+  // d(location convolution): thread = (filter f, chunk of EG_JC positions): the taps of the chunk accumulate in registers;
+  // entry att_kernel of the accumulator row is the bias.  (generic tap count: the slower (tap, filter, quarter) mapping below)
+  const bool conv10 = LOC && d.att_kernel == 10;
+  const int nchunk = (Tt + EG_JC - 1) / EG_JC;
+  const int cv_f = tid / nchunk, cv_c = tid % nchunk;
+  const bool cv_act = conv10 && cv_f < AFT;
+  float cacc[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) cacc[k] = 0.f;
   const int cf_e = tid >> 2, cf_q = tid & 3;
-  const int ntap = LOC ? (d.att_kernel + 1) * AFT : 0;
+  const int ntap = (LOC && !conv10) ? (d.att_kernel + 1) * AFT : 0;
   const int cf_k = cf_e / AFT, cf_f = cf_e % AFT;
   float dconv = 0.f;
 
-  // asynchronous loads of de_t, a_{t-1}, q_t (my channels) of the EG_TB steps starting at t0 into buffer `buf`
+  // asynchronous loads of de_t, a_{t-1}, f_t, q_t (my channels) of the EG_TB steps starting at t0 into buffer `buf`
   auto load_steps = [&](int t0, int buf) {
     for (int e = tid; e < EG_TB * Tt; e += EG_NT) {
       const int ts = e / Tt, j = e % Tt, t = t0 + ts;
@@ -113,6 +141,12 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
           if (t > 0) cl::cp_async4(&S.aprev[(buf * EG_TB + ts) * DFW + HALO + j], d.soft1 + ((long long)(t - 1) * B + b) * Tt + j);
           else S.aprev[(buf * EG_TB + ts) * DFW + HALO + j] = 0.f;
         }
+      }
+    }
+    if (LOC) {
+      for (int e = tid; e < EG_TB * Tt * 2; e += EG_NT) {          // two 16-byte halves per position
+        const int ts = e / (2 * Tt), r = e % (2 * Tt), t = t0 + ts;
+        if (t < Te) cp_async16(&S.fS[((size_t)(buf * EG_TB + ts) * TtP) * MAXF + 4 * r], fws + ((long long)t * B + b) * Tt * MAXF + 4 * r);
       }
     }
     if (tid < EG_TB * EG_CB) {
@@ -131,24 +165,18 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
     cl::cp_async_wait<0>();
     __syncthreads();                       // inputs of this iteration visible; everybody is done with the previous iteration
     load_steps(t0 + EG_TB, buf ^ 1);       // (commits an empty group past the end)
-    if (LOC) {
-      for (int ts = 0; ts < nts; ++ts)
-        arnn::location_features<AFT>(S.fS + (size_t)ts * TtP * MAXF, S.aprev + (buf * EG_TB + ts) * DFW, S.wconv, S.bconv, alen, d.att_kernel, pl,
-                                     tid, EG_NT);
-      __syncthreads();
-    }
 #pragma unroll 1
     for (int ts = 0; ts < nts; ++ts) {
       float q[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) q[i] = S.qS[(buf * EG_TB + ts) * EG_CB + ecl + 8 * i] * K2LOG2E;
+      for (int i = 0; i < 4; ++i) q[i] = S.qS[(buf * EG_TB + ts) * EG_CB + ecl + 4 * i] * K2LOG2E;
       const float* des = S.deS + (buf * EG_TB + ts) * TtP;
-      const float* fs = S.fS + (size_t)ts * TtP * MAXF;
+      const float* fs = S.fS + (size_t)(buf * EG_TB + ts) * TtP * MAXF;
       float* dfs = S.dfS + (size_t)ts * AFT * DFW;
 #pragma unroll
       for (int m = 0; m < EG_MP; ++m) {
         if (m < npass) {
-          const int jr = slot0 + 32 * m, j = min(jr, Tt - 1);
+          const int jr = slot0 + 64 * m, j = min(jr, Tt - 1);
           const float dej = (jr < Tt) ? des[j] : 0.f;
           sum_de += dej;
           float fv[AFT], dfp[AFT];
@@ -160,7 +188,7 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
           for (int f = 0; f < AFT; ++f) dfp[f] = 0.f;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            float s = S.keyS[j * EG_KS + ecl + 8 * i] + q[i];
+            float s = S.keyS[j * EG_KS + ecl + 4 * i] + q[i];
             if (LOC) {
 #pragma unroll
               for (int f = 0; f < AFT; ++f) s = fmaf(fv[f], wf[i][f], s);
@@ -183,7 +211,6 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
               float v = dfp[f];
               v += __shfl_xor_sync(0xffffffffu, v, 1);
               v += __shfl_xor_sync(0xffffffffu, v, 2);
-              v += __shfl_xor_sync(0xffffffffu, v, 4);
               if (ecl == 0 && jr < Tt) dfs[f * DFW + HALO + jr] = v * (1.f / K2LOG2E);
             }
           }
@@ -192,8 +219,32 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
     }
     if (LOC) {
       __syncthreads();
-      if (cf_e < ntap) {
-        // d(conv kernel)[k][f] += sum_j a_{t-1}[j + k - pl] df[j][f] (partial df over my 32 channels: linear, the blocks add up)
+      // d(conv kernel)[k][f] += sum_j a_{t-1}[j + k - pl] df[j][f], d(bias)[f] += sum_j df[j][f] (partial df over my channels: linear,
+      // the channel blocks add up)
+      if (cv_act) {
+        const int j0 = cv_c * EG_JC;
+        for (int ts = 0; ts < nts; ++ts) {
+          const float* ap = S.aprev + (buf * EG_TB + ts) * DFW + HALO + j0 - pl;     // 16-byte aligned: HALO = 16, pl = 4, j0 % 8 = 0
+          const float* dfs = S.dfS + (size_t)ts * AFT * DFW + cv_f * DFW + HALO + j0;
+          float a[EG_JC + 12], g[EG_JC];
+#pragma unroll
+          for (int i = 0; i < (EG_JC + 12) / 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(ap + 4 * i);
+            a[4 * i] = v.x; a[4 * i + 1] = v.y; a[4 * i + 2] = v.z; a[4 * i + 3] = v.w;
+          }
+#pragma unroll
+          for (int i = 0; i < EG_JC / 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(dfs + 4 * i);
+            g[4 * i] = v.x; g[4 * i + 1] = v.y; g[4 * i + 2] = v.z; g[4 * i + 3] = v.w;
+          }
+#pragma unroll
+          for (int jj = 0; jj < EG_JC; ++jj) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) cacc[k] = fmaf(a[jj + k], g[jj], cacc[k]);
+            cacc[10] += g[jj];
+          }
+        }
+      } else if (cf_e < ntap) {
         for (int ts = 0; ts < nts; ++ts) {
           const float* ap = S.aprev + (buf * EG_TB + ts) * DFW;
           const float* dfs = S.dfS + (size_t)ts * AFT * DFW + cf_f * DFW + HALO;
@@ -212,67 +263,83 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
 
   // ---------------- flush
   if (LOC) {
-    dconv += __shfl_xor_sync(0xffffffffu, dconv, 1);
-    dconv += __shfl_xor_sync(0xffffffffu, dconv, 2);
-    if (cf_q == 0 && cf_e < ntap && cf_f < d.att_filters) {
-      if (cf_k < d.att_kernel) atomicAdd(dd.dloc_conv_w + cf_k * d.att_filters + cf_f, dconv);
-      else atomicAdd(dd.dloc_conv_b + cf_f, dconv);
+    if (conv10) {
+      if (cv_act) {
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          if (cv_f < d.att_filters) {
+            if (k < 10) atomicAdd(dd.dloc_conv_w + k * d.att_filters + cv_f, cacc[k]);
+            else atomicAdd(dd.dloc_conv_b + cv_f, cacc[k]);
+          }
+        }
+      }
+    } else {
+      dconv += __shfl_xor_sync(0xffffffffu, dconv, 1);
+      dconv += __shfl_xor_sync(0xffffffffu, dconv, 2);
+      if (cf_q == 0 && cf_e < ntap && cf_f < d.att_filters) {
+        if (cf_k < d.att_kernel) atomicAdd(dd.dloc_conv_w + cf_k * d.att_filters + cf_f, dconv);
+        else atomicAdd(dd.dloc_conv_b + cf_f, dconv);
+      }
     }
   }
   float* dkeys = LOC ? dd.dkeys1 : dd.dkeys2;
 #pragma unroll
   for (int m = 0; m < EG_MP; ++m) {
-    const int jr = slot0 + 32 * m;
+    const int jr = slot0 + 64 * m;
     if (jr < Tt) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) dkeys[((long long)jr * B + b) * AW + cb * EG_CB + ecl + 8 * i] = dk[m][i];
+      for (int i = 0; i < 4; ++i) dkeys[((long long)jr * B + b) * AW + cb * EG_CB + ecl + 4 * i] = dk[m][i];
     }
   }
-  // d(v), d(location layer): reduce over the 4 position lanes of the warp, then over the warps through shared memory
+  // d(v), d(location layer): reduce over the 8 position lanes of the warp, then over the warps through shared memory
   __syncthreads();
-  float* stage = S.keyS;   // keys are dead: [warp][8 lanes][4 + 4*AFT]
+  float* stage = S.fS;     // dead by now: [warp][4 channel lanes][4 + 4*AFT]
   constexpr int SW = 4 + 4 * AFT;
-  // the channel lanes of one position share de: sum over the position lanes / warps of sum_de is the same for every channel
-  sum_de += __shfl_xor_sync(0xffffffffu, sum_de, 8);
-  sum_de += __shfl_xor_sync(0xffffffffu, sum_de, 16);
+  // the channel lanes of one position share de: the sum over position lanes / warps of sum_de is the same for every channel
+#pragma unroll
+  for (int o = 4; o <= 16; o <<= 1) sum_de += __shfl_xor_sync(0xffffffffu, sum_de, o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float v = dvr[i];
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if (lane < 8) stage[(warp * 8 + ecl) * SW + i] = fmaf(-2.f, v, sum_de);     // sum de * tanh
+#pragma unroll
+    for (int o = 4; o <= 16; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane < 4) stage[(warp * 4 + ecl) * SW + i] = fmaf(-2.f, v, sum_de);     // sum de * tanh
 #pragma unroll
     for (int f = 0; f < AFT; ++f) {
       float w_ = dWf[i][f];
-      w_ += __shfl_xor_sync(0xffffffffu, w_, 8);
-      w_ += __shfl_xor_sync(0xffffffffu, w_, 16);
-      if (lane < 8) stage[(warp * 8 + ecl) * SW + 4 + i * AFT + f] = w_;
+#pragma unroll
+      for (int o = 4; o <= 16; o <<= 1) w_ += __shfl_xor_sync(0xffffffffu, w_, o);
+      if (lane < 4) stage[(warp * 4 + ecl) * SW + 4 + i * AFT + f] = w_;
     }
   }
   __syncthreads();
-  if (tid < 8 * SW) {
+  if (tid < 4 * SW) {
     const int cl_ = tid / SW, e = tid % SW;
     float acc = 0.f;
 #pragma unroll
-    for (int w_ = 0; w_ < EG_NT / 32; ++w_) acc += stage[(w_ * 8 + cl_) * SW + e];
+    for (int w_ = 0; w_ < EG_NT / 32; ++w_) acc += stage[(w_ * 4 + cl_) * SW + e];
     if (e < 4) {
-      atomicAdd((LOC ? dd.dv1 : dd.dv2) + cb * EG_CB + cl_ + 8 * e, acc);
+      atomicAdd((LOC ? dd.dv1 : dd.dv2) + cb * EG_CB + cl_ + 4 * e, acc);
     } else if (LOC) {
       const int i = (e - 4) / AFT, f = (e - 4) % AFT;
-      if (f < d.att_filters) atomicAdd(dd.dloc_layer_w + (long long)f * A1 + cb * EG_CB + cl_ + 8 * i, acc);
+      if (f < d.att_filters) atomicAdd(dd.dloc_layer_w + (long long)f * A1 + cb * EG_CB + cl_ + 4 * i, acc);
     }
   }
 }
 
+// workspace: de [Td,B,2,Tt] followed by the location features [Td,B,Tt,MAXF]
 int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, cudaStream_t st) {
-  SATK_CHECK_ARG(d->f.Tt <= 32 * EG_MP, "attn_energy_grad: Tt=%d out of range", d->f.Tt);
+  SATK_CHECK_ARG(d->f.Tt <= 64 * EG_MP, "attn_energy_grad: Tt=%d out of range", d->f.Tt);
   EgSmem S;
   const size_t smem = S.carve(nullptr, d->f.Tt);
+  float* fws = const_cast<float*>(de) + (size_t)d->f.Td * d->f.B * 2 * d->f.Tt;
+  loc_features_all_kernel<<<dim3(d->f.Td, d->f.B), 256, 0, st>>>(d->f, fws);
+  SATK_LAUNCH_CHECK();
   SATK_CUDA(cudaFuncSetAttribute(attn_energy_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SATK_CUDA(cudaFuncSetAttribute(attn_energy_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_energy_grad_kernel<true><<<dim3(A1 / EG_CB, d->f.B), EG_NT, smem, st>>>(*d, de);
+  attn_energy_grad_kernel<true><<<dim3(A1 / EG_CB, d->f.B), EG_NT, smem, st>>>(*d, de, fws);
   SATK_LAUNCH_CHECK();
-  attn_energy_grad_kernel<false><<<dim3(1, d->f.B), EG_NT, smem, st>>>(*d, de);
+  attn_energy_grad_kernel<false><<<dim3(A2 / EG_CB, d->f.B), EG_NT, smem, st>>>(*d, de, fws);
   SATK_LAUNCH_CHECK();
   return SATK_OK;
 }

@@ -43,6 +43,38 @@ constexpr int NSVB = NTB - CW * 32;   // 96 service threads (global-memory traff
 #define PT2_FLUSH(n)
 #endif
 
+
+// ---- tensor memory as a parking space for the stationary recurrent weights -------------------------------------------------
+// The 64 weights a thread needs for BC are read-only for the whole launch, but pinned in registers they leave the energy phase
+// ~30 free registers (serialised ex2 / rcp chains, spills).  Tensor memory (256 KB per SM) is otherwise unused by this kernel:
+// each warp stores its 32 x 64 weights once (tcgen05.st, 32x32b: lane i <-> TMEM lane 32*(warp%4)+i, 64 columns per warp) and
+// reads them back right before BC of every step (tcgen05.ld, ~8 KB per warp from a ~TB/s datapath).
+#define SATK_TM_REGS32(r, o) \
+  "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7]), "r"(r[o + 8]), \
+  "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]), "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15]), "r"(r[o + 16]), \
+  "r"(r[o + 17]), "r"(r[o + 18]), "r"(r[o + 19]), "r"(r[o + 20]), "r"(r[o + 21]), "r"(r[o + 22]), "r"(r[o + 23]), "r"(r[o + 24]), \
+  "r"(r[o + 25]), "r"(r[o + 26]), "r"(r[o + 27]), "r"(r[o + 28]), "r"(r[o + 29]), "r"(r[o + 30]), "r"(r[o + 31])
+#define SATK_TM_OUT32(r, o) \
+  "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7]), \
+  "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15]), \
+  "=r"(r[o + 16]), "=r"(r[o + 17]), "=r"(r[o + 18]), "=r"(r[o + 19]), "=r"(r[o + 20]), "=r"(r[o + 21]), "=r"(r[o + 22]), "=r"(r[o + 23]), \
+  "=r"(r[o + 24]), "=r"(r[o + 25]), "=r"(r[o + 26]), "=r"(r[o + 27]), "=r"(r[o + 28]), "=r"(r[o + 29]), "=r"(r[o + 30]), "=r"(r[o + 31])
+#define SATK_TM_LIST32 \
+  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, " \
+  "%28, %29, %30, %31}"
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[64], int o) {
+  if (o == 0)
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], " SATK_TM_LIST32 ";" ::SATK_TM_REGS32(r, 0), "r"(taddr) : "memory");
+  else
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], " SATK_TM_LIST32 ";" ::SATK_TM_REGS32(r, 32), "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " SATK_TM_LIST32 ", [%32];" : SATK_TM_OUT32(r, 0) : "r"(taddr));
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 " SATK_TM_LIST32 ", [%32];" : SATK_TM_OUT32(r, 32) : "r"(taddr + 32u));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+constexpr int TM_COLS = 256;   // 4 warps per TMEM lane quarter x 64 columns
+
 template <int NB>
 struct BwdSmem2 {
   using GE = Geo<NB>;
@@ -330,14 +362,28 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
   // 64 gate columns): 4 x 16 weights in registers.  (A thread per row with all 64 columns would need 80 broadcast LDS.128 of
   // d(gates) per step, and a broadcast 16-byte load still costs 4 shared-memory cycles: 5 K cycles per step for 16 warps.)
   const int bc_rq = tid >> 2, bc_cq = tid & 3;
-  float wr[4][16];
+  __shared__ uint32_t tmem_base_sh;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cl::smem_u32(&tmem_base_sh)), "n"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm_addr = tmem_base_sh + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+  {
+    uint32_t wbits[64];       // [row of my quad][column of my quarter]
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const int col = 16 * bc_cq + c;                  // CTA-local gate column = gate*16 + unit
-      wr[r][c] = __ldg(d.Wrec + (long long)(4 * bc_rq + r) * (4 * H) + (col >> 4) * H + rank * UH + (col & 15));
-    }
+      for (int c = 0; c < 16; ++c) {
+        const int col = 16 * bc_cq + c;                  // CTA-local gate column = gate*16 + unit
+        wbits[r * 16 + c] = __float_as_uint(__ldg(d.Wrec + (long long)(4 * bc_rq + r) * (4 * H) + (col >> 4) * H + rank * UH + (col & 15)));
+      }
+    tmem_st32(tm_addr, wbits, 0);
+    tmem_st32(tm_addr + 32u, wbits, 32);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
   // destination of my row quad's partial results: owner of context columns 4rq..4rq+3 / hidden units 4rq-288..
   const int bc_k0 = 4 * bc_rq;
   int bc_g, bc_off;          // group member (context rows) or -1, float offset inside the destination's inbox
@@ -749,6 +795,8 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
     PT2(11)
     if (t > 0) {
       // ======================= BC: partial d([ctx | h])(t-1) over my gate columns -> the consumers
+      uint32_t wbits[64];
+      tmem_ld64(tm_addr, wbits);
       float acc[NB][4];      // [utterance][row of my quad], partial over my 16 columns
 #pragma unroll
       for (int uu = 0; uu < NB; ++uu) {
@@ -758,8 +806,10 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
           const float4 g4 = *reinterpret_cast<const float4*>(&S.dgS[uu * 64 + 16 * bc_cq + 4 * c4]);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            acc[uu][r] = fmaf(wr[r][4 * c4], g4.x, acc[uu][r]); acc[uu][r] = fmaf(wr[r][4 * c4 + 1], g4.y, acc[uu][r]);
-            acc[uu][r] = fmaf(wr[r][4 * c4 + 2], g4.z, acc[uu][r]); acc[uu][r] = fmaf(wr[r][4 * c4 + 3], g4.w, acc[uu][r]);
+            acc[uu][r] = fmaf(__uint_as_float(wbits[r * 16 + 4 * c4]), g4.x, acc[uu][r]);
+            acc[uu][r] = fmaf(__uint_as_float(wbits[r * 16 + 4 * c4 + 1]), g4.y, acc[uu][r]);
+            acc[uu][r] = fmaf(__uint_as_float(wbits[r * 16 + 4 * c4 + 2]), g4.z, acc[uu][r]);
+            acc[uu][r] = fmaf(__uint_as_float(wbits[r * 16 + 4 * c4 + 3]), g4.w, acc[uu][r]);
           }
         }
       }
@@ -842,6 +892,9 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
   }
   PT2_FLUSH(Te)
   cp_async_wait<0>();
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_sh), "n"(TM_COLS) : "memory");
   cluster.sync();
 }
 

@@ -663,7 +663,7 @@ class TacotronEngine:
             dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
             step_end=self.saved.get("step_end"),
             # workspace of the second-generation kernels (d(energies) of both mechanisms, include/satk.h)
-            de_ws=self.buf("dec.de_ws", (Td, B, 2, Tt)) if d.dual else None)
+            de_ws=self.buf("dec.de_ws", (Td, B, Tt, 2 + 8)) if d.dual else None)
         # second generation: the recurrence, then the energy gradients (dkeys, dv, location layer / conv) as a parallel launch of
         # their own; configurations it does not cover run the first-generation kernel (everything in one launch)
         if d.dual and self._timed("attn_rnn_bwd", O.attn_rnn_bwd_recurrence, bd):
