@@ -331,7 +331,7 @@ typedef struct {
    * skips (dx2 is left as it is: zero).  Ignored with cumulative != 0 (the location state is walked back from the final state).
    * NULL: all Td steps. */
   const int* step_end;
-  /* optional workspace of Td*B*Tt*10 floats (d(energies) [Td,B,2,Tt], then the location features [Td,B,Tt,8] that
+  /* optional workspace of Td*B*Tt*10 + 4 floats (d(energies) [Td,B,2,Tt], then - 16-byte aligned - the location features [Td,B,Tt,8] that
    * satk_attn_energy_grad computes once for all steps).  When it is set and the configuration is the dual-source decoder of the shipped
    * models (forward / location-sensitive first mechanism without cumulative weights or transition agent, <= 5 location
    * filters, Tt <= 192), the second-generation kernels run: the sequential kernel (one wave of 16-CTA clusters at B = 32)

@@ -332,7 +332,7 @@ int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, cu
   SATK_CHECK_ARG(d->f.Tt <= 64 * EG_MP, "attn_energy_grad: Tt=%d out of range", d->f.Tt);
   EgSmem S;
   const size_t smem = S.carve(nullptr, d->f.Tt);
-  float* fws = const_cast<float*>(de) + (size_t)d->f.Td * d->f.B * 2 * d->f.Tt;
+  float* fws = const_cast<float*>(de) + (((size_t)d->f.Td * d->f.B * 2 * d->f.Tt + 3) & ~(size_t)3);   // 16-byte aligned rows
   loc_features_all_kernel<<<dim3(d->f.Td, d->f.B), 256, 0, st>>>(d->f, fws);
   SATK_LAUNCH_CHECK();
   SATK_CUDA(cudaFuncSetAttribute(attn_energy_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

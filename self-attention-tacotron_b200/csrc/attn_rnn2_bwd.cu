@@ -187,8 +187,40 @@ __device__ __forceinline__ void energy_bwd_passes(const BwdSmem2<NB>& S, int slo
     for (int f = 0; f < AFT; ++f) dfp[m][f] = 0.f;
   }
   float* dqw = S.dqst + warp * NSLOT;
-#pragma unroll 2
-  for (int i = 0; i < NIA; ++i) {
+  // two channel iterations at a time: 2 x NACT independent ex2 / rcp chains in flight
+  static_assert(NIA % 2 == 0 || NIA == 7, "channel iterations are walked in pairs");
+#pragma unroll 1
+  for (int i = 0; i + 1 < NIA; i += 2) {
+    const float4 pa0 = S.packA[ecl + 8 * i], pb0 = S.packB[ecl + 8 * i];
+    const float4 pa1 = S.packA[ecl + 8 * i + 8], pb1 = S.packB[ecl + 8 * i + 8];
+    const int col0 = __float_as_int(pb0.w), col1 = __float_as_int(pb1.w);
+    float s0[NACT], s1[NACT];
+#pragma unroll
+    for (int m = 0; m < NACT; ++m) {
+      float a = krow[m][col0] + pa0.x, c = krow[m][col1] + pa1.x;
+      a = fmaf(fv[m][0], pa0.z, a); c = fmaf(fv[m][0], pa1.z, c);
+      a = fmaf(fv[m][1], pa0.w, a); c = fmaf(fv[m][1], pa1.w, c);
+      a = fmaf(fv[m][2], pb0.x, a); c = fmaf(fv[m][2], pb1.x, c);
+      a = fmaf(fv[m][3], pb0.y, a); c = fmaf(fv[m][3], pb1.y, c);
+      a = fmaf(fv[m][4], pb0.z, a); c = fmaf(fv[m][4], pb1.z, c);
+      s0[m] = ex2f(a); s1[m] = ex2f(c);
+    }
+    float dq0 = 0.f, dq1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < NACT; ++m) {
+      const float r0 = rcpf(1.f + s0[m]), r1 = rcpf(1.f + s1[m]);      // tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r)
+      const float d0 = (de1[m] * pa0.y) * (4.f * r0 * (1.f - r0)), d1 = (de1[m] * pa1.y) * (4.f * r1 * (1.f - r1));
+      dq0 += d0; dq1 += d1;
+      dfp[m][0] = fmaf(d0, pa0.z, fmaf(d1, pa1.z, dfp[m][0])); dfp[m][1] = fmaf(d0, pa0.w, fmaf(d1, pa1.w, dfp[m][1]));
+      dfp[m][2] = fmaf(d0, pb0.x, fmaf(d1, pb1.x, dfp[m][2])); dfp[m][3] = fmaf(d0, pb0.y, fmaf(d1, pb1.y, dfp[m][3]));
+      dfp[m][4] = fmaf(d0, pb0.z, fmaf(d1, pb1.z, dfp[m][4]));
+    }
+    dq0 += __shfl_xor_sync(0xffffffffu, dq0, 8); dq1 += __shfl_xor_sync(0xffffffffu, dq1, 8);
+    dq0 += __shfl_xor_sync(0xffffffffu, dq0, 16); dq1 += __shfl_xor_sync(0xffffffffu, dq1, 16);
+    if (lane < 8) { dqw[ecl + 8 * i] = dq0; dqw[ecl + 8 * i + 8] = dq1; }
+  }
+  if (NIA & 1) {
+    constexpr int i = NIA - 1;
     const float4 pa = S.packA[ecl + 8 * i], pb = S.packB[ecl + 8 * i];
     const int col = __float_as_int(pb.w);
     float dq = 0.f;
@@ -197,7 +229,7 @@ __device__ __forceinline__ void energy_bwd_passes(const BwdSmem2<NB>& S, int slo
       float s = krow[m][col] + pa.x;
       s = fmaf(fv[m][0], pa.z, s); s = fmaf(fv[m][1], pa.w, s);
       s = fmaf(fv[m][2], pb.x, s); s = fmaf(fv[m][3], pb.y, s); s = fmaf(fv[m][4], pb.z, s);
-      const float r = rcpf(1.f + ex2f(s));                 // tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r)
+      const float r = rcpf(1.f + ex2f(s));
       const float ds = (de1[m] * pa.y) * (4.f * r * (1.f - r));
       dq += ds;
       dfp[m][0] = fmaf(ds, pa.z, dfp[m][0]); dfp[m][1] = fmaf(ds, pa.w, dfp[m][1]);

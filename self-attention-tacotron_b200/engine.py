@@ -663,11 +663,19 @@ class TacotronEngine:
             dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
             step_end=self.saved.get("step_end"),
             # workspace of the second-generation kernels (d(energies) of both mechanisms, include/satk.h)
-            de_ws=self.buf("dec.de_ws", (Td, B, Tt, 2 + 8)) if d.dual else None)
+            de_ws=self.buf("dec.de_ws", (Td * B * Tt * (2 + 8) + 4,)) if d.dual else None)
         # second generation: the recurrence, then the energy gradients (dkeys, dv, location layer / conv) as a parallel launch of
         # their own; configurations it does not cover run the first-generation kernel (everything in one launch)
+        energy_forked = False
         if d.dual and self._timed("attn_rnn_bwd", O.attn_rnn_bwd_recurrence, bd):
-            self._timed("attn_energy_grad", O.attn_energy_grad, bd)
+            # dkeys / dv / d(location layer, conv) feed nothing before the memory-layer gradients below: the launch runs on the
+            # auxiliary stream beside the LSTM-1 input gradient, the dvalues products and the pre-net backward chain
+            if getattr(self, "_aux", None) is not None and os.environ.get("SATK_ENERGY_FORK", "1") != "0":
+                with self._fork():
+                    self._timed("attn_energy_grad", O.attn_energy_grad, bd)
+                energy_forked = True
+            else:
+                self._timed("attn_energy_grad", O.attn_energy_grad, bd)
         else:
             self._timed("attn_rnn_bwd", O.attn_rnn_bwd_launch, bd)
         # LSTM-1 weight gradients (dense over time)
@@ -692,24 +700,11 @@ class TacotronEngine:
         dval1 = self.buf("dec.dvalues1", (R, d.mem1))
         O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
                b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
-        # keys = values . W_mem ; attention bias folded into the keys
-        with self._wg():
-            if loc:
-                O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
-            O.linear_dw(sv["values1"], dkeys1, g["att1.memory.W"], R, d.mem1, d.att1)
-            if d.dual:
-                O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
-        O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
-        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
-        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
-        dmem2 = None
+        dval2 = None
         if d.dual:
             dval2 = self.buf("dec.dvalues2", (R, d.mem2))
             O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
                    b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
-            O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
-            dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
-            O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
         # decoder pre-net
         keep_scale = 1.0 / (1.0 - d.dec_prenet_drop) if training else 1.0
         dz1 = self.buf("dec.dz1", (Rd, P1))
@@ -746,6 +741,23 @@ class TacotronEngine:
             with self._wg():
                 O.linear_dw(sv["dec_in"], dz0, g["dec.prenet0.W"], Rd, d.dec_in, P0)
                 O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
+        # keys = values . W_mem ; attention bias folded into the keys.  (dkeys come from the energy-gradient launch: join it first)
+        if energy_forked:
+            self._join()
+        with self._wg():
+            if loc:
+                O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
+            O.linear_dw(sv["values1"], dkeys1, g["att1.memory.W"], R, d.mem1, d.att1)
+            if d.dual:
+                O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
+        O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
+        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
+        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
+        dmem2 = None
+        if d.dual:
+            O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
+            dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
+            O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
         return dmem1, dmem2
 
     # ------------------------------------------------------------------ model_fn body
