@@ -32,6 +32,8 @@ constexpr int RINGB = 4;     // ring slots (time-indexed)
 constexpr int PFDB = 2;      // prefetch distance (steps)
 constexpr int WQS = 260;     // row stride of the per-unit query weights: 8 units x 16 bytes hit 32 distinct banks
 constexpr int NSVB = NTB - CW * 32;   // 96 service threads (global-memory traffic)
+constexpr int DGG = 20;      // floats per gate in the d(gates) staging: the 4 column quarters of BC then hit disjoint banks
+constexpr int DGS = 4 * DGG; // floats per batch row
 
 #ifdef SATK_PHASE_TIMING
 #define PT2_DECL unsigned pt_last = (unsigned)clock();
@@ -116,7 +118,7 @@ struct BwdSmem2 {
     dqst = p; p += CW * GE::NSLOT;                      // per-warp d(query) partials
     dqS = p; p += GE::QC;
     dqB = p; p += NB * QT;                              // d(query) of every utterance of the cluster
-    dgS = p; p += NB * 64;                              // d(gates) of my 64 gate columns
+    dgS = p; p += NB * DGS;                             // d(gates) of my 64 gate columns, [row][gate][DGG] (16 used)
     ringA = p; p += RINGB * 3 * (size_t)TtP;            // soft1 / align1 / align2 of time tau
     ringB = p; p += RINGB * (size_t)RB;
     red = p; p += 96;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
   if (tid < VC) S.dctxS[tid] = 0.f;
   if (tid < QC) S.dqS[tid] = 0.f;
   if (tid < NB * UH) S.dhS[tid] = 0.f;
-  if (tid < NB * 64) S.dgS[tid] = 0.f;
+  for (int i = tid; i < NB * DGS; i += NTB) S.dgS[i] = 0.f;
   if (tid < 16) S.pt[tid] = 0u;
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) cl::mbar_init(&S.bars[i], 1);
@@ -818,8 +820,8 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
           dgf = dcn * cp * gf * (1.f - gf);
           dc_st = (1.f - mc) * dc_st + dcn * gf;
         }
-        float* dg = S.dgS + bb_u * 64 + bb_unit;
-        dg[0] = dgi; dg[16] = dgj; dg[32] = dgf; dg[48] = dgo;
+        float* dg = S.dgS + bb_u * DGS + bb_unit;
+        dg[0] = dgi; dg[DGG] = dgj; dg[2 * DGG] = dgf; dg[3 * DGG] = dgo;
       }
     }
     PT2(10)
@@ -829,13 +831,14 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
       // ======================= BC: partial d([ctx | h])(t-1) over my gate columns -> the consumers
       uint32_t wbits[64];
       tmem_ld64(tm_addr, wbits);
+      PT2(13)
       float acc[NB][4];      // [utterance][row of my quad], partial over my 16 columns
 #pragma unroll
       for (int uu = 0; uu < NB; ++uu) {
         acc[uu][0] = 0.f; acc[uu][1] = 0.f; acc[uu][2] = 0.f; acc[uu][3] = 0.f;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 g4 = *reinterpret_cast<const float4*>(&S.dgS[uu * 64 + 16 * bc_cq + 4 * c4]);
+          const float4 g4 = *reinterpret_cast<const float4*>(&S.dgS[uu * DGS + DGG * bc_cq + 4 * c4]);
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             acc[uu][r] = fmaf(__uint_as_float(wbits[r * 16 + 4 * c4]), g4.x, acc[uu][r]);
@@ -888,16 +891,18 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
         if (bc_cq < NB) st_async_v4(dsta + bc_cq * UH * 4, o4[0], o4[1], o4[2], o4[3], barr);
         if (NB == 5 && bc_cq == 0) st_async_v4(dsta + (NB - 1) * UH * 4, e4[0], e4[1], e4[2], e4[3], barr);
       }
+      PT2(14)
       // rows 512..543 (hidden units 224..255): thread = (utterance, row, half of the column quads)
       if (tid < NB * 64) {
         const int o = tid >> 1, hh = tid & 1, r = o & 31, uu = o >> 5;
         const float* wrow = S.WragS + r * WRS + 4 * hh;
-        const float* grow = S.dgS + uu * 64 + 4 * hh;
+        const float* grow = S.dgS + uu * DGS + 4 * hh;     // column quad 2i + hh = gate (i >> 1), quad ((2i + hh) & 3) of the gate
         float a0 = 0.f, a1 = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
-          const float4 w0 = *reinterpret_cast<const float4*>(wrow + 8 * i), g0 = *reinterpret_cast<const float4*>(grow + 8 * i);
-          const float4 w1 = *reinterpret_cast<const float4*>(wrow + 8 * i + 8), g1 = *reinterpret_cast<const float4*>(grow + 8 * i + 8);
+          const float4 w0 = *reinterpret_cast<const float4*>(wrow + 8 * i), g0 = *reinterpret_cast<const float4*>(grow + (i >> 1) * DGG + 8 * (i & 1));
+          const float4 w1 = *reinterpret_cast<const float4*>(wrow + 8 * i + 8),
+                       g1 = *reinterpret_cast<const float4*>(grow + ((i + 1) >> 1) * DGG + 8 * ((i + 1) & 1));
           a0 = fmaf(w0.x, g0.x, a0); a0 = fmaf(w0.y, g0.y, a0); a0 = fmaf(w0.z, g0.z, a0); a0 = fmaf(w0.w, g0.w, a0);
           a1 = fmaf(w1.x, g1.x, a1); a1 = fmaf(w1.y, g1.y, a1); a1 = fmaf(w1.z, g1.z, a1); a1 = fmaf(w1.w, g1.w, a1);
         }
@@ -917,10 +922,9 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
         const int uu = e >> 4, g4 = (e >> 2) & 3, q4 = e & 3;
         if (b0 + uu < B)
           *reinterpret_cast<float4*>(dd.dgates + ((long long)t * B + b0 + uu) * (4 * H) + g4 * H + rank * UH + 4 * q4) =
-              *reinterpret_cast<const float4*>(&S.dgS[uu * 64 + g4 * 16 + 4 * q4]);
+              *reinterpret_cast<const float4*>(&S.dgS[uu * DGS + g4 * DGG + 4 * q4]);
       }
     }
-    PT2(13)
   }
   PT2_FLUSH(Te)
   cp_async_wait<0>();

@@ -8,6 +8,7 @@
 // Math: TF LSTMCell (i,j,f,o; forget_bias) + tacotron2 ZoneoutLSTMCell, SURVEY.md A.5/A.6;
 // sequence-length semantics of tf.nn.bidirectional_dynamic_rnn (module.py:93-108).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 #include "cluster_sync.cuh"
 #include "common.cuh"
 
@@ -433,6 +434,7 @@ int lstm_max_clusters_h256() {
 }  // namespace satk
 
 namespace satk { namespace tc { int tc_trace(long long* out16); } }
+namespace satk { namespace lstm5 { int lstm5_bwd_launch(const satk_lstm_bwd_desc* d, cudaStream_t st); } }
 namespace satk { namespace arnn { int attn_fwd_phase_cycles(long long* out16); int attn_bwd_phase_cycles(long long* out16); } }
 namespace satk { namespace arnn2 { int attn2_fwd_phase_cycles(long long* out16); int attn2_bwd_phase_cycles(long long* out16); } }
 using namespace satk;
@@ -470,6 +472,9 @@ int satk_lstm_seq_bwd(const satk_lstm_bwd_desc* d, void* stream) {
   SATK_CHECK_ARG(d->H == 128 || d->H == 256, "lstm_seq_bwd: H=%d unsupported (128 or 256)", d->H);
   SATK_CHECK_ARG(d->T > 0 && d->B > 0, "lstm_seq_bwd: empty T=%d B=%d", d->T, d->B);
   SATK_CHECK_ARG(d->ld_dout >= d->H, "lstm_seq_bwd: ld_dout=%lld < H", d->ld_dout);
+  // decoder layers (H = 256, forward order, no length masking): 5 rows per cluster, one wave at B = 32 (lstm_seq5.cu)
+  const char* gen = getenv("SATK_LSTM_GEN");
+  if (d->H == 256 && !d->lengths && !d->reverse && !(gen && gen[0] == '1')) return lstm5::lstm5_bwd_launch(d, (cudaStream_t)stream);
   if (d->H == 256) return launch_cluster(lstm_bwd_kernel<256>, *d, 256, d->B, (cudaStream_t)stream);
   return launch_cluster(lstm_bwd_kernel<128>, *d, 128, d->B, (cudaStream_t)stream);
 }

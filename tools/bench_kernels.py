@@ -44,6 +44,12 @@ def lstm(H, T, B):
     f = lambda: O.lstm_seq_bwd(Wh, gates, cp, dout, dg, T, B, H, mask_c=mc, mask_h=mh)
     mn, av = timeit(f)
     print(f"lstm_bwd H={H} T={T} B={B}: {mn:.3f} ms  ({1e3 * mn / T:.2f} us/step)", flush=True)
+    if H == 256:
+        ref = dg.clone()
+        os.environ["SATK_LSTM_GEN"] = "1"
+        mn, av = timeit(f)
+        os.environ.pop("SATK_LSTM_GEN")
+        print(f"lstm_bwd (first generation) H={H} T={T} B={B}: {mn:.3f} ms; max |diff| {(dg - ref).abs().max().item():.2e} of {ref.abs().max().item():.2e}", flush=True)
 
 
 def attn(B=32, Tt=148, Tm=800):
