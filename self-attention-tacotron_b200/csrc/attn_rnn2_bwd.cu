@@ -725,36 +725,7 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
           const int gcol = a1 ? 4 * (sl.qa0 + q) : A1 + 4 * (sl.qb0 + q - sl.qan);
           st_async_v4(cl::mapa(cl::smem_u32(&S.dqB[au * QT + gcol]), dst), q4.x, q4.y, q4.z, q4.w, cl::mapa(cl::smem_u32(&barQ[cur]), dst));
         }
-      } else if (warp < CW) {
-        // partial d(a_{t-1}) = conv-transpose of my partial d(location features) -> the group (consumed by step t-1)
-        if (t > 0) {
-          for (int base = (warp - 3) * 32; base < 4 * Tt4; base += (CW - 3) * 32) {
-            const int j = base + lane;
-            float acc = 0.f;
-            if (j < Tt) {
-              const float* dfr = S.dfS + HALO + j + pl;   // columns outside [0,Tt) are zero
-              if (d.att_kernel == 10) {
-#pragma unroll
-                for (int k = 0; k < 10; ++k)
-#pragma unroll
-                  for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f * DFW - k], S.wconv[k * MAXF + f], acc);
-              } else {
-                for (int k = 0; k < d.att_kernel; ++k)
-#pragma unroll
-                  for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f * DFW - k], S.wconv[k * MAXF + f], acc);
-              }
-            }
-            const int l4 = lane & ~3;
-            const float a0 = __shfl_sync(0xffffffffu, acc, l4), a1 = __shfl_sync(0xffffffffu, acc, l4 + 1);
-            const float a2 = __shfl_sync(0xffffffffu, acc, l4 + 2), a3 = __shfl_sync(0xffffffffu, acc, l4 + 3);
-            if ((lane & 3) == 0 && j < 4 * Tt4) {
-              const uint32_t dsta = cl::smem_u32(&S.dstate_part[(nxt * G + ag) * TtP + j]), bara = cl::smem_u32(&barW[nxt]);
-#pragma unroll
-              for (int gd = 0; gd < G; ++gd) st_async_v4(cl::mapa(dsta, au * G + gd), a0, a1, a2, a3, cl::mapa(bara, au * G + gd));
-            }
-          }
-        }
-      } else if (arow_ok && dd.dq) {
+      } else if (service && arow_ok && dd.dq) {
         // service: d(query) slice of step t -> global (dense dWq afterwards): sum of the per-warp partials
         for (int q = sv; q < sl.qan + sl.qbn; q += NSVB) {
           const bool a1 = q < sl.qan;
@@ -769,13 +740,6 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
           *reinterpret_cast<float4*>(dd.dq + ((long long)t * B + arow) * QT + gcol) = v4;
         }
       }
-    }
-    // early staging of step t-1 (nothing of the current step reads these buffers after barrier #4): off the dependency chain,
-    // in the shadow of the d(query) exchange
-    if (warp < CW && t > 0) {
-      stage_inputs(t - 1);
-      cl::named_bar_sync(5, CW * 32);
-      if (grp) arnn::location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, alen, d.att_kernel, pl, tid, CW * 32);
     }
     PT2(8)
     cl::mbar_wait(&barQ[cur], par);
@@ -831,7 +795,6 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
       // ======================= BC: partial d([ctx | h])(t-1) over my gate columns -> the consumers
       uint32_t wbits[64];
       tmem_ld64(tm_addr, wbits);
-      PT2(13)
       float acc[NB][4];      // [utterance][row of my quad], partial over my 16 columns
 #pragma unroll
       for (int uu = 0; uu < NB; ++uu) {
@@ -916,6 +879,45 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
       }
     }
     PT2(12)
+    // ---- off the dependency chain, in the shadow of the exchange the next step waits for:
+    // partial d(a_{t-1}) for the group (consumed by BA2a of step t-1), then the staging / location features of step t-1
+    // (nothing of the current step reads those buffers after barrier #4)
+    if (grp && warp < CW) {
+        // partial d(a_{t-1}) = conv-transpose of my partial d(location features) -> the group (consumed by step t-1)
+        if (t > 0) {
+          for (int base = warp * 32; base < 4 * Tt4; base += CW * 32) {
+            const int j = base + lane;
+            float acc = 0.f;
+            if (j < Tt) {
+              const float* dfr = S.dfS + HALO + j + pl;   // columns outside [0,Tt) are zero
+              if (d.att_kernel == 10) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k)
+#pragma unroll
+                  for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f * DFW - k], S.wconv[k * MAXF + f], acc);
+              } else {
+                for (int k = 0; k < d.att_kernel; ++k)
+#pragma unroll
+                  for (int f = 0; f < AFT; ++f) acc = fmaf(dfr[f * DFW - k], S.wconv[k * MAXF + f], acc);
+              }
+            }
+            const int l4 = lane & ~3;
+            const float a0 = __shfl_sync(0xffffffffu, acc, l4), a1 = __shfl_sync(0xffffffffu, acc, l4 + 1);
+            const float a2 = __shfl_sync(0xffffffffu, acc, l4 + 2), a3 = __shfl_sync(0xffffffffu, acc, l4 + 3);
+            if ((lane & 3) == 0 && j < 4 * Tt4) {
+              const uint32_t dsta = cl::smem_u32(&S.dstate_part[(nxt * G + ag) * TtP + j]), bara = cl::smem_u32(&barW[nxt]);
+#pragma unroll
+              for (int gd = 0; gd < G; ++gd) st_async_v4(cl::mapa(dsta, au * G + gd), a0, a1, a2, a3, cl::mapa(bara, au * G + gd));
+            }
+          }
+        }
+    }
+    if (warp < CW && t > 0) {
+      stage_inputs(t - 1);
+      cl::named_bar_sync(5, CW * 32);
+      if (grp) arnn::location_features<AFT>(S.fS, S.aprev, S.wconv, S.bconv, alen, d.att_kernel, pl, tid, CW * 32);
+    }
+    PT2(13)
     if (service) {
       // service: d(gates) of step t -> global (after this warp's DSMEM stores of the step)
       for (int e = sv; e < NB * 16; e += NSVB) {
