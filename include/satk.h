@@ -103,6 +103,10 @@ typedef struct {
    * 3 = reduce over k >= m0 only (P^T.dO, dS^T.Q). */
   int zcoord, za_row, za_k, zb_row, zb_k, zc_col;
   long long a_rows, a_cols, b_rows, b_cols, c_cols;
+  /* tensor-core tile only: 0 = "3xTF32" (hi/lo split of both operands, three MMAs per k-step: fp32-class accuracy, the
+   * default everywhere), 1 = one TF32 pass on the raw fp32 operands (10-bit mantissas; 3x fewer MMAs, no split pass).
+   * Which GEMM groups tolerate 1 inside the 1e-3 parity budget is measured by tools/ab_tf32.py (profiles/r02_ab_tf32.md). */
+  int precision;
 } satk_gemm_desc;
 
 /* engine: 0 = auto, 1 = fp32 SIMT tile, 2 = tcgen05 3xTF32 tile (TMA-fed; falls back with an

@@ -59,6 +59,7 @@ struct Params {
   int zcoord, za_row, za_k, zb_row, zb_k, zc_col;
   int causal;               // satk_gemm_desc.causal_skip (zcoord form only)
   int c_rank3;              // output map is [z][M][N] (rank 3): rows / columns outside an entry's slab are clipped by the TMA unit
+  int prec;                 // satk_gemm_desc.precision: 1 = one TF32 pass on the raw operands (no hi/lo split)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -236,12 +237,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t sa = smem_base + s * STAGE_BYTES;
       const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_BYTES);
       const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES), b_lo = make_desc(sa + 3 * TILE_BYTES);
+      if (p.prec == 1) {
 #pragma unroll
-      for (int k = 0; k < BK / 8; ++k) {
-        const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
-        tc_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        tc_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-        tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);
+          tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);   // raw fp32: the tensor core keeps 10 mantissa bits
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < BK / 8; ++k) {
+          const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
+          tc_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
+          tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
+        }
       }
       tc_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
       TC_TRACE(3)
@@ -258,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (tid == 64 && it == 0) { TC_MARK(2) }
       uint8_t* base = smem + (smem_base - cl::smem_u32(smem)) + s * STAGE_BYTES;
 #pragma unroll 2
-      for (int i = xt; i < 2 * (TILE_BYTES / 16); i += XFORM_THREADS) {
+      for (int i = xt; i < (p.prec == 1 ? 0 : 2 * (TILE_BYTES / 16)); i += XFORM_THREADS) {
         const int which = i / (TILE_BYTES / 16), c = i % (TILE_BYTES / 16);
         float4* hi = reinterpret_cast<float4*>(base + which * 2 * TILE_BYTES) + c;
         float4* lo = reinterpret_cast<float4*>(base + which * 2 * TILE_BYTES + TILE_BYTES) + c;
@@ -497,6 +506,7 @@ static int gemm_tc_bank_launch(const satk_gemm_desc* d, cudaStream_t st, bool* s
   }
   *supported = true;
   Params p = {};
+  p.prec = d->precision == 1 ? 1 : 0;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.taps = 1; p.shift0 = 0; p.tap_dir = d->tap_dir;
   p.C = d->C; p.ldc = d->ldc;
@@ -550,6 +560,7 @@ static int gemm_tc_zcoord_launch(const satk_gemm_desc* d, cudaStream_t st, bool*
   }
   *supported = true;
   Params p = {};
+  p.prec = d->precision == 1 ? 1 : 0;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.taps = 1; p.shift0 = 0; p.tap_dir = 1;
   p.C = d->C; p.ldc = d->ldc;
@@ -590,6 +601,7 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   if (!make_map(&mapB, d->B, d->N, d->K, d->ldb, taps > 1 ? taps : 0, d->sBtap)) return SATK_OK;
   *supported = true;
   Params p;
+  p.prec = d->precision == 1 ? 1 : 0;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.taps = taps; p.shift0 = d->shift0; p.tap_dir = d->tap_dir;
   p.C = d->C; p.ldc = d->ldc;

@@ -532,7 +532,9 @@ class TacotronEngine:
                            keep_mask=m0, keep_scale=1.0 / keep)
         dp1 = self.lin(dp0, "dec.prenet1.W", self.buf("dec.p1", (Rd, d.dec_prenet[1])), bias=p["dec.prenet1.b"], act="relu",
                        keep_mask=m1, keep_scale=1.0 / keep)
+        O.tf32_push("lstmx")
         xg1 = self.lin(dp1, "dec.lstm1.W", self.buf("dec.xg1", (Rd, 4 * d.att_rnn)), K=d.dec_prenet[1], bias=p["dec.lstm1.b"])
+        O.tf32_pop()
         sv.update(dec_in=dec_in, dp0=dp0, dp1=dp1, xg1=xg1)
         return sv
 
@@ -550,12 +552,16 @@ class TacotronEngine:
         # attention memories (BahdanauAttention.__init__, A.8): values masked past length, keys = values.W_mem
         values1 = self.buf("dec.values1", (R, d.mem1))
         O.mask_rows(mem1, source_length, B, Tt, d.mem1, True, values1)
+        O.tf32_push("mem")
         keys1 = self.lin(values1, "att1.memory.W", self.buf("dec.keys1", (R, d.att1)))
+        O.tf32_pop()
         values2 = keys2 = None
         if d.dual:
             values2 = self.buf("dec.values2", (R, d.mem2))
             O.mask_rows(mem2, source_length, B, Tt, d.mem2, True, values2)
+            O.tf32_push("mem")
             keys2 = self.lin(values2, "att2.memory.W", self.buf("dec.keys2", (R, d.att2)))
+            O.tf32_pop()
         X2W = H1 + d.ctx
         x2 = self.buf("dec.x2", (Rd, X2W))
         al1 = self.buf("dec.align1", (Td, B, Tt))
@@ -586,7 +592,9 @@ class TacotronEngine:
         sv["lstm"] = []
         for li, kin in ((2, X2W), (3, HD)):
             W = p[f"dec.lstm{li}.W"]
+            O.tf32_push("lstmx")
             xg = self.lin(x, f"dec.lstm{li}.W", self.buf(f"dec.xg{li}", (Rd, 4 * HD)), K=kin, bias=p[f"dec.lstm{li}.b"])
+            O.tf32_pop()
             out = self.buf(f"dec.out{li}", (Rd, HD))
             gates = self.buf(f"dec.gates{li}", (Rd, 4 * HD))
             cp, hp_ = self.buf(f"dec.cprev{li}", (Rd, HD)), self.buf(f"dec.hprev{li}", (Rd, HD))
@@ -601,12 +609,18 @@ class TacotronEngine:
         if d.dual:
             for h in range(d.dec_sa_hops):
                 mk = masks[f"dec.sa{h}"] if training else None
+                O.tf32_push("sa")
                 x, s = self._sa_forward(x, Td, B, f"dec.sa{h}", d.dec_sa_heads, True, mk, 1.0 - d.dec_sa_drop, f"dec.sa{h}")
+                O.tf32_pop()
                 sv["sa"].append(s)
                 sa_P += [s["P"][:, i] for i in range(d.dec_sa_heads)]
         sv["proj_in"] = x
+        O.tf32_push("proj")
         mel_tm = self.lin(x, "dec.out_proj.W", self.buf("dec.mel_tm", (Rd, d.out_units)), bias=p["dec.out_proj.b"])
+        O.tf32_pop()
+        O.tf32_push("proj")
         stop_tm = self.lin(x, "dec.stop_proj.W", self.buf("dec.stop_tm", (Rd, 1)), bias=p["dec.stop_proj.b"])
+        O.tf32_pop()
         self._dec_saved = sv
         return mel_tm, stop_tm, al1, al2, sa_P
 
@@ -616,6 +630,7 @@ class TacotronEngine:
         training = self._training
         R, Rd = Tt * B, Td * B
         H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
+        O.tf32_push("proj")
         x = sv["proj_in"]
         Dp = x.shape[1]
         with self._wg():
@@ -626,8 +641,12 @@ class TacotronEngine:
         dx = self.buf("dec.dproj_in", (Rd, Dp))
         O.linear_dx(dmel_tm, p["dec.out_proj.W"], dx, Rd)
         O.linear_dx(dstop_tm, p["dec.stop_proj.W"], dx, Rd, beta=1.0)
+        O.tf32_pop()
+        O.tf32_push("sa")
         for h in reversed(range(len(sv["sa"]))):
             dx = self._sa_backward(sv["sa"][h], dx, B)
+        O.tf32_pop()
+        O.tf32_push("lstmx")
         dout = dx
         for s in reversed(sv["lstm"]):
             li, kin = s["li"], s["kin"]
@@ -696,6 +715,8 @@ class TacotronEngine:
                 O.linear_dw(sv["x2"], dq, g["att2.query.W"], Rd, H1, d.att2, ldx=X2W, ldy=QT, y_off=d.att1)
         ddp1 = self.buf("dec.ddp1", (Rd, P1))
         O.linear_dx(dg1, p["dec.lstm1.W"][:P1], ddp1, Rd)
+        O.tf32_pop()
+        O.tf32_push("mem")
         # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]   (dx2[:, H1:] now holds dctx_total)
         dval1 = self.buf("dec.dvalues1", (R, d.mem1))
         O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
@@ -705,6 +726,8 @@ class TacotronEngine:
             dval2 = self.buf("dec.dvalues2", (R, d.mem2))
             O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
                    b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
+        O.tf32_pop()
+        O.tf32_push("prenet")
         # decoder pre-net
         keep_scale = 1.0 / (1.0 - d.dec_prenet_drop) if training else 1.0
         dz1 = self.buf("dec.dz1", (Rd, P1))
@@ -741,6 +764,8 @@ class TacotronEngine:
             with self._wg():
                 O.linear_dw(sv["dec_in"], dz0, g["dec.prenet0.W"], Rd, d.dec_in, P0)
                 O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
+        O.tf32_pop()
+        O.tf32_push("mem")
         # keys = values . W_mem ; attention bias folded into the keys.  (dkeys come from the energy-gradient launch: join it first)
         if energy_forked:
             self._join()
@@ -758,6 +783,7 @@ class TacotronEngine:
             O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
             dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
             O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
+        O.tf32_pop()
         return dmem1, dmem2
 
     # ------------------------------------------------------------------ model_fn body
@@ -792,8 +818,12 @@ class TacotronEngine:
             spk = self.buf("spk_embed", (B, d.speaker_dim))
             O.embedding_fwd(features.speaker_id, self.ps.p["speaker_embedding"], spk, offset=d.speaker_offset)
         with self._fork():      # pre-net + LSTM-1 input projection do not depend on the encoder
+            O.tf32_push("prenet")
             pre = self.decoder_pre(labels.mel, spk, training, masks)
+            O.tf32_pop()
+        O.tf32_push("enc")
         mem1, mem2, enc_al = self._timed("sec.encoder_fwd", self.encoder, source, source_length, training, masks)
+        O.tf32_pop()
         # (the encoder forks / joins the auxiliary stream itself for the BiLSTM directions, which also orders `pre` before here)
         self._join()
         mel_tm, stop_tm, al1, al2, dec_sa = self._timed("sec.decoder_fwd", self.decoder, mem1, mem2, source_length, labels.mel, spk,
@@ -1096,7 +1126,9 @@ class TacotronEngine:
             if self._side is not None:
                 torch.cuda.current_stream().wait_stream(self._side)  # the decoder's weight gradients are in
             handle = allreduce(self.ps.grad[self._dec_off:], async_op=True)
+        O.tf32_push("enc")
         self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
+        O.tf32_pop()
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)      # every weight gradient is in before all-reduce / Adam
         if self.d.l2_weight > 0:

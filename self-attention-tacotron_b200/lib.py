@@ -39,6 +39,7 @@ class GemmDesc(C.Structure):
         ("bank_widths", i32), ("bank_a_kstep", i32), ("bank_c_nstep", i32),
         ("zcoord", i32), ("za_row", i32), ("za_k", i32), ("zb_row", i32), ("zb_k", i32), ("zc_col", i32),
         ("a_rows", i64), ("a_cols", i64), ("b_rows", i64), ("b_cols", i64), ("c_cols", i64),
+        ("precision", i32),
     ]
 
 

@@ -5,6 +5,7 @@ raw device pointers + the current CUDA stream; all arithmetic happens in libsatk
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 from typing import Optional
@@ -35,6 +36,44 @@ def _req(t: torch.Tensor, dtype=torch.float32) -> None:
         raise L.SatkError("satk ops need CUDA tensors (no CPU fallback)")
     if t.dtype != dtype:
         raise L.SatkError(f"expected dtype {dtype}, got {t.dtype}")
+
+
+# satk_gemm_desc.precision of the products issued inside `tf32_group(name)`: 1 (single TF32 pass) for the groups named in
+# SATK_TF32_1X (comma separated, or "all"), else 0 (3xTF32).  A/B instrument of tools/ab_tf32.py; the default is 3xTF32 everywhere.
+_PRECISION = 0
+_TF32_1X = set(x for x in os.environ.get("SATK_TF32_1X", "").split(",") if x)
+
+
+@contextlib.contextmanager
+def tf32_group(name: str):
+    global _PRECISION
+    prev = _PRECISION
+    _PRECISION = 1 if (name in _TF32_1X or "all" in _TF32_1X) else prev
+    try:
+        yield
+    finally:
+        _PRECISION = prev
+
+
+_PREC_STACK = []
+
+
+def tf32_push(name: str) -> None:
+    """Open a precision group without a `with` block (engine code marks long regions with push / pop pairs)."""
+    global _PRECISION
+    _PREC_STACK.append(_PRECISION)
+    if name in _TF32_1X or "all" in _TF32_1X:
+        _PRECISION = 1
+
+
+def tf32_pop() -> None:
+    global _PRECISION
+    _PRECISION = _PREC_STACK.pop()
+
+
+def set_tf32_1x(groups) -> None:
+    global _TF32_1X
+    _TF32_1X = set(groups)
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: int, *, lda: int, ldb: int, ldc: int,
@@ -68,6 +107,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, C_: torch.Tensor, M: int, N: int, K: 
         d.zcoord = 1
         d.za_row, d.za_k, d.zb_row, d.zb_k, d.zc_col = (zcoord.get(k, 0) for k in ("za_row", "za_k", "zb_row", "zb_k", "zc_col"))
         d.a_rows, d.a_cols, d.b_rows, d.b_cols, d.c_cols = (zcoord.get(k, 0) for k in ("a_rows", "a_cols", "b_rows", "b_cols", "c_cols"))
+    d.precision = _PRECISION
     check(load().satk_gemm(C.byref(d), GEMM_ENGINE if engine is None else engine, C.c_void_p(stream_ptr())), "satk_gemm")
     _count()
 
