@@ -92,6 +92,9 @@ class TacotronEngine:
         if self._main is not None:
             for name in ("forward", "backward", "optimizer_step"):
                 setattr(self, name, self._on_main(getattr(self, name)))
+        self.use_graph = os.environ.get("SATK_GRAPH", "1") != "0"             # CUDA-graphed train step (see _train_step_graphed)
+        self._graphs = {}
+        self._premade_masks = None
         self.sort_batches = os.environ.get("SATK_SORT_BATCHES", "1") != "0"   # TRAIN steps sort the batch by target / source length
         # first element of the decoder / attention suffix of the flat parameter buffer (ParamStore lays the tensors out in forward order)
         self._dec_off = min(off for n, (off, _) in self.ps.offsets.items() if n.startswith(("att1.", "att2.", "dec.")))
@@ -809,7 +812,8 @@ class TacotronEngine:
             if masks is not None:      # caller-provided keep masks follow their utterances (batch is dim 0 of the [B,heads,T,T] masks)
                 masks = {k: v.index_select(0 if ".sa" in k else 1, perm) for k, v in masks.items()}
         if training and masks is None:
-            masks = self.device_masks(B, Tt, Td)
+            # (under graph capture the masks are generated eagerly before every replay, into the same buffers)
+            masks = self._premade_masks if getattr(self, "_premade_masks", None) is not None else self.device_masks(B, Tt, Td)
         # descriptors saved for the backward pass hold raw device pointers: the (possibly re-ordered) inputs stay referenced until then
         self._keepalive = (features, labels, masks)
         self._training = training
@@ -1156,7 +1160,72 @@ class TacotronEngine:
         return lr
 
     def train_step(self, features, labels, masks=None, allreduce=None, world_size: int = 1):
+        if (masks is None and getattr(self, "use_graph", False) and self.timers is None and self._side is not None
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._train_step_graphed(features, labels, allreduce, world_size)
         out = self.forward(features, labels, True, masks)
         self.backward(allreduce)
         out["lr"] = self._timed("sec.optimizer", self.optimizer_step, world_size)
         return out
+
+    # ------------------------------------------------------------------ CUDA-graphed train step
+    def _train_step_graphed(self, features, labels, allreduce, world_size):
+        """forward + backward (+ bucketed all-reduce) of one shape bucket (B, T_text, T_mel) replayed from a CUDA graph: the ~350
+        launches of a step cost the host ~3 ms of enqueue time, and the bursts of short encoder / dense kernels are launch-bound.
+        The pieces that depend on host scalars stay eager around the replay: the copy of the step's inputs into the graph's static
+        buffers, the keep-mask generation (a fresh seed per step) and clip + Adam (learning rate, step count).  The first two
+        calls of a bucket run eagerly (they allocate the engine's buffers); the third one captures."""
+        B, Tt = features.source.shape
+        Tm = labels.mel.shape[1]
+        key = (B, Tt, Tm, world_size, features.speaker_id is not None)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = dict(calls=0, graph=None)
+        if st["graph"] is None:
+            st["calls"] += 1
+            if st["calls"] <= 2 or st.get("failed"):
+                out = self.forward(features, labels, True, None)
+                self.backward(allreduce)
+                out["lr"] = self.optimizer_step(world_size)
+                return out
+            try:
+                self._capture_train_graph(st, features, labels, allreduce)
+            except Exception as ex:      # noqa: BLE001 - anything the capture refuses: stay eager, say so once
+                st["failed"] = True
+                torch.cuda.synchronize()
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the train step failed ({type(ex).__name__}: {ex}); staying eager")
+                return self.train_step(features, labels, None, allreduce, world_size)
+        # eager prologue: this step's inputs and keep masks into the static buffers the graph reads
+        for dst, src in zip(st["inputs"], self._graph_inputs(features, labels)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        self.device_masks(B, Tt, Tm // self.d.r)
+        st["graph"].replay()
+        O.add_launches(st["launches"])
+        out = dict(st["out"])
+        out["lr"] = self.optimizer_step(world_size)
+        return out
+
+    @staticmethod
+    def _graph_inputs(features, labels):
+        return [features.source, features.source_length, features.speaker_id, labels.mel, labels.target_length, labels.done,
+                labels.spec_loss_mask, labels.binary_loss_mask]
+
+    def _capture_train_graph(self, st, features, labels, allreduce):
+        dev = self.device
+        ins = [None if x is None else x.to(dev).clone() for x in self._graph_inputs(features, labels)]
+        sf = features._replace(source=ins[0], source_length=ins[1], speaker_id=ins[2])
+        sl = labels._replace(mel=ins[3], target_length=ins[4], done=ins[5], spec_loss_mask=ins[6], binary_loss_mask=ins[7])
+        B, Tt = ins[0].shape
+        self._premade_masks = self.device_masks(B, Tt, ins[3].shape[1] // self.d.r)      # the buffers the captured kernels read
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        l0 = O.launches()
+        try:
+            with torch.cuda.graph(g):
+                out = self.forward(sf, sl, True, None)
+                self.backward(allreduce)
+        finally:
+            self._premade_masks = None
+        st.update(graph=g, inputs=ins, out=out, launches=O.launches() - l0, static=(sf, sl))

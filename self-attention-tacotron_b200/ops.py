@@ -21,6 +21,12 @@ GEMM_ENGINE = 0
 _launches = 0
 
 
+def add_launches(n: int) -> None:
+    """Kernel launches replayed from a CUDA graph (counted once at capture time)."""
+    global _launches
+    _launches += n
+
+
 def launches() -> int:
     """Number of libsatk kernel-launching calls issued so far (bench.py reports the per-step delta)."""
     return _launches
