@@ -1160,7 +1160,8 @@ class TacotronEngine:
         return lr
 
     def train_step(self, features, labels, masks=None, allreduce=None, world_size: int = 1):
-        if (masks is None and getattr(self, "use_graph", False) and self.timers is None and self._side is not None
+        # (data-parallel steps stay eager: capturing the NCCL collectives of the bucketed all-reduce hung at N = 2 on this software stack)
+        if (masks is None and allreduce is None and getattr(self, "use_graph", False) and self.timers is None and self._side is not None
                 and not torch.cuda.is_current_stream_capturing()):
             return self._train_step_graphed(features, labels, allreduce, world_size)
         out = self.forward(features, labels, True, masks)
