@@ -296,9 +296,19 @@ def run_satk(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e, ms_full = t.tolist()
-    if rank != 0:
+    def shutdown():
+        # captured graphs hold NCCL resources: release them before the process group goes away, and never let a teardown
+        # problem keep the ranks alive (the result line is already out)
         if world > 1:
+            killer = threading.Timer(20.0, lambda: os._exit(0))
+            killer.daemon = True
+            killer.start()
+            eng.release_graphs()
             dist.destroy_process_group()
+            killer.cancel()
+
+    if rank != 0:
+        shutdown()
         return
     frames = world * B * TM * args.steps
     value = frames / (ms * 1e-3)
@@ -374,8 +384,7 @@ def run_satk(args, rank, world, local_rank):
                                "sample": f"1 timed train step (after 1 warm-up) on the full batch ({B} utterances, T_text={TT}, T_mel={TM}); "
                                          "oracle = torch-CPU fp32 restatement of the TF1 graph"}
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

@@ -1160,8 +1160,10 @@ class TacotronEngine:
         return lr
 
     def train_step(self, features, labels, masks=None, allreduce=None, world_size: int = 1):
-        # (data-parallel steps stay eager: capturing the NCCL collectives of the bucketed all-reduce hung at N = 2 on this software stack)
-        if (masks is None and allreduce is None and getattr(self, "use_graph", False) and self.timers is None and self._side is not None
+        # (data-parallel steps: the NCCL collectives of the bucketed all-reduce are captured too — thread-local capture mode, and the
+        # graphs must be released before the process group is destroyed: `release_graphs`; SATK_GRAPH_NCCL=0 keeps those steps eager)
+        if (masks is None and (allreduce is None or os.environ.get("SATK_GRAPH_NCCL", "1") != "0") and getattr(self, "use_graph", False)
+                and self.timers is None and self._side is not None
                 and not torch.cuda.is_current_stream_capturing()):
             return self._train_step_graphed(features, labels, allreduce, world_size)
         out = self.forward(features, labels, True, masks)
@@ -1208,6 +1210,11 @@ class TacotronEngine:
         out["lr"] = self.optimizer_step(world_size)
         return out
 
+    def release_graphs(self) -> None:
+        """Drop the captured train-step graphs (they hold NCCL resources: call this before torch.distributed.destroy_process_group)."""
+        self._graphs.clear()
+        torch.cuda.synchronize()
+
     @staticmethod
     def _graph_inputs(features, labels):
         return [features.source, features.source_length, features.speaker_id, labels.mel, labels.target_length, labels.done,
@@ -1224,7 +1231,7 @@ class TacotronEngine:
         g = torch.cuda.CUDAGraph()
         l0 = O.launches()
         try:
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 out = self.forward(sf, sl, True, None)
                 self.backward(allreduce)
         finally:
