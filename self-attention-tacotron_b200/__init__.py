@@ -10,6 +10,7 @@ from .params import ModelDims, ParamStore, dims_from_hparams, num_trainable, par
 from .data import (MelData, SourceData, SourceDataForPrediction, group_by_batch, make_masks, mask_shapes, padded_batch,  # noqa: F401
                    prepare_target, synthetic_batch, tfrecord_input_fn)
 from . import tfrecord                               # noqa: F401
+from .tf_names import WarmStartSettings, select_warm_start, tf_variable_name       # noqa: F401
 
 
 def tacotron_model_factory(hparams, model_dir, run_config, warm_start_from=None, **kw):
@@ -20,4 +21,5 @@ def tacotron_model_factory(hparams, model_dir, run_config, warm_start_from=None,
 
 __all__ = ["HParams", "default_hparams", "hparams", "load_hparams", "ModelDims", "ParamStore",
            "dims_from_hparams", "SourceData", "MelData", "synthetic_batch", "make_masks", "tacotron_model_factory", "tfrecord",
-           "tfrecord_input_fn", "prepare_target", "padded_batch", "group_by_batch"]
+           "tfrecord_input_fn", "prepare_target", "padded_batch", "group_by_batch", "WarmStartSettings", "select_warm_start",
+           "tf_variable_name"]

@@ -20,6 +20,7 @@ import torch
 
 from .data import MelData, SourceData
 from .engine import TacotronEngine
+from .tf_names import WarmStartSettings, select_warm_start, tf_variable_name  # noqa: F401
 
 
 class ModeKeys:
@@ -53,10 +54,15 @@ class _TacotronEstimator:
         self.engine = TacotronEngine(params, self.device)
         self._allreduce = allreduce
         self._world_size = world_size
-        if warm_start_from:
+        if model_dir and os.path.exists(self._ckpt_path()):
+            self.restore(self._ckpt_path())          # resume = re-run with the same --checkpoint-dir (train.py:70-80); a checkpoint in
+                                                      # model_dir wins over the warm start, as in tf.estimator
+        elif isinstance(warm_start_from, WarmStartSettings):
+            # train.py:76-78: only the trainable tensors whose name matches vars_to_warm_start are initialised from the checkpoint;
+            # optimiser state, BN moving statistics and the step counter start fresh
+            self.warm_start(warm_start_from.ckpt_to_initialize_from, warm_start_from.vars_to_warm_start)
+        elif warm_start_from:
             self.restore(warm_start_from)
-        elif model_dir and os.path.exists(self._ckpt_path()):
-            self.restore(self._ckpt_path())          # resume = re-run with the same --checkpoint-dir (train.py:70-80)
 
     # ---- checkpointing (flat buffers; a TF-variable name map is a later row of SURVEY §8f)
     def _ckpt_path(self) -> str:
@@ -68,7 +74,8 @@ class _TacotronEstimator:
         ps = self.engine.ps
         torch.save(dict(flat=ps.flat.cpu(), adam_m=ps.adam_m.cpu(), adam_v=ps.adam_v.cpu(), bn_mean=ps.bn_mean_flat.cpu(),
                         bn_var=ps.bn_var_flat.cpu(), global_step=self.engine.global_step,
-                        names=list(ps.offsets.keys())), path)
+                        names=list(ps.offsets.keys()), offsets=[o for o, _ in ps.offsets.values()],
+                        shapes=[tuple(sh) for _, sh in ps.offsets.values()]), path)
         return path
 
     def restore(self, path: str) -> None:
@@ -80,6 +87,31 @@ class _TacotronEstimator:
         ps.bn_mean_flat.copy_(st["bn_mean"]); ps.bn_var_flat.copy_(st["bn_var"])
         self.engine.global_step = int(st["global_step"])
         self.engine.refresh_transposed()
+
+    def warm_start(self, path: str, vars_to_warm_start=".*") -> list:
+        """tf.estimator.WarmStartSettings(ckpt_to_initialize_from=path, vars_to_warm_start=...) (train.py:76-78, hparams.py:200-202): copy
+        the selected trainable tensors from a checkpoint of this implementation (`model.satk.pt`; TF checkpoints cannot be read without
+        TensorFlow).  The checkpoint may belong to a model with a different parameter set: tensors are matched by name and shape.
+        Returns the names that were initialised."""
+        if os.path.isdir(path):
+            path = os.path.join(path, "model.satk.pt")
+        st = torch.load(path, map_location="cpu")
+        ps = self.engine.ps
+        if "offsets" in st:
+            src_off = {n: (o, tuple(sh)) for n, o, sh in zip(st["names"], st["offsets"], st["shapes"])}
+        else:                # checkpoint written before the shape table existed: it must be this model's parameter set
+            if st["names"] != list(ps.offsets.keys()) or st["flat"].numel() != ps.flat.numel():
+                raise ValueError(f"warm start: {path} has no shape table and does not match this model's parameter set")
+            src_off = {n: (o, tuple(sh)) for n, (o, sh) in ps.offsets.items()}
+        done = []
+        for n in select_warm_start(ps.offsets.keys(), self.engine.d, vars_to_warm_start):
+            o, sh = ps.offsets[n]
+            if n in src_off and tuple(src_off[n][1]) == tuple(sh):
+                so = src_off[n][0]
+                ps.p[n].copy_(st["flat"][so:so + ps.p[n].numel()].view(sh))
+                done.append(n)
+        self.engine.refresh_transposed()
+        return done
 
     # ---- model_fn (models.py:278 / :23)
     def model_fn(self, features, labels, mode, params=None, masks=None) -> EstimatorSpec:

@@ -193,3 +193,21 @@ def test_header_is_plain_c(root, tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
+
+
+def test_warm_start_selection_by_variable_name_regex(satk, root):
+    """train.py:76-78 / hparams.py:200-202: vars_to_warm_start regular expressions select trainable tensors by (TF-style or own) name."""
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    names = list(satk.ParamStore(d, "cpu").offsets.keys())
+    assert hp.vars_to_warm_start == [".*"] and satk.select_warm_start(names, d, hp.vars_to_warm_start) == names
+    enc = satk.select_warm_start(names, d, "encoder/")
+    assert enc and all(n.startswith(("enc.", "cbhg.")) for n in enc) and "enc.prenet0.W" in enc and "dec.lstm2.W" not in enc
+    both = satk.select_warm_start(names, d, ["embedding", r"decoder/.*lstm_cell"])
+    assert set(both) == {"embedding", "dec.lstm1.W", "dec.lstm1.b", "dec.lstm2.W", "dec.lstm2.b", "dec.lstm3.W", "dec.lstm3.b"}
+    assert satk.select_warm_start(names, d, r"att1\.") == [n for n in names if n.startswith("att1.")]     # the store's own names match too
+    # in-tree anchored names (forward_attention.py:17-26,73,78; module.py:717-723)
+    assert satk.tf_variable_name("att1.loc_conv.W", d) == "decoder/ForwardAttention/location_features_convolution/kernel"
+    assert satk.tf_variable_name("att1.v", d) == "decoder/ForwardAttention/attention_variable"
+    assert satk.tf_variable_name("dec.stop_proj.W", d) == "decoder/stop_token_projection/kernel"
+    assert len({satk.tf_variable_name(n, d) for n in names}) == len(names)                                 # the map is injective

@@ -419,6 +419,13 @@ def test_estimator_surface(satk, root, tmp_path):
     model2 = M.tacotron_model_factory(hp, str(tmp_path), None)           # resume from model_dir
     assert model2.engine.global_step == 2
     assert torch.equal(model2.engine.ps.flat, model.engine.ps.flat)
+    # warm start by variable-name regular expression (train.py:76-78): only the selected tensors come from the checkpoint
+    ws = satk.WarmStartSettings(ckpt_to_initialize_from=str(tmp_path), vars_to_warm_start=["encoder/", "embedding"])
+    model3 = M.tacotron_model_factory(hp, None, None, warm_start_from=ws)
+    p3, p1 = model3.engine.ps.p, model.engine.ps.p
+    assert model3.engine.global_step == 0
+    assert torch.equal(p3["cbhg.bank3.W"], p1["cbhg.bank3.W"]) and torch.equal(p3["embedding"], p1["embedding"])
+    assert not torch.equal(p3["dec.lstm2.W"], p1["dec.lstm2.W"])
     with pytest.raises(ValueError, match="Unknown Tacotron model"):
         M.tacotron_model_factory(satk.load_hparams(None, "tacotron_model=Foo"), None, None)
 
