@@ -414,6 +414,10 @@ typedef struct {
   float* ctx_dst1; long long ld1; long long pstride1;   /* written at parity t&1: LSTM-2 input row of THIS step */
   float* align1;               /* [Tmax,B,Tt] or NULL */
   float* align2;
+  /* forced-alignment mode (teacher_forcing_attention.py:13-78, models/models.py:411-427): when forced1 is set, row t of
+   * forced1 [T,B,Tt] (and forced2 for the second mechanism) REPLACES the computed alignments of both mechanisms - no query, no energies,
+   * no softmax, the recurrent attention state is left alone; contexts and the alignment history are produced as usual. */
+  const float* forced1; const float* forced2;
 } satk_attn_step_desc;
 int satk_attn_step(const satk_attn_step_desc* d, void* stream);
 

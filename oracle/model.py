@@ -411,7 +411,7 @@ def decoder_forward(P, d, memory1, memory2, source_length, target, spk_embed, tr
     return mel.reshape(B, -1, d.n_mels), stop, al1, al2, sa_aligns            # module.py:1558
 
 
-def decoder_free_running(P, d, memory1, memory2, source_length, spk_embed, max_iters, min_iters=10, use_stop_token=True):
+def decoder_free_running(P, d, memory1, memory2, source_length, spk_embed, max_iters, min_iters=10, use_stop_token=True, forced=None):
     """PREDICT-mode decoder (module.py:762-778): dynamic_decode of
     OutputAndStopTokenTransparentWrapper(TransformerWrapper(RNNStateHistoryWrapper(decoder_cell))) driven by
     StopTokenBasedInferenceHelper.  Each step: the decoder cell (pre-net, LSTM-1 + attention(s), LSTM-2/3) on the
@@ -438,11 +438,16 @@ def decoder_free_running(P, d, memory1, memory2, source_length, spk_embed, max_i
         pre = decoder_prenet(P, d, inp, spk_embed, None, False, step=t)
         cell_in = torch.cat([pre, attn], dim=-1)
         out1, c1, h1 = zoneout_lstm_step(cell_in, c1, h1, P["dec.lstm1.W"], P["dec.lstm1.b"], None, None, d.zc, d.zh, False)
-        a1, st1 = attention1_step(P, d, out1, st1, keys1, values1, source_length)
+        if forced is not None:
+            # forced-alignment mode: TeacherForcingForwardAttention / TeacherForcingAdditiveAttention.__call__
+            # (modules/teacher_forcing_attention.py:28-35,63-70): alignments = teacher_alignments[:, index]
+            a1 = forced[0][:, :, t]
+        else:
+            a1, st1 = attention1_step(P, d, out1, st1, keys1, values1, source_length)
         ctx1 = (a1[:, None, :] @ values1).squeeze(1)
         al1.append(a1)
         if d.dual:
-            a2 = attention2_step(P, out1, keys2, source_length)
+            a2 = forced[1][:, :, t] if forced is not None else attention2_step(P, out1, keys2, source_length)
             ctx2 = (a2[:, None, :] @ values2).squeeze(1)
             al2.append(a2)
             attn = torch.cat([ctx1, ctx2], dim=-1)
@@ -467,6 +472,19 @@ def decoder_free_running(P, d, memory1, memory2, source_length, spk_embed, max_i
             break
     mel = torch.stack(mels, dim=1).reshape(B, -1, d.n_mels)
     return (mel, torch.stack(stops, dim=1), torch.stack(al1, dim=2), torch.stack(al2, dim=2) if d.dual else None)
+
+
+def model_forced_alignment(P, d, features, labels):
+    """use_forced_alignment_mode outside training (models/models.py:384-427): a teacher-forced decode gives alignment1 / alignment2
+    (B, Tt, Td); a second decode (is_validation=True, teacher_forcing=False: own outputs are fed back for Tm / r steps) runs with the
+    teacher-forcing attention mechanisms that replay them (attention_factories.py:40-66)."""
+    first = model_forward(P, d, features, labels, False)
+    spk = P["speaker_embedding"][features.speaker_id - d.speaker_offset] if d.use_speaker else None
+    mem1, mem2, _ = encoder_forward(P, d, features.source, features.source_length, False, None, None)
+    Td = labels.mel.shape[1] // d.r
+    mel, stop, al1, al2 = decoder_free_running(P, d, mem1, mem2, features.source_length, spk, Td, use_stop_token=False,
+                                               forced=(first["alignment"], first.get("alignment2")))
+    return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2, mel_with_teacher=first["mel"])
 
 
 def model_predict(P, d, features, max_iters=None, min_iters=10, use_stop_token=True):

@@ -220,6 +220,18 @@ __global__ void __cluster_dims__(ACS, 1, 1) __launch_bounds__(256) attn_step_k(c
   float* cpart = alo + Tt;                // [groups][cols per CTA]
   const bool loc = d.att_kernel > 0;
   __shared__ float part[8][33];
+  const bool forced = d.forced1 != nullptr;     // teacher_forcing_attention.py:28-35: alignments = teacher_alignments[:, index]
+  if (forced) {
+    for (int j = tid; j < Tt; j += 256) {
+      w1[j] = __ldg(d.forced1 + ((long long)tt * B + b) * Tt + j);
+      e2[j] = (A2 > 0 && d.forced2) ? __ldg(d.forced2 + ((long long)tt * B + b) * Tt + j) : 0.f;
+      if (rank == 0) {
+        if (d.align1) d.align1[((long long)tt * B + b) * Tt + j] = w1[j];
+        if (A2 > 0 && d.align2) d.align2[((long long)tt * B + b) * Tt + j] = e2[j];
+      }
+    }
+    __syncthreads();
+  } else {
   if (d.Wq1) {
     // processed queries q = out1 . Wq (query_layer of both mechanisms): each CTA computes 1/8 of the A1+A2 columns and stores its
     // slice into every peer's shared memory; the cluster barrier below (state reads) also publishes it
@@ -327,6 +339,7 @@ __global__ void __cluster_dims__(ACS, 1, 1) __launch_bounds__(256) attn_step_k(c
       if (A2 > 0 && d.align2) d.align2[((long long)tt * B + b) * Tt + j] = e2[j];
     }
   }
+  }   // !forced
   // my share of the context columns: thread = (position group, column)
   const int MC = M1 + M2;
   const int CP = (MC + ACS - 1) / ACS;           // columns per CTA
@@ -358,7 +371,7 @@ __global__ void __cluster_dims__(ACS, 1, 1) __launch_bounds__(256) attn_step_k(c
     if (d.ctx_dst1) d.ctx_dst1[(long long)(tt & 1) * d.pstride1 + (long long)b * d.ld1 + cc] = cx;
     if (d.use_agent && cc < M1) agent_part = cx * __ldg(d.agent_w + cc);
   }
-  if (d.mode == 2 && d.use_agent) {
+  if (d.mode == 2 && d.use_agent && !forced) {
     // transition agent: u = sigmoid([context1, processed_query1] . W + b)   (forward_attention.py:111-114)
     if (rank == 0)
       for (int cq = tid; cq < A1; cq += 256) agent_part = fmaf(qs[cq], __ldg(d.agent_w + M1 + cq), agent_part);

@@ -848,7 +848,7 @@ class TacotronEngine:
                     memory1_tm=mem1, memory2_tm=mem2, losses=out3, perm=perm)
 
     # ------------------------------------------------------------------ free-running decode (PREDICT)
-    def _build_decode_step(self, B, Tt, Tmax, use_stop_token, min_iters):
+    def _build_decode_step(self, B, Tt, Tmax, use_stop_token, min_iters, forced=False):
         """Descriptors + launch sequence of ONE free-running decoder step (module.py:762-778, rnn_wrappers.py:47-124,188-214).
         All tensors are persistent buffers and every kernel reads the step index from ``t_dev``, so the returned closure can
         be captured once in a CUDA graph and replayed."""
@@ -924,7 +924,10 @@ class TacotronEngine:
             v2=p["att2.v"] if d.dual else None, agent_w=p["att1.agent.W"] if agent else None,
             agent_b=p["att1.agent.b"] if agent else None, aprev=aprev, alpha=alpha, u=u,
             ctx_dst0=cell_in.data_ptr() + 4 * P1, ld0=W1C, pstride0=B * W1C,
-            ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, pstride1=B * W2C, align1=al1, align2=al2, **qkw))
+            ctx_dst1=x2c.data_ptr() + 4 * H1, ld1=W2C, pstride1=B * W2C, align1=al1, align2=al2,
+            # forced-alignment mode: the step replays given alignments (teacher_forcing_attention.py:13-78)
+            forced1=self.buf("pred.forced1", (Tmax, B, Tt)) if forced else None,
+            forced2=self.buf("pred.forced2", (Tmax, B, Tt)) if (forced and d.dual) else None, **qkw))
         # LSTM-2 / LSTM-3 (DecoderRNNV2 on ConcatOutputAndAttentionWrapper, module.py:1024,1525-1534)
         steps.append(O.rowgemm_desc(x2c, B, W2C, [dict(W=p["dec.lstm2.W"], bias=p["dec.lstm2.b"])], a_pstride=B * W2C, t_ptr=t_dev,
                                     lstm=dict(H=HD, c=st["c2"], h=st["h2"], out=x3c, ld_out=W3C, out_pstride=B * W3C,
@@ -997,10 +1000,11 @@ class TacotronEngine:
         return run_step, state
 
     def predict(self, features, max_iters: Optional[int] = None, use_stop_token: bool = True, min_iters: int = 10,
-                use_graph: bool = True, check_every: int = 64):
+                use_graph: bool = True, check_every: int = 64, forced_alignments=None):
         """Free-running inference (model_fn in PREDICT mode, models/models.py:351-408 with is_training=False; decoder
         branch module.py:762-778).  Returns mel [B, T*r, n_mels], stop logits [B, T], alignments (B, Tt, T) and the decoder
-        self-attention alignments; T = number of executed steps (stop token or max_iters)."""
+        self-attention alignments; T = number of executed steps (stop token or max_iters).
+        ``forced_alignments`` = (align1 [T,B,Tt], align2 | None), time-major: forced-alignment mode (teacher_forcing_attention.py)."""
         d = self.d
         source, source_length = features.source, features.source_length
         B, Tt = source.shape
@@ -1027,11 +1031,12 @@ class TacotronEngine:
         # the step descriptors (and the captured graph) hold raw pointers of the shared memory / key buffers: `buf` re-allocates a
         # buffer when another (B, Tt) passed through forward / train_step in between, so the pointers are part of the key
         shared = ("dec.values1", "dec.keys1", "dec.values2", "dec.keys2", "dec.sp", "spk_embed", "enc.mem1", "enc.mem2")
-        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters), bool(getattr(self, "fused_decode_tail", True)),
+        forced = forced_alignments is not None
+        key = (B, Tt, Tmax, bool(use_stop_token), int(min_iters), bool(getattr(self, "fused_decode_tail", True)), forced,
                tuple(self._bufs[k].data_ptr() for k in shared if k in self._bufs), mem1.data_ptr(), 0 if mem2 is None else mem2.data_ptr())
         cache = getattr(self, "_decode_cache", None)
         if cache is None or cache["key"] != key:
-            run_step, stt = self._build_decode_step(B, Tt, Tmax, use_stop_token, min_iters)
+            run_step, stt = self._build_decode_step(B, Tt, Tmax, use_stop_token, min_iters, forced)
             cache = self._decode_cache = dict(key=key, run_step=run_step, state=stt, graph=None)
         run_step, stt = cache["run_step"], cache["state"]
         # initial state: zero LSTM states / attention, alpha_0 = one-hot(0), u_0 = 0.5 (forward_attention.py:128-136)
@@ -1045,6 +1050,15 @@ class TacotronEngine:
         stt["t_dev"].zero_()
         stt["done"].fill_(-1)
         stt["lengths"].copy_(source_length)
+        if forced:
+            # forced-alignment mode (models/models.py:411-427): alignments [T,B,Tt] of a teacher-forced pass replace the attention
+            # mechanisms; the decoder still feeds back its own output
+            f1, f2 = forced_alignments
+            if f1.shape[0] < Tmax:
+                raise ValueError(f"forced alignments cover {f1.shape[0]} decoder steps, {Tmax} requested")
+            self._bufs["pred.forced1"].copy_(f1[:Tmax])
+            if d.dual:
+                self._bufs["pred.forced2"].copy_(f2[:Tmax])
         for pr in stt["probs"]:
             pr.zero_()
         n_run = 0
@@ -1088,14 +1102,14 @@ class TacotronEngine:
                    enc_self_P=enc_al, steps=T, steps_executed=n_run)
         return out
 
-    def validate(self, features, labels):
+    def validate(self, features, labels, forced_alignments=None):
         """EVAL-mode decode WITHOUT teacher forcing (tacotron2 ValidationHelper(teacher_forcing=False), models/models.py:384-395,
         467-482): the decoder feeds back its own output for exactly Tm / r steps (no stop token) and the losses are taken against
         the labels.  -> (losses [3] = mel, done, total; the free-running outputs of `predict`)."""
         d = self.d
         B, Tm = labels.mel.shape[0], labels.mel.shape[1]
         Td = Tm // d.r
-        out = self.predict(features, max_iters=Td, use_stop_token=False)
+        out = self.predict(features, max_iters=Td, use_stop_token=False, forced_alignments=forced_alignments)
         out3 = self.buf("val.loss3", (3,))
         mel_tm = out["mel_tm"].reshape(Td * B, d.r * d.n_mels)
         stop_tm = out["stop_tm"].reshape(Td * B, 1)

@@ -107,7 +107,7 @@ class AttnStepDesc(C.Structure):
         ("keys2", fp), ("values2", fp), ("v2", fp), ("agent_w", fp), ("agent_b", fp),
         ("aprev", fp), ("alpha", fp), ("u", fp),
         ("ctx_dst0", fp), ("ld0", i64), ("pstride0", i64), ("ctx_dst1", fp), ("ld1", i64), ("pstride1", i64),
-        ("align1", fp), ("align2", fp),
+        ("align1", fp), ("align2", fp), ("forced1", fp), ("forced2", fp),
     ]
 
 

@@ -88,6 +88,27 @@ class _TacotronEstimator:
         self.engine.global_step = int(st["global_step"])
         self.engine.refresh_transposed()
 
+    def _labels_of_prediction_record(self, features) -> MelData:
+        """MelData view of a SourceDataForPrediction record (datasets/ljspeech/dataset.py:40-49,309-322: mel, mel_width, target_length)."""
+        mel = getattr(features, "mel", None)
+        if mel is None:
+            raise ValueError("forced-alignment mode needs the ground-truth mel of the prediction records (SourceDataForPrediction.mel)")
+        r = self.engine.d.r
+        B, Tm = mel.shape[0], mel.shape[1]
+        tl = features.target_length.to(mel.device)
+        pos = torch.arange(Tm, device=mel.device)[None, :]
+        spec_mask = (pos < tl[:, None]).float()
+        dpos = torch.arange(Tm // r, device=mel.device)[None, :]
+        dl = (tl // r)[:, None]
+        return MelData(features.id, features.key, mel, features.mel_width, tl, (dpos >= dl - 1).float(), spec_mask, (dpos < dl).float())
+
+    def _forced_alignment_decode(self, features, labels):
+        eng, d = self.engine, self.engine.d
+        sfeat = SourceData(features.id, features.key, features.source, features.source_length, features.text, features.speaker_id)
+        tf_out = eng.forward(sfeat, labels, False)
+        forced = (tf_out["align1_tm"].clone(), tf_out["align2_tm"].clone() if d.dual else None)
+        return eng.predict(sfeat, max_iters=labels.mel.shape[1] // d.r, use_stop_token=False, forced_alignments=forced)
+
     def warm_start(self, path: str, vars_to_warm_start=".*") -> list:
         """tf.estimator.WarmStartSettings(ckpt_to_initialize_from=path, vars_to_warm_start=...) (train.py:76-78, hparams.py:200-202): copy
         the selected trainable tensors from a checkpoint of this implementation (`model.satk.pt`; TF checkpoints cannot be read without
@@ -118,8 +139,14 @@ class _TacotronEstimator:
         eng, d = self.engine, self.engine.d
         features = _to_device(features, self.device)
         if mode == ModeKeys.PREDICT:
-            # free-running decode (predict_mel.py:36-74; decoder branch module.py:762-778), stop-token terminated
-            out = eng.predict(features, max_iters=getattr(params or self.params, "max_iters", None))
+            if d.forced_alignment:
+                # forced-alignment mode (models/models.py:411-427, predict_mel.py with use_forced_alignment_mode): a teacher-forced pass
+                # over the ground-truth mel of the prediction record gives the alignments, a second decode that feeds back its own
+                # output replays them (TeacherForcingForwardAttention / TeacherForcingAdditiveAttention) for the target length
+                out = self._forced_alignment_decode(features, self._labels_of_prediction_record(features))
+            else:
+                # free-running decode (predict_mel.py:36-74; decoder branch module.py:762-778), stop-token terminated
+                out = eng.predict(features, max_iters=getattr(params or self.params, "max_iters", None))
             preds = {"id": features.id, "key": features.key, "mel": out["mel"], "stop_token": out["stop"],
                      "alignment": out["alignment"], "source": features.source, "text": features.text}
             gt = getattr(features, "mel", None)
@@ -139,6 +166,9 @@ class _TacotronEstimator:
         B, Tm = labels.mel.shape[0], labels.mel.shape[1]
         Td = Tm // d.r
         if training:
+            if d.forced_alignment:
+                raise NotImplementedError("use_forced_alignment_mode in TRAIN mode (a second, alignment-replaying decode that is "
+                                          "differentiated together with the first) is not built; EVAL and PREDICT are")
             out = eng.train_step(features, labels, masks, allreduce=self._allreduce, world_size=self._world_size)
             losses = out["losses"]
             scalars = {"mel_loss": losses[0], "done_loss": losses[1], "learning_rate": out["lr"]}
@@ -148,7 +178,11 @@ class _TacotronEstimator:
         # decode gives the `*_with_teacher` metrics
         tf_out = eng.forward(features, labels, False)
         with_teacher = tf_out["losses"].clone()
-        losses, out = eng.validate(features, labels)
+        if d.forced_alignment:   # models/models.py:411-427: the plain metrics / predictions come from the alignment-replaying decode
+            forced = (tf_out["align1_tm"].clone(), tf_out["align2_tm"].clone() if d.dual else None)
+            losses, out = eng.validate(features, labels, forced_alignments=forced)
+        else:
+            losses, out = eng.validate(features, labels)
         preds = {"id": features.id, "key": features.key, "mel": out["mel"], "ground_truth_mel": labels.mel, "stop_token": out["stop"],
                  "alignment": out["alignment"],                                  # (B, Tt, Td), models.py:406
                  "source": features.source, "text": features.text}

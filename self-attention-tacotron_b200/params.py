@@ -64,6 +64,7 @@ class ModelDims:
     speaker_offset: int
     max_iters: int
     l2_weight: float = 0.0  # l2_regularization_weight when use_l2_regularization, else 0 (models/models.py:470-478)
+    forced_alignment: bool = False   # use_forced_alignment_mode (models/models.py:411-427): EVAL / PREDICT decode with replayed alignments
 
     @property
     def mem1(self) -> int:      # depth of attention-1 memory (BiLSTM output)
@@ -102,13 +103,16 @@ def dims_from_hparams(hp) -> ModelDims:
         raise ValueError("only decoder_version=v2 (DecoderRNNV2) is on the hot path")
     if hp.attention not in ("forward", "location_sensitive", "additive"):
         raise ValueError(f"Unknown attention mechanism: {hp.attention}")
+    if bool(getattr(hp, "use_forced_alignment_mode", False)) and (
+            hp.forced_alignment_attention not in ("teacher_forcing_forward", "teacher_forcing_additive")
+            or (dual and hp.forced_alignment_attention2 not in ("teacher_forcing_forward", "teacher_forcing_additive"))):
+        raise ValueError("forced_alignment_attention[2] must be teacher_forcing_forward or teacher_forcing_additive (attentions.py:40-52)")
     if dual and hp.attention2 != "additive":
         raise ValueError("attention2 must be 'additive' on the hot path")
     if not hp.use_zoneout_at_encoder:
         raise ValueError("use_zoneout_at_encoder=False (plain CBHG with GRU) is out of scope")
     # switches of the reference's model_fn that this implementation does not build (SURVEY §8 f3 / out of scope): refuse loudly
     for flag, what in (("use_postnet_v2", "PostNetV2 (models/models.py:440-462)"),
-                       ("use_forced_alignment_mode", "forced-alignment attention (teacher_forcing_attention.py)"),
                        ("use_external_speaker_embedding", "external speaker embeddings (multi_speaker_tacotron)"),
                        ("use_language_embedding", "language embeddings (multi_speaker_tacotron)"),
                        ("speaker_embedd_to_postnet", "speaker embedding into the post-net"),
@@ -159,7 +163,7 @@ def dims_from_hparams(hp) -> ModelDims:
         zc=hp.zoneout_factor_cell, zh=hp.zoneout_factor_output,
         use_speaker=bool(hp.use_speaker_embedding), num_speakers=hp.num_speakers,
         speaker_dim=hp.speaker_embedding_dim, speaker_offset=hp.speaker_embedding_offset,
-        max_iters=hp.max_iters,
+        max_iters=hp.max_iters, forced_alignment=bool(getattr(hp, "use_forced_alignment_mode", False)),
         l2_weight=float(hp.l2_regularization_weight) if bool(getattr(hp, "use_l2_regularization", False)) else 0.0)
 
 

@@ -146,10 +146,17 @@ def test_data_parallel_gradient_mean_gloo(root, tmp_path):
 def test_unbuilt_model_switches_are_refused(satk, root):
     """Options of the reference's model_fn that are not built must fail loudly, never be silently ignored."""
     cfg = os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json")
-    for flag in ("use_postnet_v2", "use_forced_alignment_mode", "use_external_speaker_embedding",
-                 "use_language_embedding", "use_accent_type"):
+    for flag in ("use_postnet_v2", "use_external_speaker_embedding", "use_language_embedding", "use_accent_type",
+                 "speaker_embedd_to_decoder", "apply_dropout_on_inference", "language_embedd_to_input", "language_embedd_to_decoder"):
         with pytest.raises(NotImplementedError, match=flag):
             satk.dims_from_hparams(satk.load_hparams(cfg, f"{flag}=True"))
+    for ov in ("speaker_for_synthesis=3", "attention_filters=32", "attention_kernel=40", "attention_out_units=128"):
+        with pytest.raises(NotImplementedError):
+            satk.dims_from_hparams(satk.load_hparams(cfg, ov))
+    with pytest.raises(NotImplementedError, match="speaker_embedd_to_prenet"):
+        satk.dims_from_hparams(satk.load_hparams(os.path.join(root, "examples", "vctk_self-attention-tacotron.json"), "speaker_embedd_to_prenet=False"))
+    # forced-alignment mode is built for EVAL / PREDICT (tests/test_predict_gpu.py); TRAIN refuses at the call
+    assert satk.dims_from_hparams(satk.load_hparams(cfg, "use_forced_alignment_mode=True")).forced_alignment
     satk.dims_from_hparams(satk.load_hparams(cfg, "cumulative_weights=True,use_forward_attention_transition_agent=True,use_l2_regularization=True"))
 
 

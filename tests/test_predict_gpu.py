@@ -206,3 +206,38 @@ def test_tfrecord_files_to_prediction_files(satk, root, tmp_path):
         assert np.array_equal(np.frombuffer(ex["source"][0], "<i8"), srcs[i].source)
         gt = np.frombuffer(ex["ground_truth_mel"][0], "<f4").reshape(-1, hp.num_mels)
         assert gt.shape[0] == int(ex["ground_truth_mel_length"][0]) == (mels[i].target_length + 2 * hp.outputs_per_step + 1) // 2 * 2
+
+
+@pytest.mark.parametrize("cfg", ["ljspeech_self-attention-tacotron.json", "ljspeech_tacotron.json"])
+def test_forced_alignment_mode_matches_oracle(satk, root, cfg):
+    """use_forced_alignment_mode outside training (models/models.py:384-427, modules/teacher_forcing_attention.py:13-78,
+    models/attention_factories.py:40-66): a teacher-forced pass gives the alignments, the second decode feeds back its own output
+    while the attention mechanisms replay them.  EVAL metrics / predictions and PREDICT (from a SourceDataForPrediction record)."""
+    from importlib import import_module
+    M = import_module("self-attention-tacotron_b200.models")
+    hp = satk.load_hparams(os.path.join(root, "examples", cfg), "use_forced_alignment_mode=True")
+    d = satk.dims_from_hparams(hp)
+    assert d.forced_alignment
+    ps = satk.ParamStore(d).init(5, "random")
+    B, Tt, Tm = 3, 21, 24
+    f, l = satk.synthetic_batch(hp, B, Tt, Tm, seed=9)
+    ref = OR.model_forced_alignment(ps.as_dict(), d, f, l)
+    model = M.tacotron_model_factory(hp, None, None)
+    model.engine.ps.flat.copy_(ps.flat.cuda())
+    model.engine.ps.bn_mean_flat.copy_(ps.bn_mean_flat.cuda())
+    model.engine.ps.bn_var_flat.copy_(ps.bn_var_flat.cuda())
+    model.engine.refresh_transposed()
+    spec = model.model_fn(f, l, M.ModeKeys.EVAL, hp)
+    scale = ref["mel"].abs().max().item()
+    assert (spec.predictions["mel"].cpu() - ref["mel"]).abs().max().item() <= 1e-3 * scale
+    assert (spec.predictions["alignment"].cpu() - ref["alignment"]).abs().max().item() <= 1e-5
+    want = OR.spec_loss_l1(ref["mel"], l.mel, l.spec_loss_mask)
+    assert abs(float(spec.scalars["mel_loss"]) - float(want)) <= 1e-3 * float(want)
+    # the replayed alignments are those of the teacher-forced pass, the mel is not
+    tf = OR.model_forward(ps.as_dict(), d, f, l, False)
+    assert torch.allclose(ref["alignment"], tf["alignment"]) and (ref["mel"] - tf["mel"]).abs().max().item() > 1e-4
+    rec = satk.SourceDataForPrediction(f.id, f.key, f.source, f.source_length, f.text, f.speaker_id, l.mel, l.mel_width, l.target_length)
+    pred = model.model_fn(rec, None, M.ModeKeys.PREDICT, hp).predictions
+    assert (pred["mel"].cpu() - ref["mel"]).abs().max().item() <= 1e-3 * scale
+    with pytest.raises(NotImplementedError, match="TRAIN"):
+        model.model_fn(f, l, M.ModeKeys.TRAIN, hp)
