@@ -351,6 +351,11 @@ int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
  * Both return SATK_ERR_UNSUPPORTED when the configuration is not covered (see de_ws). */
 int satk_attn_rnn_bwd_recurrence(const satk_attn_rnn_bwd_desc* d, void* stream);
 int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream);
+/* The same in two parts: SATK_EG_FEATURES fills the location-feature half of de_ws (it reads only what the forward pass saved, so
+ * it may be issued before / beside the recurrence), SATK_EG_GRADIENTS is the gradient launch proper (both mechanisms in one grid). */
+#define SATK_EG_FEATURES 1
+#define SATK_EG_GRADIENTS 2
+int satk_attn_energy_grad_parts(const satk_attn_rnn_bwd_desc* d, int parts, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Free-running decoder step (PREDICT mode, predict_mel.py:36-74): the inference-branch cells of

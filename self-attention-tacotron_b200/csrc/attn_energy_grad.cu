@@ -61,11 +61,10 @@ __global__ void __launch_bounds__(256) loc_features_all_kernel(const satk_attn_r
 }
 
 template <bool LOC>
-__global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_attn_rnn_bwd_desc dd, const float* __restrict__ de,
-                                                                    const float* __restrict__ fws) {
+__device__ __forceinline__ void energy_grad_body(const satk_attn_rnn_bwd_desc& dd, const float* __restrict__ de,
+                                                 const float* __restrict__ fws, const int cb /* channel block inside the mechanism */) {
   const satk_attn_rnn_fwd_desc& d = dd.f;
   const int b = blockIdx.y;
-  const int cb = blockIdx.x;                       // channel block inside the mechanism
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int Tt = d.Tt, B = d.B, Td = d.Td;
   const int alen = min((int)d.lengths[b], Tt);
@@ -327,20 +326,29 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
   }
 }
 
+// One grid for both mechanisms: channel blocks 0..A1/EG_CB-1 belong to mechanism 1 (location features), the rest to mechanism 2.
+// The short mechanism-2 CTAs fill the slots that the second, partial wave of mechanism-1 CTAs leaves idle.
+__global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_attn_rnn_bwd_desc dd, const float* __restrict__ de,
+                                                                    const float* __restrict__ fws) {
+  if (blockIdx.x < A1 / EG_CB) energy_grad_body<true>(dd, de, fws, blockIdx.x);
+  else energy_grad_body<false>(dd, de, fws, blockIdx.x - A1 / EG_CB);
+}
+
 // workspace: de [Td,B,2,Tt] followed by the location features [Td,B,Tt,MAXF]
-int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, cudaStream_t st) {
+int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, int parts, cudaStream_t st) {
   SATK_CHECK_ARG(d->f.Tt <= 64 * EG_MP, "attn_energy_grad: Tt=%d out of range", d->f.Tt);
   EgSmem S;
   const size_t smem = S.carve(nullptr, d->f.Tt);
   float* fws = const_cast<float*>(de) + (((size_t)d->f.Td * d->f.B * 2 * d->f.Tt + 3) & ~(size_t)3);   // 16-byte aligned rows
-  loc_features_all_kernel<<<dim3(d->f.Td, d->f.B), 256, 0, st>>>(d->f, fws);
-  SATK_LAUNCH_CHECK();
-  SATK_CUDA(cudaFuncSetAttribute(attn_energy_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SATK_CUDA(cudaFuncSetAttribute(attn_energy_grad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_energy_grad_kernel<true><<<dim3(A1 / EG_CB, d->f.B), EG_NT, smem, st>>>(*d, de, fws);
-  SATK_LAUNCH_CHECK();
-  attn_energy_grad_kernel<false><<<dim3(A2 / EG_CB, d->f.B), EG_NT, smem, st>>>(*d, de, fws);
-  SATK_LAUNCH_CHECK();
+  if (parts & 1) {      // location features of every step: they depend on the forward pass only
+    loc_features_all_kernel<<<dim3(d->f.Td, d->f.B), 256, 0, st>>>(d->f, fws);
+    SATK_LAUNCH_CHECK();
+  }
+  if (parts & 2) {
+    SATK_CUDA(cudaFuncSetAttribute(attn_energy_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_energy_grad_kernel<<<dim3((A1 + A2) / EG_CB, d->f.B), EG_NT, smem, st>>>(*d, de, fws);
+    SATK_LAUNCH_CHECK();
+  }
   return SATK_OK;
 }
 

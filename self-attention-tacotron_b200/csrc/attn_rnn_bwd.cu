@@ -891,10 +891,10 @@ using namespace satk::arnn;
 namespace satk { namespace arnn2 {
 bool v2_eligible(const satk_attn_rnn_fwd_desc* d);
 int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, cudaStream_t st);
-int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, cudaStream_t st);
+int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, int parts, cudaStream_t st);
 } }
 
-static int bwd2_check(const satk_attn_rnn_bwd_desc* d) {
+static int bwd2_check(const satk_attn_rnn_bwd_desc* d, bool features_only = false) {
   bool has2;
   int rc = attn_rnn_check(&d->f, has2);
   if (rc) return rc;
@@ -902,6 +902,7 @@ static int bwd2_check(const satk_attn_rnn_bwd_desc* d) {
     satk::set_error("attn_rnn_bwd: configuration not covered by the second-generation kernels (or de_ws missing)");
     return SATK_ERR_UNSUPPORTED;
   }
+  if (features_only) return SATK_OK;     // reads the saved alignments and the location convolution only
   SATK_CHECK_ARG(d->f.gates && d->f.c_prev && d->f.q_save && d->f.soft1 && d->dkeys1 && d->dkeys2 && d->dv1 && d->dv2 &&
                  d->dloc_conv_w && d->dloc_conv_b && d->dloc_layer_w,
                  "attn_rnn_bwd: forward must have saved gates/c_prev/q_save/soft1 and every gradient buffer must be set");
@@ -914,10 +915,15 @@ extern "C" int satk_attn_rnn_bwd_recurrence(const satk_attn_rnn_bwd_desc* d, voi
   return arnn2::attn_rnn2_bwd_launch(d, d->de_ws, (cudaStream_t)stream);
 }
 
-extern "C" int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream) {
-  int rc = bwd2_check(d);
+extern "C" int satk_attn_energy_grad_parts(const satk_attn_rnn_bwd_desc* d, int parts, void* stream) {
+  SATK_CHECK_ARG(parts >= 1 && parts <= 3, "attn_energy_grad: parts=%d", parts);
+  int rc = bwd2_check(d, /*features_only=*/parts == SATK_EG_FEATURES);
   if (rc) return rc;
-  return arnn2::attn_energy_grad_launch(d, d->de_ws, (cudaStream_t)stream);
+  return arnn2::attn_energy_grad_launch(d, d->de_ws, parts, (cudaStream_t)stream);
+}
+
+extern "C" int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream) {
+  return satk_attn_energy_grad_parts(d, SATK_EG_FEATURES | SATK_EG_GRADIENTS, stream);
 }
 
 extern "C" int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream) {

@@ -83,6 +83,12 @@ class TacotronEngine:
         # weight-gradient products have no consumer before the optimiser: they run on a second stream beside the critical path
         # (dX chain + recurrent kernels, which leave most SMs idle); SATK_WGRAD_STREAM=0 keeps everything on one stream
         self._side = torch.cuda.Stream(device=self.device) if os.environ.get("SATK_WGRAD_STREAM", "1") != "0" else None
+        # ... several of them, taken round-robin by the weight-gradient sections: most of those are chains of small launches
+        # (transposes, a split-K product, a column sum) that fill a fraction of the SMs, so independent sections run side by side
+        # (SATK_WGRAD_LANES=1: one stream, every section behind the previous one)
+        self._sides = [] if self._side is None else \
+            [self._side] + [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(os.environ.get("SATK_WGRAD_LANES", "3"))) - 1)]
+        self._side_rr = 0
         # independent branches of the graph (decoder pre-net beside the encoder, the two BiLSTM directions) fork onto a third stream
         self._aux = torch.cuda.Stream(device=self.device) if self._side is not None else None
         # the critical path runs on a high-priority stream of its own, so that pending CTAs of the recurrent cluster kernels are
@@ -113,15 +119,34 @@ class TacotronEngine:
 
     # ------------------------------------------------------------------ helpers
     @contextlib.contextmanager
-    def _wg(self):
-        """Weight-gradient section: launches inside run on the side stream, ordered after everything issued so far on the main
-        stream.  Only tensors that the main stream does not write again during this backward pass may be read here."""
+    def _wg(self, after=None):
+        """Weight-gradient section: launches inside run on one of the side streams (round-robin), ordered after everything issued
+        so far on the main stream and after the event ``after`` (`_wg_event` of an earlier section whose results this one reads).
+        Only tensors that the main stream does not write again during this backward pass may be read here, and two sections must
+        not accumulate into the same gradient tensor."""
         if self._side is None:
             yield
             return
-        self._side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._side):
+        st = self._sides[self._side_rr % len(self._sides)]
+        self._side_rr += 1
+        self._last_side = st
+        st.wait_stream(torch.cuda.current_stream())
+        if after is not None:
+            st.wait_event(after)
+        with torch.cuda.stream(st):
             yield
+
+    def _wg_event(self):
+        """Event behind the weight-gradient section issued last (None without side streams)."""
+        if self._side is None:
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self._last_side)
+        return ev
+
+    def _wg_join(self):
+        for st in self._sides:
+            torch.cuda.current_stream().wait_stream(st)
 
     def refresh_transposed(self):
         """K-contiguous copies of all matrices (ps.flat -> ps.flat_t), one batched launch."""
@@ -441,10 +466,10 @@ class TacotronEngine:
                      act=s["act"], maxpool_seq_len=Tt if s["maxpool"] else 0, pos_stride=B, use_batch_stats=training)
 
         def conv_back(x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None, xT=None,
-                      drawT=None, drawT_row0=0, skip_dx=False):
+                      drawT=None, drawT_row0=0, skip_dx=False, after=None):
             """draw: gradient wrt the raw conv output [R, cout] (ld draw_ld); accumulates dW, writes/accumulates dx."""
             pl = (k - 1) // 2
-            with self._wg():
+            with self._wg(after):
                 if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
                     # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
                     if xT is None:
@@ -477,6 +502,7 @@ class TacotronEngine:
         with self._wg():
             inpT = O.transposed_rows(sv["inp"], R, cin) if bank_tc else None      # shared by all bank widths
             drawT = O.transposed_rows(draw, R, KC) if bank_tc else None
+        bank_ev = self._wg_event() if bank_tc else None     # the per-width sections below run on other side streams
         one = bank_tc and self._bank_one_launch(R, cin, d.conv_ch)
         if one:
             # dinp = dhw (residual branch, module.py:86) + sum over widths and taps of the transposed convs: ONE launch, every width a
@@ -489,7 +515,7 @@ class TacotronEngine:
         for k in range(1, d.bank_k + 1):   # weight gradients per width (+ the per-width input gradient when not fused above)
             conv_back(sv["inp"], f"cbhg.bank{k}.W", k, cin, d.conv_ch, draw, dinp, 0.0 if k == 1 else 1.0, draw_ld=KC,
                       draw_off=(k - 1) * d.conv_ch, residual=dhw if k == 1 else None, xT=inpT, drawT=drawT,
-                      drawT_row0=(k - 1) * d.conv_ch, skip_dx=one)
+                      drawT_row0=(k - 1) * d.conv_ch, skip_dx=one, after=bank_ev)
         # encoder pre-net
         dy = dinp
         n = len(d.enc_prenet)
@@ -633,6 +659,12 @@ class TacotronEngine:
         training = self._training
         R, Rd = Tt * B, Td * B
         H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
+        # second-generation attention backward: its location features need the forward pass only -> first thing on the auxiliary stream
+        de_ws = self.buf("dec.de_ws", (Td * B * Tt * (2 + 8) + 4,)) if d.dual else None
+        feats_early = False
+        if d.dual and getattr(self, "_aux", None) is not None and os.environ.get("SATK_ENERGY_FORK", "1") != "0":
+            with self._fork():
+                feats_early = O.attn_energy_grad(O.attn_rnn_bwd_desc(sv["fd"], de_ws=de_ws), O.EG_FEATURES, optional=True)
         O.tf32_push("proj")
         x = sv["proj_in"]
         Dp = x.shape[1]
@@ -685,7 +717,7 @@ class TacotronEngine:
             dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
             step_end=self.saved.get("step_end"),
             # workspace of the second-generation kernels (d(energies) of both mechanisms, include/satk.h)
-            de_ws=self.buf("dec.de_ws", (Td * B * Tt * (2 + 8) + 4,)) if d.dual else None)
+            de_ws=de_ws)
         # second generation: the recurrence, then the energy gradients (dkeys, dv, location layer / conv) as a parallel launch of
         # their own; configurations it does not cover run the first-generation kernel (everything in one launch)
         energy_forked = False
@@ -694,7 +726,7 @@ class TacotronEngine:
             # auxiliary stream beside the LSTM-1 input gradient, the dvalues products and the pre-net backward chain
             if getattr(self, "_aux", None) is not None and os.environ.get("SATK_ENERGY_FORK", "1") != "0":
                 with self._fork():
-                    self._timed("attn_energy_grad", O.attn_energy_grad, bd)
+                    self._timed("attn_energy_grad", O.attn_energy_grad, bd, O.EG_GRADIENTS if feats_early else O.EG_FEATURES | O.EG_GRADIENTS)
                 energy_forked = True
             else:
                 self._timed("attn_energy_grad", O.attn_energy_grad, bd)
@@ -1141,14 +1173,12 @@ class TacotronEngine:
         overlapped = (allreduce is not None and getattr(allreduce, "supports_async", False) and self.d.l2_weight == 0
                       and os.environ.get("SATK_AR_OVERLAP", "1") != "0")
         if overlapped:
-            if self._side is not None:
-                torch.cuda.current_stream().wait_stream(self._side)  # the decoder's weight gradients are in
+            self._wg_join()                                          # the decoder's weight gradients are in
             handle = allreduce(self.ps.grad[self._dec_off:], async_op=True)
         O.tf32_push("enc")
         self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
         O.tf32_pop()
-        if self._side is not None:
-            torch.cuda.current_stream().wait_stream(self._side)      # every weight gradient is in before all-reduce / Adam
+        self._wg_join()                                              # every weight gradient is in before all-reduce / Adam
         if self.d.l2_weight > 0:
             # gradient of l2_regularization_loss (models/models.py:470-478): scale * w on the regularised tensors.  Every replica adds it
             # (TF: each replica's loss carries the term, gradients are averaged), the 1/world_size after the all-reduce restores it.

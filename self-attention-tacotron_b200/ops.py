@@ -463,6 +463,9 @@ def attn_rnn_fwd(d: AttnRnnFwdDesc):
     _count()
 
 
+SATK_ERR_UNSUPPORTED = -3
+
+
 def attn_rnn_bwd_desc(f: AttnRnnFwdDesc, **kw) -> AttnRnnBwdDesc:
     d = AttnRnnBwdDesc()
     d.f = f
@@ -484,9 +487,6 @@ def attn_rnn_bwd_launch(d: AttnRnnBwdDesc):
     _count()
 
 
-SATK_ERR_UNSUPPORTED = -3
-
-
 def attn_rnn_bwd_recurrence(d: AttnRnnBwdDesc) -> bool:
     """Sequential half of the second-generation backward (include/satk.h).  False: configuration not covered, nothing launched."""
     rc = load().satk_attn_rnn_bwd_recurrence(C.byref(d), C.c_void_p(stream_ptr()))
@@ -497,9 +497,19 @@ def attn_rnn_bwd_recurrence(d: AttnRnnBwdDesc) -> bool:
     return True
 
 
-def attn_energy_grad(d: AttnRnnBwdDesc):
-    check(load().satk_attn_energy_grad(C.byref(d), C.c_void_p(stream_ptr())), "satk_attn_energy_grad")
-    _count(2)
+EG_FEATURES, EG_GRADIENTS = 1, 2
+
+
+def attn_energy_grad(d: AttnRnnBwdDesc, parts: int = EG_FEATURES | EG_GRADIENTS, optional: bool = False) -> bool:
+    """Parallel half of the second-generation backward; ``parts`` selects the location-feature precomputation (needs the forward pass
+    only) and / or the gradient launch (include/satk.h).  ``optional``: False is returned instead of an error when the
+    configuration is not covered by the second-generation kernels."""
+    rc = load().satk_attn_energy_grad_parts(C.byref(d), parts, C.c_void_p(stream_ptr()))
+    if optional and rc == SATK_ERR_UNSUPPORTED:
+        return False
+    check(rc, "satk_attn_energy_grad")
+    _count(bin(parts).count("1"))
+    return True
 
 
 # ---------------------------------------------------------------------------------------------- free-running decode step

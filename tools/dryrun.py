@@ -106,6 +106,7 @@ def run(cfg, B, Tt, Tm, overrides=None):
     eng._sumsq = torch.zeros(1)
     eng.timers = None
     eng._side = None
+    eng._sides = []
     eng.refresh_transposed()
     f, l = satk.synthetic_batch(hp, B, Tt, Tm)
     for training in (False, True):
