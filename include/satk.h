@@ -335,15 +335,20 @@ typedef struct {
    * skips (dx2 is left as it is: zero).  Ignored with cumulative != 0 (the location state is walked back from the final state).
    * NULL: all Td steps. */
   const int* step_end;
-  /* optional workspace of Td*B*Tt*10 + 4 floats (d(energies) [Td,B,2,Tt], then - 16-byte aligned - the location features [Td,B,Tt,8] that
-   * satk_attn_energy_grad computes once for all steps).  When it is set and the configuration is the dual-source decoder of the shipped
+  /* optional workspace of Td*B*(2*SATK_DE_ROW(Tt) + 8*Tt) floats (d(energies) [Td,B,2,SATK_DE_ROW(Tt)] - rows padded to whole
+   * 128-byte lines -, then the location features [Td,B,Tt,8] that satk_attn_energy_grad computes once for all steps).  When it is set and the configuration is the dual-source decoder of the shipped
    * models (forward / location-sensitive first mechanism without cumulative weights or transition agent, <= 5 location
    * filters, Tt <= 192), the second-generation kernels run: the sequential kernel (one wave of 16-CTA clusters at B = 32)
    * only walks the recurrence and leaves d(energies) of both mechanisms here, and dkeys / dv / d(location layer / conv),
    * which do not feed the recurrence, come from a second, fully parallel launch over all (step, utterance) pairs
    * (forward_attention.py:13-26,98-100).  NULL: first-generation kernel, everything in one launch. */
   float* de_ws;
+  /* with de_ws: SATK_EG_SYNC_INTS(B) ints (unit queue of the energy-gradient workers and the per-utterance progress flags the
+   * recurrence publishes for them); no initialisation needed.  NULL: first-generation kernel. */
+  int* sync_ws;
 } satk_attn_rnn_bwd_desc;
+#define SATK_DE_ROW(Tt) (((Tt) + 31) / 32 * 32)
+#define SATK_EG_SYNC_INTS(B) (4 + 2 * (B))
 int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream);
 /* The two launches of the second-generation path separately (satk_attn_rnn_bwd issues both on one stream): the sequential
  * recurrence (fills dx2[:, H:], dgates, dq, de_ws) and the parallel energy gradients (reads de_ws; fills dkeys1/2 and adds
@@ -356,6 +361,11 @@ int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream);
 #define SATK_EG_FEATURES 1
 #define SATK_EG_GRADIENTS 2
 int satk_attn_energy_grad_parts(const satk_attn_rnn_bwd_desc* d, int parts, void* stream);
+/* Both launches as an overlapped pair on one stream: the gradient launch is a programmatic dependent of the recurrence (it starts
+ * when every recurrence CTA is resident, on the SMs the clusters leave idle, and consumes d(energies) chunk by chunk behind the
+ * recurrence's progress flags), so little of it is left when the recurrence ends.  features != 0: the location features are
+ * computed first (0: the caller has issued SATK_EG_FEATURES already and ordered `stream` behind it). */
+int satk_attn_rnn_bwd_overlapped(const satk_attn_rnn_bwd_desc* d, int features, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Free-running decoder step (PREDICT mode, predict_mel.py:36-74): the inference-branch cells of

@@ -32,6 +32,11 @@ constexpr int PSL = CW * 4;         // position slots per pass of the energy pha
 constexpr int SMW = 6;              // warps per softmax group (one position per thread): Tt <= 192
 constexpr float K2LOG2E = 2.885390081777927f;   // 2*log2(e): tanh(x) = 1 - 2 / (1 + 2^(K2LOG2E x))
 
+// d(energies) workspace of the backward pass: rows [Td][B][2] of de_row_stride(Tt) floats.  Rows start on 128-byte lines so that a
+// consumer running beside the recurrence never pulls a line into L1 that holds part of a row which is not written yet.
+__host__ __device__ inline int de_row_stride(int Tt) { return (Tt + 31) & ~31; }
+constexpr int EG_PUB = 8;          // the recurrence publishes its progress (lowest finished step) every EG_PUB steps
+
 template <int NB>
 struct Geo {
   static constexpr int G = (NB == 5) ? 3 : 4;

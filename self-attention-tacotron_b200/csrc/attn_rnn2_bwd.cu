@@ -270,7 +270,10 @@ __device__ __forceinline__ void energy_bwd_passes(const BwdSmem2<NB>& S, int slo
 }
 
 template <int NB, int NP>
-__global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_rnn_bwd_desc dd, float* __restrict__ de_out) {
+__global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_rnn_bwd_desc dd, float* __restrict__ de_out,
+                                                                 int* __restrict__ prog /* [B][2] progress flags or NULL */) {
+  // a dependent launch (the streaming energy-gradient kernel) may start as soon as every CTA of this grid is resident
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   using GE = Geo<NB>;
   constexpr int G = GE::G, QA = GE::QA, QC = GE::QC, VA = GE::VA, VC = GE::VC, VAq = GE::VAq, VBq = GE::VBq, VCq = GE::VCq;
   constexpr int NIA = GE::NIA, NSLOT = GE::NSLOT, KSTR = GE::KSTR;
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
   const int pl = (d.att_kernel - 1) / 2;
   const Slice<NB> sl(ag);
   const int Tt4 = (Tt + 3) >> 2;     // 16-byte chunks of a per-position row
+  const int DEL = de_row_stride(Tt); // row stride of the d(energies) workspace
 
   // ---------------- one-time loads
   for (int i = tid; i < TtP * KSTR; i += NTB) {
@@ -515,8 +519,8 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
         float* qz = dd.dq + ((long long)tz * B + bz) * QT;
         for (int i = tid; i < QT; i += NTB) qz[i] = 0.f;
       }
-      float* ez = de_out + ((long long)tz * B + bz) * 2 * Tt;
-      for (int i = tid; i < 2 * Tt; i += NTB) ez[i] = 0.f;
+      float* ez = de_out + ((long long)tz * B + bz) * 2 * DEL;
+      for (int i = tid; i < 2 * DEL; i += NTB) ez[i] = 0.f;
     }
   }
 
@@ -691,7 +695,13 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
         }
       } else if (arow_ok && ag < 2) {
         // service: d(energies) of step t -> global (input of satk_attn_energy_grad): member 0 mechanism 1, member 1 mechanism 2
-        float* dst = de_out + (((long long)t * B + arow) * 2 + ag) * Tt;
+        if (prog && (t + 1) % EG_PUB == 0 && t + 1 < Te) {
+          // the rows of the steps >= t + 1 left a whole step ago: make them visible, then publish the progress
+          __threadfence();
+          cl::named_bar_sync(7, NSVB);
+          if (sv == 0) *reinterpret_cast<volatile int*>(prog + arow * 2 + ag) = t + 1;
+        }
+        float* dst = de_out + (((long long)t * B + arow) * 2 + ag) * DEL;
         const float* src = S.deS + ag * TtP;
         if ((Tt & 3) == 0) {
           for (int q = sv; q < Tt4; q += NSVB) *reinterpret_cast<float4*>(dst + 4 * q) = *reinterpret_cast<const float4*>(src + 4 * q);
@@ -929,6 +939,11 @@ __global__ void __launch_bounds__(NTB, 1) attn_rnn2_bwd_kernel(const satk_attn_r
     }
   }
   PT2_FLUSH(Te)
+  if (prog && service && arow_ok && ag < 2) {      // every row of my utterance / mechanism is out
+    __threadfence();
+    cl::named_bar_sync(7, NSVB);
+    if (sv == 0) *reinterpret_cast<volatile int*>(prog + arow * 2 + ag) = 0;
+  }
   cp_async_wait<0>();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -943,7 +958,7 @@ static size_t bwd2_smem_bytes(int np) {
 }
 
 template <typename Kern>
-static int launch16b(Kern kern, const satk_attn_rnn_bwd_desc& d, float* de, int nb, size_t smem, cudaStream_t st) {
+static int launch16b(Kern kern, const satk_attn_rnn_bwd_desc& d, float* de, int* prog, int nb, size_t smem, cudaStream_t st) {
   SATK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   SATK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};
@@ -958,7 +973,7 @@ static int launch16b(Kern kern, const satk_attn_rnn_bwd_desc& d, float* de, int 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  SATK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, de));
+  SATK_CUDA(cudaLaunchKernelEx(&cfg, kern, d, de, prog));
   return SATK_OK;
 }
 
@@ -976,7 +991,7 @@ int v2_pick_nb_bwd(const satk_attn_rnn_fwd_desc* d) {
 }
 
 // `de` [Td,B,2,Tt]: d(energies) of both mechanisms, consumed by satk_attn_energy_grad
-int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, cudaStream_t st) {
+int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, int* prog, cudaStream_t st) {
   const int nb = v2_pick_nb_bwd(&d->f);
   const int np = (d->f.Tt + PSL - 1) / PSL;
   SATK_CHECK_ARG(np <= 4, "attn_rnn2_bwd: Tt=%d out of range", d->f.Tt);
@@ -984,11 +999,11 @@ int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, cudaStream_
   const size_t smem = attn_rnn2_bwd_smem(nb, d->f.Tt);
   SATK_CHECK_ARG(smem <= 227 * 1024, "attn_rnn2_bwd: Tt=%d needs %zu B of shared memory (> 227 KB)", d->f.Tt, smem);
   if (nb == 5) {
-    if (npv == 3) return launch16b(attn_rnn2_bwd_kernel<5, 3>, *d, de, nb, smem, st);
-    return launch16b(attn_rnn2_bwd_kernel<5, 4>, *d, de, nb, smem, st);
+    if (npv == 3) return launch16b(attn_rnn2_bwd_kernel<5, 3>, *d, de, prog, nb, smem, st);
+    return launch16b(attn_rnn2_bwd_kernel<5, 4>, *d, de, prog, nb, smem, st);
   }
-  if (npv == 3) return launch16b(attn_rnn2_bwd_kernel<4, 3>, *d, de, nb, smem, st);
-  return launch16b(attn_rnn2_bwd_kernel<4, 4>, *d, de, nb, smem, st);
+  if (npv == 3) return launch16b(attn_rnn2_bwd_kernel<4, 3>, *d, de, prog, nb, smem, st);
+  return launch16b(attn_rnn2_bwd_kernel<4, 4>, *d, de, prog, nb, smem, st);
 }
 
 int attn2_bwd_phase_cycles(long long* out16) {

@@ -890,16 +890,17 @@ using namespace satk::arnn;
 
 namespace satk { namespace arnn2 {
 bool v2_eligible(const satk_attn_rnn_fwd_desc* d);
-int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, cudaStream_t st);
-int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, int parts, cudaStream_t st);
+int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, int* prog, cudaStream_t st);
+int attn_energy_grad_prepare(const satk_attn_rnn_bwd_desc* d, cudaStream_t st);
+int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, int parts, int dependent, cudaStream_t st);
 } }
 
 static int bwd2_check(const satk_attn_rnn_bwd_desc* d, bool features_only = false) {
   bool has2;
   int rc = attn_rnn_check(&d->f, has2);
   if (rc) return rc;
-  if (!d->de_ws || !arnn2::v2_eligible(&d->f)) {
-    satk::set_error("attn_rnn_bwd: configuration not covered by the second-generation kernels (or de_ws missing)");
+  if (!d->de_ws || !d->sync_ws || !arnn2::v2_eligible(&d->f)) {
+    satk::set_error("attn_rnn_bwd: configuration not covered by the second-generation kernels (or de_ws / sync_ws missing)");
     return SATK_ERR_UNSUPPORTED;
   }
   if (features_only) return SATK_OK;     // reads the saved alignments and the location convolution only
@@ -912,14 +913,32 @@ static int bwd2_check(const satk_attn_rnn_bwd_desc* d, bool features_only = fals
 extern "C" int satk_attn_rnn_bwd_recurrence(const satk_attn_rnn_bwd_desc* d, void* stream) {
   int rc = bwd2_check(d);
   if (rc) return rc;
-  return arnn2::attn_rnn2_bwd_launch(d, d->de_ws, (cudaStream_t)stream);
+  return arnn2::attn_rnn2_bwd_launch(d, d->de_ws, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int satk_attn_energy_grad_parts(const satk_attn_rnn_bwd_desc* d, int parts, void* stream) {
   SATK_CHECK_ARG(parts >= 1 && parts <= 3, "attn_energy_grad: parts=%d", parts);
   int rc = bwd2_check(d, /*features_only=*/parts == SATK_EG_FEATURES);
   if (rc) return rc;
-  return arnn2::attn_energy_grad_launch(d, d->de_ws, parts, (cudaStream_t)stream);
+  return arnn2::attn_energy_grad_launch(d, d->de_ws, parts, 0, (cudaStream_t)stream);
+}
+
+// Recurrence + energy gradients as ONE overlapped pair on one stream: the gradient grid is a programmatic dependent of the
+// recurrence grid (it starts once every recurrence CTA is resident, runs on the SMs the clusters leave idle and follows the
+// progress flags), so only its last chunks remain when the recurrence ends.
+extern "C" int satk_attn_rnn_bwd_overlapped(const satk_attn_rnn_bwd_desc* d, int features, void* stream) {
+  int rc = bwd2_check(d);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = arnn2::attn_energy_grad_prepare(d, st);
+  if (rc) return rc;
+  if (features) {
+    rc = arnn2::attn_energy_grad_launch(d, d->de_ws, SATK_EG_FEATURES, 0, st);
+    if (rc) return rc;
+  }
+  rc = arnn2::attn_rnn2_bwd_launch(d, d->de_ws, d->sync_ws + 4, st);
+  if (rc) return rc;
+  return arnn2::attn_energy_grad_launch(d, d->de_ws, SATK_EG_GRADIENTS, 1, st);
 }
 
 extern "C" int satk_attn_energy_grad(const satk_attn_rnn_bwd_desc* d, void* stream) {
@@ -930,7 +949,7 @@ extern "C" int satk_attn_rnn_bwd(const satk_attn_rnn_bwd_desc* d, void* stream) 
   bool has2;
   int rc = attn_rnn_check(&d->f, has2);
   if (rc) return rc;
-  if (d->de_ws && arnn2::v2_eligible(&d->f)) {
+  if (d->de_ws && d->sync_ws && arnn2::v2_eligible(&d->f)) {
     rc = satk_attn_rnn_bwd_recurrence(d, stream);
     if (rc) return rc;
     return satk_attn_energy_grad(d, stream);

@@ -91,6 +91,8 @@ class TacotronEngine:
         self._side_rr = 0
         # independent branches of the graph (decoder pre-net beside the encoder, the two BiLSTM directions) fork onto a third stream
         self._aux = torch.cuda.Stream(device=self.device) if self._side is not None else None
+        # ... and a fourth: the LSTM-1 / pre-net tail of the decoder's backward pass, which only the weight gradients wait for
+        self._aux2 = torch.cuda.Stream(device=self.device) if self._side is not None else None
         # the critical path runs on a high-priority stream of its own, so that pending CTAs of the recurrent cluster kernels are
         # placed before pending CTAs of the weight-gradient products (SATK_MAIN_PRIORITY=0 switches it off; the caller's stream is joined on both sides)
         self._main = torch.cuda.Stream(device=self.device, priority=-1) \
@@ -199,18 +201,20 @@ class TacotronEngine:
         return out
 
     @contextlib.contextmanager
-    def _fork(self):
-        """Independent branch: runs on the auxiliary stream after everything issued so far; `_join` merges it back."""
-        if getattr(self, "_aux", None) is None:
+    def _fork(self, which=0):
+        """Independent branch: runs on an auxiliary stream after everything issued so far; `_join` merges it back."""
+        aux = getattr(self, "_aux2" if which else "_aux", None)
+        if aux is None:
             yield
             return
-        self._aux.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self._aux):
+        aux.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(aux):
             yield
 
-    def _join(self):
-        if getattr(self, "_aux", None) is not None:
-            torch.cuda.current_stream().wait_stream(self._aux)
+    def _join(self, which=0):
+        aux = getattr(self, "_aux2" if which else "_aux", None)
+        if aux is not None:
+            torch.cuda.current_stream().wait_stream(aux)
 
     # ------------------------------------------------------------------ self-attention block
     def _sa_forward(self, x, T, B, name, heads, causal, mask, keep, key):
@@ -660,7 +664,8 @@ class TacotronEngine:
         R, Rd = Tt * B, Td * B
         H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
         # second-generation attention backward: its location features need the forward pass only -> first thing on the auxiliary stream
-        de_ws = self.buf("dec.de_ws", (Td * B * Tt * (2 + 8) + 4,)) if d.dual else None
+        de_ws = self.buf("dec.de_ws", (O.de_ws_floats(Td, B, Tt),)) if d.dual else None
+        sync_ws = self.buf("dec.eg_sync", (O.eg_sync_ints(B),), torch.int32) if d.dual else None
         feats_early = False
         if d.dual and getattr(self, "_aux", None) is not None and os.environ.get("SATK_ENERGY_FORK", "1") != "0":
             with self._fork():
@@ -717,11 +722,21 @@ class TacotronEngine:
             dagent_b=g["att1.agent.b"] if (d.attention == "forward" and d.transition_agent) else None,
             step_end=self.saved.get("step_end"),
             # workspace of the second-generation kernels (d(energies) of both mechanisms, include/satk.h)
-            de_ws=de_ws)
-        # second generation: the recurrence, then the energy gradients (dkeys, dv, location layer / conv) as a parallel launch of
-        # their own; configurations it does not cover run the first-generation kernel (everything in one launch)
+            de_ws=de_ws, sync_ws=sync_ws)
+        # second generation: the recurrence, and the energy gradients (dkeys, dv, location layer / conv) as a parallel launch of
+        # their own; configurations it does not cover run the first-generation kernel (everything in one launch).
+        # Default: the overlapped pair — the gradient workers start beside the recurrence (programmatic dependent launch) and follow
+        # its progress, so only their last chunks are left when it ends (SATK_EG_OVERLAP=0, or per-kernel timers: one after the other)
         energy_forked = False
-        if d.dual and self._timed("attn_rnn_bwd", O.attn_rnn_bwd_recurrence, bd):
+        overlapped = (d.dual and getattr(self, "_aux2", None) is not None and self.timers is None
+                      and os.environ.get("SATK_EG_OVERLAP", "1") != "0")
+        if overlapped:
+            if feats_early:
+                self._join()                   # location features (auxiliary stream) before the pair
+            overlapped = O.attn_rnn_bwd_overlapped(bd, not feats_early)
+        if overlapped:
+            pass
+        elif d.dual and self._timed("attn_rnn_bwd", O.attn_rnn_bwd_recurrence, bd):
             # dkeys / dv / d(location layer, conv) feed nothing before the memory-layer gradients below: the launch runs on the
             # auxiliary stream beside the LSTM-1 input gradient, the dvalues products and the pre-net backward chain
             if getattr(self, "_aux", None) is not None and os.environ.get("SATK_ENERGY_FORK", "1") != "0":
@@ -732,6 +747,31 @@ class TacotronEngine:
                 self._timed("attn_energy_grad", O.attn_energy_grad, bd)
         else:
             self._timed("attn_rnn_bwd", O.attn_rnn_bwd_launch, bd)
+        with (self._fork(1) if overlapped else contextlib.nullcontext()):
+            # nothing below feeds the encoder: with the overlapped pair it runs on its own stream beside the memory-layer gradients
+            # and the encoder's backward pass (`backward` joins it)
+            self._lstm1_prenet_backward(sv, dg1, dq, B, Td, training)
+        O.tf32_push("mem")
+        if energy_forked:
+            self._join()
+        dval1, dval2 = self._memory_backward(sv, dx2, dkeys1, dkeys2, B, Tt, Td, loc)
+        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
+        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
+        dmem2 = None
+        if d.dual:
+            dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
+            O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
+        O.tf32_pop()
+        return dmem1, dmem2
+
+    def _lstm1_prenet_backward(self, sv, dg1, dq, B, Td, training):
+        """Weight gradients of LSTM-1 and the query layers, then the decoder pre-net backwards (module.py:1509-1511,
+        multi_speaker_modules.py:27-32).  Reads d(gates) / d(queries) of the attention-RNN backward; feeds weight gradients only."""
+        d, p, g = self.d, self.ps.p, self.ps.g
+        Rd = Td * B
+        H1, P1 = d.att_rnn, d.dec_prenet[1]
+        X2W = H1 + d.ctx
+        QT = d.att1 + d.att2
         # LSTM-1 weight gradients (dense over time)
         gW1 = g["dec.lstm1.W"]
         N4 = 4 * H1
@@ -750,18 +790,6 @@ class TacotronEngine:
                 O.linear_dw(sv["x2"], dq, g["att2.query.W"], Rd, H1, d.att2, ldx=X2W, ldy=QT, y_off=d.att1)
         ddp1 = self.buf("dec.ddp1", (Rd, P1))
         O.linear_dx(dg1, p["dec.lstm1.W"][:P1], ddp1, Rd)
-        O.tf32_pop()
-        O.tf32_push("mem")
-        # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]   (dx2[:, H1:] now holds dctx_total)
-        dval1 = self.buf("dec.dvalues1", (R, d.mem1))
-        O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
-               b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
-        dval2 = None
-        if d.dual:
-            dval2 = self.buf("dec.dvalues2", (R, d.mem2))
-            O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
-                   b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
-        O.tf32_pop()
         O.tf32_push("prenet")
         # decoder pre-net
         keep_scale = 1.0 / (1.0 - d.dec_prenet_drop) if training else 1.0
@@ -800,10 +828,23 @@ class TacotronEngine:
                 O.linear_dw(sv["dec_in"], dz0, g["dec.prenet0.W"], Rd, d.dec_in, P0)
                 O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
         O.tf32_pop()
-        O.tf32_push("mem")
-        # keys = values . W_mem ; attention bias folded into the keys.  (dkeys come from the energy-gradient launch: join it first)
-        if energy_forked:
-            self._join()
+
+    def _memory_backward(self, sv, dx2, dkeys1, dkeys2, B, Tt, Td, loc):
+        """d(values) of both sources: through the contexts (dx2[:, H1:] holds d(context) of every step) and through the keys
+        (keys = values . W_mem, attention bias folded in); weight gradients of the memory layers.  -> (dval1, dval2 | None)"""
+        d, p, g = self.d, self.ps.p, self.ps.g
+        R = Tt * B
+        H1 = d.att_rnn
+        X2W = H1 + d.ctx
+        # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]
+        dval1 = self.buf("dec.dvalues1", (R, d.mem1))
+        O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
+               b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
+        dval2 = None
+        if d.dual:
+            dval2 = self.buf("dec.dvalues2", (R, d.mem2))
+            O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
+                   b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
         with self._wg():
             if loc:
                 O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
@@ -811,15 +852,9 @@ class TacotronEngine:
             if d.dual:
                 O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
         O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
-        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
-        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
-        dmem2 = None
         if d.dual:
             O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
-            dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
-            O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
-        O.tf32_pop()
-        return dmem1, dmem2
+        return dval1, dval2
 
     # ------------------------------------------------------------------ model_fn body
     def forward(self, features, labels, training: bool, masks: Optional[Dict[str, torch.Tensor]] = None):
@@ -1161,6 +1196,7 @@ class TacotronEngine:
         dmem1, dmem2 = self._timed("sec.decoder_bwd", self.decoder_backward, s["dmel"], s["dstop"], s["B"], s["Tt"], s["Td"],
                                    s["source_length"])
         if self.d.use_speaker:
+            self._join(1)                      # the pre-net chain (its own stream beside the overlapped attention backward)
             g, p = self.ps.g, self.ps.p
             dsp_pre = self._dspk_pre
             spk = self._bufs["spk_embed"]
@@ -1173,11 +1209,13 @@ class TacotronEngine:
         overlapped = (allreduce is not None and getattr(allreduce, "supports_async", False) and self.d.l2_weight == 0
                       and os.environ.get("SATK_AR_OVERLAP", "1") != "0")
         if overlapped:
+            self._join(1)
             self._wg_join()                                          # the decoder's weight gradients are in
             handle = allreduce(self.ps.grad[self._dec_off:], async_op=True)
         O.tf32_push("enc")
         self._timed("sec.encoder_bwd", self.encoder_backward, dmem1, dmem2, s["B"], s["Tt"], s["source_length"])
         O.tf32_pop()
+        self._join(1)
         self._wg_join()                                              # every weight gradient is in before all-reduce / Adam
         if self.d.l2_weight > 0:
             # gradient of l2_regularization_loss (models/models.py:470-478): scale * w on the regularised tensors.  Every replica adds it

@@ -500,6 +500,27 @@ def attn_rnn_bwd_recurrence(d: AttnRnnBwdDesc) -> bool:
 EG_FEATURES, EG_GRADIENTS = 1, 2
 
 
+def de_ws_floats(Td: int, B: int, Tt: int) -> int:
+    """Size of satk_attn_rnn_bwd_desc.de_ws (include/satk.h: SATK_DE_ROW)."""
+    return Td * B * (2 * ((Tt + 31) // 32 * 32) + 8 * Tt)
+
+
+def eg_sync_ints(B: int) -> int:
+    """Size of satk_attn_rnn_bwd_desc.sync_ws in int32 (include/satk.h: SATK_EG_SYNC_INTS)."""
+    return 4 + 2 * B
+
+
+def attn_rnn_bwd_overlapped(d: AttnRnnBwdDesc, features: bool) -> bool:
+    """Recurrence + streaming energy gradients as a programmatic-dependent pair (include/satk.h).  False: configuration not covered
+    by the second-generation kernels, nothing launched."""
+    rc = load().satk_attn_rnn_bwd_overlapped(C.byref(d), int(features), C.c_void_p(stream_ptr()))
+    if rc == SATK_ERR_UNSUPPORTED:
+        return False
+    check(rc, "satk_attn_rnn_bwd_overlapped")
+    _count(2 + int(features))
+    return True
+
+
 def attn_energy_grad(d: AttnRnnBwdDesc, parts: int = EG_FEATURES | EG_GRADIENTS, optional: bool = False) -> bool:
     """Parallel half of the second-generation backward; ``parts`` selects the location-feature precomputation (needs the forward pass
     only) and / or the gradient launch (include/satk.h).  ``optional``: False is returned instead of an error when the
