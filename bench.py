@@ -328,7 +328,7 @@ def run_satk(args, rank, world, local_rank):
     kt = {}
     for name, evs in (timers or {}).items():
         torch.cuda.synchronize()
-        kt[name] = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        kt[name] = statistics.median(a.elapsed_time(b) for a, b in evs)    # (a first use inside this eager pass can carry a one-time cost)
     roof = None
     # fraction of the (utterance, decoder step) pairs that carry a loss: the backward walk skips the others (engine.forward: step_end)
     loss_frac = statistics.mean(float((l_.binary_loss_mask != 0).sum()) / (B * td) for _, l_ in host)

@@ -2,6 +2,8 @@
 // backward, column sums, masks, softmax rows, teacher inputs, losses, optimiser.
 // Grid sizes are multiples of the SM count (148) where the problem is large enough; reductions use
 // warp shuffles.
+#include <initializer_list>
+#include <stdint.h>
 #include "common.cuh"
 
 namespace satk {
@@ -177,6 +179,160 @@ __global__ void bn_bwd_apply_k(const float* __restrict__ x, long long ldx, int r
     dx[(long long)r * lddx + c] = g;
   }
 }
+// ---- 16-byte variants (C, every leading dimension and every base pointer multiples of 4 floats): a thread owns 4 consecutive
+// channels; the per-channel constants are hoisted when the grid stride keeps the channel quad fixed.
+struct BnQuad { float inv[4], sh[4], mu[4], rstd[4]; };
+__device__ __forceinline__ void f4_to(const float4 v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ BnQuad bn_quad(const float* mean, const float* var, const float* gamma, const float* beta, float eps, int c) {
+  BnQuad q;
+  float m[4], v[4], g[4], b[4];
+  f4_to(ldg4(mean + c), m); f4_to(ldg4(var + c), v); f4_to(ldg4(gamma + c), g); f4_to(ldg4(beta + c), b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    q.rstd[i] = rsqrtf(v[i] + eps);
+    q.inv[i] = q.rstd[i] * g[i];
+    q.sh[i] = b[i] - m[i] * q.inv[i];
+    q.mu[i] = m[i];
+  }
+  return q;
+}
+// dz of 4 channels of row r (see bn_dz); xr receives the row's x values
+__device__ __forceinline__ void bn_dz4(const float* __restrict__ x, long long ldx, int r, int c, const BnQuad& q, int act, int mp_len,
+                                       int ps, const float* __restrict__ dy, long long lddy, float* dz, float* xr) {
+  float z[4], a[4], g[4];
+  f4_to(ldg4(x + (long long)r * ldx + c), xr);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { z[i] = fmaf(xr[i], q.inv[i], q.sh[i]); a[i] = apply_act(z[i], act); g[i] = 0.f; }
+  if (mp_len > 0) {
+    const int t = (r / ps) % mp_len;
+    float d0[4];
+    f4_to(ldg4(dy + (long long)r * lddy + c), d0);
+    if (t == mp_len - 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) g[i] = d0[i];
+    } else {
+      float xn[4];
+      f4_to(ldg4(x + (long long)(r + ps) * ldx + c), xn);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (a[i] >= apply_act(fmaf(xn[i], q.inv[i], q.sh[i]), act)) g[i] = d0[i];
+    }
+    if (t > 0) {
+      float xp[4], dp[4];
+      f4_to(ldg4(x + (long long)(r - ps) * ldx + c), xp);
+      f4_to(ldg4(dy + (long long)(r - ps) * lddy + c), dp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) if (a[i] > apply_act(fmaf(xp[i], q.inv[i], q.sh[i]), act)) g[i] += dp[i];
+    }
+  } else {
+    f4_to(ldg4(dy + (long long)r * lddy + c), g);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (act == SATK_ACT_RELU) g[i] = (z[i] > 0.f) ? g[i] : 0.f;
+    else if (act == SATK_ACT_TANH) g[i] *= (1.f - a[i] * a[i]);
+    else if (act == SATK_ACT_SIGMOID) g[i] *= a[i] * (1.f - a[i]);
+    dz[i] = g[i];
+  }
+}
+// grid (C/128, RS), block (32, 8): thread = channel quad x row slice
+__global__ void bn_bwd_reduce4_k(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ mean,
+                                 const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, int act, int mp_len, int ps, const float* __restrict__ dy, long long lddy,
+                                 float* __restrict__ sum_dz, float* __restrict__ sum_dzx) {
+  __shared__ float4 s1[8][33], s2[8][33];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < C) {
+    const BnQuad q = bn_quad(mean, var, gamma, beta, eps, c);
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += gridDim.y * 8) {
+      float dz[4], xr[4];
+      bn_dz4(x, ldx, r, c, q, act, mp_len, ps, dy, lddy, dz, xr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] += dz[i]; b[i] = fmaf(dz[i], (xr[i] - q.mu[i]) * q.rstd[i], b[i]); }
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = make_float4(a[0], a[1], a[2], a[3]);
+  s2[threadIdx.y][threadIdx.x] = make_float4(b[0], b[1], b[2], b[3]);
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) {
+      const float4 u = s1[i][threadIdx.x], v = s2[i][threadIdx.x];
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+      b[0] += v.x; b[1] += v.y; b[2] += v.z; b[3] += v.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { atomicAdd(sum_dz + c + i, a[i]); atomicAdd(sum_dzx + c + i, b[i]); }
+  }
+}
+// thread = channel quad, rows by grid stride (a whole number of rows per stride: the quad of a thread is fixed)
+__global__ void bn_bwd_apply4_k(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ mean,
+                                const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                float eps, int act, int mp_len, int ps, int batch_stats, const float* __restrict__ dy, long long lddy,
+                                const float* __restrict__ sum_dz, const float* __restrict__ sum_dzx, float* __restrict__ dx,
+                                long long lddx) {
+  const int C4 = C >> 2;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;     // nt is a multiple of C4
+  const int c = (gt % C4) * 4;
+  const BnQuad q = bn_quad(mean, var, gamma, beta, eps, c);
+  const float invn = 1.f / rows;
+  float k1[4], k2[4];
+  f4_to(ldg4(sum_dz + c), k1); f4_to(ldg4(sum_dzx + c), k2);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { k1[i] *= invn; k2[i] *= invn; }
+  for (int r = gt / C4; r < rows; r += nt / C4) {
+    float dz[4], xr[4], g[4];
+    bn_dz4(x, ldx, r, c, q, act, mp_len, ps, dy, lddy, dz, xr);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      g[i] = batch_stats ? q.inv[i] * (dz[i] - k1[i] - (xr[i] - q.mu[i]) * q.rstd[i] * k2[i]) : q.inv[i] * dz[i];
+    *reinterpret_cast<float4*>(dx + (long long)r * lddx + c) = make_float4(g[0], g[1], g[2], g[3]);
+  }
+}
+__global__ void bn_apply4_k(const float* __restrict__ x, long long ldx, int rows, int C, const float* __restrict__ mean,
+                            const float* __restrict__ var, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            float eps, int act, const float* __restrict__ residual, int mp_len, int ps, float* __restrict__ y, long long ldy) {
+  const int C4 = C >> 2;
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;     // nt is a multiple of C4
+  const int c = (gt % C4) * 4;
+  const BnQuad q = bn_quad(mean, var, gamma, beta, eps, c);
+  for (int r = gt / C4; r < rows; r += nt / C4) {
+    float xr[4], v[4];
+    f4_to(ldg4(x + (long long)r * ldx + c), xr);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = apply_act(fmaf(xr[i], q.inv[i], q.sh[i]), act);
+    if (mp_len > 0 && ((r / ps) % mp_len) != mp_len - 1) {
+      float xn[4];
+      f4_to(ldg4(x + (long long)(r + ps) * ldx + c), xn);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], apply_act(fmaf(xn[i], q.inv[i], q.sh[i]), act));
+    }
+    if (residual) {
+      float rr[4];
+      f4_to(ldg4(residual + (long long)r * C + c), rr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += rr[i];
+    }
+    *reinterpret_cast<float4*>(y + (long long)r * ldy + c) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+// launch geometry of the quad kernels: 256-thread blocks, a whole number of rows per grid stride, about 8 blocks per SM at most
+static inline bool bn_quad_ok(int C, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+  if (C % 4 != 0 || (C / 4) > 256 * 1184 || (256 % (C / 4) != 0 && (C / 4) % 256 != 0)) return false;
+  for (long long l : lds) if (l % 4 != 0) return false;
+  for (const void* q : ptrs) if (q && ((uintptr_t)q & 15)) return false;
+  return true;
+}
+static inline int bn_quad_grid(int rows, int C) {
+  const int C4 = C / 4;
+  const long long quads = (long long)rows * C4;
+  const int unit = C4 > 256 ? C4 / 256 : 1;            // blocks per row when a row is wider than a block
+  long long blocks = (quads + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  blocks = (blocks + unit - 1) / unit * unit;
+  return (int)blocks;
+}
+
 __global__ void bn_bwd_param_k(const float* sum_dz, const float* sum_dzx, int C, float* dgamma, float* dbeta) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
@@ -564,8 +720,12 @@ int satk_bn_apply(const float* x, long long ldx, int rows, int C, const float* m
                   void* stream) {
   SATK_CHECK_ARG(maxpool_seq_len == 0 || (pos_stride >= 1 && rows % maxpool_seq_len == 0), "bn_apply: rows %d not a multiple of seq_len %d", rows, maxpool_seq_len);
   if (pos_stride < 1) pos_stride = 1;
-  bn_apply_k<<<grid_for((long long)rows * C, 256), 256, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, residual,
-                                                                maxpool_seq_len, pos_stride, y, ldy);
+  if (bn_quad_ok(C, {ldx, ldy}, {x, y, mean, var, gamma, beta, residual}))
+    bn_apply4_k<<<bn_quad_grid(rows, C), 256, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, residual, maxpool_seq_len,
+                                                       pos_stride, y, ldy);
+  else
+    bn_apply_k<<<grid_for((long long)rows * C, 256), 256, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, residual,
+                                                                  maxpool_seq_len, pos_stride, y, ldy);
   SATK_LAUNCH_CHECK();
   return 0;
 }
@@ -576,11 +736,19 @@ int satk_bn_bwd(const float* x, long long ldx, int rows, int C, const float* mea
   SATK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * C, ST));
   int rs = min(64, max(1, rows / 64));
   dim3 grid(ceil_div(C, 32), rs), block(32, 8);
-  bn_bwd_reduce_k<<<grid, block, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, maxpool_seq_len, pos_stride, dy, lddy, scratch,
-                                          scratch + C);
-  bn_bwd_apply_k<<<grid_for((long long)rows * C, 256), 256, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act,
-                                                                    maxpool_seq_len, pos_stride, use_batch_stats, dy, lddy, scratch,
-                                                                    scratch + C, dx, lddx);
+  if (bn_quad_ok(C, {ldx, lddy, lddx}, {x, dy, dx, mean, var, gamma, beta, scratch})) {
+    dim3 grid4(ceil_div(C, 128), rs);
+    bn_bwd_reduce4_k<<<grid4, block, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, maxpool_seq_len, pos_stride, dy, lddy,
+                                              scratch, scratch + C);
+    bn_bwd_apply4_k<<<bn_quad_grid(rows, C), 256, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, maxpool_seq_len, pos_stride,
+                                                           use_batch_stats, dy, lddy, scratch, scratch + C, dx, lddx);
+  } else {
+    bn_bwd_reduce_k<<<grid, block, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act, maxpool_seq_len, pos_stride, dy, lddy, scratch,
+                                            scratch + C);
+    bn_bwd_apply_k<<<grid_for((long long)rows * C, 256), 256, 0, ST>>>(x, ldx, rows, C, mean, var, gamma, beta, eps, act,
+                                                                      maxpool_seq_len, pos_stride, use_batch_stats, dy, lddy, scratch,
+                                                                      scratch + C, dx, lddx);
+  }
   bn_bwd_param_k<<<ceil_div(C, 128), 128, 0, ST>>>(scratch, scratch + C, C, dgamma, dbeta);
   SATK_LAUNCH_CHECK();
   return 0;

@@ -434,7 +434,10 @@ int lstm_max_clusters_h256() {
 }  // namespace satk
 
 namespace satk { namespace tc { int tc_trace(long long* out16); } }
-namespace satk { namespace lstm5 { int lstm5_bwd_launch(const satk_lstm_bwd_desc* d, cudaStream_t st); } }
+namespace satk { namespace lstm5 {
+int lstm5_bwd_launch(const satk_lstm_bwd_desc* d, cudaStream_t st);
+int lstm5_fwd_launch(const satk_lstm_fwd_desc* d, cudaStream_t st);
+} }
 namespace satk { namespace arnn { int attn_fwd_phase_cycles(long long* out16); int attn_bwd_phase_cycles(long long* out16); } }
 namespace satk { namespace arnn2 { int attn2_fwd_phase_cycles(long long* out16); int attn2_bwd_phase_cycles(long long* out16); } }
 using namespace satk;
@@ -464,6 +467,9 @@ int satk_lstm_seq_fwd(const satk_lstm_fwd_desc* d, void* stream) {
   SATK_CHECK_ARG((d->gates == nullptr) == (d->c_prev == nullptr) && (d->gates == nullptr) == (d->h_prev == nullptr),
                  "lstm_seq_fwd: gates/c_prev/h_prev must be all set or all NULL");
   // H = 256: 32 units per CTA (clusters of 8 x 512 threads, one CTA per SM); H = 128: 16 units per CTA (clusters of 8 x 256 threads)
+  // decoder layers (H = 256, forward order, no length masking): 5 rows per 16-CTA cluster, one wave at B = 32 (lstm_seq5.cu)
+  const char* gen = getenv("SATK_LSTM_GEN");
+  if (d->H == 256 && !d->lengths && !d->reverse && !(gen && gen[0] == '1')) return lstm5::lstm5_fwd_launch(d, (cudaStream_t)stream);
   if (d->H == 256) return launch_cluster(lstm_fwd_kernel<256, 32>, *d, 256, d->B, (cudaStream_t)stream, 32);
   return launch_cluster(lstm_fwd_kernel<128, 16>, *d, 128, d->B, (cudaStream_t)stream, 16);
 }

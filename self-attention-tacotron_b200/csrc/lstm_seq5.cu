@@ -215,6 +215,203 @@ __global__ void __launch_bounds__(NT, 1) lstm5_bwd_kernel(const satk_lstm_bwd_de
   cluster.sync();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Forward, same geometry: a cluster of 16 CTAs owns 5 batch rows; a CTA owns 16 hidden units (64 gate columns, its slice of Wh in
+// registers).  Per step: gates = xg[t] + h_{t-1} . Wh over the full 256-wide state (thread = 16 k's x 4 columns, the 20 partial
+// sums reduce-scattered over the 16 k lanes), the LSTM cell on my 16 units, then the new 16 x 5 state slice goes to every CTA of
+// the cluster (st.async completing the mbarrier transaction of the next step; rows 0..3 of a unit are one 16-byte packet, the
+// fifth rows of 4 neighbouring units another).
+constexpr int FRING = cl::RING, FPFD = cl::PFD;
+constexpr int PWF = NB * UH;        // pointwise threads: tid < 64 -> (row tid & 3, unit tid >> 2); 64..79 -> (row 4, unit tid - 64)
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(NT, 1) lstm5_fwd_kernel(const satk_lstm_fwd_desc d) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b0 = (blockIdx.x / CS) * NB;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int T = d.T, B = d.B;
+  constexpr int K4 = 4 * H;
+  constexpr uint32_t RX_BYTES = (CS - 1) * UH * NB * 4;
+
+  __shared__ __align__(16) float hq[2][H][4];             // hidden state, rows 0..3
+  __shared__ __align__(16) float h4[2][H];                // hidden state, row 4
+  __shared__ float gsm[NB][4 * UH];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ float xg_ring[FRING][NT + 64];               // x-projection elements of the lanes that finalise a (row, column)
+  __shared__ __align__(4) uint8_t mk_ring[FRING][2][NB][UH];
+  __shared__ float save_st[7][PWF];
+
+  // gate-GEMM role: thread = (kq = tid & 15, column group cgp = tid >> 4): 4 gate columns x the 16 k's congruent to kq mod 16
+  const int kq = tid & 15, cgp = tid >> 4;
+  float w[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int colc = cgp * 4 + c;                                  // CTA-local gate column = gate*UH + unit
+      w[i][c] = __ldg(d.Wh + (long long)(kq + 16 * i) * K4 + (colc / UH) * H + rank * UH + (colc % UH));
+    }
+  const int col = cgp * 4 + ((kq >> 2) & 3);                         // the column this lane finalises (rows kq & 3 and, lanes kq & 3 == 0, row 4)
+  const int gcol = (col / UH) * H + rank * UH + (col % UH);
+  const int myb = b0 + (kq & 3);
+  const bool myb_ok = myb < B;
+  const bool my4 = (kq & 3) == 0 && (b0 + 4) < B;
+
+  // pointwise role
+  const bool pw = tid < PWF;
+  const int pb = tid < 64 ? (tid & 3) : 4, pu = tid < 64 ? (tid >> 2) : ((tid - 64) & 15);
+  const bool prow_ok = pw && (b0 + pb) < B;
+  const int pidx = rank * UH + pu;
+  const int pslot = pb * UH + pu;
+  float c_st = 0.f, h_st = 0.f;
+  // saver / mask-prefetch role: tid in [96, 96 + 80) -> (row sb, unit su)
+  const int se = tid - 96;
+  const int sb = se >= 0 ? se / UH : 0, su = se >= 0 ? se % UH : 0;
+  const int srow = b0 + sb;
+  const bool srow_ok = se >= 0 && se < PWF && srow < B;
+
+  if (tid == 0) {
+    cl::mbar_init(&bars[0], 1);
+    cl::mbar_init(&bars[1], 1);
+    cl::fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * H * 4; i += NT) (&hq[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * H; i += NT) (&h4[0][0])[i] = 0.f;
+  for (int i = tid; i < FRING * 2 * NB * UH; i += NT) (&mk_ring[0][0][0][0])[i] = 0;
+  for (int i = tid; i < FRING * (NT + 64); i += NT) (&xg_ring[0][0])[i] = 0.f;
+  __syncthreads();
+  cluster.sync();
+
+  auto prefetch = [&](int s) {
+    if (s < T) {
+      if (myb_ok) cl::cp_async4(&xg_ring[s % FRING][tid], d.xg + ((long long)s * B + myb) * K4 + gcol);
+      if (my4) cl::cp_async4(&xg_ring[s % FRING][NT + (tid >> 2)], d.xg + ((long long)s * B + b0 + 4) * K4 + gcol);
+      if (srow_ok && (su & 3) == 0) {
+        const long long om = ((long long)s * B + srow) * H + rank * UH + su;
+        if (d.mask_c) cl::cp_async4(&mk_ring[s % FRING][0][sb][su], d.mask_c + om);
+        if (d.mask_h) cl::cp_async4(&mk_ring[s % FRING][1][sb][su], d.mask_h + om);
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll 1
+  for (int s = 0; s < FPFD; ++s) prefetch(s);
+
+#pragma unroll 1
+  for (int s = 0; s < T; ++s) {
+    const int cur = s & 1, nxt = cur ^ 1;
+    prefetch(s + FPFD);
+    cp_async_wait<FPFD>();
+    if (s > 0) cl::mbar_wait(&bars[cur], ((s - 1) >> 1) & 1);         // the peers' slices of h(s) have landed
+    if (tid == 0 && s + 1 < T) cl::mbar_arrive_expect_tx(&bars[nxt], RX_BYTES);
+    float acc[16], a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 hv = *reinterpret_cast<const float4*>(&hq[cur][kq + 16 * i][0]);
+      const float he = h4[cur][kq + 16 * i];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[c * 4 + 0] = fmaf(w[i][c], hv.x, acc[c * 4 + 0]);
+        acc[c * 4 + 1] = fmaf(w[i][c], hv.y, acc[c * 4 + 1]);
+        acc[c * 4 + 2] = fmaf(w[i][c], hv.z, acc[c * 4 + 2]);
+        acc[c * 4 + 3] = fmaf(w[i][c], hv.w, acc[c * 4 + 3]);
+        a4[c] = fmaf(w[i][c], he, a4[c]);
+      }
+    }
+    const float mine = cl::reduce_scatter16(acc, lane);               // (column (kq >> 2) & 3, row kq & 3)
+    // fifth row: 4 columns reduce-scattered over the 4 lane quads, then summed inside the quad
+    {
+      const bool up8 = (kq & 8) != 0, up4 = (kq & 4) != 0;
+      const float k0 = (up8 ? a4[2] : a4[0]) + __shfl_xor_sync(0xffffffffu, up8 ? a4[0] : a4[2], 8);
+      const float k1 = (up8 ? a4[3] : a4[1]) + __shfl_xor_sync(0xffffffffu, up8 ? a4[1] : a4[3], 8);
+      float m = (up4 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up4 ? k0 : k1, 4);
+      m += __shfl_xor_sync(0xffffffffu, m, 2);
+      m += __shfl_xor_sync(0xffffffffu, m, 1);
+      if ((kq & 3) == 0) gsm[4][col] = m + xg_ring[s % FRING][NT + (tid >> 2)];
+    }
+    gsm[kq & 3][col] = mine + xg_ring[s % FRING][tid];
+    __syncthreads();
+    if (pw) {
+      float gi = 0.f, gj = 0.f, gf = 0.f, go = 0.f, h_new = 0.f;
+      const float c_old = c_st, h_old = h_st;
+      if (prow_ok) {
+        const float mc = d.mask_c ? (float)mk_ring[s % FRING][0][pb][pu] : (1.f - d.zc);
+        const float mh = d.mask_h ? (float)mk_ring[s % FRING][1][pb][pu] : (1.f - d.zh);
+        gi = fast_sigmoid(gsm[pb][0 * UH + pu]);
+        gj = fast_tanh(gsm[pb][1 * UH + pu]);
+        gf = fast_sigmoid(gsm[pb][2 * UH + pu] + d.forget_bias);
+        go = fast_sigmoid(gsm[pb][3 * UH + pu]);
+        const float c_new = gf * c_st + gi * gj;
+        h_new = go * fast_tanh(c_new);
+        c_st = c_st + mc * (c_new - c_st);
+        h_st = h_st + mh * (h_new - h_st);
+      }
+      if (s + 1 < T) {
+        // publish h(s+1): the 4 lanes of a packet (4 rows of a unit / fifth rows of 4 units) all hold it and share the 15 peers
+        const int l4 = lane & ~3;
+        const unsigned pm = tid < 64 ? 0xffffffffu : 0x0000ffffu;      // the third warp is only half in this role
+        const float p0 = __shfl_sync(pm, h_st, l4), p1 = __shfl_sync(pm, h_st, l4 + 1);
+        const float p2 = __shfl_sync(pm, h_st, l4 + 2), p3 = __shfl_sync(pm, h_st, l4 + 3);
+        float* dstp = tid < 64 ? &hq[nxt][pidx][0] : &h4[nxt][rank * UH + (pu & ~3)];
+        if (tid < 64) hq[nxt][pidx][pb] = h_st; else h4[nxt][pidx] = h_st;
+        const uint32_t dsta = cl::smem_u32(dstp), bara = cl::smem_u32(&bars[nxt]);
+#pragma unroll
+        for (int r4 = 0; r4 < CS; r4 += 4) {
+          const int r = r4 + (lane & 3);
+          if (r != rank) st_async_v4(cl::mapa(dsta, r), p0, p1, p2, p3, cl::mapa(bara, r));
+        }
+      }
+      save_st[0][pslot] = gi; save_st[1][pslot] = gj; save_st[2][pslot] = gf; save_st[3][pslot] = go;
+      save_st[4][pslot] = prow_ok ? c_old : 0.f;
+      save_st[5][pslot] = prow_ok ? h_old : 0.f;
+      save_st[6][pslot] = h_new;
+    }
+    __syncthreads();
+    if (srow_ok) {
+      // saver warps: staged activations -> global memory, off the exchange's critical path
+      const int sidx = rank * UH + su;
+      const long long o1 = ((long long)s * B + srow) * H + sidx;
+      d.out[((long long)s * B + srow) * d.ld_out + sidx] = save_st[6][se];
+      if (d.gates) {
+        const long long o4 = ((long long)s * B + srow) * K4 + sidx;
+        d.gates[o4] = save_st[0][se];
+        d.gates[o4 + H] = save_st[1][se];
+        d.gates[o4 + 2 * H] = save_st[2][se];
+        d.gates[o4 + 3 * H] = save_st[3][se];
+        d.c_prev[o1] = save_st[4][se];
+        d.h_prev[o1] = save_st[5][se];
+      }
+    }
+  }
+  cp_async_wait<0>();
+  cluster.sync();  // nobody leaves while a peer may still be writing into its shared memory
+}
+
+template <typename Kern, typename Desc>
+static int launch5(Kern kern, const Desc& d, cudaStream_t st) {
+  SATK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(((d.B + NB - 1) / NB) * CS);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SATK_CUDA(cudaLaunchKernelEx(&cfg, kern, d));
+  return SATK_OK;
+}
+
+int lstm5_fwd_launch(const satk_lstm_fwd_desc* d, cudaStream_t st) { return launch5(lstm5_fwd_kernel, *d, st); }
+
 int lstm5_bwd_launch(const satk_lstm_bwd_desc* d, cudaStream_t st) {
   SATK_CUDA(cudaFuncSetAttribute(lstm5_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg = {};

@@ -386,8 +386,9 @@ class TacotronEngine:
         sv["lstm_in"] = hw
         mem1 = self.buf("enc.mem1", (Tt, B, 2 * Hn))
         sv["lstm"] = {}
-        for j, dr in enumerate(("fw", "bw")):
+        for j, dr in ((1, "bw"), (0, "fw")):
             # the two directions are independent (disjoint column halves of mem1): the backward one runs on the auxiliary stream
+            # (forked first: a fork issued after the forward direction would queue behind it)
             with (self._fork() if j == 1 else contextlib.nullcontext()):
                 W = p[f"cbhg.lstm_{dr}.W"]
                 xg = self.lin(hw, f"cbhg.lstm_{dr}.W", self.buf(f"enc.xg_{dr}", (R, 4 * Hn)), K=Hn, bias=p[f"cbhg.lstm_{dr}.b"])

@@ -218,14 +218,21 @@ def test_softmax_causal_dropout_fwd_bwd():
     _close(dS, Sr.grad, 1e-5, "dS")
 
 
-@pytest.mark.parametrize("H,Bb,T,rev", [(128, 5, 9, False), (128, 5, 9, True), (256, 3, 7, False), (256, 9, 12, True)])
-def test_zoneout_lstm_sequence(H, Bb, T, rev):
+@pytest.mark.parametrize("H,Bb,T,rev,ragged", [(128, 5, 9, False, True), (128, 5, 9, True, True), (256, 3, 7, False, True),
+                                               (256, 9, 12, True, True),
+                                               # no per-row lengths: the decoder layers' 5-rows-per-cluster kernels (lstm_seq5.cu),
+                                               # one partial cluster / two clusters with a ragged last one / 7 clusters
+                                               (256, 3, 7, False, False), (256, 9, 12, False, False), (256, 32, 21, False, False)])
+def test_zoneout_lstm_sequence(H, Bb, T, rev, ragged):
     O = _O()
     g = torch.Generator().manual_seed(4)
     W, b = torch.randn(2 * H, 4 * H, generator=g) * 0.08, torch.randn(4 * H, generator=g) * 0.1
     x = torch.randn(Bb, T, H, generator=g)
     lens = torch.randint(1, T + 1, (Bb,), generator=g)
     lens[0] = T
+    if not ragged:
+        lens[:] = T
+    dev_lens = lens.cuda() if ragged else None
     mc = (torch.rand(T, Bb, H, generator=g) < 0.9).to(torch.uint8)
     mh = (torch.rand(T, Bb, H, generator=g) < 0.9).to(torch.uint8)
     Wr, br, xr = W.clone().requires_grad_(True), b.clone().requires_grad_(True), x.clone().requires_grad_(True)
@@ -238,11 +245,11 @@ def test_zoneout_lstm_sequence(H, Bb, T, rev):
     O.linear(x_tm, Wd[:H], xg, bias=b.cuda())
     out = torch.full((T, Bb, H), 7.0, device="cuda")
     gates, cp, hp = (torch.empty(T * Bb, 4 * H, device="cuda"), torch.empty(T * Bb, H, device="cuda"), torch.empty(T * Bb, H, device="cuda"))
-    O.lstm_seq_fwd(xg, Wd[H:], out, T, Bb, H, reverse=rev, lengths=lens.cuda(), mask_c=mc.cuda(), mask_h=mh.cuda(), gates=gates,
+    O.lstm_seq_fwd(xg, Wd[H:], out, T, Bb, H, reverse=rev, lengths=dev_lens, mask_c=mc.cuda(), mask_h=mh.cuda(), gates=gates,
                    c_prev=cp, h_prev=hp)
     _close(out.transpose(0, 1), yr, 1e-4, "lstm out")
     dg = torch.empty(T * Bb, 4 * H, device="cuda")
-    O.lstm_seq_bwd(Wd[H:], gates, cp, dy.transpose(0, 1).contiguous().cuda(), dg, T, Bb, H, reverse=rev, lengths=lens.cuda(),
+    O.lstm_seq_bwd(Wd[H:], gates, cp, dy.transpose(0, 1).contiguous().cuda(), dg, T, Bb, H, reverse=rev, lengths=dev_lens,
                    mask_c=mc.cuda(), mask_h=mh.cuda())
     dW = torch.zeros(2 * H, 4 * H, device="cuda")
     O.linear_dw(x_tm, dg, dW, T * Bb, H, 4 * H)
@@ -254,7 +261,7 @@ def test_zoneout_lstm_sequence(H, Bb, T, rev):
     _close(dx.view(T, Bb, H).transpose(0, 1), xr.grad, 1e-3, "lstm dx")
     # eval-mode interpolation (no masks)
     yr2 = OR.zoneout_lstm_sequence(x, lens, W, b, None, None, 0.1, 0.1, False, reverse=rev)
-    O.lstm_seq_fwd(xg, Wd[H:], out, T, Bb, H, reverse=rev, lengths=lens.cuda(), zc=0.1, zh=0.1)
+    O.lstm_seq_fwd(xg, Wd[H:], out, T, Bb, H, reverse=rev, lengths=dev_lens, zc=0.1, zh=0.1)
     _close(out.transpose(0, 1), yr2, 1e-4, "lstm eval out")
 
 

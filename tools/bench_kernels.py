@@ -40,6 +40,13 @@ def lstm(H, T, B):
     f = lambda: O.lstm_seq_fwd(xg, Wh, out, T, B, H, mask_c=mc, mask_h=mh, gates=gates, c_prev=cp, h_prev=hp)
     mn, av = timeit(f)
     print(f"lstm_fwd H={H} T={T} B={B}: {mn:.3f} ms  ({1e3 * mn / T:.2f} us/step)", flush=True)
+    if H == 256:
+        ref = out.clone()
+        os.environ["SATK_LSTM_GEN"] = "1"
+        mn, av = timeit(f)
+        os.environ.pop("SATK_LSTM_GEN")
+        print(f"lstm_fwd (first generation) H={H} T={T} B={B}: {mn:.3f} ms; max |diff| {(out - ref).abs().max().item():.2e}", flush=True)
+        f()
     dout, dg = torch.randn(T, B, H, device=dev), torch.empty(T * B, 4 * H, device=dev)
     f = lambda: O.lstm_seq_bwd(Wh, gates, cp, dout, dg, T, B, H, mask_c=mc, mask_h=mh)
     mn, av = timeit(f)
