@@ -31,6 +31,7 @@ WORKLOADS = {
     "location_sensitive": ("ljspeech_self-attention-tacotron.json", "attention=location_sensitive", 32, 148, 800, "train"),   # configs[3]
     "transition_agent": ("ljspeech_self-attention-tacotron.json", "use_forward_attention_transition_agent=True", 32, 148, 800, "train"),
     "predict": ("ljspeech_self-attention-tacotron.json", None, 16, 148, 1000, "predict"),                    # configs[4]: free-running
+    "postnet_v2": ("ljspeech_self-attention-tacotron.json", "use_postnet_v2=True", 32, 148, 800, "train"),   # SURVEY f3 option (off in the public configs)
 }
 CFG, OVR, B, TT, TM, MODE = WORKLOADS["ljspeech"]
 

@@ -151,6 +151,9 @@ int satk_highway_bwd(const float* H, const float* T, const float* x, const float
  * NULL: a dropped unit has y == 0 and relu'(0) = 0 already zeroes it. */
 int satk_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, const uint8_t* keep_mask,
                  float keep_scale, void* stream);
+/* dropout with an explicit keep mask (tf.layers.dropout behind a batch-normalised layer: the PostNetV2 convolutions,
+ * models/models.py:92-100): y = keep_mask ? x * keep_scale : 0; also its own backward pass (dx from dy).  y may alias x. */
+int satk_mask_scale(const float* x, const uint8_t* keep_mask, float keep_scale, float* y, long long n, void* stream);
 /* column sums: out[c] += sum_r x[r,c]  (bias gradients) */
 int satk_colsum_acc(const float* x, long long ldx, int rows, int C, float* out, void* stream);
 int satk_add(const float* a, const float* b, float* out, long long n, void* stream);          /* out = a + b */

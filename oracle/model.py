@@ -487,6 +487,21 @@ def model_forced_alignment(P, d, features, labels):
     return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2, mel_with_teacher=first["mel"])
 
 
+def postnet_v2(P, d, mel, training, masks=None, stats_out=None):
+    """PostNetV2 (models/models.py:92-100,440-462; class tacotron2.tacotron.tacotron_v2.PostNetV2 of the un-vendored dependency,
+    RECALLED): num_postnet_v2_layers tacotron2 Conv1d layers (conv SAME without bias -> BN -> tanh, no activation on the last one,
+    dropout postnet_v2_drop_rate behind each in training), a Dense projection back to num_mels and the residual connection.
+    mel [B, T_mel, num_mels]; masks["postnet.conv<i>"] are frame-major [T_mel, B, channels] keep masks."""
+    x = mel
+    keep = 1.0 - d.postnet_drop
+    for i in range(d.postnet_layers):
+        act = torch.tanh if i < d.postnet_layers - 1 else None
+        x = conv1d_bn(x, P, f"postnet.conv{i}", act, training, stats_out)
+        if training:
+            x = dropout_mask(x, masks[f"postnet.conv{i}"].transpose(0, 1), keep)
+    return mel + dense(x, P["postnet.proj.W"], P["postnet.proj.b"])
+
+
 def model_predict(P, d, features, max_iters=None, min_iters=10, use_stop_token=True):
     """model_fn in PREDICT mode (models/models.py:351-408 with is_training=False, no labels)."""
     spk = None
@@ -495,7 +510,10 @@ def model_predict(P, d, features, max_iters=None, min_iters=10, use_stop_token=T
     mem1, mem2, enc_aligns = encoder_forward(P, d, features.source, features.source_length, False, None, None)
     mel, stop, al1, al2 = decoder_free_running(P, d, mem1, mem2, features.source_length, spk, max_iters or d.max_iters,
                                                min_iters, use_stop_token)
-    return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2)
+    out = dict(mel=mel, stop=stop, alignment=al1, alignment2=al2)
+    if getattr(d, "postnet_v2", False):
+        out["mel_postnet"] = postnet_v2(P, d, mel, False)              # models/models.py:210 "mel_postnet"
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
@@ -526,11 +544,16 @@ def model_forward(P, d, features, labels, training, masks=None, stats_out=None):
     mel_loss = spec_loss_l1(mel, labels.mel.to(mel.dtype), labels.spec_loss_mask.to(mel.dtype))
     done_loss = binary_loss(stop, labels.done.to(mel.dtype), labels.binary_loss_mask.to(mel.dtype))
     reg_loss = l2_regularization_loss(P, d) if getattr(d, "l2_weight", 0.0) > 0 else torch.zeros((), dtype=mel.dtype)
+    post, post_loss = None, torch.zeros((), dtype=mel.dtype)
+    if getattr(d, "postnet_v2", False):                                # models/models.py:92-100,116-118 / 440-462,479-482
+        post = postnet_v2(P, d, mel, training, masks, stats_out)
+        post_loss = spec_loss_l1(post, labels.mel.to(mel.dtype), labels.spec_loss_mask.to(mel.dtype))
     return dict(mel=mel, stop=stop, alignment=al1, alignment2=al2, regularization_loss=reg_loss,
+                mel_postnet=post, postnet_v2_mel_loss=post_loss,
                 enc_self_alignments=[a.transpose(1, 2) for a in enc_aligns],  # models.py:398 (B, T_mem, T_query)
                 dec_self_alignments=[a.transpose(1, 2) for a in dec_sa],
                 memory1=mem1, memory2=mem2,
-                mel_loss=mel_loss, done_loss=done_loss, loss=mel_loss + done_loss + reg_loss)   # models.py:482 (no PostNetV2)
+                mel_loss=mel_loss, done_loss=done_loss, loss=mel_loss + done_loss + reg_loss + post_loss)   # models.py:482
 
 
 # models/models.py:470-473

@@ -372,6 +372,14 @@ __global__ void act_bwd_k(const float* __restrict__ y, const float* __restrict__
     dz[i] = g;
   }
 }
+__global__ void mask_scale_k(const float* __restrict__ x, const uint8_t* __restrict__ mask, float scale, float* __restrict__ y, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    const uchar4 m = reinterpret_cast<const uchar4*>(mask)[i];
+    reinterpret_cast<float4*>(y)[i] = make_float4(m.x ? v.x * scale : 0.f, m.y ? v.y * scale : 0.f, m.z ? v.z * scale : 0.f,
+                                                  m.w ? v.w * scale : 0.f);
+  }
+}
 __global__ void colsum_k(const float* __restrict__ x, long long ldx, int rows, int C, float* __restrict__ out) {
   __shared__ float s1[8][33];
   int c = blockIdx.x * 32 + threadIdx.x;
@@ -767,6 +775,13 @@ int satk_highway_bwd(const float* H, const float* T, const float* x, const float
 int satk_act_bwd(const float* y, const float* dy, float* dz, long long n, int act, const uint8_t* keep_mask, float keep_scale,
                  void* stream) {
   act_bwd_k<<<grid_for(n, 256), 256, 0, ST>>>(y, dy, dz, n, act, keep_mask, keep_scale);
+  SATK_LAUNCH_CHECK();
+  return 0;
+}
+int satk_mask_scale(const float* x, const uint8_t* keep_mask, float keep_scale, float* y, long long n, void* stream) {
+  SATK_CHECK_ARG(n % 4 == 0 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && ((uintptr_t)keep_mask & 3) == 0,
+                 "mask_scale: n=%lld and the buffers must be multiples of 4 elements / 16-byte aligned", n);
+  mask_scale_k<<<grid_for(n / 4, 256), 256, 0, ST>>>(x, keep_mask, keep_scale, y, n / 4);
   SATK_LAUNCH_CHECK();
   return 0;
 }

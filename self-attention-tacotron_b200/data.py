@@ -92,6 +92,9 @@ def mask_shapes(d, B: int, Tt: int, Td: int) -> Dict[str, tuple]:
     for i, u in ((1, d.att_rnn), (2, d.dec_out), (3, d.dec_out)):
         m[f"dec.lstm{i}.c"] = (Td, B, u)
         m[f"dec.lstm{i}.h"] = (Td, B, u)
+    if getattr(d, "postnet_v2", False):              # dropout behind every PostNetV2 convolution, frame-major [T_mel, B, channels]
+        for i in range(d.postnet_layers):
+            m[f"postnet.conv{i}"] = (Td * d.r, B, d.postnet_ch)
     return m
 
 
@@ -104,6 +107,8 @@ def mask_keep_prob(d, name: str) -> float:
         return 1.0 - d.enc_sa_drop
     if name.startswith("dec.sa"):
         return 1.0 - d.dec_sa_drop
+    if name.startswith("postnet."):
+        return 1.0 - d.postnet_drop
     if name.endswith(".c"):
         return 1.0 - d.zc
     if name.endswith(".h"):

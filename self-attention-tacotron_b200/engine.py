@@ -309,6 +309,51 @@ class TacotronEngine:
                 O.linear_dx(dt, p[f"{name}.{nm}.W"], dx, R, beta=1.0)
         return dx
 
+    def _bn_forward(self, xraw, R, Cc, first, gname, act, out, training, residual=None, maxpool_T=0, B=1):
+        """tf.layers.batch_normalization (+ activation, + max-pool over time) of xraw [R, Cc]: batch statistics in training (the moving
+        ones are updated), moving statistics otherwise.  -> what `_bn_backward` needs."""
+        gamma = self._span(self.ps.p, gname + ".gamma", Cc)
+        beta = self._span(self.ps.p, gname + ".beta", Cc)
+        o = self.ps.bn_off[first]
+        mm, mv = self.ps.bn_mean_flat[o:o + Cc], self.ps.bn_var_flat[o:o + Cc]
+        if training:
+            mean, var = self.buf(first + ".bmean", (Cc,)), self.buf(first + ".bvar", (Cc,))
+            O.bn_stats(xraw, R, Cc, mean, var, mov_mean=mm, mov_var=mv, momentum=BN_MOMENTUM, bessel=True)
+        else:
+            mean, var = mm, mv
+        O.bn_apply(xraw, R, Cc, mean, var, gamma, beta, out, eps=BN_EPS, act=act, residual=residual,
+                   maxpool_seq_len=maxpool_T, pos_stride=B)
+        return dict(x=xraw, C=Cc, mean=mean, var=var, gamma=gamma, beta=beta, act=act, maxpool=maxpool_T > 0, gname=gname)
+
+    def _bn_backward(self, s, R, dy, dx, scratch, training, T, B):
+        first = s["gname"]
+        dgamma = self._span(self.ps.g, first + ".gamma", s["C"])
+        dbeta = self._span(self.ps.g, first + ".beta", s["C"])
+        O.bn_bwd(s["x"], R, s["C"], s["mean"], s["var"], s["gamma"], s["beta"], dy, dx, dgamma, dbeta, scratch, eps=BN_EPS,
+                 act=s["act"], maxpool_seq_len=T if s["maxpool"] else 0, pos_stride=B, use_batch_stats=training)
+
+    def _conv_backward(self, R, B, x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None,
+                       xT=None, drawT=None, drawT_row0=0, skip_dx=False, after=None):
+        """Backward of a SAME conv1d over time-major rows.  draw: gradient wrt the raw conv output [R, cout] (ld draw_ld);
+        accumulates dW (weight-gradient stream), writes / accumulates dx."""
+        p, g = self.ps.p, self.ps.g
+        pl = (k - 1) // 2
+        with self._wg(after):
+            if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
+                # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
+                if xT is None:
+                    xT = O.transposed_rows(x, R, cin, x_ld)
+                if drawT is None:
+                    drawT, drawT_row0 = O.transposed_rows(draw, R, cout, draw_ld, draw_off), 0
+                O.conv_dw_tc(xT, drawT, g[Wname], R, cin, cout, k, B, drawT_row0)
+            else:
+                O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True,
+                       b_off=draw_off, batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B,
+                       split_k=max(1, min(32, R // 512)), beta=1.0)
+        if not skip_dx:
+            O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
+                   taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
+
     def _bank_one_launch(self, R, cin, C):
         """The conv bank runs as one z-batched tcgen05 launch when its tiles are whole (128-wide convs over 128 channels)."""
         return getattr(self, "bank_one_launch", True) and C == 128 and cin % 32 == 0 and R >= 64
@@ -348,18 +393,7 @@ class TacotronEngine:
                        taps=k, shift0=-pl * B, tap_dir=B, sBtap=cin * C)
 
         def bn(xraw, Cc, first, gname, act, out, residual=None, maxpool=False):
-            gamma = self._span(self.ps.p, gname + ".gamma", Cc)
-            beta = self._span(self.ps.p, gname + ".beta", Cc)
-            o = self.ps.bn_off[first]
-            mm, mv = self.ps.bn_mean_flat[o:o + Cc], self.ps.bn_var_flat[o:o + Cc]
-            if training:
-                mean, var = self.buf(first + ".bmean", (Cc,)), self.buf(first + ".bvar", (Cc,))
-                O.bn_stats(xraw, R, Cc, mean, var, mov_mean=mm, mov_var=mv, momentum=BN_MOMENTUM, bessel=True)
-            else:
-                mean, var = mm, mv
-            O.bn_apply(xraw, R, Cc, mean, var, gamma, beta, out, eps=BN_EPS, act=act, residual=residual,
-                       maxpool_seq_len=Tt if maxpool else 0, pos_stride=B)
-            return dict(x=xraw, C=Cc, mean=mean, var=var, gamma=gamma, beta=beta, act=act, maxpool=maxpool, gname=gname)
+            return self._bn_forward(xraw, R, Cc, first, gname, act, out, training, residual, Tt if maxpool else 0, B)
 
         mp = self.buf("enc.mp", (R, KC))
         sv["bn_bank"] = bn(raw, KC, "cbhg.bank1", "cbhg.bank1", "relu", mp, maxpool=True)
@@ -464,31 +498,10 @@ class TacotronEngine:
         training = self._training
 
         def bn_back(s, dy, dx):
-            first = s["gname"]
-            dgamma = self._span(self.ps.g, first + ".gamma", s["C"])
-            dbeta = self._span(self.ps.g, first + ".beta", s["C"])
-            O.bn_bwd(s["x"], R, s["C"], s["mean"], s["var"], s["gamma"], s["beta"], dy, dx, dgamma, dbeta, scratch, eps=BN_EPS,
-                     act=s["act"], maxpool_seq_len=Tt if s["maxpool"] else 0, pos_stride=B, use_batch_stats=training)
+            self._bn_backward(s, R, dy, dx, scratch, training, Tt, B)
 
-        def conv_back(x, Wname, k, cin, cout, draw, dx, beta, x_ld=None, draw_ld=None, draw_off=0, residual=None, xT=None,
-                      drawT=None, drawT_row0=0, skip_dx=False, after=None):
-            """draw: gradient wrt the raw conv output [R, cout] (ld draw_ld); accumulates dW, writes/accumulates dx."""
-            pl = (k - 1) // 2
-            with self._wg(after):
-                if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
-                    # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
-                    if xT is None:
-                        xT = O.transposed_rows(x, R, cin, x_ld)
-                    if drawT is None:
-                        drawT, drawT_row0 = O.transposed_rows(draw, R, cout, draw_ld, draw_off), 0
-                    O.conv_dw_tc(xT, drawT, g[Wname], R, cin, cout, k, B, drawT_row0)
-                else:
-                    O.gemm(x, draw, g[Wname], cin, cout, R, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True,
-                           b_off=draw_off, batch1=k, sC=(cin * cout, 0), shift0=-pl * B, shift_per_batch1=B,
-                           split_k=max(1, min(32, R // 512)), beta=1.0)
-            if not skip_dx:
-                O.gemm(draw, p[Wname], dx, R, cin, cout, lda=draw_ld or cout, ldb=cout, ldc=cin, transB=True, a_off=draw_off,
-                       taps=k, shift0=pl * B, tap_dir=-B, sBtap=cin * cout, beta=beta, residual=residual, ldres=cin)
+        def conv_back(x, Wname, k, cin, cout, draw, dx, beta, **kw):
+            self._conv_backward(R, B, x, Wname, k, cin, cout, draw, dx, beta, **kw)
 
         draw2 = self.buf("enc.draw2", (R, d.proj2))
         bn_back(sv["bn_p2"], dhw, draw2)
@@ -858,6 +871,78 @@ class TacotronEngine:
         return dval1, dval2
 
     # ------------------------------------------------------------------ model_fn body
+    # ------------------------------------------------------------------ PostNetV2 (models/models.py:92-100,440-462)
+    def _frames_of(self, x_tm, Td, B, name):
+        """decoder rows [Td*B, r*n_mels] (r frames per row) -> frame-major rows [T_mel*B, n_mels] (frame f = t*r + i)."""
+        d = self.d
+        out = self.buf(name, (Td, d.r, B, d.n_mels))
+        out.copy_(x_tm.view(Td, B, d.r, d.n_mels).permute(0, 2, 1, 3))
+        return out.view(Td * d.r * B, d.n_mels)
+
+    def _rows_of(self, x_fm, Td, B, name):
+        """frame-major rows [T_mel*B, n_mels] -> decoder rows [Td*B, r*n_mels]."""
+        d = self.d
+        out = self.buf(name, (Td, B, d.r, d.n_mels))
+        out.copy_(x_fm.view(Td, d.r, B, d.n_mels).permute(0, 2, 1, 3))
+        return out.view(Td * B, d.r * d.n_mels)
+
+    def postnet(self, mel_tm, Td, B, training, masks, key="post"):
+        """PostNetV2 on the decoder's mel output: conv1d (SAME, no bias) -> BN -> tanh (none on the last layer) -> dropout, x
+        num_postnet_v2_layers, Dense(num_mels), residual (tacotron2 PostNetV2, RECALLED; oracle/model.py: postnet_v2).
+        The convolutions run over FRAMES, so the rows are re-ordered frame-major first.  -> postnet output as decoder rows."""
+        d, p = self.d, self.ps.p
+        R, C, k = Td * d.r * B, d.postnet_ch, d.postnet_kernel
+        pl = (k - 1) // 2
+        x0 = self._frames_of(mel_tm, Td, B, key + ".x0")
+        sv = dict(x=[x0], bn=[], Td=Td, B=B, training=training, masks=masks)
+        x, cin = x0, d.n_mels
+        O.tf32_push("postnet")
+        for i in range(d.postnet_layers):
+            raw = self.buf(f"{key}.raw{i}", (R, C))
+            O.gemm(x, self.ps.pt[f"postnet.conv{i}.W"], raw, R, C, cin, lda=cin, ldb=cin, ldc=C, transB=True, taps=k, shift0=-pl * B,
+                   tap_dir=B, sBtap=cin * C)
+            a = self.buf(f"{key}.a{i}", (R, C))
+            act = "tanh" if i < d.postnet_layers - 1 else None
+            sv["bn"].append(self._bn_forward(raw, R, C, f"postnet.conv{i}", f"postnet.conv{i}", act, a, training))
+            if training:
+                O.mask_scale(a, masks[f"postnet.conv{i}"], 1.0 / (1.0 - d.postnet_drop), a)
+            sv["x"].append(a)
+            x, cin = a, C
+        out = self.buf(key + ".out", (R, d.n_mels))
+        self.lin(x, "postnet.proj.W", out, bias=p["postnet.proj.b"], residual=x0)
+        O.tf32_pop()
+        self._post_saved = sv
+        return self._rows_of(out, Td, B, key + ".out_tm")
+
+    def postnet_backward(self, dpost_tm, dmel_tm):
+        """Backward of `postnet`: weight gradients, and d(postnet output) through the residual and the convolutions added onto
+        d(mel output) (decoder rows)."""
+        d, p, g, sv = self.d, self.ps.p, self.ps.g, self._post_saved
+        Td, B, training, masks = sv["Td"], sv["B"], sv["training"], sv["masks"]
+        R, C, k = Td * d.r * B, d.postnet_ch, d.postnet_kernel
+        dout = self._frames_of(dpost_tm, Td, B, "post.dout")
+        O.tf32_push("postnet")
+        xL = sv["x"][-1]
+        with self._wg():
+            O.linear_dw(xL, dout, g["postnet.proj.W"], R, C, d.n_mels)
+            O.colsum_acc(dout, R, d.n_mels, g["postnet.proj.b"])
+        dx = self.buf("post.dx_last", (R, C))
+        O.linear_dx(dout, p["postnet.proj.W"], dx, R)
+        scratch = self.buf("post.bn_scratch", (2 * C,))
+        for i in reversed(range(d.postnet_layers)):
+            if training:
+                O.mask_scale(dx, masks[f"postnet.conv{i}"], 1.0 / (1.0 - d.postnet_drop), dx)
+            draw = self.buf(f"post.draw{i}", (R, C))
+            self._bn_backward(sv["bn"][i], R, dx, draw, scratch, training, 0, B)
+            cin = d.n_mels if i == 0 else C
+            dxi = self.buf(f"post.dx{i % 2}", (R, cin)) if i > 0 else self.buf("post.dx0", (R, cin))
+            self._conv_backward(R, B, sv["x"][i], f"postnet.conv{i}.W", k, cin, C, draw, dxi, 0.0)
+            dx = dxi
+        O.tf32_pop()
+        # residual branch + convolution branch, back in decoder rows
+        O.axpy(1.0, dpost_tm, dmel_tm)
+        O.axpy(1.0, self._rows_of(dx, Td, B, "post.dx0_tm"), dmel_tm)
+
     def forward(self, features, labels, training: bool, masks: Optional[Dict[str, torch.Tensor]] = None):
         """Forward pass + losses (+ loss gradients wrt the predictions).  Inputs must be CUDA tensors."""
         d = self.d
@@ -909,11 +994,22 @@ class TacotronEngine:
             l2 = self.buf("l2_loss", (1,), zero=True)
             O.l2_reg(self.ps.flat, self.ps.l2_mask(), d.l2_weight, loss_acc=l2)
             O.add(out3[2:], l2, out3[2:])
+        post_tm, dpost, post3 = None, None, None
+        if d.postnet_v2:        # + postnet_v2_mel_loss (models/models.py:116-118, 479-482)
+            post_tm = self.postnet(mel_tm, Td, B, training, masks)
+            post3 = self.buf("post.loss3", (3,))
+            dpost = self.buf("post.dpost_tm", post_tm.shape)
+            O.losses(post_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
+                     post3, dpost, self.buf("post.dstop_unused", stop_tm.shape), self.buf("post.loss_scratch", (4,)))
+            O.add(out3[2:], post3[:1], out3[2:])
         self.saved = dict(B=B, Tt=Tt, Td=Td, Tm=Tm, source_length=source_length, dmel=dmel, dstop=dstop, features=features,
-                          step_end=step_end if getattr(self, "skip_masked_steps", True) else None)
+                          dpost=dpost,
+                          # (PostNetV2 spreads gradient onto the masked frames — conv taps, batch statistics —: no step is skipped)
+                          step_end=step_end if (getattr(self, "skip_masked_steps", True) and not d.postnet_v2) else None)
         # with a sorted batch every per-utterance output is in SORTED order: row i belongs to utterance perm[i] of the caller's batch
         return dict(mel_tm=mel_tm, stop_tm=stop_tm, align1_tm=al1, align2_tm=al2, enc_self_P=enc_al, dec_self_P=dec_sa,
-                    memory1_tm=mem1, memory2_tm=mem2, losses=out3, perm=perm)
+                    memory1_tm=mem1, memory2_tm=mem2, losses=out3, perm=perm, mel_postnet_tm=post_tm,
+                    postnet_v2_mel_loss=None if post3 is None else post3[:1])
 
     # ------------------------------------------------------------------ free-running decode (PREDICT)
     def _build_decode_step(self, B, Tt, Tmax, use_stop_token, min_iters, forced=False):
@@ -1168,6 +1264,10 @@ class TacotronEngine:
                    alignment2=stt["al2"][:T].permute(1, 2, 0) if d.dual else None,
                    dec_self_P=[pr[:, i, :T, :T] for pr in stt["probs"] for i in range(d.dec_sa_heads)],
                    enc_self_P=enc_al, steps=T, steps_executed=n_run)
+        if d.postnet_v2:       # "mel_postnet" of the prediction dict (models/models.py:210)
+            post_tm = self.postnet(stt["mel_hist"][1:T + 1].reshape(T * B, d.r * d.n_mels), T, B, False, None, key="pred.post")
+            out["mel_postnet_tm"] = post_tm.view(T, B, d.r * d.n_mels)
+            out["mel_postnet"] = post_tm.view(T, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, T * d.r, d.n_mels)
         return out
 
     def validate(self, features, labels, forced_alignments=None):
@@ -1183,6 +1283,14 @@ class TacotronEngine:
         stop_tm = out["stop_tm"].reshape(Td * B, 1)
         O.losses(mel_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
                  out3, self.buf("val.dmel", mel_tm.shape), self.buf("val.dstop", stop_tm.shape), self.buf("val.scratch", (4,)))
+        if d.postnet_v2:
+            post_tm = self.postnet(mel_tm, Td, B, False, None, key="val.post")
+            post3 = self.buf("val.post.loss3", (3,))
+            O.losses(post_tm, stop_tm, labels.mel, labels.done, labels.spec_loss_mask, labels.binary_loss_mask, B, Tm, d.n_mels, d.r,
+                     post3, self.buf("val.post.dmel", mel_tm.shape), self.buf("val.post.dstop", stop_tm.shape),
+                     self.buf("val.post.scratch", (4,)))
+            O.add(out3[2:], post3[:1], out3[2:])
+            out = dict(out, mel_postnet_tm=post_tm.view(Td, B, d.r * d.n_mels), postnet_v2_mel_loss=post3[:1])
         return out3, out
 
     def backward(self, allreduce=None):
@@ -1194,6 +1302,8 @@ class TacotronEngine:
         right after it."""
         s = self.saved
         self.ps.grad.zero_()
+        if s.get("dpost") is not None:         # PostNetV2 first: it adds onto d(mel output)
+            self.postnet_backward(s["dpost"], s["dmel"])
         dmem1, dmem2 = self._timed("sec.decoder_bwd", self.decoder_backward, s["dmel"], s["dstop"], s["B"], s["Tt"], s["Td"],
                                    s["source_length"])
         if self.d.use_speaker:

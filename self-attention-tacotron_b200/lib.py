@@ -145,7 +145,7 @@ _lib: Optional[C.CDLL] = None
 SYMBOLS = [
     "satk_last_error", "satk_version", "satk_device_info", "satk_struct_sizes", "satk_gemm",
     "satk_embedding_fwd", "satk_embedding_bwd", "satk_bn_stats", "satk_bn_apply", "satk_bn_bwd",
-    "satk_highway_fwd", "satk_highway_bwd", "satk_act_bwd", "satk_colsum_acc", "satk_add", "satk_axpy",
+    "satk_highway_fwd", "satk_highway_bwd", "satk_act_bwd", "satk_mask_scale", "satk_colsum_acc", "satk_add", "satk_axpy",
     "satk_transpose", "satk_transpose_batched", "satk_transpose_strided", "satk_mask_rows", "satk_softsign_fwd", "satk_softsign_bwd", "satk_add_rowvec_tb",
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_l2_reg", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",

@@ -149,6 +149,8 @@ class _TacotronEstimator:
                 out = eng.predict(features, max_iters=getattr(params or self.params, "max_iters", None))
             preds = {"id": features.id, "key": features.key, "mel": out["mel"], "stop_token": out["stop"],
                      "alignment": out["alignment"], "source": features.source, "text": features.text}
+            if d.postnet_v2:
+                preds["mel_postnet"] = out["mel_postnet"]                        # models/models.py:210
             gt = getattr(features, "mel", None)
             if gt is None and labels is not None:
                 gt = labels.mel
@@ -178,6 +180,7 @@ class _TacotronEstimator:
         # decode gives the `*_with_teacher` metrics
         tf_out = eng.forward(features, labels, False)
         with_teacher = tf_out["losses"].clone()
+        post_with_teacher = tf_out["postnet_v2_mel_loss"].clone() if d.postnet_v2 else None
         if d.forced_alignment:   # models/models.py:411-427: the plain metrics / predictions come from the alignment-replaying decode
             forced = (tf_out["align1_tm"].clone(), tf_out["align2_tm"].clone() if d.dual else None)
             losses, out = eng.validate(features, labels, forced_alignments=forced)
@@ -194,6 +197,11 @@ class _TacotronEstimator:
                 preds[f"alignment{5 + i}"] = a.transpose(1, 2)
         scalars = {"loss": losses[2], "mel_loss": losses[0], "done_loss": losses[1],
                    "loss_with_teacher": with_teacher[2], "mel_loss_with_teacher": with_teacher[0], "done_loss_with_teacher": with_teacher[1]}
+        if d.postnet_v2:                                                         # models/models.py:174-187,260-269
+            B_, Td_ = labels.mel.shape[0], labels.mel.shape[1] // d.r
+            preds["mel_postnet"] = out["mel_postnet_tm"].view(Td_, B_, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B_, Td_ * d.r, d.n_mels)
+            scalars["postnet_v2_mel_loss"] = out["postnet_v2_mel_loss"][0]
+            scalars["postnet_v2_mel_loss_with_teacher"] = post_with_teacher[0]
         return EstimatorSpec(mode=mode, loss=losses[2], train_op=None, predictions=preds, eval_metric_ops=dict(scalars), scalars=scalars)
 
     # ---- drivers (tf.estimator.Estimator.train / evaluate / predict)

@@ -298,6 +298,14 @@ def act_bwd(y, dy, dz, act, keep_mask=None, keep_scale=1.0):
     _count()
 
 
+def mask_scale(x, keep_mask, keep_scale, y):
+    """y = keep_mask ? x * keep_scale : 0 (dropout with an explicit mask, forward and backward; include/satk.h)."""
+    _req(x); _req(y)
+    check(load().satk_mask_scale(C.c_void_p(x.data_ptr()), C.c_void_p(keep_mask.data_ptr()), C.c_float(keep_scale),
+                                 C.c_void_p(y.data_ptr()), C.c_longlong(y.numel()), C.c_void_p(stream_ptr())), "satk_mask_scale")
+    _count()
+
+
 def add(a, b, out):
     check(load().satk_add(C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), C.c_void_p(out.data_ptr()),
                           C.c_longlong(out.numel()), C.c_void_p(stream_ptr())), "satk_add")

@@ -65,6 +65,13 @@ class ModelDims:
     max_iters: int
     l2_weight: float = 0.0  # l2_regularization_weight when use_l2_regularization, else 0 (models/models.py:470-478)
     forced_alignment: bool = False   # use_forced_alignment_mode (models/models.py:411-427): EVAL / PREDICT decode with replayed alignments
+    # PostNetV2 (models/models.py:92-100,440-462; tacotron2.tacotron.tacotron_v2.PostNetV2, RECALLED): postnet_layers x
+    # [conv1d(kernel, channels, no bias) -> BN -> tanh (none on the last) -> dropout], Dense(num_mels), residual onto mel_output
+    postnet_v2: bool = False
+    postnet_layers: int = 5
+    postnet_kernel: int = 5
+    postnet_ch: int = 512
+    postnet_drop: float = 0.5
 
     @property
     def mem1(self) -> int:      # depth of attention-1 memory (BiLSTM output)
@@ -112,8 +119,7 @@ def dims_from_hparams(hp) -> ModelDims:
     if not hp.use_zoneout_at_encoder:
         raise ValueError("use_zoneout_at_encoder=False (plain CBHG with GRU) is out of scope")
     # switches of the reference's model_fn that this implementation does not build (SURVEY §8 f3 / out of scope): refuse loudly
-    for flag, what in (("use_postnet_v2", "PostNetV2 (models/models.py:440-462)"),
-                       ("use_external_speaker_embedding", "external speaker embeddings (multi_speaker_tacotron)"),
+    for flag, what in (("use_external_speaker_embedding", "external speaker embeddings (multi_speaker_tacotron)"),
                        ("use_language_embedding", "language embeddings (multi_speaker_tacotron)"),
                        ("speaker_embedd_to_postnet", "speaker embedding into the post-net"),
                        ("channel_id_to_postnet", "channel labels into the post-net"),
@@ -164,6 +170,9 @@ def dims_from_hparams(hp) -> ModelDims:
         use_speaker=bool(hp.use_speaker_embedding), num_speakers=hp.num_speakers,
         speaker_dim=hp.speaker_embedding_dim, speaker_offset=hp.speaker_embedding_offset,
         max_iters=hp.max_iters, forced_alignment=bool(getattr(hp, "use_forced_alignment_mode", False)),
+        postnet_v2=bool(getattr(hp, "use_postnet_v2", False)), postnet_layers=int(getattr(hp, "num_postnet_v2_layers", 5)),
+        postnet_kernel=int(getattr(hp, "postnet_v2_kernel_size", 5)), postnet_ch=int(getattr(hp, "postnet_v2_out_channels", 512)),
+        postnet_drop=float(getattr(hp, "postnet_v2_drop_rate", 0.5)),
         l2_weight=float(hp.l2_regularization_weight) if bool(getattr(hp, "use_l2_regularization", False)) else 0.0)
 
 
@@ -263,6 +272,13 @@ def param_specs(d: ModelDims) -> List[ParamSpec]:
         proj_in = d.dec_out
     S += [("dec.out_proj.W", (proj_in, d.out_units), "glorot"), ("dec.out_proj.b", (d.out_units,), "zeros"),   # module.py:718-724
           ("dec.stop_proj.W", (proj_in, 1), "glorot"), ("dec.stop_proj.b", (1,), "zeros")]
+    if d.postnet_v2:                                                                 # models/models.py:92-100,440-462
+        cin = d.n_mels
+        for i in range(d.postnet_layers):
+            S += [(f"postnet.conv{i}.W", (d.postnet_kernel, cin, d.postnet_ch), "glorot"),
+                  (f"postnet.conv{i}.gamma", (d.postnet_ch,), "ones"), (f"postnet.conv{i}.beta", (d.postnet_ch,), "zeros")]
+            cin = d.postnet_ch
+        S += [("postnet.proj.W", (cin, d.n_mels), "glorot"), ("postnet.proj.b", (d.n_mels,), "zeros")]
     return S
 
 
@@ -270,6 +286,8 @@ def bn_names(d: ModelDims) -> List[Tuple[str, int]]:
     """Batch-norm layers carrying (non-trainable) moving mean / variance."""
     out = [(f"cbhg.bank{k}", d.conv_ch) for k in range(1, d.bank_k + 1)]
     out += [("cbhg.proj1", d.proj1), ("cbhg.proj2", d.proj2)]
+    if d.postnet_v2:
+        out += [(f"postnet.conv{i}", d.postnet_ch) for i in range(d.postnet_layers)]
     return out
 
 

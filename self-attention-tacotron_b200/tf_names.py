@@ -75,6 +75,13 @@ def tf_variable_name(n: str, d) -> str:
             inner = ".".join(parts[2:-1])
             return f"decoder/self_attention/{sub}/{inner}/{kind}" if inner else f"decoder/self_attention/{sub}/{kind}"
         return "decoder/" + "/".join(parts[1:-1]) + f"/{kind}"
+    if head == "postnet":                                            # models/models.py:92-100,440-462 (layer names RECALLED)
+        sub = parts[1]
+        if sub == "proj":
+            return f"postnet_v2/dense/{kind}"
+        if leaf in ("gamma", "beta"):
+            return f"postnet_v2/conv1d_{int(sub[4:]) + 1}/batch_normalization/{leaf}"
+        return f"postnet_v2/conv1d_{int(sub[4:]) + 1}/conv1d/{kind}"
     return n.replace(".", "/")
 
 

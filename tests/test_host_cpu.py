@@ -146,7 +146,7 @@ def test_data_parallel_gradient_mean_gloo(root, tmp_path):
 def test_unbuilt_model_switches_are_refused(satk, root):
     """Options of the reference's model_fn that are not built must fail loudly, never be silently ignored."""
     cfg = os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json")
-    for flag in ("use_postnet_v2", "use_external_speaker_embedding", "use_language_embedding", "use_accent_type",
+    for flag in ("use_external_speaker_embedding", "use_language_embedding", "use_accent_type",
                  "speaker_embedd_to_decoder", "apply_dropout_on_inference", "language_embedd_to_input", "language_embedd_to_decoder"):
         with pytest.raises(NotImplementedError, match=flag):
             satk.dims_from_hparams(satk.load_hparams(cfg, f"{flag}=True"))
@@ -157,6 +157,15 @@ def test_unbuilt_model_switches_are_refused(satk, root):
         satk.dims_from_hparams(satk.load_hparams(os.path.join(root, "examples", "vctk_self-attention-tacotron.json"), "speaker_embedd_to_prenet=False"))
     # forced-alignment mode is built for EVAL / PREDICT (tests/test_predict_gpu.py); TRAIN refuses at the call
     assert satk.dims_from_hparams(satk.load_hparams(cfg, "use_forced_alignment_mode=True")).forced_alignment
+    # PostNetV2 is built (tests/test_parity_gpu.py::test_postnet_v2); its speaker / channel conditioned variants are not
+    dp = satk.dims_from_hparams(satk.load_hparams(cfg, "use_postnet_v2=True"))
+    assert dp.postnet_v2 and (dp.postnet_layers, dp.postnet_kernel, dp.postnet_ch, dp.postnet_drop) == (5, 5, 512, 0.5)
+    names = [n for n, _, _ in satk.param_specs(dp)]
+    assert "postnet.conv4.gamma" in names and names[-1] == "postnet.proj.b"
+    assert len({satk.tf_variable_name(n, dp) for n in names}) == len(names)
+    for flag in ("speaker_embedd_to_postnet", "channel_id_to_postnet"):
+        with pytest.raises(NotImplementedError, match=flag):
+            satk.dims_from_hparams(satk.load_hparams(cfg, f"use_postnet_v2=True,{flag}=True"))
     satk.dims_from_hparams(satk.load_hparams(cfg, "cumulative_weights=True,use_forward_attention_transition_agent=True,use_l2_regularization=True"))
 
 

@@ -82,8 +82,9 @@ def _unsort(out, B):
     for k in ("memory1_tm", "memory2_tm", "align1_tm", "align2_tm"):
         if o.get(k) is not None:
             o[k] = o[k].reshape(-1, B, o[k].shape[-1]).index_select(1, inv)
-    for k in ("mel_tm", "stop_tm"):
-        o[k] = o[k].view(-1, B, o[k].shape[-1] if k == "mel_tm" else 1).index_select(1, inv)
+    for k in ("mel_tm", "stop_tm", "mel_postnet_tm"):
+        if o.get(k) is not None:
+            o[k] = o[k].view(-1, B, 1 if k == "stop_tm" else o[k].shape[-1]).index_select(1, inv)
     for k in ("enc_self_P", "dec_self_P"):
         o[k] = [a.index_select(0, inv) for a in o[k]]
     return o
@@ -116,6 +117,10 @@ def _case(satk, root, cfg, B, Tt, Tm, training, overrides=None, grads=True, seed
     _close(out["mel_tm"].view(Td, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, Tm, d.n_mels), ref["mel"], RTOL_OUT, "mel")
     _close(out["stop_tm"].view(Td, B).t(), ref["stop"].squeeze(-1), RTOL_OUT, "stop logits")
     _close(out["losses"], torch.stack([ref["mel_loss"], ref["done_loss"], ref["loss"]]), RTOL_OUT, "losses")
+    if d.postnet_v2:
+        _close(out["mel_postnet_tm"].view(Td, B, d.r, d.n_mels).permute(1, 0, 2, 3).reshape(B, Tm, d.n_mels), ref["mel_postnet"], RTOL_OUT,
+               "PostNetV2 output")
+        _close(out["postnet_v2_mel_loss"][0], ref["postnet_v2_mel_loss"], RTOL_OUT, "postnet_v2_mel_loss")
     if grads:
         eng.backward()
         _check_grads(eng, tr, rg)
@@ -124,6 +129,23 @@ def _case(satk, root, cfg, B, Tt, Tm, training, overrides=None, grads=True, seed
             _close(eng.ps.bn[key + ".mean"], 0.99 * ps.bn[key + ".mean"] + 0.01 * mean, 1e-4, f"moving mean {key}")
             _close(eng.ps.bn[key + ".var"], 0.99 * ps.bn[key + ".var"] + 0.01 * var, 1e-4, f"moving var {key}")
     return eng, tr, (fd, ld, md), (f, l, masks)
+
+
+def test_postnet_v2(satk, root):
+    """use_postnet_v2 (models/models.py:92-100,116-118,210,440-462): output, loss term, every gradient, BN moving statistics of the
+    post-net, in TRAIN (dropout masks) and EVAL mode; then the free-running `mel_postnet` of PREDICT against the oracle.  The second
+    case is large enough (T_mel * B = 2048 rows, 128 channels) for the tcgen05 weight-gradient path of the convolutions."""
+    ov = "use_postnet_v2=True,postnet_v2_out_channels=128,num_postnet_v2_layers=3"
+    _case(satk, root, "ljspeech_self-attention-tacotron.json", 5, 23, 28, True, overrides=ov)
+    _case(satk, root, "ljspeech_tacotron.json", 3, 17, 20, False, overrides="use_postnet_v2=True,postnet_v2_out_channels=64")
+    eng, tr, (fd, ld, md), (f, l, masks) = _case(satk, root, "ljspeech_self-attention-tacotron.json", 8, 30, 256, True,
+                                                 overrides="use_postnet_v2=True,postnet_v2_out_channels=128,num_postnet_v2_layers=2")
+    d = eng.d
+    out = eng.predict(fd, max_iters=12, use_stop_token=False)
+    with torch.no_grad():      # the engine's parameters and (just updated) BN moving statistics
+        ref = OR.model_predict({k: v.detach().cpu() for k, v in eng.ps.as_dict().items()}, d, f, max_iters=12, use_stop_token=False)
+    _close(out["mel"], ref["mel"], RTOL_OUT, "free-running mel")
+    _close(out["mel_postnet"], ref["mel_postnet"], RTOL_OUT, "free-running mel_postnet")
 
 
 def test_dual_eval_ragged_batch(satk, root):
@@ -378,6 +400,36 @@ def test_vctk_config3_per_replica_batch_runs_full_size(satk, root):
     pos = torch.arange(148, device="cuda")[None, None, :]
     assert a.masked_select(pos >= f.source_length[None, :, None]).abs().max().item() == 0      # zero past the source length
     assert torch.isfinite(eng.ps.grad).all() and (eng.ps.flat - w0).abs().max().item() > 0
+
+
+def test_estimator_surface_postnet_v2(satk, root, tmp_path):
+    """use_postnet_v2 through model_fn: TRAIN (four steps, the last ones replayed from the CUDA graph), EVAL metrics
+    (models/models.py:174-187,260-269) and the "mel_postnet" prediction of EVAL / PREDICT (models.py:210)."""
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"),
+                           "max_iters=12,use_postnet_v2=True,postnet_v2_out_channels=128,num_postnet_v2_layers=3")
+    model = M.tacotron_model_factory(hp, str(tmp_path), None)
+    f, l = satk.synthetic_batch(hp, 4, 20, 24, seed=2)
+
+    def input_fn():
+        for _ in range(5):
+            yield f, l
+    losses = []
+    for _ in range(4):
+        losses.append(float(model.model_fn(f, l, M.ModeKeys.TRAIN, hp).loss))
+    # (fresh dropout masks every step and the noam warm-up: four steps need not lower the loss; it must stay finite and the
+    # post-net must have moved)
+    assert all(x == x and abs(x) < 1e3 for x in losses) and model.engine.global_step == 4
+    assert float(model.engine.ps.adam_m[model.engine.ps.offsets["postnet.conv1.W"][0]:][:1000].abs().max()) > 0
+    ev = model.model_fn(f, l, M.ModeKeys.EVAL, hp)
+    assert ev.predictions["mel_postnet"].shape == (4, 24, 80)
+    assert {"postnet_v2_mel_loss", "postnet_v2_mel_loss_with_teacher"} <= set(ev.scalars)
+    want = OR.spec_loss_l1(ev.predictions["mel_postnet"].cpu(), l.mel, l.spec_loss_mask)
+    _close(ev.scalars["postnet_v2_mel_loss"], want, 1e-4, "postnet_v2_mel_loss of the validation decode")
+    total = ev.scalars["mel_loss"] + ev.scalars["done_loss"] + ev.scalars["postnet_v2_mel_loss"]
+    _close(ev.scalars["loss"], total, 1e-5, "loss = mel_loss + done_loss + postnet_v2_mel_loss (models.py:482)")
+    pred = next(model.predict(input_fn))
+    assert pred["mel_postnet"].shape == pred["mel"].shape and torch.isfinite(pred["mel_postnet"]).all()
 
 
 def test_estimator_surface(satk, root, tmp_path):
