@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
 }
 
 size_t attn_energy_grad_sync_ints(int B) { return EGQ_PROG + 2 * (size_t)B; }
+int* attn_energy_grad_progress(const satk_attn_rnn_bwd_desc* d) { return d->sync_ws + EGQ_PROG; }   // what the recurrence publishes into
 
 static int eg_chunk() {
   const char* e = getenv("SATK_EG_CHUNK");

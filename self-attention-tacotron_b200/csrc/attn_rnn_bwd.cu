@@ -892,6 +892,7 @@ namespace satk { namespace arnn2 {
 bool v2_eligible(const satk_attn_rnn_fwd_desc* d);
 int attn_rnn2_bwd_launch(const satk_attn_rnn_bwd_desc* d, float* de, int* prog, cudaStream_t st);
 int attn_energy_grad_prepare(const satk_attn_rnn_bwd_desc* d, cudaStream_t st);
+int* attn_energy_grad_progress(const satk_attn_rnn_bwd_desc* d);
 int attn_energy_grad_launch(const satk_attn_rnn_bwd_desc* d, const float* de, int parts, int dependent, cudaStream_t st);
 } }
 
@@ -936,7 +937,7 @@ extern "C" int satk_attn_rnn_bwd_overlapped(const satk_attn_rnn_bwd_desc* d, int
     rc = arnn2::attn_energy_grad_launch(d, d->de_ws, SATK_EG_FEATURES, 0, st);
     if (rc) return rc;
   }
-  rc = arnn2::attn_rnn2_bwd_launch(d, d->de_ws, d->sync_ws + 4, st);
+  rc = arnn2::attn_rnn2_bwd_launch(d, d->de_ws, arnn2::attn_energy_grad_progress(d), st);
   if (rc) return rc;
   return arnn2::attn_energy_grad_launch(d, d->de_ws, SATK_EG_GRADIENTS, 1, st);
 }
