@@ -90,7 +90,10 @@ class TacotronEngine:
             [self._side] + [torch.cuda.Stream(device=self.device) for _ in range(max(1, int(os.environ.get("SATK_WGRAD_LANES", "3"))) - 1)]
         self._side_rr = 0
         # independent branches of the graph (decoder pre-net beside the encoder, the two BiLSTM directions) fork onto a third stream
-        self._aux = torch.cuda.Stream(device=self.device) if self._side is not None else None
+        # (high priority like the main stream below: its branches — a BiLSTM direction, dV / dK of a self-attention block, d(memory) of
+        # the second source — are joined by the critical path, and must not queue behind the weight-gradient products)
+        self._aux = torch.cuda.Stream(device=self.device, priority=-1 if os.environ.get("SATK_MAIN_PRIORITY", "1") != "0" else 0) \
+            if self._side is not None else None
         # ... and a fourth: the LSTM-1 / pre-net tail of the decoder's backward pass, which only the weight gradients wait for
         self._aux2 = torch.cuda.Stream(device=self.device) if self._side is not None else None
         # the critical path runs on a high-priority stream of its own, so that pending CTAs of the recurrent cluster kernels are
@@ -279,14 +282,19 @@ class TacotronEngine:
         if O.attn_tc_ok(T, dh):
             # the four gradient products on the tcgen05 tile: operands that are reduced over their row index are transposed once
             # (the stacked [z][T][T] matrices as ONE [z*T, T] matrix, entry z = columns z*T.. of the transpose)
+            # dV does not depend on d(scores), dK and dQ only share dS: the dV and dK branches run on the auxiliary stream
             nz, W = B * heads, B * D
+            with self._fork():
+                dOT = O.transposed_rows(dO, T, W)
+                O.attn_apply_t_tc(O.transposed_rows(sv["Pd"], nz * T, T), dOT, dV, T, nz, dh, causal=causal)
+                del dOT
             O.attn_scores_tc(dO, sv["V"], dPd, T, nz, dh, causal=causal)
-            dOT = O.transposed_rows(dO, T, W)
-            O.attn_apply_t_tc(O.transposed_rows(sv["Pd"], nz * T, T), dOT, dV, T, nz, dh, causal=causal)
             O.softmax_bwd(sv["P"], dPd, nz, T, causal, dS, sv["mask"], 1.0 / sv["keep"])
+            with self._fork():
+                O.attn_apply_t_tc(O.transposed_rows(dS, nz * T, T), O.transposed_rows(sv["Q"], T, W), dK, T, nz, dh, alpha=scale,
+                                  causal=causal)
             O.attn_apply_tc(dS, O.transposed_rows(sv["K"], T, W), dQ, T, nz, dh, alpha=scale, causal=causal)
-            O.attn_apply_t_tc(O.transposed_rows(dS, nz * T, T), O.transposed_rows(sv["Q"], T, W), dK, T, nz, dh, alpha=scale,
-                              causal=causal)
+            self._join()
         else:
             O.gemm(dO, sv["V"], dPd, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, sA=sX, sB=sX, sC=sP,
                    causal_skip=1 if causal else 0, **bs)
@@ -768,13 +776,7 @@ class TacotronEngine:
         O.tf32_push("mem")
         if energy_forked:
             self._join()
-        dval1, dval2 = self._memory_backward(sv, dx2, dkeys1, dkeys2, B, Tt, Td, loc)
-        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
-        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
-        dmem2 = None
-        if d.dual:
-            dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
-            O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
+        dmem1, dmem2 = self._memory_backward(sv, dx2, dkeys1, dkeys2, B, Tt, Td, loc, source_length)
         O.tf32_pop()
         return dmem1, dmem2
 
@@ -843,32 +845,39 @@ class TacotronEngine:
                 O.colsum_acc(dz0, Rd, P0, g["dec.prenet0.b"])
         O.tf32_pop()
 
-    def _memory_backward(self, sv, dx2, dkeys1, dkeys2, B, Tt, Td, loc):
-        """d(values) of both sources: through the contexts (dx2[:, H1:] holds d(context) of every step) and through the keys
-        (keys = values . W_mem, attention bias folded in); weight gradients of the memory layers.  -> (dval1, dval2 | None)"""
+    def _memory_backward(self, sv, dx2, dkeys1, dkeys2, B, Tt, Td, loc, source_length):
+        """d(memory) of both sources: through the contexts (dx2[:, H1:] holds d(context) of every step) and through the keys
+        (keys = values . W_mem, attention bias folded in), masked past the source lengths; weight gradients of the memory layers.
+        The two sources are independent: the second one runs on the auxiliary stream.  -> (dmem1, dmem2 | None)"""
         d, p, g = self.d, self.ps.p, self.ps.g
         R = Tt * B
         H1 = d.att_rnn
         X2W = H1 + d.ctx
-        # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]
-        dval1 = self.buf("dec.dvalues1", (R, d.mem1))
-        O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
-               b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
-        dval2 = None
-        if d.dual:
-            dval2 = self.buf("dec.dvalues2", (R, d.mem2))
-            O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
-                   b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
         with self._wg():
             if loc:
                 O.colsum_acc(dkeys1, R, d.att1, g["att1.b"])
             O.linear_dw(sv["values1"], dkeys1, g["att1.memory.W"], R, d.mem1, d.att1)
             if d.dual:
                 O.linear_dw(sv["values2"], dkeys2, g["att2.memory.W"], R, d.mem2, d.att2)
-        O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
+        dmem2 = None
         if d.dual:
-            O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
-        return dval1, dval2
+            with self._fork():
+                dval2 = self.buf("dec.dvalues2", (R, d.mem2))
+                O.gemm(self._bufs["dec.align2"], dx2, dval2, Tt, d.mem2, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem2, transA=True,
+                       b_off=H1 + d.mem1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem2, 0))
+                O.linear_dx(dkeys2, p["att2.memory.W"], dval2, R, beta=1.0)
+                dmem2 = self.buf("dec.dmem2", (Tt, B, d.mem2))
+                O.mask_rows(dval2, source_length, B, Tt, d.mem2, True, dmem2)
+        # values: dvalues[j,b,:] = sum_t align[t,b,j] * dctx_total[t,b,:]
+        dval1 = self.buf("dec.dvalues1", (R, d.mem1))
+        O.gemm(self._bufs["dec.align1"], dx2, dval1, Tt, d.mem1, Td, lda=B * Tt, ldb=B * X2W, ldc=B * d.mem1, transA=True,
+               b_off=H1, batch1=B, sA=(Tt, 0), sB=(X2W, 0), sC=(d.mem1, 0))
+        O.linear_dx(dkeys1, p["att1.memory.W"], dval1, R, beta=1.0)
+        dmem1 = self.buf("dec.dmem1", (Tt, B, d.mem1))
+        O.mask_rows(dval1, source_length, B, Tt, d.mem1, True, dmem1)
+        if d.dual:
+            self._join()
+        return dmem1, dmem2
 
     # ------------------------------------------------------------------ model_fn body
     # ------------------------------------------------------------------ PostNetV2 (models/models.py:92-100,440-462)
