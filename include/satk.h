@@ -176,6 +176,10 @@ int satk_add_rowvec_tb(float* y, const float* v, int T, int B, int C, void* stre
 int satk_sum_over_t(const float* dy, int T, int B, int C, float* dv, void* stream);
 /* uint8 keep-mask generator: counter-based hash RNG (not TF's Philox stream; only the Bernoulli law matters) */
 int satk_bernoulli_mask(uint8_t* out, long long n, float keep_prob, unsigned long long seed, void* stream);
+/* the same mask as satk_bernoulli_mask(seed = seed_dev[0] * 1000003 + salt), the step's seed read from DEVICE memory: the launch can sit
+ * inside a captured CUDA graph and still draw fresh masks on every replay (the host updates seed_dev[0] before it) */
+int satk_bernoulli_mask_dev(uint8_t* out, long long n, float keep_prob, const unsigned long long* seed_dev, unsigned long long salt,
+                            void* stream);
 
 /* Row softmax with optional causal mask + dropout, self_attention.py:45-65,80-86.
  * S [rows_total = nmat*T, T] in place -> probabilities P (kept for backward / alignments);

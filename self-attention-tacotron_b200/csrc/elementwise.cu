@@ -497,6 +497,14 @@ __global__ void bernoulli_k(uint8_t* __restrict__ out, long long n, float keep, 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = hash32(seed * 0x9e3779b97f4a7c15ULL + (uint64_t)i) < thr ? 1 : 0;
 }
+// the same with the step's seed read from device memory (a captured CUDA graph replays the launch with a new seed every step)
+__global__ void bernoulli_dev_k(uint8_t* __restrict__ out, long long n, float keep, const unsigned long long* __restrict__ seed_dev,
+                                unsigned long long salt) {
+  const unsigned long long seed = seed_dev[0] * 1000003ULL + salt;
+  uint32_t thr = (keep >= 1.f) ? 0xffffffffu : (uint32_t)(keep * 4294967296.0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = hash32(seed * 0x9e3779b97f4a7c15ULL + (uint64_t)i) < thr ? 1 : 0;
+}
 
 // ---------------------------------------------------------------- softmax rows (T <= 1024)
 // one warp per row; S row-major [nmat*T, T]
@@ -850,6 +858,13 @@ int satk_sum_over_t(const float* dy, int T, int B, int C, float* dv, void* strea
 }
 int satk_bernoulli_mask(uint8_t* out, long long n, float keep_prob, unsigned long long seed, void* stream) {
   bernoulli_k<<<grid_for(n, 256), 256, 0, ST>>>(out, n, keep_prob, seed);
+  SATK_LAUNCH_CHECK();
+  return 0;
+}
+int satk_bernoulli_mask_dev(uint8_t* out, long long n, float keep_prob, const unsigned long long* seed_dev, unsigned long long salt,
+                            void* stream) {
+  SATK_CHECK_ARG(seed_dev != nullptr, "bernoulli_mask_dev: seed_dev is NULL%s", "");
+  bernoulli_dev_k<<<grid_for(n, 256), 256, 0, ST>>>(out, n, keep_prob, seed_dev, salt);
   SATK_LAUNCH_CHECK();
   return 0;
 }

@@ -105,7 +105,8 @@ class TacotronEngine:
                 setattr(self, name, self._on_main(getattr(self, name)))
         self.use_graph = os.environ.get("SATK_GRAPH", "1") != "0"             # CUDA-graphed train step (see _train_step_graphed)
         self._graphs = {}
-        self._premade_masks = None
+        self._capture_seed_dev = None
+        self._seed_dev = None
         self.sort_batches = os.environ.get("SATK_SORT_BATCHES", "1") != "0"   # TRAIN steps sort the batch by target / source length
         # first element of the decoder / attention suffix of the flat parameter buffer (ParamStore lays the tensors out in forward order)
         self._dec_off = min(off for n, (off, _) in self.ps.offsets.items() if n.startswith(("att1.", "att2.", "dec.")))
@@ -193,14 +194,19 @@ class TacotronEngine:
         off = self.ps.offsets[first][0]
         return base[off:off + n]
 
-    def device_masks(self, B, Tt, Td) -> Dict[str, torch.Tensor]:
-        """TRAIN-mode Bernoulli keep masks generated on the device (satk_bernoulli_mask)."""
+    def device_masks(self, B, Tt, Td, seed_dev=None) -> Dict[str, torch.Tensor]:
+        """TRAIN-mode Bernoulli keep masks generated on the device (satk_bernoulli_mask).  ``seed_dev``: the step's seed is read from
+        that device word instead of being a launch argument (the launches of a captured graph), same masks for the same seed."""
         out = {}
         for i, (name, shape) in enumerate(mask_shapes(self.d, B, Tt, Td).items()):
             m = self.buf("mask." + name, shape, torch.uint8)
-            O.bernoulli_mask(m, mask_keep_prob(self.d, name), self._mask_seed * 1000003 + i)
+            if seed_dev is not None:
+                O.bernoulli_mask(m, mask_keep_prob(self.d, name), i, seed_dev=seed_dev)
+            else:
+                O.bernoulli_mask(m, mask_keep_prob(self.d, name), self._mask_seed * 1000003 + i)
             out[name] = m
-        self._mask_seed += 1
+        if seed_dev is None:
+            self._mask_seed += 1
         return out
 
     @contextlib.contextmanager
@@ -974,8 +980,8 @@ class TacotronEngine:
             if masks is not None:      # caller-provided keep masks follow their utterances (batch is dim 0 of the [B,heads,T,T] masks)
                 masks = {k: v.index_select(0 if ".sa" in k else 1, perm) for k, v in masks.items()}
         if training and masks is None:
-            # (under graph capture the masks are generated eagerly before every replay, into the same buffers)
-            masks = self._premade_masks if getattr(self, "_premade_masks", None) is not None else self.device_masks(B, Tt, Td)
+            # (under graph capture the mask launches are part of the graph and read the step's seed from a device word)
+            masks = self.device_masks(B, Tt, Td, seed_dev=getattr(self, "_capture_seed_dev", None))
         # descriptors saved for the backward pass hold raw device pointers: the (possibly re-ordered) inputs stay referenced until then
         self._keepalive = (features, labels, masks)
         self._training = training
@@ -1378,8 +1384,9 @@ class TacotronEngine:
         """forward + backward (+ bucketed all-reduce) of one shape bucket (B, T_text, T_mel) replayed from a CUDA graph: the ~350
         launches of a step cost the host ~3 ms of enqueue time, and the bursts of short encoder / dense kernels are launch-bound.
         The pieces that depend on host scalars stay eager around the replay: the copy of the step's inputs into the graph's static
-        buffers, the keep-mask generation (a fresh seed per step) and clip + Adam (learning rate, step count).  The first two
-        calls of a bucket run eagerly (they allocate the engine's buffers); the third one captures."""
+        buffers, the step's mask seed (one device word: the keep-mask launches themselves are part of the graph and read it) and
+        clip + Adam (learning rate, step count).  The first two calls of a bucket run eagerly (they allocate the engine's buffers);
+        the third one captures."""
         B, Tt = features.source.shape
         Tm = labels.mel.shape[1]
         key = (B, Tt, Tm, world_size, features.speaker_id is not None)
@@ -1405,7 +1412,8 @@ class TacotronEngine:
         for dst, src in zip(st["inputs"], self._graph_inputs(features, labels)):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)
-        self.device_masks(B, Tt, Tm // self.d.r)
+        self._seed_dev.fill_(self._mask_seed)      # the mask launches inside the graph draw from this step's seed
+        self._mask_seed += 1
         st["graph"].replay()
         O.add_launches(st["launches"])
         out = dict(st["out"])
@@ -1428,7 +1436,12 @@ class TacotronEngine:
         sf = features._replace(source=ins[0], source_length=ins[1], speaker_id=ins[2])
         sl = labels._replace(mel=ins[3], target_length=ins[4], done=ins[5], spec_loss_mask=ins[6], binary_loss_mask=ins[7])
         B, Tt = ins[0].shape
-        self._premade_masks = self.device_masks(B, Tt, ins[3].shape[1] // self.d.r)      # the buffers the captured kernels read
+        seed0 = self._mask_seed
+        self.device_masks(B, Tt, ins[3].shape[1] // self.d.r)      # allocates the mask buffers outside the capture
+        self._mask_seed = seed0                                    # (that draw does not count: the replay below is this step)
+        if getattr(self, "_seed_dev", None) is None:
+            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._capture_seed_dev = self._seed_dev
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         l0 = O.launches()
@@ -1437,5 +1450,5 @@ class TacotronEngine:
                 out = self.forward(sf, sl, True, None)
                 self.backward(allreduce)
         finally:
-            self._premade_masks = None
+            self._capture_seed_dev = None
         st.update(graph=g, inputs=ins, out=out, launches=O.launches() - l0, static=(sf, sl))

@@ -147,7 +147,7 @@ SYMBOLS = [
     "satk_embedding_fwd", "satk_embedding_bwd", "satk_bn_stats", "satk_bn_apply", "satk_bn_bwd",
     "satk_highway_fwd", "satk_highway_bwd", "satk_act_bwd", "satk_mask_scale", "satk_colsum_acc", "satk_add", "satk_axpy",
     "satk_transpose", "satk_transpose_batched", "satk_transpose_strided", "satk_mask_rows", "satk_softsign_fwd", "satk_softsign_bwd", "satk_add_rowvec_tb",
-    "satk_sum_over_t", "satk_bernoulli_mask", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
+    "satk_sum_over_t", "satk_bernoulli_mask", "satk_bernoulli_mask_dev", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_l2_reg", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
     "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_attn_rnn_bwd_recurrence", "satk_attn_energy_grad", "satk_attn_energy_grad_parts", "satk_attn_rnn_bwd_overlapped", "satk_debug_phase_cycles",
     "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_sa_tail", "satk_mlp_chain", "satk_decode_tick",

@@ -370,7 +370,15 @@ def sum_over_t(dy, T, B, Cc, dv):
     _count()
 
 
-def bernoulli_mask(out, keep_prob, seed):
+def bernoulli_mask(out, keep_prob, seed, seed_dev=None):
+    """Keep mask with P(1) = keep_prob.  With ``seed_dev`` (a 1-element int64 CUDA tensor) the seed is seed_dev[0] * 1000003 + seed, read
+    on the device at run time (graph-capturable, include/satk.h)."""
+    if seed_dev is not None:
+        check(load().satk_bernoulli_mask_dev(C.c_void_p(out.data_ptr()), C.c_longlong(out.numel()), C.c_float(keep_prob),
+                                             C.c_void_p(seed_dev.data_ptr()), C.c_ulonglong(seed), C.c_void_p(stream_ptr())),
+              "satk_bernoulli_mask_dev")
+        _count()
+        return
     check(load().satk_bernoulli_mask(C.c_void_p(out.data_ptr()), C.c_longlong(out.numel()), C.c_float(keep_prob),
                                      C.c_ulonglong(seed), C.c_void_p(stream_ptr())), "satk_bernoulli_mask")
     _count()

@@ -402,6 +402,27 @@ def test_vctk_config3_per_replica_batch_runs_full_size(satk, root):
     assert torch.isfinite(eng.ps.grad).all() and (eng.ps.flat - w0).abs().max().item() > 0
 
 
+def test_graphed_train_step_equals_eager(satk, root):
+    """The CUDA-graphed train step (engine._train_step_graphed: third call of a shape bucket on) draws the same dropout / zoneout masks
+    (same seed sequence, read from a device word by the captured launches) and lands on the same weights as the eager step."""
+    E, O, L, M = _mods()
+    hp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"))
+    d = satk.dims_from_hparams(hp)
+    ps = satk.ParamStore(d).init(11, "random")
+    f, l = satk.synthetic_batch(hp, 6, 25, 32, seed=3, device="cuda")
+    res = {}
+    for graph in (False, True):
+        eng = E.TacotronEngine(hp, "cuda", params=ps, seed=5)
+        eng.use_graph = graph
+        losses = [eng.train_step(f, l)["losses"].clone() for _ in range(5)]
+        torch.cuda.synchronize()
+        assert graph == any(g.get("graph") is not None for g in eng._graphs.values())
+        res[graph] = (torch.stack(losses), eng.ps.flat.clone(), eng._bufs["mask.dec.prenet0"].clone())
+    assert torch.equal(res[False][2], res[True][2]), "keep masks of the fifth step differ between the eager and the graphed step"
+    _close(res[True][0], res[False][0], 1e-4, "losses of five steps, graphed vs eager")
+    _close(res[True][1], res[False][1], 1e-4, "weights after five steps, graphed vs eager")
+
+
 def test_estimator_surface_postnet_v2(satk, root, tmp_path):
     """use_postnet_v2 through model_fn: TRAIN (four steps, the last ones replayed from the CUDA graph), EVAL metrics
     (models/models.py:174-187,260-269) and the "mel_postnet" prediction of EVAL / PREDICT (models.py:210)."""
