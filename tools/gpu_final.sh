@@ -9,3 +9,4 @@ for c in vctk location_sensitive transition_agent predict; do
   python -c "
 import json,sys; d=json.loads(open('gpurun_out/bench_$c.json').readlines()[-1]); print('$c', d['ms_per_step'], d['value'], d['unit'])"
 done
+timeout 200 python tools/timeline.py graph 2>&1 | tail -1; gzip -f gpurun_out/trace_graph.json
