@@ -373,6 +373,11 @@ int satk_attn_energy_grad_parts(const satk_attn_rnn_bwd_desc* d, int parts, void
  * recurrence's progress flags), so little of it is left when the recurrence ends.  features != 0: the location features are
  * computed first (0: the caller has issued SATK_EG_FEATURES already and ordered `stream` behind it). */
 int satk_attn_rnn_bwd_overlapped(const satk_attn_rnn_bwd_desc* d, int features, void* stream);
+/* `features` is a bit set: SATK_EG_FEATURES as above; SATK_EG_PREPARED: the caller has already issued satk_attn_energy_grad_prepare
+ * (zeroing of the dkeys accumulators, the work queue and the progress flags) earlier on `stream` — hoisting those few memsets away from
+ * the recurrence launch lets its clusters claim their SMs the moment the producer of dx2 ends. */
+#define SATK_EG_PREPARED 4
+int satk_attn_energy_grad_prepare(const satk_attn_rnn_bwd_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Free-running decoder step (PREDICT mode, predict_mel.py:36-74): the inference-branch cells of

@@ -900,7 +900,7 @@ static int bwd2_check(const satk_attn_rnn_bwd_desc* d, bool features_only = fals
   bool has2;
   int rc = attn_rnn_check(&d->f, has2);
   if (rc) return rc;
-  if (!d->de_ws || !d->sync_ws || !arnn2::v2_eligible(&d->f)) {
+  if (!d->de_ws || (!d->sync_ws && !features_only) || !arnn2::v2_eligible(&d->f)) {
     satk::set_error("attn_rnn_bwd: configuration not covered by the second-generation kernels (or de_ws / sync_ws missing)");
     return SATK_ERR_UNSUPPORTED;
   }
@@ -927,13 +927,21 @@ extern "C" int satk_attn_energy_grad_parts(const satk_attn_rnn_bwd_desc* d, int 
 // Recurrence + energy gradients as ONE overlapped pair on one stream: the gradient grid is a programmatic dependent of the
 // recurrence grid (it starts once every recurrence CTA is resident, runs on the SMs the clusters leave idle and follows the
 // progress flags), so only its last chunks remain when the recurrence ends.
+extern "C" int satk_attn_energy_grad_prepare(const satk_attn_rnn_bwd_desc* d, void* stream) {
+  int rc = bwd2_check(d);
+  if (rc) return rc;
+  return arnn2::attn_energy_grad_prepare(d, (cudaStream_t)stream);
+}
+
 extern "C" int satk_attn_rnn_bwd_overlapped(const satk_attn_rnn_bwd_desc* d, int features, void* stream) {
   int rc = bwd2_check(d);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  rc = arnn2::attn_energy_grad_prepare(d, st);
-  if (rc) return rc;
-  if (features) {
+  if (!(features & SATK_EG_PREPARED)) {
+    rc = arnn2::attn_energy_grad_prepare(d, st);
+    if (rc) return rc;
+  }
+  if (features & SATK_EG_FEATURES) {
     rc = arnn2::attn_energy_grad_launch(d, d->de_ws, SATK_EG_FEATURES, 0, st);
     if (rc) return rc;
   }

@@ -698,6 +698,14 @@ class TacotronEngine:
         if d.dual and getattr(self, "_aux", None) is not None and os.environ.get("SATK_ENERGY_FORK", "1") != "0":
             with self._fork():
                 feats_early = O.attn_energy_grad(O.attn_rnn_bwd_desc(sv["fd"], de_ws=de_ws), O.EG_FEATURES, optional=True)
+        # ... and the few memsets of the overlapped pair now, so that nothing sits between the producer of dx2 and the recurrence
+        # launch (its clusters need whole SMs: a weight-gradient product that becomes ready in that gap takes them for 0.1 ms)
+        prepared = False
+        if feats_early and getattr(self, "_aux2", None) is not None and self.timers is None and os.environ.get("SATK_EG_OVERLAP", "1") != "0":
+            prepared = O.attn_energy_grad_prepare(O.attn_rnn_bwd_desc(
+                sv["fd"], de_ws=de_ws, sync_ws=sync_ws, dkeys1=self.buf("dec.dkeys1", (Tt * B, d.att1)),
+                dkeys2=self.buf("dec.dkeys2", (Tt * B, d.att2)), dv1=g["att1.v"], dv2=g["att2.v"],
+                dloc_conv_w=g.get("att1.loc_conv.W"), dloc_conv_b=g.get("att1.loc_conv.b"), dloc_layer_w=g.get("att1.loc_layer.W")))
         O.tf32_push("proj")
         x = sv["proj_in"]
         Dp = x.shape[1]
@@ -761,7 +769,7 @@ class TacotronEngine:
         if overlapped:
             if feats_early:
                 self._join()                   # location features (auxiliary stream) before the pair
-            overlapped = O.attn_rnn_bwd_overlapped(bd, not feats_early)
+            overlapped = O.attn_rnn_bwd_overlapped(bd, not feats_early, prepared)
         if overlapped:
             pass
         elif d.dual and self._timed("attn_rnn_bwd", O.attn_rnn_bwd_recurrence, bd):

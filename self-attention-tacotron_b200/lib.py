@@ -149,7 +149,7 @@ SYMBOLS = [
     "satk_transpose", "satk_transpose_batched", "satk_transpose_strided", "satk_mask_rows", "satk_softsign_fwd", "satk_softsign_bwd", "satk_add_rowvec_tb",
     "satk_sum_over_t", "satk_bernoulli_mask", "satk_bernoulli_mask_dev", "satk_softmax_fwd", "satk_softmax_bwd", "satk_teacher_inputs",
     "satk_losses", "satk_grad_sumsq", "satk_adam_clip", "satk_l2_reg", "satk_lstm_seq_fwd", "satk_lstm_seq_bwd",
-    "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_attn_rnn_bwd_recurrence", "satk_attn_energy_grad", "satk_attn_energy_grad_parts", "satk_attn_rnn_bwd_overlapped", "satk_debug_phase_cycles",
+    "satk_attn_rnn_fwd", "satk_attn_rnn_bwd", "satk_attn_rnn_bwd_recurrence", "satk_attn_energy_grad", "satk_attn_energy_grad_parts", "satk_attn_rnn_bwd_overlapped", "satk_attn_energy_grad_prepare", "satk_debug_phase_cycles",
     "satk_struct_sizes_decode", "satk_rowgemm", "satk_attn_step", "satk_sa_step", "satk_sa_tail", "satk_mlp_chain", "satk_decode_tick",
 ]
 

@@ -526,10 +526,24 @@ def eg_sync_ints(B: int) -> int:
     return 4 + 2 * B
 
 
-def attn_rnn_bwd_overlapped(d: AttnRnnBwdDesc, features: bool) -> bool:
+EG_PREPARED = 4
+
+
+def attn_energy_grad_prepare(d: AttnRnnBwdDesc) -> bool:
+    """Zeroes the dkeys accumulators, the work queue and the progress flags of the overlapped pair ahead of time (include/satk.h).
+    False: configuration not covered by the second-generation kernels."""
+    rc = load().satk_attn_energy_grad_prepare(C.byref(d), C.c_void_p(stream_ptr()))
+    if rc == SATK_ERR_UNSUPPORTED:
+        return False
+    check(rc, "satk_attn_energy_grad_prepare")
+    return True
+
+
+def attn_rnn_bwd_overlapped(d: AttnRnnBwdDesc, features: bool, prepared: bool = False) -> bool:
     """Recurrence + streaming energy gradients as a programmatic-dependent pair (include/satk.h).  False: configuration not covered
     by the second-generation kernels, nothing launched."""
-    rc = load().satk_attn_rnn_bwd_overlapped(C.byref(d), int(features), C.c_void_p(stream_ptr()))
+    flags = (EG_FEATURES if features else 0) | (EG_PREPARED if prepared else 0)
+    rc = load().satk_attn_rnn_bwd_overlapped(C.byref(d), flags, C.c_void_p(stream_ptr()))
     if rc == SATK_ERR_UNSUPPORTED:
         return False
     check(rc, "satk_attn_rnn_bwd_overlapped")
