@@ -9,6 +9,11 @@
 // * one elected thread issues the MMAs; tcgen05.commit releases ring slots / signals the epilogue;
 // * the epilogue reads the 128x128 fp32 accumulator with tcgen05.ld and applies bias / activation /
 //   dropout mask / residual / beta exactly like the SIMT tile (gemm_simt.cu).
+// Weight-gradient form (round 2): C[M,N] = sum_k A[k,m] . B[k,n] with BOTH operands "MN-major" (row-major [K, M] / [K, N], the
+// reduction index k = the row): X^T.dY straight from the activations and their gradients, no transposed copies.  A 128 x 32 tile is
+// four TMA boxes of 32 k-rows x 128 bytes (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B); the shared-memory descriptors say MN-major with
+// layout type 128B_BASE32B (leading byte offset = distance of the 32-float MN blocks, stride byte offset = distance of the 4-row k
+// groups) and the instruction descriptor sets the a_major / b_major bits.
 // Convolution taps = extra iterations of the K loop with a row-shifted TMA coordinate for A (time-major rows:
 // a tap is a shift by B rows; out-of-range rows are zero-filled by TMA) and the tap index as third coordinate of B.
 #include <cuda.h>
@@ -60,6 +65,7 @@ struct Params {
   int causal;               // satk_gemm_desc.causal_skip (zcoord form only)
   int c_rank3;              // output map is [z][M][N] (rank 3): rows / columns outside an entry's slab are clipped by the TMA unit
   int prec;                 // satk_gemm_desc.precision: 1 = one TF32 pass on the raw operands (no hi/lo split)
+  int mn;                   // 1: both operands MN-major (row-major [K, M] and [K, N]): weight-gradient products
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -96,6 +102,20 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows x 128 B
   d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+
+// MN-major fp32 / tf32 operand: layout type 128B_BASE32B (the 128-byte swizzle whose atom is 32 bytes: Swizzle<2,5,2>, what a TMA map
+// with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes), 32-float MN blocks of [32 k-rows x 128 B] 4096 bytes apart (leading byte offset),
+// 4-row k groups 512 bytes apart (stride byte offset); an 8-deep k step advances the start address by 1024 bytes.  Measured with
+// tools/micro/mn_probe.cu: with the plain SWIZZLE_128B layout type a tf32 MMA with a_major / b_major = MN returns zeros on sm_100a.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;                  // leading byte offset
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -220,6 +240,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
       TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
+      if (p.mn) {
+        // MN-major: coordinate 0 = the M / N column, coordinate 1 = the reduction row; one box per 32-float column block
+#pragma unroll
+        for (int j = 0; j < BM / 32; ++j) {
+          tma_load_2d(sa + j * 4096, &mapA, m0 + 32 * j, kb * BK + a_kshift, cl::smem_u32(&full_bar[s]));
+          tma_load_2d(sb + j * 4096, &mapB, n0 + 32 * j, kb * BK, cl::smem_u32(&full_bar[s]));
+        }
+        continue;
+      }
       tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + a_rowoff + shift0_eff + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
       if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap_base + tap, cl::smem_u32(&full_bar[s]));
       else tma_load_2d(sb, &mapB, kb * BK + b_kshift, n0 + b_rowoff, cl::smem_u32(&full_bar[s]));
@@ -227,7 +256,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
+                           (p.mn ? ((1u << 15) | (1u << 16)) : 0u);                       // a_major / b_major = MN
+    const uint32_t kstep = p.mn ? 1024u : 32u;       // bytes per 8-deep k step: one 8-row group (MN-major) / 32 bytes of the row
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       cl::mbar_wait(&xform_bar[s], use & 1);
@@ -235,18 +266,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TC_TRACE(2)
       tc_fence_after();
       const uint32_t sa = smem_base + s * STAGE_BYTES;
-      const uint64_t a_hi = make_desc(sa), a_lo = make_desc(sa + TILE_BYTES);
-      const uint64_t b_hi = make_desc(sa + 2 * TILE_BYTES), b_lo = make_desc(sa + 3 * TILE_BYTES);
+      const uint64_t a_hi = p.mn ? make_desc_mn(sa) : make_desc(sa), a_lo = p.mn ? make_desc_mn(sa + TILE_BYTES) : make_desc(sa + TILE_BYTES);
+      const uint64_t b_hi = p.mn ? make_desc_mn(sa + 2 * TILE_BYTES) : make_desc(sa + 2 * TILE_BYTES);
+      const uint64_t b_lo = p.mn ? make_desc_mn(sa + 3 * TILE_BYTES) : make_desc(sa + 3 * TILE_BYTES);
       if (p.prec == 1) {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 32) >> 4);
+          const uint64_t koff = (uint64_t)((k * kstep) >> 4);
           tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);   // raw fp32: the tensor core keeps 10 mantissa bits
         }
       } else {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * 32) >> 4);   // 8 tf32 = 32 bytes along the swizzled row
+          const uint64_t koff = (uint64_t)((k * kstep) >> 4);   // 8 tf32 = 32 bytes along the swizzled row / one 8-row group
           tc_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);
           tc_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
           tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
@@ -477,6 +509,21 @@ static bool make_map(CUtensorMap* map, const float* base, long long rows, long l
   return r == CUDA_SUCCESS;
 }
 
+// rank-2 map over a row-major [K, MN] operand (the reduction index is the row): box = 32 columns (128 B) x BK rows, 128-byte swizzle
+// with 32-byte atoms (the layout the MN-major tf32 descriptors read)
+static bool make_map_mn(CUtensorMap* map, const float* base, long long krows, long long mn, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)krows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int tc_trace(long long* out16) {
 #ifdef SATK_PHASE_TIMING
   SATK_CUDA(cudaMemcpyFromSymbol(out16, satk::g_phase, sizeof(long long) * 16));
@@ -591,16 +638,28 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   if (d->zcoord) return gemm_tc_zcoord_launch(d, st, supported);
   const bool zform = batches > 1 && (d->batch2 <= 1) && d->sA1 == 0 && d->sB1 == 0 && taps == 1 && !d->bias && d->act == 0 &&
                      !d->residual && !d->keep_mask;
-  if ((batches != 1 && !zform) || d->transA != 0 || d->transB != 1 || d->causal_skip != 0 || d->seq_len != 0 || d->shift_per_batch1 != 0) return SATK_OK;
+  // weight-gradient form: A [K, M] and B [K, N] row-major (transA, !transB), reduction over the rows, no epilogue options; the
+  // SIMT tile's shift0 / shift_per_batch1 (row shift of A per z-batch) are shifts of the reduction coordinate here
+  const bool mn = d->transA == 1 && d->transB == 0 && taps == 1 && !d->bias && d->act == 0 && !d->residual && !d->keep_mask &&
+                  (batches == 1 || zform) && getenv("SATK_TC_MN") == nullptr;
+  if ((batches != 1 && !zform) || (!mn && (d->transA != 0 || d->transB != 1)) || d->causal_skip != 0 || d->seq_len != 0 ||
+      (!mn && d->shift_per_batch1 != 0))
+    return SATK_OK;
   if (d->M < 64 || d->N < 48 || d->K < 32) return SATK_OK;                       // tiny problems stay on the SIMT tile
-  if ((d->lda % 4) || (d->ldb % 4) || (d->K % 4) || ((uintptr_t)d->A % 16) || ((uintptr_t)d->B % 16)) return SATK_OK;
+  if ((d->lda % 4) || (d->ldb % 4) || (!mn && (d->K % 4)) || ((uintptr_t)d->A % 16) || ((uintptr_t)d->B % 16)) return SATK_OK;
+  if (mn && (d->beta != 0.0f && d->beta != 1.0f)) return SATK_OK;
   if (taps > 1 && (d->sBtap % 4)) return SATK_OK;
   if (d->keep_mask && d->split_k > 1) return SATK_OK;
   CUtensorMap mapA, mapB;
-  if (!make_map(&mapA, d->A, d->M, d->K, d->lda, 0, 0)) return SATK_OK;
-  if (!make_map(&mapB, d->B, d->N, d->K, d->ldb, taps > 1 ? taps : 0, d->sBtap)) return SATK_OK;
+  if (mn) {
+    if (!make_map_mn(&mapA, d->A, d->K, d->M, d->lda) || !make_map_mn(&mapB, d->B, d->K, d->N, d->ldb)) return SATK_OK;
+  } else {
+    if (!make_map(&mapA, d->A, d->M, d->K, d->lda, 0, 0)) return SATK_OK;
+    if (!make_map(&mapB, d->B, d->N, d->K, d->ldb, taps > 1 ? taps : 0, d->sBtap)) return SATK_OK;
+  }
   *supported = true;
   Params p;
+  p.mn = mn ? 1 : 0;
   p.prec = d->precision == 1 ? 1 : 0;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.taps = taps; p.shift0 = d->shift0; p.tap_dir = d->tap_dir;
@@ -613,6 +672,10 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   p.bank = 0; p.bank_a_kstep = 0; p.bank_c_nstep = 0;
   p.zcoord = 0; p.za_row = p.za_k = p.zb_row = p.zb_k = p.zc_col = 0; p.causal = 0; p.c_rank3 = 0;
   p.zbatch = batches; p.kshift0 = d->kshift0; p.kshift_step = d->kshift_per_batch1; p.c_zstride = d->sC1;
+  if (mn) {
+    p.kshift0 += d->shift0; p.kshift_step += d->shift_per_batch1;
+    p.shift0 = 0; p.tap_dir = 0;
+  }
   const int kblocks = (d->K + BK - 1) / BK;
   const int tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN);
   const bool linear_epi = !d->bias && d->act == 0 && !d->residual && !d->keep_mask && (d->beta == 0.0f || d->beta == 1.0f);

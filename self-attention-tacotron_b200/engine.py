@@ -353,7 +353,11 @@ class TacotronEngine:
         p, g = self.ps.p, self.ps.g
         pl = (k - 1) // 2
         with self._wg(after):
-            if R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
+            if O.DW_MN and R >= O.DW_TC_MIN_ROWS and cin >= 64 and cout >= 48 and (x_ld or cin) % 4 == 0 and \
+                    (draw_ld or cout) % 4 == 0 and draw_off % 4 == 0:
+                # all taps in one tcgen05 launch straight from x and draw (the tap is a shift of the reduction coordinate)
+                O.conv_dw_mn(x, draw, g[Wname], R, cin, cout, k, B, x_ld, draw_ld, draw_off)
+            elif R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and cout >= 48:
                 # all taps in one tcgen05 launch on row-contiguous transposes (the tap is a shift of the reduction coordinate)
                 if xT is None:
                     xT = O.transposed_rows(x, R, cin, x_ld)
@@ -532,8 +536,8 @@ class TacotronEngine:
         dinp = self.buf("enc.dinp", (R, cin))
         bank_tc = R >= O.DW_TC_MIN_ROWS and cin % 128 == 0 and d.conv_ch >= 48
         with self._wg():
-            inpT = O.transposed_rows(sv["inp"], R, cin) if bank_tc else None      # shared by all bank widths
-            drawT = O.transposed_rows(draw, R, KC) if bank_tc else None
+            inpT = O.transposed_rows(sv["inp"], R, cin) if (bank_tc and not O.DW_MN) else None      # shared by all bank widths
+            drawT = O.transposed_rows(draw, R, KC) if (bank_tc and not O.DW_MN) else None
         bank_ev = self._wg_event() if bank_tc else None     # the per-width sections below run on other side streams
         one = bank_tc and self._bank_one_launch(R, cin, d.conv_ch)
         if one:
@@ -732,7 +736,7 @@ class TacotronEngine:
                            step_end=self.saved.get("step_end"))
             gW = g[f"dec.lstm{li}.W"]
             with self._wg():
-                dgT = O.transposed_rows(dg, Rd, 4 * HD) if Rd >= O.DW_TC_MIN_ROWS else None
+                dgT = O.transposed_rows(dg, Rd, 4 * HD) if (Rd >= O.DW_TC_MIN_ROWS and not O.DW_MN) else None
                 O.linear_dw(s["x"], dg, gW, Rd, kin, 4 * HD, yT=dgT)
                 O.linear_dw(s["h_prev"], dg, gW, Rd, HD, 4 * HD, w_off=kin * 4 * HD, yT=dgT)
                 del dgT
@@ -807,7 +811,7 @@ class TacotronEngine:
         N4 = 4 * H1
         tc_dw = Rd >= O.DW_TC_MIN_ROWS
         with self._wg():
-            dg1T = O.transposed_rows(dg1, Rd, N4) if tc_dw else None     # shared by the three row blocks of dec.lstm1.W
+            dg1T = O.transposed_rows(dg1, Rd, N4) if (tc_dw and not O.DW_MN) else None     # shared by the three row blocks of dec.lstm1.W
             O.linear_dw(sv["dp1"], dg1, gW1, Rd, P1, N4, yT=dg1T)
             # context rows: input of step t is the context of step t-1 (zero at t=0) -> shift by one time step (B rows)
             O.linear_dw(sv["x2"], dg1, gW1, Rd, d.ctx, N4, ldx=X2W, x_off=H1, w_off=P1 * N4, shift0=-B, yT=dg1T)

@@ -204,6 +204,26 @@ def conv_dw_tc(xT: torch.Tensor, drawT: torch.Tensor, dW: torch.Tensor, rows: in
 
 
 DW_TC_MIN_ROWS = 2048      # below this the two transposes cost more than the SIMT split-K product saves
+# weight-gradient products straight from the row-major operands (MN-major tcgen05 descriptors, gemm_tc.cu) instead of from
+# transposed copies; SATK_DW_MN=0 restores the transposes
+DW_MN = os.environ.get("SATK_DW_MN", "1") != "0"
+
+
+def _mn_ok(x, ld, off) -> bool:
+    return ld % 4 == 0 and off % 4 == 0 and x.data_ptr() % 16 == 0
+
+
+def conv_dw_mn(x: torch.Tensor, draw: torch.Tensor, dW: torch.Tensor, rows: int, cin: int, cout: int, taps: int, B: int, x_ld=None,
+               draw_ld=None, draw_off=0) -> None:
+    """dW[tap, cin, cout] += sum_r x[r + (tap - (taps-1)//2) * B, :]^T draw[r, :] for every tap in ONE tcgen05 launch, both operands
+    read as they are (row-major, the reduction index is the row: MN-major descriptors); the tap is a shift of the reduction
+    coordinate of x (TMA zero-fills outside the sequence), the taps are the z-batches of the launch.  (module.py:46-68)"""
+    pl = (taps - 1) // 2
+    tiles = ((cin + 127) // 128) * ((cout + 127) // 128) * taps
+    kblocks = (rows + 31) // 32
+    sk = max(1, min(kblocks // 4, 148 // tiles))
+    gemm(x, draw, dW, cin, cout, rows, lda=x_ld or cin, ldb=draw_ld or cout, ldc=cout, transA=True, b_off=draw_off, batch1=taps,
+         sC=(cin * cout, 0), kshift0=-pl * B, kshift_per_batch1=B, split_k=sk, beta=1.0, engine=2)
 
 
 def linear_dw(x: torch.Tensor, dy: torch.Tensor, dW: torch.Tensor, rows: int, K: int, N: int, ldx=None, x_off=0, ldy=None,
@@ -213,6 +233,13 @@ def linear_dw(x: torch.Tensor, dy: torch.Tensor, dW: torch.Tensor, rows: int, K:
     Large products run on the tcgen05 tile: both operands are first transposed so that the reduction (row) index is contiguous
     (``xT`` / ``yT`` may be passed in when the caller already holds a transposed copy, see ``transposed_rows``); a negative
     ``shift0`` (x delayed by -shift0 rows, zeros before the start) becomes leading zero columns of xT."""
+    if (DW_MN and rows >= DW_TC_MIN_ROWS and K >= 64 and N >= 48 and split_k is None and _mn_ok(x, ldx or K, x_off)
+            and _mn_ok(dy, ldy or N, y_off) and (ldw or N) % 4 == 0 and w_off % 4 == 0):
+        tiles = ((K + 127) // 128) * ((N + 127) // 128)
+        sk = max(1, min(rows // 128, (148 + tiles // 2) // tiles))
+        gemm(x, dy, dW, K, N, rows, lda=ldx or K, ldb=ldy or N, ldc=ldw or N, transA=True, a_off=x_off, b_off=y_off, c_off=w_off,
+             shift0=shift0, split_k=sk, beta=1.0, engine=2)
+        return
     if rows >= DW_TC_MIN_ROWS and K >= 64 and N >= 48 and shift0 <= 0 and split_k is None:
         front = -shift0
         if xT is None:

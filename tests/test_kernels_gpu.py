@@ -107,6 +107,34 @@ def test_conv_weight_gradient_all_taps_one_tensor_core_launch():
         drawT = O.transposed_rows(draw_full.cuda(), R, ld_draw)
         O.conv_dw_tc(xT, drawT, dW, R, cin, cout, k, Bb, drawT_row0=off)
         _close(dW, (dW0.double() + W.grad).float(), 1e-7 * R, f"conv dW tc k={k} cin={cin} cout={cout}")
+        # the same straight from x and draw (MN-major operands, no transposed copies)
+        dW = dW0.clone().cuda()
+        O.conv_dw_mn(x.cuda(), draw_full.cuda(), dW, R, cin, cout, k, Bb, draw_ld=ld_draw, draw_off=off)
+        _close(dW, (dW0.double() + W.grad).float(), 1e-7 * R, f"conv dW tc (MN-major) k={k} cin={cin} cout={cout}")
+
+
+def test_weight_gradient_products_mn_major_operands():
+    """dW += X^T dY with both operands read row-major as they are (the reduction index is the row): MN-major shared-memory
+    descriptors of the tcgen05 tile.  Ragged M / N / row counts, strided operands with offsets, a delayed and an advanced X; against
+    fp64, and against the transposed-operand path."""
+    O = _O()
+    assert O.DW_MN
+    g = torch.Generator().manual_seed(12)
+    for (rows, K, N, ldx, x_off, ldy, y_off, shift0) in ((2304, 96, 80, None, 0, None, 0, 0), (4096, 288, 1024, 544, 256, None, 0, -32),
+                                                         (2051, 64, 48, None, 0, 112, 60, -3), (2500, 200, 130, 260, 8, None, 0, 5),
+                                                         (12800, 544, 1024, None, 0, None, 0, 0)):
+        x = torch.randn(rows, ldx or K, generator=g)
+        dy = torch.randn(rows, ldy or N, generator=g)
+        dW0 = torch.randn(K, N, generator=g)
+        xs = x[:, x_off:x_off + K].double()
+        if shift0 < 0:
+            xs = torch.cat([torch.zeros(-shift0, K, dtype=torch.float64), xs[:shift0]], 0)
+        elif shift0 > 0:
+            xs = torch.cat([xs[shift0:], torch.zeros(shift0, K, dtype=torch.float64)], 0)
+        ref = (dW0.double() + xs.t() @ dy[:, y_off:y_off + N].double()).float()
+        dW = dW0.clone().cuda()
+        O.linear_dw(x.cuda(), dy.cuda(), dW, rows, K, N, ldx=ldx, x_off=x_off, ldy=ldy, y_off=y_off, shift0=shift0)
+        _close(dW, ref, 1e-7 * rows, f"dW MN-major {rows}x{K}x{N}")
 
 
 def test_conv_bank_one_launch_forward_and_input_gradient():
