@@ -10,3 +10,5 @@ for c in vctk location_sensitive transition_agent predict; do
 import json,sys; d=json.loads(open('gpurun_out/bench_$c.json').readlines()[-1]); print('$c', d['ms_per_step'], d['value'], d['unit'])"
 done
 timeout 200 python tools/timeline.py graph 2>&1 | tail -1; gzip -f gpurun_out/trace_graph.json
+SATK_GRAPH=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_ncu.log 2>&1
+python tools/agg_launches.py gpurun_out/r02_launches.csv 2>/dev/null | head -8
