@@ -59,6 +59,11 @@ typedef struct {
   int M, N, K;
   int transA;              /* 0: A is [M,K] (lda = row stride); 1: A is [K,M] */
   int transB;              /* 0: B is [K,N]; 1: B is [N,K] */
+  /* On the tcgen05 tile: (transA, transB) = (0, 1) — both operands contiguous along the reduction index — is the general form;
+   * (1, 0) is the weight-gradient form C = A^T.B (X^T.dY, module.py's dense / conv layers differentiated): both operands are read
+   * row-major as they are through MN-major shared-memory descriptors (no epilogue options, beta in {0, 1}, taps = 1; shift0 /
+   * shift_per_batch1 / kshift0 / kshift_per_batch1 all shift A's reduction row, rows outside A read as zero).  Other combinations
+   * and small shapes run on the SIMT tile. */
   const float* A; long long lda;
   const float* B; long long ldb;
   float* C; long long ldc;
