@@ -358,7 +358,13 @@ __global__ void __launch_bounds__(EG_NT, 2) attn_energy_grad_kernel(const satk_a
     if (wait_progress) {
       if (tid == 0) {
         const volatile int* flag = sync + EGQ_PROG + b * 2 + (loc ? 0 : 1);
-        while (*flag > ta) __nanosleep(256);
+        // bounded: the recurrence needs ~4 ms for all its steps; if its flag has not moved after ~1 s something upstream died —
+        // fail loudly (a trap surfaces as a CUDA error at the next synchronisation) instead of spinning forever
+        long long spins = 0;
+        while (*flag > ta) {
+          __nanosleep(256);
+          if (++spins > (1ll << 22)) __trap();
+        }
         __threadfence();
       }
       __syncthreads();
