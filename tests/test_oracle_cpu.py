@@ -225,3 +225,38 @@ def test_l2_regularization_selection_and_value(satk, root):
         assert float(ps.l2_mask().sum()) == sum(ps.p[n].numel() for n in mine)
     d0 = satk.dims_from_hparams(satk.load_hparams(os.path.join(root, "examples", "ljspeech_tacotron.json")))
     assert d0.l2_weight == 0.0
+
+
+def test_postnet_v2_restatement(satk, root):
+    """PostNetV2 (models/models.py:92-100,116-118,210,440-462): residual structure, loss term, train / eval batch-norm modes, dropout
+    scaling, gradients reach every post-net tensor; the numpy conv twin agrees with the torch conv used inside it."""
+    ov = "use_postnet_v2=True,postnet_v2_out_channels=16,num_postnet_v2_layers=3"
+    hp, d, ps, f, l, masks = _small(satk, root=root, overrides=ov)
+    assert d.postnet_v2 and {"postnet.conv0", "postnet.conv1", "postnet.conv2"} <= set(masks)
+    assert masks["postnet.conv1"].shape == (l.mel.shape[1], l.mel.shape[0], 16)            # frame-major [T_mel, B, channels]
+    P = {k: v.clone() for k, v in ps.as_dict().items()}
+    import dataclasses
+    base = OR.model_forward(P, dataclasses.replace(d, postnet_v2=False), f, l, True, masks)
+    out = OR.model_forward(P, d, f, l, True, masks)
+    assert torch.allclose(out["mel"], base["mel"])                                          # the post-net does not touch the decoder
+    assert torch.allclose(out["loss"], base["loss"] + out["postnet_v2_mel_loss"], atol=1e-6)  # models.py:118 / 482
+    assert torch.allclose(out["postnet_v2_mel_loss"], OR.spec_loss_l1(out["mel_postnet"], l.mel, l.spec_loss_mask))
+    # zero projection -> the residual connection alone
+    P0 = dict(P, **{"postnet.proj.W": torch.zeros_like(P["postnet.proj.W"]), "postnet.proj.b": torch.zeros_like(P["postnet.proj.b"])})
+    assert torch.allclose(OR.postnet_v2(P0, d, out["mel"], False), out["mel"])
+    # eval mode: moving statistics, no dropout -> deterministic and different from the training pass
+    ev1, ev2 = OR.postnet_v2(P, d, out["mel"], False), OR.postnet_v2(P, d, out["mel"], False)
+    assert torch.equal(ev1, ev2) and not torch.allclose(ev1, out["mel_postnet"])
+    # dropout: all-ones masks scale every layer by 1 / keep
+    ones = {k: torch.ones_like(v) for k, v in masks.items()}
+    stats = {}
+    OR.postnet_v2(P, d, out["mel"], True, ones, stats)
+    assert set(stats) == {"postnet.conv0", "postnet.conv1", "postnet.conv2"}
+    # gradients
+    tr = OR.OracleTrainer(d, hp, ps.as_dict())
+    _, grads, _ = tr.loss_and_grads(f, l, masks, True)
+    for n in ("postnet.conv0.W", "postnet.conv2.gamma", "postnet.conv1.beta", "postnet.proj.W", "postnet.proj.b", "dec.out_proj.W"):
+        assert float(grads[n].abs().max()) > 0, n
+    x = torch.randn(2, 9, 5)
+    W = torch.randn(5, 5, 4)
+    assert np.allclose(NP.conv1d_same(x.numpy(), W.numpy()), OR.conv1d_same(x, W).numpy(), atol=1e-5)
