@@ -98,8 +98,10 @@ typedef struct {
   int bank_widths, bank_a_kstep, bank_c_nstep;
   /* batched products of the self-attention block (self_attention.py:45-65 and their gradients) on the tensor-core tile:
    * zcoord = 1 makes the batch1*batch2 entries share ONE 2-D view of each operand — A is [a_rows, a_cols] (row stride lda),
-   * B is [b_rows, b_cols] (row stride ldb), both with the reduction index contiguous (transA = 0, transB = 1) — and entry z
-   * reads A at (row + z*za_row, k + z*za_k) and B at (row + z*zb_row, k + z*zb_k); coordinates outside a view read as zero.
+   * B is [b_rows, b_cols] (row stride ldb) — and entry z reads A at (m + z*za_row, k + z*za_k) and B at (n + z*zb_row, k + z*zb_k);
+   * coordinates outside a view read as zero.  An operand is stored with the reduction index contiguous ([index rows, reduction
+   * columns]: A with transA = 0, B with transB = 1) or with the reduction index as its ROW ([reduction rows, index columns]: transA = 1 /
+   * transB = 0, read through MN-major descriptors — P.V and dS.K take V / K that way, P^T.dO and dS^T.Q both operands).
    * The result of entry z is slab z of a stacked output (sC1 = slab stride in elements, rows >= M / columns >= N clipped)
    * when sC1 != 0, otherwise columns [z*zc_col, z*zc_col + N) of one [M, c_cols] matrix.  Heads of a time-major
    * [T, B*D] activation are k-shifts (z*d_head) or, in its transpose, row shifts; stacked [z][T][T] score matrices are

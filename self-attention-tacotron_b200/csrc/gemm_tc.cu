@@ -65,7 +65,8 @@ struct Params {
   int causal;               // satk_gemm_desc.causal_skip (zcoord form only)
   int c_rank3;              // output map is [z][M][N] (rank 3): rows / columns outside an entry's slab are clipped by the TMA unit
   int prec;                 // satk_gemm_desc.precision: 1 = one TF32 pass on the raw operands (no hi/lo split)
-  int mn;                   // 1: both operands MN-major (row-major [K, M] and [K, N]): weight-gradient products
+  int a_mn, b_mn;           // 1: the operand is MN-major (stored row-major [K, M] / [K, N], the reduction index is the row): both for the
+                            // weight-gradient products; B (P.V, dS.K) or both (P^T.dO, dS^T.Q) for the self-attention products
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -240,25 +241,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + 2 * TILE_BYTES;
       TC_TRACE(0)
       cl::mbar_arrive_expect_tx(&full_bar[s], 2 * TILE_BYTES);
-      if (p.mn) {
-        // MN-major: coordinate 0 = the M / N column, coordinate 1 = the reduction row; one box per 32-float column block
+      // MN-major operand: coordinate 0 = the M / N column, coordinate 1 = the reduction row; one box per 32-float column block
+      if (p.a_mn) {
 #pragma unroll
-        for (int j = 0; j < BM / 32; ++j) {
-          tma_load_2d(sa + j * 4096, &mapA, m0 + 32 * j, kb * BK + a_kshift, cl::smem_u32(&full_bar[s]));
-          tma_load_2d(sb + j * 4096, &mapB, n0 + 32 * j, kb * BK, cl::smem_u32(&full_bar[s]));
-        }
-        continue;
+        for (int j = 0; j < BM / 32; ++j)
+          tma_load_2d(sa + j * 4096, &mapA, m0 + a_rowoff + 32 * j, kb * BK + a_kshift, cl::smem_u32(&full_bar[s]));
+      } else {
+        tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + a_rowoff + shift0_eff + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
       }
-      tma_load_2d(sa, &mapA, kb * BK + a_kshift, m0 + a_rowoff + shift0_eff + tap * p.tap_dir, cl::smem_u32(&full_bar[s]));
-      if (b_rank3) tma_load_3d(sb, &mapB, kb * BK, n0, tap_base + tap, cl::smem_u32(&full_bar[s]));
-      else tma_load_2d(sb, &mapB, kb * BK + b_kshift, n0 + b_rowoff, cl::smem_u32(&full_bar[s]));
+      if (p.b_mn) {
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_2d(sb + j * 4096, &mapB, n0 + b_rowoff + 32 * j, kb * BK + b_kshift, cl::smem_u32(&full_bar[s]));
+      } else if (b_rank3) {
+        tma_load_3d(sb, &mapB, kb * BK, n0, tap_base + tap, cl::smem_u32(&full_bar[s]));
+      } else {
+        tma_load_2d(sb, &mapB, kb * BK + b_kshift, n0 + b_rowoff, cl::smem_u32(&full_bar[s]));
+      }
       if (it == 0) { TC_MARK(1) }
     }
   } else if (warp == 1 && lane == 0) {
     // ===== MMA issuer
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24) |
-                           (p.mn ? ((1u << 15) | (1u << 16)) : 0u);                       // a_major / b_major = MN
-    const uint32_t kstep = p.mn ? 1024u : 32u;       // bytes per 8-deep k step: one 8-row group (MN-major) / 32 bytes of the row
+                           (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);       // a_major / b_major = MN
+    // bytes per 8-deep k step: two 4-row groups (MN-major) / 32 bytes of the row (K-major)
+    const uint32_t a_kstep = p.a_mn ? 1024u : 32u, b_kstep = p.b_mn ? 1024u : 32u;
     for (int it = 0; it < iters; ++it) {
       const int s = it % STAGES, use = it / STAGES;
       cl::mbar_wait(&xform_bar[s], use & 1);
@@ -266,22 +273,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       TC_TRACE(2)
       tc_fence_after();
       const uint32_t sa = smem_base + s * STAGE_BYTES;
-      const uint64_t a_hi = p.mn ? make_desc_mn(sa) : make_desc(sa), a_lo = p.mn ? make_desc_mn(sa + TILE_BYTES) : make_desc(sa + TILE_BYTES);
-      const uint64_t b_hi = p.mn ? make_desc_mn(sa + 2 * TILE_BYTES) : make_desc(sa + 2 * TILE_BYTES);
-      const uint64_t b_lo = p.mn ? make_desc_mn(sa + 3 * TILE_BYTES) : make_desc(sa + 3 * TILE_BYTES);
+      const uint64_t a_hi = p.a_mn ? make_desc_mn(sa) : make_desc(sa), a_lo = p.a_mn ? make_desc_mn(sa + TILE_BYTES) : make_desc(sa + TILE_BYTES);
+      const uint64_t b_hi = p.b_mn ? make_desc_mn(sa + 2 * TILE_BYTES) : make_desc(sa + 2 * TILE_BYTES);
+      const uint64_t b_lo = p.b_mn ? make_desc_mn(sa + 3 * TILE_BYTES) : make_desc(sa + 3 * TILE_BYTES);
       if (p.prec == 1) {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * kstep) >> 4);
-          tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);   // raw fp32: the tensor core keeps 10 mantissa bits
+          const uint64_t ak = (uint64_t)((k * a_kstep) >> 4), bk = (uint64_t)((k * b_kstep) >> 4);
+          tc_mma_tf32(tmem_base, a_hi + ak, b_hi + bk, idesc, (it > 0 || k > 0) ? 1u : 0u);   // raw fp32: the tensor core keeps 10 mantissa bits
         }
       } else {
 #pragma unroll
         for (int k = 0; k < BK / 8; ++k) {
-          const uint64_t koff = (uint64_t)((k * kstep) >> 4);   // 8 tf32 = 32 bytes along the swizzled row / one 8-row group
-          tc_mma_tf32(tmem_base, a_lo + koff, b_hi + koff, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_base, a_hi + koff, b_lo + koff, idesc, 1u);
-          tc_mma_tf32(tmem_base, a_hi + koff, b_hi + koff, idesc, 1u);
+          const uint64_t ak = (uint64_t)((k * a_kstep) >> 4), bk = (uint64_t)((k * b_kstep) >> 4);
+          tc_mma_tf32(tmem_base, a_lo + ak, b_hi + bk, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_base, a_hi + ak, b_lo + bk, idesc, 1u);
+          tc_mma_tf32(tmem_base, a_hi + ak, b_hi + bk, idesc, 1u);
         }
       }
       tc_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
@@ -575,19 +582,24 @@ static int gemm_tc_zcoord_launch(const satk_gemm_desc* d, cudaStream_t st, bool*
   using namespace tc;
   const int batches = (d->batch1 < 1 ? 1 : d->batch1) * (d->batch2 < 1 ? 1 : d->batch2);
   const int taps = d->taps < 1 ? 1 : d->taps;
-  SATK_CHECK_ARG(d->transA == 0 && d->transB == 1 && taps == 1 && d->seq_len == 0 && !d->bias && d->act == 0 && !d->residual &&
+  // operand storage: transA = 0 -> A is [M-index rows, reduction columns] (K-major), 1 -> [reduction rows, M-index columns] (MN-major);
+  // transB = 1 -> B is [N-index rows, reduction columns] (K-major), 0 -> [reduction rows, N-index columns] (MN-major).  The per-entry
+  // shifts keep their meaning (za_row / zb_row: M / N index, za_k / zb_k: reduction index) whichever way an operand is stored.
+  const bool a_mn = d->transA == 1, b_mn = d->transB == 0;
+  SATK_CHECK_ARG(taps == 1 && d->seq_len == 0 && !d->bias && d->act == 0 && !d->residual &&
                      !d->keep_mask && d->beta == 0.0f && d->split_k <= 1 && d->causal_skip >= 0 && d->causal_skip <= 3,
-                 "satk_gemm: the zcoord form takes K-contiguous operands, no epilogue options, beta = 0");
+                 "satk_gemm: the zcoord form takes no epilogue options, beta = 0");
   SATK_CHECK_ARG(d->a_rows > 0 && d->a_cols > 0 && d->b_rows > 0 && d->b_cols > 0 && (d->sC1 != 0 || d->c_cols > 0),
                  "satk_gemm: the zcoord form needs the extents of the operand views");
   SATK_CHECK_ARG((d->lda % 4) == 0 && (d->ldb % 4) == 0 && (d->ldc % 4) == 0 && (d->sC1 % 4) == 0 && ((uintptr_t)d->A % 16) == 0 &&
-                     ((uintptr_t)d->B % 16) == 0 && ((uintptr_t)d->C % 16) == 0 && (d->za_k % 4) == 0 && (d->zb_k % 4) == 0 &&
-                     (d->zc_col % 4) == 0,
+                     ((uintptr_t)d->B % 16) == 0 && ((uintptr_t)d->C % 16) == 0 && ((a_mn ? d->za_row : d->za_k) % 4) == 0 &&
+                     ((b_mn ? d->zb_row : d->zb_k) % 4) == 0 && (d->zc_col % 4) == 0,
                  "satk_gemm: zcoord operands must be 16-byte addressable");
   SATK_CHECK_ARG(d->causal_skip == 0 || (d->causal_skip == 1 ? d->M == d->N : d->M == d->K),
                  "satk_gemm: causal_skip needs a square (query, key) index pair");
   CUtensorMap mapA, mapB, mapC;
-  bool ok = make_map(&mapA, d->A, d->a_rows, d->a_cols, d->lda, 0, 0) && make_map(&mapB, d->B, d->b_rows, d->b_cols, d->ldb, 0, 0);
+  bool ok = (a_mn ? make_map_mn(&mapA, d->A, d->a_rows, d->a_cols, d->lda) : make_map(&mapA, d->A, d->a_rows, d->a_cols, d->lda, 0, 0)) &&
+            (b_mn ? make_map_mn(&mapB, d->B, d->b_rows, d->b_cols, d->ldb) : make_map(&mapB, d->B, d->b_rows, d->b_cols, d->ldb, 0, 0));
   if (ok) {
     if (d->sC1 != 0) {
       EncodeTiledFn enc = get_encode();
@@ -615,6 +627,7 @@ static int gemm_tc_zcoord_launch(const satk_gemm_desc* d, cudaStream_t st, bool*
   p.split_k = 1;
   p.zbatch = batches;
   p.zcoord = 1; p.za_row = d->za_row; p.za_k = d->za_k; p.zb_row = d->zb_row; p.zb_k = d->zb_k; p.zc_col = d->zc_col;
+  p.a_mn = a_mn ? 1 : 0; p.b_mn = b_mn ? 1 : 0;
   p.causal = d->causal_skip;
   p.c_rank3 = d->sC1 != 0 ? 1 : 0;
   p.tma_store = 1;
@@ -659,7 +672,7 @@ int gemm_tc_launch(const satk_gemm_desc* d, cudaStream_t st, bool* supported) {
   }
   *supported = true;
   Params p;
-  p.mn = mn ? 1 : 0;
+  p.a_mn = p.b_mn = mn ? 1 : 0;
   p.prec = d->precision == 1 ? 1 : 0;
   p.M = d->M; p.N = d->N; p.K = d->K;
   p.taps = taps; p.shift0 = d->shift0; p.tap_dir = d->tap_dir;

@@ -248,7 +248,7 @@ class TacotronEngine:
         Pu = Pd if Pd is not None else S
         Oc = self.buf(key + ".O", (R, D))
         if tc:
-            O.attn_apply_tc(Pu, O.transposed_rows(Vp, T, B * D), Oc, T, B * heads, dh, causal=causal)
+            O.attn_apply_tc(Pu, Vp, Oc, T, B * heads, dh, causal=causal)
         else:
             O.gemm(Pu, Vp, Oc, T, dh, T, lda=T, ldb=B * D, ldc=B * D, batch1=B, batch2=heads,
                    sA=(heads * T * T, T * T), sB=(D, dh), sC=(D, dh), causal_skip=2 if causal else 0)
@@ -286,20 +286,17 @@ class TacotronEngine:
         dQ = self.buf(key + ".dQ", (R, D))
         dK = self.buf(key + ".dK", (R, D))
         if O.attn_tc_ok(T, dh):
-            # the four gradient products on the tcgen05 tile: operands that are reduced over their row index are transposed once
-            # (the stacked [z][T][T] matrices as ONE [z*T, T] matrix, entry z = columns z*T.. of the transpose)
+            # the four gradient products on the tcgen05 tile; operands that are reduced over their row index are read as they are
+            # (MN-major descriptors; the stacked [z][T][T] matrices as ONE [z*T, T] matrix, entry z = rows z*T..)
             # dV does not depend on d(scores), dK and dQ only share dS: the dV and dK branches run on the auxiliary stream
             nz, W = B * heads, B * D
             with self._fork():
-                dOT = O.transposed_rows(dO, T, W)
-                O.attn_apply_t_tc(O.transposed_rows(sv["Pd"], nz * T, T), dOT, dV, T, nz, dh, causal=causal)
-                del dOT
+                O.attn_apply_t_tc(sv["Pd"], dO, dV, T, nz, dh, causal=causal)
             O.attn_scores_tc(dO, sv["V"], dPd, T, nz, dh, causal=causal)
             O.softmax_bwd(sv["P"], dPd, nz, T, causal, dS, sv["mask"], 1.0 / sv["keep"])
             with self._fork():
-                O.attn_apply_t_tc(O.transposed_rows(dS, nz * T, T), O.transposed_rows(sv["Q"], T, W), dK, T, nz, dh, alpha=scale,
-                                  causal=causal)
-            O.attn_apply_tc(dS, O.transposed_rows(sv["K"], T, W), dQ, T, nz, dh, alpha=scale, causal=causal)
+                O.attn_apply_t_tc(dS, sv["Q"], dK, T, nz, dh, alpha=scale, causal=causal)
+            O.attn_apply_tc(dS, sv["K"], dQ, T, nz, dh, alpha=scale, causal=causal)
             self._join()
         else:
             O.gemm(dO, sv["V"], dPd, T, T, dh, lda=B * D, ldb=B * D, ldc=T, transB=True, sA=sX, sB=sX, sC=sP,

@@ -142,7 +142,8 @@ def linear_dx(dy: torch.Tensor, W: torch.Tensor, dx: torch.Tensor, rows: int, be
 
 def attn_tc_ok(T: int, dh: int) -> bool:
     """Shapes of the batched self-attention products that the tcgen05 tile takes (``attn_scores_tc`` / ``attn_apply_tc`` /
-    ``attn_apply_t_tc``): a head is a k-shift of the time-major activation, so d_head must be whole 32-float k-blocks."""
+    ``attn_apply_t_tc``): a head is a k-shift (or, for an MN-major operand, a column shift) of the time-major activation, so d_head
+    must be whole 32-float blocks."""
     return T >= 128 and T % 4 == 0 and dh % 32 == 0 and 32 <= dh <= 128 and os.environ.get("SATK_ATTN_TC", "1") != "0"
 
 
@@ -155,23 +156,23 @@ def attn_scores_tc(X: torch.Tensor, Y: torch.Tensor, S: torch.Tensor, T: int, nz
          zcoord=dict(za_k=dh, zb_k=dh, a_rows=T, a_cols=W, b_rows=T, b_cols=W))
 
 
-def attn_apply_tc(P: torch.Tensor, YT: torch.Tensor, Out: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
-    """Out[:, z*dh..] = alpha * P[z] @ Y_z with P [nz, T, T] and YT [nz*dh, T] the transpose of time-major Y (``transposed_rows``):
-    P.V (self_attention.py:63-65) and dQ = dS K."""
+def attn_apply_tc(P: torch.Tensor, Y: torch.Tensor, Out: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
+    """Out[:, z*dh..] = alpha * P[z] @ Y_z with P [nz, T, T] and Y time-major [T, nz*dh], read as it is (the reduction index of Y is its
+    row: MN-major B operand, entry z = columns z*dh..): P.V (self_attention.py:63-65) and dQ = dS K."""
     W = nz * dh
-    gemm(P, YT, Out, T, dh, T, lda=T, ldb=YT.shape[1], ldc=W, transB=True, alpha=alpha, batch1=nz,
+    gemm(P, Y, Out, T, dh, T, lda=T, ldb=W, ldc=W, transB=False, alpha=alpha, batch1=nz,
          causal_skip=2 if causal else 0, engine=2,
-         zcoord=dict(za_row=T, zb_row=dh, zc_col=dh, a_rows=nz * T, a_cols=T, b_rows=W, b_cols=T, c_cols=W))
+         zcoord=dict(za_row=T, zb_row=dh, zc_col=dh, a_rows=nz * T, a_cols=T, b_rows=T, b_cols=W, c_cols=W))
 
 
-def attn_apply_t_tc(PT: torch.Tensor, YT: torch.Tensor, Out: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
-    """Out[:, z*dh..] = alpha * P[z]^T @ Y_z with PT [T, nz*T] the transpose of the stacked [nz*T, T] matrices as ONE matrix
-    (entry z = columns z*T..) and YT as above: dV = P^T dO and dK = dS^T Q.  The last k-block of an entry runs into the next
-    entry's columns of PT; YT reads as zero there."""
+def attn_apply_t_tc(P: torch.Tensor, Y: torch.Tensor, Out: torch.Tensor, T: int, nz: int, dh: int, alpha=1.0, causal=False) -> None:
+    """Out[:, z*dh..] = alpha * P[z]^T @ Y_z with P the stacked [nz*T, T] matrices and Y time-major [T, nz*dh], both read as they are
+    (both reduce over their row index: MN-major A and B; entry z = rows z*T.. of P, columns z*dh.. of Y): dV = P^T dO and
+    dK = dS^T Q.  The last k-block of an entry runs into the next entry's rows of P; Y has no such rows and reads as zero there."""
     W = nz * dh
-    gemm(PT, YT, Out, T, dh, T, lda=PT.shape[1], ldb=YT.shape[1], ldc=W, transB=True, alpha=alpha, batch1=nz,
+    gemm(P, Y, Out, T, dh, T, lda=T, ldb=W, ldc=W, transA=True, transB=False, alpha=alpha, batch1=nz,
          causal_skip=3 if causal else 0, engine=2,
-         zcoord=dict(za_k=T, zb_row=dh, zc_col=dh, a_rows=T, a_cols=nz * T, b_rows=W, b_cols=T, c_cols=W))
+         zcoord=dict(za_k=T, zb_row=dh, zc_col=dh, a_rows=nz * T, a_cols=T, b_rows=T, b_cols=W, c_cols=W))
 
 
 def transposed_rows(x: torch.Tensor, rows: int, cols: int, ldx=None, x_off=0, front=0) -> torch.Tensor:

@@ -342,7 +342,8 @@ def test_bernoulli_mask_rate():
 def test_self_attention_products_tensor_core_zbatches(T, nz, dh, causal):
     """QK^T, P.V and the four gradient products of the self-attention block (self_attention.py:45-65) as z-batches of the
     tcgen05 tile over shared 2-D operand views (satk_gemm_desc.zcoord): heads as k-shifts of the time-major activations, stacked
-    score matrices as row shifts / k-shifts of their transpose, ragged last tiles clipped by the TMA stores, causal tile /
+    score matrices as row shifts, operands reduced over their row index read through MN-major descriptors, ragged last tiles
+    clipped by the TMA stores, causal tile /
     k-range skipping.  Against fp64; entries the causal softmax never reads are not compared."""
     O = _O()
     g = torch.Generator().manual_seed(T + dh)
@@ -365,12 +366,12 @@ def test_self_attention_products_tensor_core_zbatches(T, nz, dh, causal):
     _close(S, ref.float(), tol, "scores")
 
     Out = torch.full((T, W), float("nan"), device="cuda")
-    O.attn_apply_tc(P.cuda(), O.transposed_rows(Y.cuda(), T, W), Out, T, nz, dh, alpha=0.5, causal=causal)
+    O.attn_apply_tc(P.cuda(), Y.cuda(), Out, T, nz, dh, alpha=0.5, causal=causal)
     ref = 0.5 * (P.double() @ Yz).transpose(0, 1).reshape(T, W)
     _close(Out, ref.float(), tol, "apply")
 
     Out = torch.full((T, W), float("nan"), device="cuda")
-    O.attn_apply_t_tc(O.transposed_rows(P.cuda(), nz * T, T), O.transposed_rows(Y.cuda(), T, W), Out, T, nz, dh, alpha=2.0, causal=causal)
+    O.attn_apply_t_tc(P.cuda(), Y.cuda(), Out, T, nz, dh, alpha=2.0, causal=causal)
     ref = 2.0 * (P.double().transpose(1, 2) @ Yz).transpose(0, 1).reshape(T, W)
     _close(Out, ref.float(), tol, "apply_t")
 

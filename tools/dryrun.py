@@ -34,11 +34,15 @@ def gemm(A, B, C_, M, N, K, *, lda, ldb, ldc, transA=False, transB=False, alpha=
         z = dict(za_row=0, za_k=0, zb_row=0, zb_k=0, zc_col=0, c_cols=0)
         z.update(zcoord)
         nz = batch1 * batch2
-        assert not transA and transB and taps == 1 and beta == 0.0 and bias is None and residual is None and keep_mask is None
+        assert taps == 1 and beta == 0.0 and bias is None and residual is None and keep_mask is None
         _extent(A, a_off, (z["a_rows"] - 1) * lda + z["a_cols"], "zcoord A")
         _extent(B, b_off, (z["b_rows"] - 1) * ldb + z["b_cols"], "zcoord B")
-        assert (nz - 1) * z["za_row"] + M <= z["a_rows"] and (nz - 1) * z["za_k"] + K <= z["a_cols"], "zcoord A shifts"
-        assert (nz - 1) * z["zb_row"] + N <= z["b_rows"] and (nz - 1) * z["zb_k"] + K <= z["b_cols"], "zcoord B shifts"
+        # an operand is stored [index rows, reduction columns] (K-major: A with transA = 0, B with transB = 1) or
+        # [reduction rows, index columns] (MN-major); the shifts keep their meaning either way
+        a_idx, a_red = (z["a_cols"], z["a_rows"]) if transA else (z["a_rows"], z["a_cols"])
+        b_idx, b_red = (z["b_rows"], z["b_cols"]) if transB else (z["b_cols"], z["b_rows"])
+        assert (nz - 1) * z["za_row"] + M <= a_idx and (nz - 1) * z["za_k"] + K <= a_red, "zcoord A shifts"
+        assert (nz - 1) * z["zb_row"] + N <= b_idx and (nz - 1) * z["zb_k"] + K <= b_red, "zcoord B shifts"
         assert lda >= z["a_cols"] and ldb >= z["b_cols"] and lda % 4 == 0 and ldb % 4 == 0 and ldc % 4 == 0
         if sC[0]:
             _extent(C_, c_off, (nz - 1) * sC[0] + (M - 1) * ldc + N, "zcoord C")
