@@ -201,20 +201,57 @@ def group_by_batch(pairs, hp, batch_size=None):
             yield padded_batch([x[0] for x in w[i:i + bs]], [x[1] for x in w[i:i + bs]], hp)
 
 
-def tfrecord_input_fn(source_files, target_files, hp, batch_size=None, for_prediction=False):
+def tfrecord_input_fn(source_files, target_files, hp, batch_size=None, for_prediction=False, filter_max_output_length=None,
+                      repeat=False, shuffle_buffer_size=0, seed=0, max_source_length=None):
     """input_fn over the reference's pre-processed TFRecord files (train.py:40-66 / predict_mel.py:39-45): source and target files
     are read in the given order and zipped record by record.  `for_prediction` applies `merge_target_to_source`
-    (datasets/ljspeech/dataset.py:309-322): features become SourceDataForPrediction carrying the ground-truth mel."""
+    (datasets/ljspeech/dataset.py:309-322): features become SourceDataForPrediction carrying the ground-truth mel.
+
+    The stages of the reference's training / evaluation pipeline (train.py:53-54,65), in its order:
+      * ``filter_max_output_length`` — `filter_by_max_output_length` (dataset.py:197-202): utterances whose padded target is longer
+        than ``max_iters * outputs_per_step`` frames are dropped (None = the reference's behaviour: on for training / evaluation as
+        in train.py, off with ``for_prediction`` — predict_mel.py does not filter);
+      * ``repeat`` — `.repeat(count=None)`: start over when the files are exhausted (the caller bounds the run with ``steps``);
+      * ``shuffle_buffer_size`` — `.shuffle(hparams.suffle_buffer_size)`: a sliding buffer of that many utterances, one drawn at
+        random per step (tf.data semantics; ``seed`` makes the order reproducible); 0 = file order;
+      * `group_by_batch` (bucketed, padded batches).
+    ``max_source_length`` (not in the reference, which has no T_text limit): drop utterances with more symbols than that — the
+    attention-RNN kernels take T_text <= 192 and refuse longer batches loudly."""
     from . import tfrecord as TF
+    import random
+
+    max_out = int(hp.max_iters) * int(hp.outputs_per_step)
+    do_filter = (not for_prediction) if filter_max_output_length is None else bool(filter_max_output_length)
 
     def gen():
         def pairs():
-            for sf, tf_ in zip(source_files, target_files):
-                for s, t in zip(TF.read_source_file(sf), TF.read_mel_file(tf_)):
-                    if s.key != t.key:
-                        raise ValueError(f"source / target records out of step: {s.key} vs {t.key}")
-                    yield s, prepare_target(t, hp)
-        for feats, labels in group_by_batch(pairs(), hp, batch_size):
+            while True:
+                for sf, tf_ in zip(source_files, target_files):
+                    for s, t in zip(TF.read_source_file(sf), TF.read_mel_file(tf_)):
+                        if s.key != t.key:
+                            raise ValueError(f"source / target records out of step: {s.key} vs {t.key}")
+                        tgt = prepare_target(t, hp)
+                        if do_filter and int(tgt["target_length"]) > max_out:
+                            continue
+                        if max_source_length is not None and int(s.source_length) > max_source_length:
+                            continue
+                        yield s, tgt
+                if not repeat:
+                    return
+
+        def shuffled(it):
+            if shuffle_buffer_size <= 1:
+                yield from it
+                return
+            rng, buf = random.Random(seed), []
+            for x in it:
+                buf.append(x)
+                if len(buf) >= shuffle_buffer_size:
+                    yield buf.pop(rng.randrange(len(buf)))
+            while buf:
+                yield buf.pop(rng.randrange(len(buf)))
+
+        for feats, labels in group_by_batch(shuffled(pairs()), hp, batch_size):
             if for_prediction:
                 feats = SourceDataForPrediction(feats.id, feats.key, feats.source, feats.source_length, feats.text, feats.speaker_id,
                                                 labels.mel, labels.mel_width, labels.target_length)

@@ -143,6 +143,18 @@ def test_prepare_target_and_batching_follow_the_reference(satk, root, tmp_path):
     assert l.spec_loss_mask[0].tolist() == [1.0] * 10 + [0.0] * 2 and l.binary_loss_mask[0].tolist() == [1.0] * 5 + [0.0]
     fp, lp = next(iter(satk.tfrecord_input_fn([sp], [mp], hp, batch_size=1, for_prediction=True)()))
     assert type(fp).__name__ == "SourceDataForPrediction" and fp.mel.shape == (1, 10, nm) and fp.target_length.tolist() == [10]
+    # the stages of train.py:53-54: filter_by_max_output_length (max_iters * r frames), repeat, shuffle buffer
+    hp5 = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"),
+                            "batch_size=2,approx_min_target_length=4,batch_bucket_width=3,batch_num_buckets=5,max_iters=5")
+    kept = [k for b in satk.tfrecord_input_fn([sp], [mp], hp5)() for k in b[0].key]
+    assert kept == ["utt0", "utt2", "utt3"]                        # padded targets 10, 12, 10, 8, 14 frames against 5 * 2
+    assert len([k for b in satk.tfrecord_input_fn([sp], [mp], hp5, filter_max_output_length=False)() for k in b[0].key]) == 5
+    assert len([k for b in satk.tfrecord_input_fn([sp], [mp], hp5, batch_size=1, for_prediction=True)() for k in b[0].key]) == 5
+    it = satk.tfrecord_input_fn([sp], [mp], hp, repeat=True, shuffle_buffer_size=3, seed=4)()
+    first = [k for _ in range(5) for k in next(it)[0].key]
+    again = [k for _, b in zip(range(5), satk.tfrecord_input_fn([sp], [mp], hp, repeat=True, shuffle_buffer_size=3, seed=4)()) for k in b[0].key]
+    assert len(first) == 10 and first == again and set(first) == {f"utt{i}" for i in range(5)} and first[:5] != [f"utt{i}" for i in range(5)]
+    assert [k for b in satk.tfrecord_input_fn([sp], [mp], hp, max_source_length=6)() for k in b[0].key] == ["utt0", "utt1", "utt2"]
 
 
 def test_prediction_outputs_round_trip(tmp_path):
