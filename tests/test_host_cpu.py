@@ -74,6 +74,27 @@ def test_abi_symbols_and_struct_sizes(satk, root):
     assert lib.satk_version() >= 100
 
 
+def test_workspace_size_helpers_follow_the_header(root):
+    """ops.de_ws_floats / eg_sync_ints / SUMSQ_SCRATCH restate macros of include/satk.h: evaluate the macros and compare."""
+    import re
+    from importlib import import_module
+    O = import_module("self-attention-tacotron_b200.ops")
+    src = open(os.path.join(root, "include", "satk.h")).read()
+    de_row = re.search(r"#define SATK_DE_ROW\(Tt\) (.+)", src).group(1)
+    sync = re.search(r"#define SATK_EG_SYNC_INTS\(B\) (.+)", src).group(1)
+    sumsq = int(re.search(r"#define SATK_SUMSQ_SCRATCH (\d+)", src).group(1))
+    assert O.SUMSQ_SCRATCH == sumsq
+    for Tt in (1, 31, 32, 33, 148, 192):
+        row = eval(de_row.replace("/", "//"), {"Tt": Tt})
+        assert row % 32 == 0 and row >= Tt and row - Tt < 32
+        for Td, B in ((1, 1), (400, 32), (7, 5)):
+            assert O.de_ws_floats(Td, B, Tt) == Td * B * (2 * row + 8 * Tt)
+    for B in (1, 5, 32, 64):
+        assert O.eg_sync_ints(B) == eval(sync, {"B": B})
+    assert (O.EG_FEATURES, O.EG_GRADIENTS, O.EG_PREPARED) == tuple(
+        int(re.search(rf"#define SATK_EG_{n} (\d+)", src).group(1)) for n in ("FEATURES", "GRADIENTS", "PREPARED"))
+
+
 def test_engine_refuses_cpu(satk, root):
     from importlib import import_module
     E = import_module("self-attention-tacotron_b200.engine")
