@@ -215,12 +215,14 @@ def tfrecord_input_fn(source_files, target_files, hp, batch_size=None, for_predi
       * ``shuffle_buffer_size`` — `.shuffle(hparams.suffle_buffer_size)`: a sliding buffer of that many utterances, one drawn at
         random per step (tf.data semantics; ``seed`` makes the order reproducible); 0 = file order;
       * `group_by_batch` (bucketed, padded batches).
+    ``hparams.source == 'phone'`` selects the phone sequence of VCTK records as the source (datasets/vctk/dataset.py:144-146).
     ``max_source_length`` (not in the reference, which has no T_text limit): drop utterances with more symbols than that — the
     attention-RNN kernels take T_text <= 192 and refuse longer batches loudly."""
     from . import tfrecord as TF
     import random
 
     max_out = int(hp.max_iters) * int(hp.outputs_per_step)
+    use_phone = getattr(hp, "source", None) == "phone"
     do_filter = (not for_prediction) if filter_max_output_length is None else bool(filter_max_output_length)
 
     def gen():
@@ -230,6 +232,10 @@ def tfrecord_input_fn(source_files, target_files, hp, batch_size=None, for_predi
                     for s, t in zip(TF.read_source_file(sf), TF.read_mel_file(tf_)):
                         if s.key != t.key:
                             raise ValueError(f"source / target records out of step: {s.key} vs {t.key}")
+                        if use_phone:       # datasets/vctk/dataset.py:144-146: hparams.source == 'phone' selects the phone sequence
+                            if s.phone is None:
+                                raise ValueError(f"hparams.source='phone' but record {s.key} carries no phone / phone_length / phone_txt")
+                            s = s._replace(source=s.phone, source_length=s.phone_length, text=s.phone_txt or "")
                         tgt = prepare_target(t, hp)
                         if do_filter and int(tgt["target_length"]) > max_out:
                             continue

@@ -198,7 +198,8 @@ def decode_example(buf: bytes) -> Dict[str, FeatureValue]:
 
 # ------------------------------------------------------------------------------------------------ the reference's record types
 PreprocessedSourceData = namedtuple("PreprocessedSourceData", ["id", "key", "source", "source_length", "text", "speaker_id",
-                                                               "age", "gender"])
+                                                               "age", "gender", "phone", "phone_length", "phone_txt"])
+PreprocessedSourceData.__new__.__defaults__ = (None, None, None)     # the phone fields exist in VCTK records only (vctk/dataset.py:74-76)
 PreprocessedMelData = namedtuple("PreprocessedMelData", ["id", "key", "mel", "mel_width", "target_length"])
 
 
@@ -212,7 +213,8 @@ def _scalar(ex, name, default=None):
 
 
 def decode_source_record(buf: bytes) -> PreprocessedSourceData:
-    """datasets/ljspeech/dataset.py:50-72 (+ speaker_id / age / gender of datasets/vctk/dataset.py:64-98 when present)."""
+    """datasets/ljspeech/dataset.py:50-72 (+ speaker_id / age / gender / phone, phone_length, phone_txt of
+    datasets/vctk/dataset.py:64-98 when present)."""
     ex = decode_example(buf)
     source = np.frombuffer(_scalar(ex, "source"), dtype="<i8").copy()
     spk = ex.get("speaker_id")
@@ -221,7 +223,10 @@ def decode_source_record(buf: bytes) -> PreprocessedSourceData:
         source_length=int(_scalar(ex, "source_length")), text=_scalar(ex, "text", b"").decode("utf-8"),
         speaker_id=int(spk[0]) if spk is not None and len(spk) else None,
         age=int(ex["age"][0]) if "age" in ex and len(ex["age"]) else None,
-        gender=int(ex["gender"][0]) if "gender" in ex and len(ex["gender"]) else None)
+        gender=int(ex["gender"][0]) if "gender" in ex and len(ex["gender"]) else None,
+        phone=np.frombuffer(_scalar(ex, "phone"), dtype="<i8").copy() if "phone" in ex and len(ex["phone"]) else None,
+        phone_length=int(ex["phone_length"][0]) if "phone_length" in ex and len(ex["phone_length"]) else None,
+        phone_txt=_scalar(ex, "phone_txt", b"").decode("utf-8") if "phone_txt" in ex and len(ex["phone_txt"]) else None)
 
 
 def encode_source_record(d: PreprocessedSourceData) -> bytes:
@@ -232,6 +237,9 @@ def encode_source_record(d: PreprocessedSourceData) -> bytes:
     if d.speaker_id is not None:
         feats.update(speaker_id=np.array([d.speaker_id], np.int64), age=np.array([d.age or 0], np.int64),
                      gender=np.array([d.gender or 0], np.int64))
+    if d.phone is not None:
+        feats.update(phone=[np.asarray(d.phone, dtype="<i8").tobytes()], phone_length=np.array([d.phone_length], np.int64),
+                     phone_txt=[(d.phone_txt or "").encode("utf-8")])
     return encode_example(feats)
 
 

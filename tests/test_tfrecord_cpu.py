@@ -108,7 +108,13 @@ def test_source_and_mel_records_round_trip(tmp_path):
     TF.write_records(mp, [TF.encode_mel_record(mel)])
     s2, m2 = next(TF.read_source_file(sp)), next(TF.read_mel_file(mp))
     assert s2.key == "p225_001" and s2.speaker_id == 225 and np.array_equal(s2.source, src.source) and s2.text == "hello"
+    assert s2.phone is None and s2.phone_length is None
     assert m2.target_length == 4 and m2.mel_width == 3 and np.array_equal(m2.mel, mel.mel)
+    # VCTK records also carry a phone sequence (datasets/vctk/dataset.py:74-76)
+    src_p = src._replace(phone=np.array([0, 40, 41, 0], np.int64), phone_length=4, phone_txt="HH AH")
+    TF.write_records(sp, [TF.encode_source_record(src_p)])
+    s3 = next(TF.read_source_file(sp))
+    assert np.array_equal(s3.phone, src_p.phone) and s3.phone_length == 4 and s3.phone_txt == "HH AH" and np.array_equal(s3.source, src.source)
 
 
 def test_prepare_target_and_batching_follow_the_reference(satk, root, tmp_path):
@@ -155,6 +161,15 @@ def test_prepare_target_and_batching_follow_the_reference(satk, root, tmp_path):
     again = [k for _, b in zip(range(5), satk.tfrecord_input_fn([sp], [mp], hp, repeat=True, shuffle_buffer_size=3, seed=4)()) for k in b[0].key]
     assert len(first) == 10 and first == again and set(first) == {f"utt{i}" for i in range(5)} and first[:5] != [f"utt{i}" for i in range(5)]
     assert [k for b in satk.tfrecord_input_fn([sp], [mp], hp, max_source_length=6)() for k in b[0].key] == ["utt0", "utt1", "utt2"]
+    # hparams.source == 'phone' (datasets/vctk/dataset.py:144-146): the phone sequence is the source; records without one are refused
+    hpp = satk.load_hparams(os.path.join(root, "examples", "ljspeech_self-attention-tacotron.json"),
+                            "batch_size=2,approx_min_target_length=4,batch_bucket_width=3,batch_num_buckets=5,source=phone")
+    with pytest.raises(ValueError, match="phone"):
+        next(iter(satk.tfrecord_input_fn([sp], [mp], hpp)()))
+    srcs_p = [x._replace(phone=np.array([0, 50 + i, 0], np.int64), phone_length=3, phone_txt=f"P{i}") for i, x in enumerate(srcs)]
+    TF.write_records(sp, [TF.encode_source_record(x) for x in srcs_p])
+    f, l = next(iter(satk.tfrecord_input_fn([sp], [mp], hpp)()))
+    assert f.source.tolist() == [[0, 50, 0], [0, 51, 0]] and f.source_length.tolist() == [3, 3] and f.text == ["P0", "P1"]
 
 
 def test_prediction_outputs_round_trip(tmp_path):
