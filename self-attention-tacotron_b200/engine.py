@@ -691,7 +691,7 @@ class TacotronEngine:
         d, p, g, sv = self.d, self.ps.p, self.ps.g, self._dec_saved
         training = self._training
         R, Rd = Tt * B, Td * B
-        H1, HD, P1 = d.att_rnn, d.dec_out, d.dec_prenet[1]
+        H1, HD = d.att_rnn, d.dec_out
         # second-generation attention backward: its location features need the forward pass only -> first thing on the auxiliary stream
         de_ws = self.buf("dec.de_ws", (O.de_ws_floats(Td, B, Tt),)) if d.dual else None
         sync_ws = self.buf("dec.eg_sync", (O.eg_sync_ints(B),), torch.int32) if d.dual else None
@@ -742,7 +742,6 @@ class TacotronEngine:
             O.linear_dx(dg, W[:kin], dxl, Rd)
             dout = dxl
         dx2 = dout                                     # [Rd, H1 + ctx]
-        X2W = H1 + d.ctx
         fd = sv["fd"]
         loc = d.attention in ("forward", "location_sensitive")
         QT = d.att1 + d.att2
